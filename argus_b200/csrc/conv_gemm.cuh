@@ -1,0 +1,531 @@
+// Implicit-GEMM convolution / linear kernels on tcgen05 tensor cores (sm_100a), fed by TMA.
+//
+//   conv_gemm_kernel<BLOCK_N, B_MN>  : D[pixels, Cout] = sum_taps A_tap[pixels, Cin] * W_tap          (forward, B_MN=0)
+//                                      dX[pixels, Cin] = sum_taps dY_tap[pixels, Cout] * W_tap^T      (dgrad,   B_MN=1)
+//   wgrad_kernel<BLOCK_N>            : dW[Cout, tap, Cin] += sum_pixels dY[p, Cout]^T * A_tap[p, Cin] (split-K, fp32 red)
+//
+// Layout: activations are NHWC bf16. An M tile is 128 consecutive output pixels (= a (bw, bh, bn) box of the
+// (W, H, N) grid because H and W are powers of two), so one 4-D TMA box per filter tap lands a K-major,
+// 128B-swizzled [128 x 64] operand tile in shared memory; padding is TMA out-of-bounds zero fill and stride-2
+// convolutions read parity-strided tensor maps. Accumulators live in TMEM (double buffered) so the epilogue of
+// tile i overlaps the main loop of tile i+1. Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// alloc), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store, BN statistics, fused
+// scale/shift/residual/ReLU).
+//
+// Reference semantics being replaced: torch.nn.Conv2d / nn.Linear inside torchvision resnet50 as called at
+// /root/reference/argus/models.py:84 (cuDNN/cuBLAS in the reference).
+#pragma once
+#include "ptx.cuh"
+
+namespace argus {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom row
+constexpr int kNumThreads = 192;
+constexpr int kMaxTaps = 16;
+
+struct Tap {
+  int8_t map;   // which A tensor map (parity plane) this tap reads
+  int8_t dh;    // row offset added to the tile's h0
+  int8_t dw;    // column offset added to the tile's w0
+  int8_t pad_;
+  int32_t b_off;  // element offset of this tap inside the weight matrix (K offset for K-major B, N offset for MN-major)
+};
+
+struct ConvGemmParams {
+  CUtensorMap a_map[4];
+  CUtensorMap b_map;
+  CUtensorMap out_map;
+  Tap taps[kMaxTaps];
+  int num_taps;
+  int kblocks_per_tap;
+  int num_m_tiles;
+  int num_n_tiles;
+  int log2_wo;     // output pixel grid: width
+  int log2_howo;   // output pixel grid: rows*cols per image
+  int m_total;     // number of valid output pixels (rows of D)
+  int n_total;     // number of output channels (columns of D)
+  // epilogue (all optional)
+  const float* scale;            // per output channel multiplier (folded BN)
+  const float* shift;            // per output channel offset (folded BN / bias)
+  const __nv_bfloat16* residual; // [m_total, n_total] added before ReLU
+  int relu;
+  float* stat_sum;               // per-channel sum of the stored bf16 outputs (train-mode BN)
+  float* stat_sqsum;             // per-channel sum of squares
+};
+
+template <int BLOCK_N>
+struct ConvGemmSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = 196608 / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
+  static constexpr int kOffStaging = kStages * kStageBytes;
+  static constexpr int kOffStats = kOffStaging + 2 * kStagingBytes;
+  static constexpr int kOffBars = kOffStats + 2 * BLOCK_N * 4;
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemPtr + 16;
+};
+
+template <int BLOCK_N, int B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  using L = ConvGemmSmem<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+  static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const uint32_t bar_base = smem_base + L::kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
+  float* s_stats = reinterpret_cast<float*>(smem + L::kOffStats);
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    tma_prefetch_desc(&p.b_map);
+    tma_prefetch_desc(&p.out_map);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+    tmem_relinquish();
+  }
+  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kNumThreads) s_stats[i] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+  const int num_kblocks = p.num_taps * p.kblocks_per_tap;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.num_n_tiles;
+        const int n_tile = tile - m_tile * p.num_n_tiles;
+        const int m0 = m_tile * kBlockM;
+        const int img0 = m0 >> p.log2_howo;
+        const int rem = m0 & ((1 << p.log2_howo) - 1);
+        const int h0 = rem >> p.log2_wo;
+        const int w0 = rem & ((1 << p.log2_wo) - 1);
+        const int n0 = n_tile * BLOCK_N;
+        for (int t = 0; t < p.num_taps; ++t) {
+          const Tap tap = p.taps[t];
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1);
+            const uint32_t sa = smem_base + stage * L::kStageBytes;
+            const uint32_t sb = sa + L::kABytes;
+            mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+            tma_load_4d(&p.a_map[tap.map], full_bar(stage), sa, kb * kBlockK, w0 + tap.dw, h0 + tap.dh, img0);
+            if (B_MN == 0) {
+              // weights [n_total rows, K]: one box of BLOCK_N rows x 64 k
+              tma_load_2d(&p.b_map, full_bar(stage), sb, tap.b_off + kb * kBlockK, n0);
+            } else {
+              // weights [K rows, N cols]: BLOCK_N/64 boxes of 64 k-rows x 64 n
+#pragma unroll
+              for (int j = 0; j < BLOCK_N / 64; ++j)
+                tma_load_2d(&p.b_map, full_bar(stage), sb + j * 8192, tap.b_off + n0 + j * 64, kb * kBlockK);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kblocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 32, 0, 1024);
+            const uint64_t db = (B_MN == 0) ? make_smem_desc_sw128(sb + k * 32, 0, 1024)
+                                            : make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == num_kblocks - 1) umma_commit(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int wq = warp & 3;              // TMEM lane quarter this warp may access
+    const int r = wq * 32 + lane;         // row of the tile owned by this thread
+    const int et = threadIdx.x - 64;      // 0..127 among epilogue threads
+    const bool store_leader = (et == 0);
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int buf = 0;
+    int cur_n = -1;
+    const bool do_stats = (p.stat_sum != nullptr);
+
+    auto flush_stats = [&](int n_tile) {
+      named_bar_sync(1, 128);
+      for (int c = et; c < BLOCK_N; c += 128) {
+        const int gc = n_tile * BLOCK_N + c;
+        if (gc < p.n_total) {
+          atomicAdd(p.stat_sum + gc, s_stats[c]);
+          atomicAdd(p.stat_sqsum + gc, s_stats[BLOCK_N + c]);
+        }
+        s_stats[c] = 0.f;
+        s_stats[BLOCK_N + c] = 0.f;
+      }
+      named_bar_sync(1, 128);
+    };
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m0 = m_tile * kBlockM;
+      const int img0 = m0 >> p.log2_howo;
+      const int rem = m0 & ((1 << p.log2_howo) - 1);
+      const int h0 = rem >> p.log2_wo;
+      const int w0 = rem & ((1 << p.log2_wo) - 1);
+      const int n0 = n_tile * BLOCK_N;
+      const int m = m0 + r;
+      if (do_stats && n_tile != cur_n) {
+        if (cur_n >= 0) flush_stats(cur_n);
+        cur_n = n_tile;
+      }
+
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+        // staging buffer `buf` was handed to a TMA store two chunks ago: wait until that store has read it.
+        if (store_leader) tma_store_wait_read<1>();
+        named_bar_sync(1, 128);
+        uint8_t* stg = smem + L::kOffStaging + buf * L::kStagingBytes;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + ch * 64 + h * 32;
+          tmem_ld_32x32(taddr, v);
+          tmem_ld_wait();
+          const int c0 = n0 + ch * 64 + h * 32;
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.scale != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + i));
+              f[i] *= s.x; f[i + 1] *= s.y; f[i + 2] *= s.z; f[i + 3] *= s.w;
+            }
+          }
+          if (p.shift != nullptr) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + i));
+              f[i] += s.x; f[i + 1] += s.y; f[i + 2] += s.z; f[i + 3] += s.w;
+            }
+          }
+          if (p.residual != nullptr && m < p.m_total) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.n_total + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 rv = __ldg(rp + q);
+              float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
+              f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+            }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 o;
+            o.x = pack_bf16x2(f[q * 8 + 0], f[q * 8 + 1]);
+            o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
+            o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
+            o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
+            const int j = h * 4 + q;                     // logical 16-byte chunk of the 128-byte row
+            const int phys = j ^ (r & 7);                // SWIZZLE_128B
+            *reinterpret_cast<uint4*>(stg + r * 128 + phys * 16) = o;
+          }
+        }
+        if (ch == BLOCK_N / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1, 128);
+        if (store_leader) {
+          tma_store_4d(&p.out_map, smem_u32(stg), n0 + ch * 64, w0, h0, img0);
+          tma_store_commit();
+        }
+        if (do_stats) {
+          // column pair `lane` of the 32 rows owned by this warp; swizzled reads are bank-conflict free
+          float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+          const int jl = lane >> 2;
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = wq * 32 + rr;
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(stg + row * 128 + ((jl ^ (row & 7)) << 4) + ((lane & 3) << 2));
+            const float2 x = unpack_bf16x2(w);
+            s0 += x.x; s1 += x.y;
+            q0 = fmaf(x.x, x.x, q0); q1 = fmaf(x.y, x.y, q1);
+          }
+          const int c = ch * 64 + lane * 2;
+          atomicAdd(&s_stats[c], s0);
+          atomicAdd(&s_stats[c + 1], s1);
+          atomicAdd(&s_stats[BLOCK_N + c], q0);
+          atomicAdd(&s_stats[BLOCK_N + c + 1], q1);
+        }
+        buf ^= 1;
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (do_stats && cur_n >= 0) flush_stats(cur_n);
+    if (store_leader) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient: dW[co, tap, ci] += sum over a K-chunk of pixels of dY[p, co] * A_tap[p, ci].
+// Both operands are MN-major in shared memory (pixels are the GEMM K dimension and the slow memory dimension).
+// Work item = (co tile of 128, ci tile of BLOCK_N, tap, K split); results are reduced into fp32 with red.add.
+// ---------------------------------------------------------------------------------------------------------
+struct WgradParams {
+  CUtensorMap dy_map;     // 2-D [pixels, Cout], box (64 co, 64 pixels)
+  CUtensorMap a_map[4];   // 4-D activation maps (C, W, H, N) by parity, box (64 ci, 64-pixel box)
+  Tap taps[kMaxTaps];     // b_off = element offset of the tap inside one dW row
+  int num_taps;
+  int num_co_tiles;       // ceil(Cout / 128)
+  int num_ci_tiles;       // ceil(Cin / BLOCK_N)
+  int num_ksplits;
+  int kblocks_total;      // ceil(pixels / 64)
+  int log2_wo, log2_howo; // pixel grid of dY
+  int cout, cin;
+  int dw_row_stride;      // elements between consecutive co rows of dW
+  float* dw;
+};
+
+template <int BLOCK_N>
+struct WgradSmem {
+  static constexpr int kABytes = 2 * 8192;                 // 128 co x 64 pixels
+  static constexpr int kBBytes = (BLOCK_N / 64) * 8192;    // BLOCK_N ci x 64 pixels
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStagesRaw = 196608 / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kOffBars = kStages * kStageBytes;
+  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemPtr + 16;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using L = WgradSmem<BLOCK_N>;
+  constexpr int kStages = L::kStages;
+  constexpr int kTmemCols = 2 * BLOCK_N;
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base + L::kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.dy_map);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // work item order: ksplit fastest so that concurrently running CTAs share the same weight tile's operands in L2
+  const int items_per_tap = p.num_co_tiles * p.num_ci_tiles * p.num_ksplits;
+  const int num_items = items_per_tap * p.num_taps;
+  const int kb_per_split = (p.kblocks_total + p.num_ksplits - 1) / p.num_ksplits;
+
+  auto decode = [&](int item, int& tap, int& co_t, int& ci_t, int& kb0, int& kb1) {
+    int ks = item % p.num_ksplits;
+    int rest = item / p.num_ksplits;
+    tap = rest % p.num_taps;
+    rest /= p.num_taps;
+    ci_t = rest % p.num_ci_tiles;
+    co_t = rest / p.num_ci_tiles;
+    kb0 = ks * kb_per_split;
+    kb1 = min(kb0 + kb_per_split, p.kblocks_total);
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int t, co_t, ci_t, kb0, kb1;
+        decode(item, t, co_t, ci_t, kb0, kb1);
+        const Tap tap = p.taps[t];
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int p0 = kb * 64;
+          const int img0 = p0 >> p.log2_howo;
+          const int rem = p0 & ((1 << p.log2_howo) - 1);
+          const int h0 = rem >> p.log2_wo;
+          const int w0 = rem & ((1 << p.log2_wo) - 1);
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+          mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
+          tma_load_2d(&p.dy_map, full_bar(stage), sa, co_t * 128, p0);
+          tma_load_2d(&p.dy_map, full_bar(stage), sa + 8192, co_t * 128 + 64, p0);
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 64; ++j)
+            tma_load_4d(&p.a_map[tap.map], full_bar(stage), sb + j * 8192, ci_t * BLOCK_N + j * 64, w0 + tap.dw,
+                        h0 + tap.dh, img0);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        int t, co_t, ci_t, kb0, kb1;
+        decode(item, t, co_t, ci_t, kb0, kb1);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * L::kStageBytes;
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sa + k * 2048, 8192, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+            umma_bf16(tmem_d, da, db, idesc, (kb > kb0) || (k != 0));
+          }
+          umma_commit(empty_bar(stage));
+          if (kb == kb1 - 1) umma_commit(tfull_bar(acc));
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (kb1 <= kb0) umma_commit(tfull_bar(acc));  // empty split: nothing accumulated (epilogue skips it)
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+      int t, co_t, ci_t, kb0, kb1;
+      decode(item, t, co_t, ci_t, kb0, kb1);
+      const Tap tap = p.taps[t];
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const int co = co_t * 128 + r;
+      float* row = p.dw + static_cast<size_t>(co) * p.dw_row_stride + tap.b_off + ci_t * BLOCK_N;
+#pragma unroll 1
+      for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + ch * 32;
+        tmem_ld_32x32(taddr, v);
+        tmem_ld_wait();
+        if (kb1 > kb0 && co < p.cout) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int ci = ci_t * BLOCK_N + ch * 32 + i;
+            if (ci < p.cin) atomicAdd(row + ch * 32 + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace argus

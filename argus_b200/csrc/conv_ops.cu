@@ -1,0 +1,376 @@
+#include "conv_ops.h"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace argus {
+
+// ------------------------------------------------------------------------------------------------
+// runtime helpers
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(sym);
+  });
+  ARGUS_CHECK(fn != nullptr, "cuTensorMapEncodeTiled not available from the CUDA driver");
+  return fn;
+}
+
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box) {
+  CUtensorMap m;
+  std::memset(&m, 0, sizeof(m));
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[4];
+  cuuint32_t bdim[5];
+  cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  ARGUS_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base address must be 16-byte aligned");
+  ARGUS_CHECK(box[0] * 2 == 128, "SWIZZLE_128B boxes are 64 bf16 wide");
+  CUresult r = get_encode_fn()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(base), gdim, gstr, bdim,
+                               estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    std::string msg = "cuTensorMapEncodeTiled failed (" + std::to_string(static_cast<int>(r)) + ") rank=" +
+                      std::to_string(rank) + " dims=";
+    for (int i = 0; i < rank; ++i) msg += std::to_string(dims[i]) + ",";
+    msg += " strides=";
+    for (int i = 0; i + 1 < rank; ++i) msg += std::to_string(strides_bytes[i]) + ",";
+    msg += " box=";
+    for (int i = 0; i < rank; ++i) msg += std::to_string(box[i]) + ",";
+    throw Error(msg);
+  }
+  return m;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    ARGUS_CUDA(cudaGetDevice(&dev));
+    ARGUS_CUDA(cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev));
+  }
+  return n;
+}
+
+void require_sm100() {
+  int dev = 0, major = 0;
+  ARGUS_CUDA(cudaGetDevice(&dev));
+  ARGUS_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  ARGUS_CHECK(major == 10, "argus_b200 kernels are built for sm_100a only; no fallback path exists");
+}
+
+// ------------------------------------------------------------------------------------------------
+// shape handling
+// ------------------------------------------------------------------------------------------------
+void validate_shape(const ConvShape& s) {
+  ARGUS_CHECK(s.N > 0 && s.H > 0 && s.W > 0, "empty convolution input");
+  ARGUS_CHECK(is_pow2(s.H) && is_pow2(s.W), "spatial sizes must be powers of two (tiles are linear pixel runs)");
+  if (s.kind == 1) {
+    ARGUS_CHECK(s.Cout == 64 && s.stride == 2 && s.H >= 2 && s.W >= 2, "stem convolution is 3->64, stride 2");
+    return;
+  }
+  ARGUS_CHECK(s.k == 1 || s.k == 3, "kernel size must be 1 or 3");
+  ARGUS_CHECK(s.stride == 1 || s.stride == 2, "stride must be 1 or 2");
+  ARGUS_CHECK(s.Cin % 64 == 0 && s.Cout % 64 == 0, "channel counts must be multiples of 64");
+  ARGUS_CHECK(s.H % s.stride == 0 && s.W % s.stride == 0, "spatial size must be divisible by the stride");
+}
+
+static int pick_block_n(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
+
+// box of `pixels` consecutive pixels of an (N, Ho, Wo) grid, as (bw, bh, bn)
+static void pixel_box(int Wo, int Ho, int pixels, uint32_t& bw, uint32_t& bh, uint32_t& bn) {
+  bw = std::min(Wo, pixels);
+  bh = std::min(Ho, pixels / static_cast<int>(bw));
+  bn = pixels / (bw * bh);
+}
+
+// activation tensor maps for reading the conv INPUT x as seen from the output pixel grid
+static void make_input_maps(const ConvShape& s, const __nv_bfloat16* x, int pixels, CUtensorMap* maps) {
+  uint32_t bw, bh, bn;
+  pixel_box(s.Wo(), s.Ho(), pixels, bw, bh, bn);
+  const uint32_t box[4] = {64, bw, bh, bn};
+  if (s.kind == 1) {
+    const uint64_t Hs = s.H / 2, Ws = s.W / 2, Wp = Ws + 4;
+    const uint64_t dims[4] = {64, Ws, Hs, static_cast<uint64_t>(s.N)};
+    const uint64_t str[3] = {32, Wp * 32, Hs * Wp * 32};  // overlapping 128-byte windows, 32 bytes apart
+    maps[0] = make_tmap_bf16(x, 4, dims, str, box);
+    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
+    return;
+  }
+  const uint64_t C = s.Cin, H = s.H, W = s.W;
+  if (s.stride == 1) {
+    const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(s.N)};
+    const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+    maps[0] = make_tmap_bf16(x, 4, dims, str, box);
+    for (int i = 1; i < 4; ++i) maps[i] = maps[0];
+  } else {
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const uint64_t dims[4] = {C, W / 2, H / 2, static_cast<uint64_t>(s.N)};
+        const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+        maps[a * 2 + b] = make_tmap_bf16(x + (a * W + b) * C, 4, dims, str, box);
+      }
+  }
+}
+
+static int fill_forward_taps(const ConvShape& s, Tap* taps) {
+  int n = 0;
+  if (s.kind == 1) {
+    for (int pi = 0; pi < 4; ++pi) taps[n++] = Tap{0, static_cast<int8_t>(pi - 2), 0, 0, pi * 64};
+    return n;
+  }
+  const int pad = s.k / 2;
+  for (int kh = 0; kh < s.k; ++kh)
+    for (int kw = 0; kw < s.k; ++kw) {
+      Tap t{};
+      t.b_off = (kh * s.k + kw) * s.Cin;
+      const int eh = kh - pad, ew = kw - pad;
+      if (s.stride == 1) {
+        t.map = 0;
+        t.dh = static_cast<int8_t>(eh);
+        t.dw = static_cast<int8_t>(ew);
+      } else {
+        const int a = eh & 1, b = ew & 1;  // parity plane (two's complement & works for -1)
+        t.map = static_cast<int8_t>(a * 2 + b);
+        t.dh = static_cast<int8_t>((eh - a) / 2);
+        t.dw = static_cast<int8_t>((ew - b) / 2);
+      }
+      taps[n++] = t;
+    }
+  return n;
+}
+
+ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y) {
+  validate_shape(s);
+  ConvLaunch l;
+  std::memset(&l.p, 0, sizeof(l.p));
+  l.block_n = pick_block_n(s.Cout);
+  l.b_mn = 0;
+  ConvGemmParams& p = l.p;
+  make_input_maps(s, x, kBlockM, p.a_map);
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(s.Ktot()), static_cast<uint64_t>(s.Cout)};
+    const uint64_t str[1] = {static_cast<uint64_t>(s.Ktot()) * 2};
+    const uint32_t box[2] = {64, static_cast<uint32_t>(l.block_n)};
+    p.b_map = make_tmap_bf16(w, 2, dims, str, box);
+  }
+  {
+    uint32_t bw, bh, bn;
+    pixel_box(s.Wo(), s.Ho(), kBlockM, bw, bh, bn);
+    const uint64_t C = s.Cout, Ho = s.Ho(), Wo = s.Wo();
+    const uint64_t dims[4] = {C, Wo, Ho, static_cast<uint64_t>(s.N)};
+    const uint64_t str[3] = {C * 2, Wo * C * 2, Ho * Wo * C * 2};
+    const uint32_t box[4] = {64, bw, bh, bn};
+    p.out_map = make_tmap_bf16(y, 4, dims, str, box);
+  }
+  p.num_taps = fill_forward_taps(s, p.taps);
+  p.kblocks_per_tap = (s.kind == 1) ? 1 : s.Cin / 64;
+  p.m_total = static_cast<int>(s.out_pixels());
+  p.n_total = s.Cout;
+  p.num_m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
+  p.num_n_tiles = (s.Cout + l.block_n - 1) / l.block_n;
+  p.log2_wo = ilog2(s.Wo());
+  p.log2_howo = ilog2(s.Ho() * s.Wo());
+  return l;
+}
+
+std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* w,
+                                        __nv_bfloat16* dx) {
+  validate_shape(s);
+  ARGUS_CHECK(s.kind == 0, "the stem has no input gradient");
+  std::vector<ConvLaunch> out;
+  const int pad = s.k / 2;
+  const int Ho = s.Ho(), Wo = s.Wo();
+  const int block_n = pick_block_n(s.Cin);
+  const int classes = (s.stride == 1) ? 1 : 4;
+  for (int cls = 0; cls < classes; ++cls) {
+    const int a = cls >> 1, b = cls & 1;
+    ConvLaunch l;
+    std::memset(&l.p, 0, sizeof(l.p));
+    l.block_n = block_n;
+    l.b_mn = 1;
+    ConvGemmParams& p = l.p;
+    // taps: which (kh, kw) reach input pixels of this parity class, and from which dy pixel offset
+    int n = 0;
+    for (int kh = 0; kh < s.k; ++kh)
+      for (int kw = 0; kw < s.k; ++kw) {
+        Tap t{};
+        t.map = 0;
+        t.b_off = (kh * s.k + kw) * s.Cin;
+        if (s.stride == 1) {
+          t.dh = static_cast<int8_t>(pad - kh);
+          t.dw = static_cast<int8_t>(pad - kw);
+        } else {
+          const int eh = a + pad - kh, ew = b + pad - kw;
+          if ((eh & 1) || (ew & 1)) continue;
+          t.dh = static_cast<int8_t>(eh / 2);
+          t.dw = static_cast<int8_t>(ew / 2);
+        }
+        p.taps[n++] = t;
+      }
+    if (n == 0) continue;  // this parity class receives no gradient (caller zero-filled dx)
+    p.num_taps = n;
+    p.kblocks_per_tap = s.Cout / 64;
+    // A = dy on the (N, Ho, Wo) grid
+    uint32_t bw, bh, bn;
+    pixel_box(Wo, Ho, kBlockM, bw, bh, bn);
+    {
+      const uint64_t C = s.Cout;
+      const uint64_t dims[4] = {C, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(s.N)};
+      const uint64_t str[3] = {C * 2, Wo * C * 2, static_cast<uint64_t>(Ho) * Wo * C * 2};
+      const uint32_t box[4] = {64, bw, bh, bn};
+      p.a_map[0] = make_tmap_bf16(dy, 4, dims, str, box);
+      for (int i = 1; i < 4; ++i) p.a_map[i] = p.a_map[0];
+    }
+    {
+      // weights [Cout rows][k*k*Cin]: MN-major B operand (K = Cout is the slow dimension)
+      const uint64_t dims[2] = {static_cast<uint64_t>(s.Ktot()), static_cast<uint64_t>(s.Cout)};
+      const uint64_t str[1] = {static_cast<uint64_t>(s.Ktot()) * 2};
+      const uint32_t box[2] = {64, 64};
+      p.b_map = make_tmap_bf16(w, 2, dims, str, box);
+    }
+    {
+      const uint64_t C = s.Cin, H = s.H, W = s.W;
+      const uint32_t box[4] = {64, bw, bh, bn};
+      if (s.stride == 1) {
+        const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(s.N)};
+        const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+        p.out_map = make_tmap_bf16(dx, 4, dims, str, box);
+      } else {
+        const uint64_t dims[4] = {C, W / 2, H / 2, static_cast<uint64_t>(s.N)};
+        const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
+        p.out_map = make_tmap_bf16(dx + (a * W + b) * C, 4, dims, str, box);
+      }
+    }
+    p.m_total = s.N * Ho * Wo;
+    p.n_total = s.Cin;
+    p.num_m_tiles = (p.m_total + kBlockM - 1) / kBlockM;
+    p.num_n_tiles = (s.Cin + block_n - 1) / block_n;
+    p.log2_wo = ilog2(Wo);
+    p.log2_howo = ilog2(Ho * Wo);
+    out.push_back(l);
+  }
+  return out;
+}
+
+WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw) {
+  validate_shape(s);
+  WgradLaunch l;
+  std::memset(&l.p, 0, sizeof(l.p));
+  WgradParams& p = l.p;
+  const int cin_tile_extent = (s.kind == 1) ? 64 : s.Cin;  // stem: each tap is one 64-wide window
+  l.block_n = pick_block_n(cin_tile_extent);
+  const int64_t pixels = s.out_pixels();
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cout), static_cast<uint64_t>(pixels)};
+    const uint64_t str[1] = {static_cast<uint64_t>(s.Cout) * 2};
+    const uint32_t box[2] = {64, 64};
+    p.dy_map = make_tmap_bf16(dy, 2, dims, str, box);
+  }
+  make_input_maps(s, x, 64, p.a_map);
+  p.num_taps = fill_forward_taps(s, p.taps);
+  p.num_co_tiles = (s.Cout + 127) / 128;
+  p.num_ci_tiles = (cin_tile_extent + l.block_n - 1) / l.block_n;
+  p.kblocks_total = static_cast<int>((pixels + 63) / 64);
+  const int base_items = p.num_co_tiles * p.num_ci_tiles * p.num_taps;
+  int splits = (3 * num_sms() + base_items - 1) / base_items;
+  splits = std::min(splits, std::max(1, p.kblocks_total / 8));
+  splits = std::max(splits, 1);
+  // no empty splits: shrink until the last split still owns at least one k-block
+  while (splits > 1) {
+    const int per = (p.kblocks_total + splits - 1) / splits;
+    if (per * (splits - 1) < p.kblocks_total) break;
+    --splits;
+  }
+  p.num_ksplits = splits;
+  p.log2_wo = ilog2(s.Wo());
+  p.log2_howo = ilog2(s.Ho() * s.Wo());
+  p.cout = s.Cout;
+  p.cin = cin_tile_extent;
+  p.dw_row_stride = s.Ktot();
+  p.dw = dw;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launches
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BMN>
+static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
+  using L = ConvGemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int tiles = p.num_m_tiles * p.num_n_tiles;
+  const int grid = std::min(tiles, num_sms());
+  conv_gemm_kernel<BN, BMN><<<grid, kNumThreads, L::kTotal, stream>>>(p);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
+  ConvGemmParams p = l.p;
+  p.scale = e.scale;
+  p.shift = e.shift;
+  p.residual = e.residual;
+  p.relu = e.relu;
+  p.stat_sum = e.stat_sum;
+  p.stat_sqsum = e.stat_sqsum;
+  ARGUS_CHECK((e.stat_sum == nullptr) == (e.stat_sqsum == nullptr), "BN statistic pointers come in pairs");
+  const int key = l.block_n * 2 + l.b_mn;
+  switch (key) {
+    case 64 * 2 + 0: launch_conv_t<64, 0>(p, stream); break;
+    case 128 * 2 + 0: launch_conv_t<128, 0>(p, stream); break;
+    case 256 * 2 + 0: launch_conv_t<256, 0>(p, stream); break;
+    case 64 * 2 + 1: launch_conv_t<64, 1>(p, stream); break;
+    case 128 * 2 + 1: launch_conv_t<128, 1>(p, stream); break;
+    case 256 * 2 + 1: launch_conv_t<256, 1>(p, stream); break;
+    default: throw Error("unsupported conv tile configuration");
+  }
+}
+
+template <int BN>
+static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
+  using L = WgradSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    ARGUS_CUDA(cudaFuncSetAttribute(wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  const int items = p.num_co_tiles * p.num_ci_tiles * p.num_ksplits * p.num_taps;
+  const int grid = std::min(items, num_sms());
+  wgrad_kernel<BN><<<grid, kNumThreads, L::kTotal, stream>>>(p);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+void launch_wgrad(const WgradLaunch& l, cudaStream_t stream) {
+  switch (l.block_n) {
+    case 64: launch_wgrad_t<64>(l.p, stream); break;
+    case 128: launch_wgrad_t<128>(l.p, stream); break;
+    case 256: launch_wgrad_t<256>(l.p, stream); break;
+    default: throw Error("unsupported wgrad tile configuration");
+  }
+}
+
+}  // namespace argus

@@ -1,0 +1,59 @@
+// Host-side planning for the tcgen05 convolution kernels: turns a convolution shape plus device pointers into
+// kernel parameter blocks (TMA tensor maps, filter-tap tables, tile counts) once, so the hot path only launches.
+#pragma once
+#include "conv_gemm.cuh"
+#include "runtime.h"
+
+namespace argus {
+
+// A convolution over NHWC bf16 activations with [Cout][kh][kw][Cin] bf16 weights.
+// kind: 0 = ordinary k x k convolution (k in {1,3}, stride in {1,2}, pad = k/2)
+//       1 = ResNet stem: 7x7 stride-2 pad-3 convolution over 3 channels, expressed on the space-to-depth
+//           input written by the input-packing kernel: x_s2d[N][H/2][W/2 + 4][16], so that every output pixel
+//           reads four 128-byte windows (one per s2d row offset); weights are repacked to [64][4][64].
+struct ConvShape {
+  int N = 0, H = 0, W = 0;  // input image count and spatial size (stem: the ORIGINAL image size)
+  int Cin = 0, Cout = 0;
+  int k = 1, stride = 1;
+  int kind = 0;
+  int Ho() const { return H / stride; }
+  int Wo() const { return W / stride; }
+  int Ktot() const { return kind == 1 ? 256 : k * k * Cin; }
+  int64_t out_pixels() const { return static_cast<int64_t>(N) * Ho() * Wo(); }
+};
+
+struct Epilogue {
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  const __nv_bfloat16* residual = nullptr;
+  int relu = 0;
+  float* stat_sum = nullptr;
+  float* stat_sqsum = nullptr;
+};
+
+struct ConvLaunch {
+  ConvGemmParams p;
+  int block_n = 64;
+  int b_mn = 0;
+};
+
+struct WgradLaunch {
+  WgradParams p;
+  int block_n = 64;
+};
+
+void validate_shape(const ConvShape& s);
+
+// y[N,Ho,Wo,Cout] = conv(x, w)   (epilogue pointers are patched per launch)
+ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y);
+// dx[N,H,W,Cin] = conv_transpose(dy, w); stride-2 convolutions need one launch per input-pixel parity class.
+// Pixels that receive no contribution (1x1 stride 2) are NOT written: the caller zero-fills dx first.
+std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* w,
+                                        __nv_bfloat16* dx);
+// dw[Cout][Ktot] (fp32, accumulated with atomics: caller zero-fills) = dy^T * im2col(x)
+WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
+
+void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);
+void launch_wgrad(const WgradLaunch& l, cudaStream_t stream);
+
+}  // namespace argus

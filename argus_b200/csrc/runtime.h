@@ -1,0 +1,65 @@
+// Host-side runtime helpers shared by every translation unit of libargus_b200.so:
+// error reporting across the C ABI, TMA tensor-map encoding, device buffers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace argus {
+
+// Every C-ABI entry point wraps its body in ARGUS_API_BEGIN/END: C++ exceptions never cross the boundary,
+// they become a non-zero return code plus a thread-local message (argus_last_error_string()).
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define ARGUS_CHECK(cond, msg)                                                                        \
+  do {                                                                                                \
+    if (!(cond)) throw ::argus::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + \
+                                      std::string(msg));                                              \
+  } while (0)
+
+#define ARGUS_CUDA(expr)                                                                                \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw ::argus::Error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + ": " + #expr + ": " + \
+                           cudaGetErrorString(_e));                                                     \
+  } while (0)
+
+#define ARGUS_API_BEGIN try {
+#define ARGUS_API_END                          \
+  return 0;                                    \
+  }                                            \
+  catch (const std::exception& e) {            \
+    ::argus::set_last_error(e.what());         \
+    return 1;                                  \
+  }                                            \
+  catch (...) {                                \
+    ::argus::set_last_error("unknown error");  \
+    return 2;                                  \
+  }
+
+// bf16 tiled tensor map with SWIZZLE_128B. dims/strides innermost first; strides[i] is the byte stride of
+// dimension i+1 (dimension 0 is contiguous). Out-of-bounds elements read as zero.
+CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                           const uint32_t* box);
+
+int num_sms();
+void require_sm100();
+
+inline int ilog2(int v) {
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
+inline bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+}  // namespace argus

@@ -2,7 +2,11 @@
 #include "../../include/argus_b200.h"
 
 #include "conv_ops.h"
+#include "kernels.h"
+#include "model.h"
 #include "runtime.h"
+
+#include <cstring>
 
 using namespace argus;
 
@@ -59,6 +63,128 @@ int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, i
   ConvShape s = make_shape(N, H, W, Cin, Cout, k, stride, kind);
   WgradLaunch l = plan_conv_wgrad(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw);
   launch_wgrad(l, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_pose_loss(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
+                    float grad_scale, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(B >= 0, "negative batch");
+  pose_loss_fwd_bwd(pred, target, loss, loss_mean, grad, B, grad_scale, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_pose_exp(const float* pred, float* pose, int B, int wxyz, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  pose_exp(pred, pose, B, wxyz, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         float* scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                         int step, float* norm_out, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(step >= 1, "Adam step counter starts at 1");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int np = grad_sqnorm_partials(grads, n, scratch, s);
+  clip_adam_step(params, grads, exp_avg, exp_avg_sq, n, scratch, np, gscale, max_norm, lr, beta1, beta2, eps, step,
+                 norm_out, s);
+  ARGUS_API_END
+}
+
+struct argus_model {
+  Model impl;
+  argus_model(int n_cams, int dim) : impl(n_cams, dim) {}
+};
+
+int argus_model_create(argus_model** out, int n_cams, int resnet_output_dim) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(out != nullptr, "null out pointer");
+  *out = new argus_model(n_cams, resnet_output_dim);
+  ARGUS_API_END
+}
+int argus_model_destroy(argus_model* m) {
+  ARGUS_API_BEGIN
+  delete m;
+  ARGUS_API_END
+}
+int argus_model_counts(argus_model* m, int* n_params, int* n_buffers, int64_t* param_elems, int64_t* buffer_elems) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  if (n_params) *n_params = static_cast<int>(m->impl.params().size());
+  if (n_buffers) *n_buffers = static_cast<int>(m->impl.buffers().size());
+  if (param_elems) *param_elems = m->impl.num_param_elems();
+  if (buffer_elems) *buffer_elems = m->impl.num_buffer_elems();
+  ARGUS_API_END
+}
+int argus_model_tensor_info(argus_model* m, int is_buffer, int index, char* name, int name_cap, int64_t* offset,
+                            int64_t* numel, int* ndim, int64_t* shape) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  const auto& v = is_buffer ? m->impl.buffers() : m->impl.params();
+  ARGUS_CHECK(index >= 0 && index < static_cast<int>(v.size()), "tensor index out of range");
+  const TensorInfo& t = v[index];
+  if (name && name_cap > 0) {
+    std::strncpy(name, t.name.c_str(), name_cap - 1);
+    name[name_cap - 1] = 0;
+  }
+  if (offset) *offset = t.offset;
+  if (numel) *numel = t.numel;
+  if (ndim) *ndim = t.ndim;
+  if (shape) for (int i = 0; i < 4; ++i) shape[i] = t.shape[i];
+  ARGUS_API_END
+}
+int argus_model_bind(argus_model* m, float* params, float* grads, float* buffers) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.bind(params, grads, buffers);
+  ARGUS_API_END
+}
+int argus_model_reserve(argus_model* m, int max_batch, int H, int W, int training) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.reserve(max_batch, H, W, training != 0);
+  ARGUS_API_END
+}
+int argus_model_sync_weights(argus_model* m, void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.sync_weights(static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, int W, int training, float* out,
+                        void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.forward(x, is_u8 != 0, B, H, W, training != 0, out, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_zero_grads(argus_model* m, void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.zero_grads(static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_backward(argus_model* m, const float* d_out, int stage_begin, int stage_end, void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  ARGUS_CHECK(0 <= stage_begin && stage_begin <= stage_end && stage_end <= 4, "bad stage range");
+  m->impl.backward(d_out, stage_begin, stage_end, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_stage_range(argus_model* m, int stage, int64_t* begin, int64_t* end) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.stage_param_range(stage, begin, end);
+  ARGUS_API_END
+}
+int argus_model_arena_bytes(argus_model* m, int64_t* bytes) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  *bytes = static_cast<int64_t>(m->impl.arena_bytes());
   ARGUS_API_END
 }
 

@@ -1,0 +1,590 @@
+// Memory-bound kernels of the hot path: input/weight packing, batch-norm (finalize / apply / backward), pooling.
+// Every kernel moves 16 bytes per thread per access (8 bf16 channels of one pixel), is coalesced along the
+// channel-contiguous NHWC layout, and reduces with warp shuffles / shared memory before touching global atomics.
+// Reference semantics: torch.nn.BatchNorm2d, ReLU, MaxPool2d(3,2,1), AdaptiveAvgPool2d(1) inside torchvision
+// resnet50 as called from /root/reference/argus/models.py:84.
+#include "kernels.h"
+#include "ptx.cuh"
+#include "runtime.h"
+
+#include <algorithm>
+
+namespace argus {
+
+static inline int grid_for(int64_t work_items, int threads, int max_blocks_per_sm = 8) {
+  int64_t blocks = (work_items + threads - 1) / threads;
+  int64_t cap = static_cast<int64_t>(num_sms()) * max_blocks_per_sm;
+  return static_cast<int>(std::max<int64_t>(1, std::min(blocks, cap)));
+}
+
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 unpack8(const uint4& u) {
+  F8 r;
+  float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = b.x; r.v[3] = b.y; r.v[4] = c.x; r.v[5] = c.y; r.v[6] = d.x; r.v[7] = d.y;
+  return r;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+  uint4 u;
+  u.x = pack_bf16x2(f.v[0], f.v[1]);
+  u.y = pack_bf16x2(f.v[2], f.v[3]);
+  u.z = pack_bf16x2(f.v[4], f.v[5]);
+  u.w = pack_bf16x2(f.v[6], f.v[7]);
+  return u;
+}
+__device__ __forceinline__ F8 load8f(const float* p) {
+  F8 r;
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w; r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// input packing: NCHW fp32 (or HWC u8) -> space-to-depth bf16 [n][H/2][W/2+4][16]
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pack_input_f32_kernel(const float* __restrict__ x, uint4* __restrict__ out, int n_images, int H,
+                                      int W) {
+  const int Hs = H >> 1, Ws = W >> 1, Wp = Ws + 4;
+  const int64_t total = static_cast<int64_t>(n_images) * Hs * Wp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int jp = static_cast<int>(i % Wp);
+    const int64_t t = i / Wp;
+    const int is = static_cast<int>(t % Hs);
+    const int n = static_cast<int>(t / Hs);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+    const int j = jp - 2;
+    if (j >= 0 && j < Ws) {
+      const float* img = x + static_cast<int64_t>(n) * 3 * H * W;  // image n = channels [3n, 3n+3) of sample n / n_cams
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+          const float2 p = __ldg(reinterpret_cast<const float2*>(img + (static_cast<int64_t>(c) * H + 2 * is + a) * W + 2 * j));
+          v[(a * 2 + 0) * 3 + c] = p.x;
+          v[(a * 2 + 1) * 3 + c] = p.y;
+        }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    out[2 * i] = o0;
+    out[2 * i + 1] = o1;
+  }
+}
+
+__global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int n_images, int H,
+                                     int W) {
+  const int Hs = H >> 1, Ws = W >> 1, Wp = Ws + 4;
+  const int64_t total = static_cast<int64_t>(n_images) * Hs * Wp;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int jp = static_cast<int>(i % Wp);
+    const int64_t t = i / Wp;
+    const int is = static_cast<int>(t % Hs);
+    const int n = static_cast<int>(t / Hs);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;
+    const int j = jp - 2;
+    if (j >= 0 && j < Ws) {
+      const uint8_t* img = x + static_cast<int64_t>(n) * H * W * 3;
+#pragma unroll
+      for (int a = 0; a < 2; ++a) {
+        const uint8_t* px = img + (static_cast<int64_t>(2 * is + a) * W + 2 * j) * 3;  // 6 contiguous bytes, 2-byte aligned
+        const uint16_t* p16 = reinterpret_cast<const uint16_t*>(px);
+        const uint32_t w0 = p16[0], w1 = p16[1], w2 = p16[2];
+        const float r0 = (w0 & 0xff), g0 = (w0 >> 8), b0 = (w1 & 0xff), r1 = (w1 >> 8), g1 = (w2 & 0xff), b1 = (w2 >> 8);
+        const float k = 1.0f / 255.0f;
+        v[(a * 2 + 0) * 3 + 0] = r0 * k; v[(a * 2 + 0) * 3 + 1] = g0 * k; v[(a * 2 + 0) * 3 + 2] = b0 * k;
+        v[(a * 2 + 1) * 3 + 0] = r1 * k; v[(a * 2 + 1) * 3 + 1] = g1 * k; v[(a * 2 + 1) * 3 + 2] = b1 * k;
+      }
+    }
+    uint4 o0, o1;
+    o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]); o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+    o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]); o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
+    out[2 * i] = o0;
+    out[2 * i + 1] = o1;
+  }
+}
+
+void pack_input_f32(const float* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
+  pack_input_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
+  ARGUS_CUDA(cudaGetLastError());
+}
+void pack_input_u8(const uint8_t* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
+  pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// weight packing / gradient unpacking (table driven: one launch for all layers)
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int64_t packed_count(const WeightPackEntry& e) {
+  return e.kind == 1 ? 64 * 256 : static_cast<int64_t>(e.cout) * e.cin * e.kk;
+}
+// maps a packed index to the PyTorch-layout index (or -1 for a zero-padding slot of the stem)
+__device__ __forceinline__ int64_t packed_to_torch(const WeightPackEntry& e, int64_t i) {
+  if (e.kind == 1) {
+    const int ch = static_cast<int>(i & 15);
+    const int q = static_cast<int>((i >> 4) & 3);
+    const int p = static_cast<int>((i >> 6) & 3);
+    const int co = static_cast<int>(i >> 8);
+    if (ch >= 12) return -1;
+    const int ab = ch / 3, c = ch - ab * 3;
+    const int a = ab >> 1, b = ab & 1;
+    const int kh = 2 * p + a - 1, kw = 2 * q + b - 1;
+    if (kh < 0 || kh > 6 || kw < 0 || kw > 6) return -1;
+    return ((static_cast<int64_t>(co) * 3 + c) * 7 + kh) * 7 + kw;
+  }
+  const int ci = static_cast<int>(i % e.cin);
+  const int64_t r = i / e.cin;
+  const int t = static_cast<int>(r % e.kk);
+  const int co = static_cast<int>(r / e.kk);
+  return (static_cast<int64_t>(co) * e.cin + ci) * e.kk + t;
+}
+
+__global__ void pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ packed,
+                                    const WeightPackEntry* __restrict__ table) {
+  const WeightPackEntry e = table[blockIdx.y];
+  const int64_t n = packed_count(e);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t src = packed_to_torch(e, i);
+    packed[e.dst_off + i] = __float2bfloat16(src >= 0 ? params[e.src_off + src] : 0.f);
+  }
+}
+__global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, float* __restrict__ grads,
+                                     const WeightPackEntry* __restrict__ table) {
+  const WeightPackEntry e = table[blockIdx.y];
+  if (e.kind == 0 && e.kk == 1) return;  // 1x1 / linear layers accumulate straight into the gradient arena
+  const int64_t n = packed_count(e);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t dst = packed_to_torch(e, i);
+    if (dst >= 0) grads[e.src_off + dst] += packed_grads[e.dst_off + i];
+  }
+}
+void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries,
+                  cudaStream_t s) {
+  pack_weights_kernel<<<dim3(32, n_entries), 256, 0, s>>>(params, packed, table_dev);
+  ARGUS_CUDA(cudaGetLastError());
+}
+void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
+                   cudaStream_t s) {
+  unpack_wgrads_kernel<<<dim3(32, n_entries), 256, 0, s>>>(packed_grads, grads, table_dev);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// batch norm: finalize / fold
+// ------------------------------------------------------------------------------------------------------------
+__global__ void bn_finalize_kernel(const float* sum, const float* sqsum, double count, const float* gamma,
+                                   const float* beta, float* running_mean, float* running_var, float momentum,
+                                   float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
+                                   int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = static_cast<double>(sum[c]) / count;
+  double var = static_cast<double>(sqsum[c]) / count - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - static_cast<float>(mean) * sc;
+  save_mean[c] = static_cast<float>(mean);
+  save_invstd[c] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+  }
+}
+void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                 float* save_mean, float* save_invstd, int C, cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
+                                                     momentum, eps, scale, shift, save_mean, save_invstd, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
+__global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
+                                    float* scale, float* shift, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] - rm[c] * sc;
+}
+void bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                  float eps, float* scale, float* shift, int C, cudaStream_t s) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// batch norm apply (+ residual, + ReLU)
+// ------------------------------------------------------------------------------------------------------------
+template <int RES>  // 0 none, 1 plain residual, 2 residual with its own scale/shift (downsample branch)
+__global__ void bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
+                                const float* __restrict__ shift, const uint4* __restrict__ res,
+                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
+                                uint4* __restrict__ y, int64_t nvec, int cvec) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i & (cvec - 1)) * 8;
+    const F8 xv = unpack8(ldg_stream(x + i));
+    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
+    if (RES == 1) {
+      const F8 rv = unpack8(ldg_stream(res + i));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
+    } else if (RES == 2) {
+      const F8 rv = unpack8(ldg_stream(res + i));
+      const F8 rs = load8f(rscale + c0), rb = load8f(rshift + c0);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
+    }
+    if (relu) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
+    }
+    y[i] = pack8(o);
+  }
+}
+void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
+              const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s) {
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_apply: C/8 must be a power of two");
+  const int64_t nvec = rows * (C / 8);
+  const int grid = grid_for(nvec, 256);
+  auto X = reinterpret_cast<const uint4*>(x);
+  auto R = reinterpret_cast<const uint4*>(res);
+  auto Y = reinterpret_cast<uint4*>(y);
+  if (res == nullptr)
+    bn_apply_kernel<0><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+  else if (rscale == nullptr)
+    bn_apply_kernel<1><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+  else
+    bn_apply_kernel<2><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// batch norm backward: per-channel reductions, then the elementwise input gradient
+// ------------------------------------------------------------------------------------------------------------
+template <int MASK>
+__device__ __forceinline__ F8 masked_grad(const F8& dy, const F8& x, const uint4* out, int64_t i, const F8& sc,
+                                          const F8& sh) {
+  F8 g = dy;
+  if (MASK == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(x.v[k], sc.v[k], sh.v[k]) > 0.f ? dy.v[k] : 0.f;
+  } else if (MASK == 2) {
+    const F8 o = unpack8(ldg_stream(out + i));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? dy.v[k] : 0.f;
+  }
+  return g;
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(256)
+bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                     int64_t rows, int cvec) {
+  __shared__ float red[16][256];
+  const int lanes = cvec < 256 ? cvec : 256;   // threads along the channel dimension
+  const int row_lanes = 256 / lanes;           // rows processed concurrently by one block
+  const int rl = threadIdx.x / lanes;
+  const int oc = threadIdx.x % lanes;
+  float a_dy[8], a_dyx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a_dy[k] = a_dyx[k] = 0.f;
+  for (int ocb = oc; ocb < cvec; ocb += lanes) {  // (cvec > 256 never happens for C <= 2048; kept for safety)
+    const int c0 = ocb * 8;
+    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0), mu = load8f(mean + c0), is = load8f(invstd + c0);
+    for (int64_t row = static_cast<int64_t>(blockIdx.x) * row_lanes + rl; row < rows;
+         row += static_cast<int64_t>(gridDim.x) * row_lanes) {
+      const int64_t i = row * cvec + ocb;
+      const F8 d = unpack8(ldg_stream(dy + i));
+      const F8 xv = unpack8(ldg_stream(x + i));
+      const F8 g = masked_grad<MASK>(d, xv, out, i, sc, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a_dy[k] += g.v[k];
+        a_dyx[k] = fmaf(g.v[k], (xv.v[k] - mu.v[k]) * is.v[k], a_dyx[k]);
+      }
+    }
+    if (cvec > lanes) {  // flush per channel block (rare path)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        atomicAdd(dbeta + c0 + k, a_dy[k]);
+        atomicAdd(dgamma + c0 + k, a_dyx[k]);
+        a_dy[k] = a_dyx[k] = 0.f;
+      }
+    }
+  }
+  if (cvec > lanes) return;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    red[k][threadIdx.x] = a_dy[k];
+    red[8 + k][threadIdx.x] = a_dyx[k];
+  }
+  __syncthreads();
+  if (rl == 0) {
+    const int c0 = oc * 8;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int r = 0; r < row_lanes; ++r) {
+        s0 += red[k][r * lanes + oc];
+        s1 += red[8 + k][r * lanes + oc];
+      }
+      atomicAdd(dbeta + c0 + k, s0);
+      atomicAdd(dgamma + c0 + k, s1);
+    }
+  }
+}
+
+void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
+                   const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
+                   int mask_mode, cudaStream_t s) {
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_bwd_reduce: C/8 must be a power of two");
+  const int cvec = C / 8;
+  const int lanes = std::min(cvec, 256);
+  const int row_lanes = 256 / lanes;
+  const int64_t row_groups = (rows + row_lanes - 1) / row_lanes;
+  const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(row_groups, 4LL * num_sms())));
+  auto DY = reinterpret_cast<const uint4*>(dy);
+  auto X = reinterpret_cast<const uint4*>(x);
+  auto O = reinterpret_cast<const uint4*>(out);
+  switch (mask_mode) {
+    case 0: bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec); break;
+    case 1: bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec); break;
+    case 2:
+      ARGUS_CHECK(out != nullptr, "mask_mode 2 needs the block output");
+      bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec);
+      break;
+    default: throw Error("bad mask_mode");
+  }
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+template <int MASK>
+__global__ void bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
+                                    uint4* __restrict__ dx, int64_t nvec, int cvec, float inv_rows) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int c0 = static_cast<int>(i & (cvec - 1)) * 8;
+    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0), mu = load8f(mean + c0), is = load8f(invstd + c0);
+    const F8 dg = load8f(dgamma + c0), db = load8f(dbeta + c0);
+    const F8 d = unpack8(dy[i]);
+    const F8 xv = unpack8(ldg_stream(x + i));
+    const F8 g = masked_grad<MASK>(d, xv, out, i, sc, sh);
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float xhat = (xv.v[k] - mu.v[k]) * is.v[k];
+      o.v[k] = sc.v[k] * (g.v[k] - db.v[k] * inv_rows - xhat * dg.v[k] * inv_rows);
+    }
+    dx[i] = pack8(o);
+    if (MASK == 2) dy[i] = pack8(g);
+  }
+}
+
+void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
+                  int64_t rows, int C, int mask_mode, cudaStream_t s) {
+  const int cvec = C / 8;
+  const int64_t nvec = rows * cvec;
+  const int grid = grid_for(nvec, 256);
+  const float inv_rows = static_cast<float>(1.0 / static_cast<double>(rows));
+  auto DY = reinterpret_cast<uint4*>(dy);
+  auto X = reinterpret_cast<const uint4*>(x);
+  auto O = reinterpret_cast<const uint4*>(out);
+  auto DX = reinterpret_cast<uint4*>(dx);
+  switch (mask_mode) {
+    case 0: bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 1: bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 2: bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    default: throw Error("bad mask_mode");
+  }
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pooling
+// ------------------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
+                                   const float* __restrict__ shift, uint4* __restrict__ y, uint2* __restrict__ idx,
+                                   int N, int H, int W, int cvec) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    int64_t t = i / cvec;
+    const int pw = static_cast<int>(t % Wo);
+    t /= Wo;
+    const int ph = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    F8 sc, sh;
+    if (scale != nullptr) {
+      sc = load8f(scale + cv * 8);
+      sh = load8f(shift + cv * 8);
+    }
+    float best[8];
+    int bi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = 2 * ph - 1 + kh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = 2 * pw - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        F8 v = unpack8(__ldg(x + ((static_cast<int64_t>(n) * H + h) * W + w) * cvec + cv));
+        if (scale != nullptr) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (v.v[k] > best[k]) { best[k] = v.v[k]; bi[k] = kh * 3 + kw; }
+      }
+    }
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = best[k];
+    y[i] = pack8(o);
+    if (idx != nullptr) {
+      uint2 p;
+      p.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
+      p.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      idx[i] = p;
+    }
+  }
+}
+void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y, uint8_t* idx, int N, int H, int W,
+                 int C, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
+  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), scale, shift,
+                                                          reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),
+                                                          N, H, W, C / 8);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+__global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
+                                   int N, int H, int W, int cvec) {
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int64_t total = static_cast<int64_t>(N) * H * W * cvec;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    int64_t t = i / cvec;
+    const int w = static_cast<int>(t % W);
+    t /= W;
+    const int h = static_cast<int>(t % H);
+    const int n = static_cast<int>(t / H);
+    F8 g;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+    // pooled windows containing (h, w): ph in {h/2, (h+1)/2}, pw likewise
+    for (int ph = h >> 1; ph <= ((h + 1) >> 1); ++ph) {
+      if (ph >= Ho) continue;
+      const int kh = h - (2 * ph - 1);
+      for (int pw = w >> 1; pw <= ((w + 1) >> 1); ++pw) {
+        if (pw >= Wo) continue;
+        const int kw = w - (2 * pw - 1);
+        const int code = kh * 3 + kw;
+        const int64_t j = ((static_cast<int64_t>(n) * Ho + ph) * Wo + pw) * cvec + cv;
+        const uint2 id = __ldg(idx + j);
+        const F8 d = unpack8(__ldg(dy + j));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int b = (k < 4 ? (id.x >> (8 * k)) : (id.y >> (8 * (k - 4)))) & 0xff;
+          if (b == code) g.v[k] += d.v[k];
+        }
+      }
+    }
+    dx[i] = pack8(g);
+  }
+}
+void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int W, int C, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
+                                                          reinterpret_cast<const uint2*>(idx),
+                                                          reinterpret_cast<uint4*>(dx), N, H, W, C / 8);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+__global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int HW, int cvec) {
+  const int64_t total = static_cast<int64_t>(N) * cvec;
+  const float inv = 1.0f / HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    const int n = static_cast<int>(i / cvec);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int p = 0; p < HW; ++p) {
+      const F8 v = unpack8(ldg_stream(x + (static_cast<int64_t>(n) * HW + p) * cvec + cv));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+    }
+    F8 o;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o.v[k] = acc[k] * inv;
+    y[i] = pack8(o);
+  }
+}
+void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(N) * (C / 8);
+  avgpool_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(x),
+                                                          reinterpret_cast<uint4*>(y), N, HW, C / 8);
+  ARGUS_CUDA(cudaGetLastError());
+}
+__global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int HW, int cvec) {
+  const int64_t total = static_cast<int64_t>(N) * HW * cvec;
+  const float inv = 1.0f / HW;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int cv = static_cast<int>(i % cvec);
+    const int n = static_cast<int>(i / (static_cast<int64_t>(HW) * cvec));
+    F8 v = unpack8(__ldg(dy + static_cast<int64_t>(n) * cvec + cv));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v.v[k] *= inv;
+    dx[i] = pack8(v);
+  }
+}
+void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(N) * HW * (C / 8);
+  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
+                                                          reinterpret_cast<uint4*>(dx), N, HW, C / 8);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+}  // namespace argus

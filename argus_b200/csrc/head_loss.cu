@@ -1,0 +1,247 @@
+// Regression head (fp32), SE(3) pose loss and the optimizer step tail.
+//   head:  argus/models.py:58-64,88-90  (GELU -> Linear(2048,128) -> GELU -> Linear(128,128) -> GELU -> Linear(128,6))
+//   loss:  argus/train.py:105-119       (|Log(Exp(pred) T^-1)|^2, forward + analytic gradient in one launch)
+//   step:  argus/train.py:318-319       (clip_grad_norm_ + Adam)
+// These operate on a few hundred KB: they are latency-bound, so they are written for few launches and exact
+// fp32/fp64 arithmetic rather than for bandwidth.
+#include "kernels.h"
+#include "ptx.cuh"
+#include "runtime.h"
+#include "se3_math.cuh"
+
+#include <algorithm>
+
+namespace argus {
+
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_grad_f(float x) {
+  const float cdf = 0.5f * (1.f + erff(x * 0.70710678118654752440f));
+  const float pdf = 0.39894228040143267794f * __expf(-0.5f * x * x);
+  return cdf + x * pdf;
+}
+
+__global__ void gelu_fwd_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    y[i] = gelu_f(__bfloat162float(x[i]));
+}
+void gelu_fwd_bf16(const bf16* x, float* y, int64_t n, cudaStream_t s) {
+  gelu_fwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(x, y, n);
+  ARGUS_CUDA(cudaGetLastError());
+}
+__global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dz, const bf16* __restrict__ x, bf16* __restrict__ dx,
+                                     int64_t n) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+    dx[i] = __float2bfloat16(dz[i] * gelu_grad_f(__bfloat162float(x[i])));
+}
+void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStream_t s) {
+  gelu_bwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(dz, x, dx, n);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// one warp per output element: y[b, o] = dot(x[b, :], w[o, :]) + bias[o]
+__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                  float* __restrict__ y, float* __restrict__ act, int B, int In, int Out) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= B * Out) return;
+  const int bi = warp / Out, o = warp - bi * Out;
+  const float* xr = x + static_cast<int64_t>(bi) * In;
+  const float* wr = w + static_cast<int64_t>(o) * In;
+  float acc = 0.f;
+  for (int i = lane; i < In; i += 32) acc = fmaf(xr[i], __ldg(wr + i), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const float v = acc + b[o];
+    y[warp] = v;
+    if (act != nullptr) act[warp] = gelu_f(v);
+  }
+}
+void linear_fwd(const float* x, const float* w, const float* b, float* y, float* act, int B, int In, int Out,
+                cudaStream_t s) {
+  const int64_t threads = static_cast<int64_t>(B) * Out * 32;
+  linear_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, s>>>(x, w, b, y, act, B, In, Out);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+__global__ void gelu_grad_inplace_kernel(float* dy, const float* __restrict__ pre, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dy[i] *= gelu_grad_f(pre[i]);
+}
+// dw[o, i] += sum_b dy[b, o] x[b, i]   (thread per (o, i): x reads coalesced over i, dy reads broadcast)
+__global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* dw, float* db,
+                                    int B, int In, int Out) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(Out) * In) return;
+  const int o = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(o) * In);
+  float acc = 0.f, accb = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const float d = __ldg(dy + static_cast<int64_t>(b) * Out + o);
+    acc = fmaf(d, __ldg(x + static_cast<int64_t>(b) * In + i), acc);
+    accb += d;
+  }
+  dw[t] += acc;
+  if (i == 0) db[o] += accb;
+}
+// dx[b, i] = sum_o dy[b, o] w[o, i]
+__global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
+                                    int B, int In, int Out) {
+  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (t >= static_cast<int64_t>(B) * In) return;
+  const int b = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(b) * In);
+  float acc = 0.f;
+  for (int o = 0; o < Out; ++o) acc = fmaf(__ldg(dy + static_cast<int64_t>(b) * Out + o), __ldg(w + static_cast<int64_t>(o) * In + i), acc);
+  dx[t] = acc;
+}
+void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
+                int In, int Out, cudaStream_t s) {
+  if (pre != nullptr) {
+    gelu_grad_inplace_kernel<<<(B * Out + 255) / 256, 256, 0, s>>>(dy, pre, B * Out);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+  const int64_t nw = static_cast<int64_t>(Out) * In;
+  linear_bwd_w_kernel<<<static_cast<int>((nw + 127) / 128), 128, 0, s>>>(dy, x, dw, db, B, In, Out);
+  ARGUS_CUDA(cudaGetLastError());
+  if (dx != nullptr) {
+    const int64_t nx = static_cast<int64_t>(B) * In;
+    linear_bwd_x_kernel<<<static_cast<int>((nx + 127) / 128), 128, 0, s>>>(dy, w, dx, B, In, Out);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pose loss (forward + analytic backward) and pose exponential
+// ------------------------------------------------------------------------------------------------------------
+__global__ void pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                 float* __restrict__ loss, float* loss_mean, float* __restrict__ grad, int B,
+                                 float grad_scale) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  float l = 0.f;
+  if (b < B) {
+    double p[6], t[7], g[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) p[k] = pred[b * 6 + k];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) t[k] = target[b * 7 + k];
+    const double lv = se3::pose_loss_and_grad(p, t, g);
+    l = static_cast<float>(lv);
+    if (loss != nullptr) loss[b] = l;
+    if (grad != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) grad[b * 6 + k] = static_cast<float>(g[k] * grad_scale);
+    }
+  }
+  if (loss_mean != nullptr) {
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0) atomicAdd(loss_mean, l / B);
+  }
+}
+void pose_loss_fwd_bwd(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
+                       float grad_scale, cudaStream_t s) {
+  if (B <= 0) return;
+  pose_loss_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, target, loss, loss_mean, grad, B, grad_scale);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+__global__ void pose_exp_kernel(const float* __restrict__ pred, float* __restrict__ pose, int B, int wxyz) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  se3::V3 t;
+  se3::Quat q;
+  se3::exp_se3(se3::v3(pred[b * 6 + 0], pred[b * 6 + 1], pred[b * 6 + 2]),
+               se3::v3(pred[b * 6 + 3], pred[b * 6 + 4], pred[b * 6 + 5]), t, q);
+  float* o = pose + b * 7;
+  o[0] = static_cast<float>(t.x); o[1] = static_cast<float>(t.y); o[2] = static_cast<float>(t.z);
+  if (wxyz) {
+    o[3] = static_cast<float>(q.w); o[4] = static_cast<float>(q.v.x); o[5] = static_cast<float>(q.v.y); o[6] = static_cast<float>(q.v.z);
+  } else {
+    o[3] = static_cast<float>(q.v.x); o[4] = static_cast<float>(q.v.y); o[5] = static_cast<float>(q.v.z); o[6] = static_cast<float>(q.w);
+  }
+}
+void pose_exp(const float* pred, float* pose, int B, int wxyz, cudaStream_t s) {
+  if (B <= 0) return;
+  pose_exp_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, pose, B, wxyz);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// optimizer step tail: global grad norm (deterministic two-stage), clip, Adam
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kNormBlocks = 592;  // 4 per SM
+
+__global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, int64_t n, float* partial) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = __ldg(g4 + i);
+    acc = fmaf(v.x, v.x, acc); acc = fmaf(v.y, v.y, acc); acc = fmaf(v.z, v.z, acc); acc = fmaf(v.w, v.w, acc);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const float v = g[(n4 << 2) + threadIdx.x];
+    acc = fmaf(v, v, acc);
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < 8 ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  }
+}
+int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t s) {
+  grad_sqnorm_kernel<<<kNormBlocks, 256, 0, s>>>(g, n, partial);
+  ARGUS_CUDA(cudaGetLastError());
+  return kNormBlocks;
+}
+
+__global__ void __launch_bounds__(256)
+clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, const float* __restrict__ partial, int n_partial, float gscale, float max_norm, float lr,
+                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float* norm_out) {
+  __shared__ float red[8];
+  __shared__ float s_coef;
+  // every block reduces the partial sums in the same order -> identical clip coefficient everywhere
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int i = 0; i < 8; ++i) tot += red[i];
+    const float norm = sqrtf(tot) * gscale;
+    float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
+    coef = fminf(coef, 1.f);
+    s_coef = coef * gscale;
+    if (blockIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
+  }
+  __syncthreads();
+  const float coef = s_coef;
+  const float step_size = lr / bc1;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+  }
+}
+void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* partial, int n_partial,
+                    float gscale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
+                    float* norm_out, cudaStream_t s) {
+  const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
+  clip_adam_kernel<<<4 * num_sms(), 256, 0, s>>>(p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,
+                                                 beta2, eps, bc1, bc2_sqrt, norm_out);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+}  // namespace argus

@@ -1,0 +1,93 @@
+// Launchers of the memory-bound / latency-bound kernels (everything that is not a tensor-core GEMM).
+// All tensors are device pointers; activations NHWC bf16; per-channel vectors fp32.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace argus {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- input / weight packing -------------------------------------------------------------------------------
+// x: (B, 3*n_cams, H, W) fp32 NCHW in [0,1] (argus/models.py:81 folds views into the batch: image = b*n_cams + v)
+// out: [B*n_cams][H/2][W/2+4][16] bf16 space-to-depth layout consumed by the stem convolution.
+void pack_input_f32(const float* x, bf16* out, int n_images, int H, int W, cudaStream_t s);
+// u8 HWC images (n_images, H, W, 3) -> same layout, scaled by 1/255 (argus/data.py:218)
+void pack_input_u8(const uint8_t* x, bf16* out, int n_images, int H, int W, cudaStream_t s);
+
+struct WeightPackEntry {
+  int64_t src_off;  // element offset into the fp32 parameter (or gradient) arena, PyTorch layout [Cout][Cin][kh][kw]
+  int64_t dst_off;  // element offset into the packed arena, layout [Cout][kh][kw][Cin] (stem: [64][4][4][16])
+  int cout, cin, kk;
+  int kind;         // 0 conv / linear, 1 stem
+};
+// fp32 PyTorch-layout parameters -> bf16 packed weights, all layers in one launch (table lives on the device)
+void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries, cudaStream_t s);
+// fp32 packed-layout weight gradients -> PyTorch-layout gradient arena (only entries with kk > 1 or kind 1)
+void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
+                   cudaStream_t s);
+
+// ---- batch norm -------------------------------------------------------------------------------------------
+// train: batch statistics -> scale/shift (+ saved mean/invstd, running-stat update, torch.nn.BatchNorm2d semantics)
+void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                 float* save_mean, float* save_invstd, int C, cudaStream_t s);
+// eval: running statistics -> scale/shift
+void bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                  float eps, float* scale, float* shift, int C, cudaStream_t s);
+// y = [relu]( x*scale+shift  [+ res]  or  [+ res*rscale+rshift] )
+void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
+              const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s);
+// mask_mode: 0 = no ReLU after this BN, 1 = ReLU directly after (mask recomputed from x), 2 = ReLU after a residual
+// add (mask = out > 0). Accumulates dgamma += sum(g * xhat), dbeta += sum(g) with g = masked dy.
+void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
+                   const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
+                   int mask_mode, cudaStream_t s);
+// dx = scale * (g - dbeta/rows - xhat * dgamma/rows); mask_mode 2 also overwrites dy with g (the identity branch
+// of the residual block consumes it).
+void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
+                  const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
+                  int64_t rows, int C, int mask_mode, cudaStream_t s);
+
+// ---- pooling ----------------------------------------------------------------------------------------------
+// 3x3 stride-2 pad-1 max pooling of relu(x*scale+shift) (scale == nullptr: x is already activated).
+// idx (optional) records the arg-max tap (0..8) for the backward pass.
+void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y, uint8_t* idx, int N, int H, int W,
+                 int C, cudaStream_t s);
+void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int W, int C, cudaStream_t s);
+// global average pooling (N, HW, C) -> (N, C) and its backward
+void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s);
+void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s);
+
+// ---- head MLP (fp32 SIMT; argus/models.py:58-64,88-90) -----------------------------------------------------
+// z = gelu(feat) ; feat bf16 (rows, cols) -> z fp32
+void gelu_fwd_bf16(const bf16* x, float* y, int64_t n, cudaStream_t s);
+// dfeat = dz * gelu'(feat) -> bf16
+void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStream_t s);
+// y = x W^T + b ; optionally a = gelu(y)
+void linear_fwd(const float* x, const float* w, const float* b, float* y, float* act, int B, int In, int Out,
+                cudaStream_t s);
+// given dy (grad wrt the linear output y; if pre != nullptr the incoming grad is wrt gelu(y) and is first multiplied
+// by gelu'(pre) in place): dw += dy^T x, db += sum dy, dx = dy W
+void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
+                int In, int Out, cudaStream_t s);
+
+// ---- loss / pose ------------------------------------------------------------------------------------------
+// per-sample loss (argus/train.py:119), its mean accumulated into *loss_mean (caller zeroes), and
+// grad = grad_scale * dloss/dpred
+void pose_loss_fwd_bwd(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
+                       float grad_scale, cudaStream_t s);
+// pp.se3(pred).Exp() (argus/utils.py:189); wxyz != 0 writes [t, qw, qx, qy, qz] (argus/utils.py:130-145)
+void pose_exp(const float* pred, float* pose, int B, int wxyz, cudaStream_t s);
+
+// ---- optimizer step tail (argus/train.py:318-319) ------------------------------------------------------------
+// partial[b] = sum of squares of block b's slice (deterministic two-stage reduction); returns number of partials
+int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t s);
+// clip_grad_norm_(max_norm) + Adam, fused: every block first reduces `partial` to the global norm.
+// gscale multiplies gradients before the norm (1/world for data-parallel averaging).
+void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* partial, int n_partial,
+                    float gscale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
+                    float* norm_out, cudaStream_t s);
+
+}  // namespace argus

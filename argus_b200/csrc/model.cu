@@ -1,0 +1,549 @@
+#include "model.h"
+
+#include <algorithm>
+#include <cstring>
+#include <tuple>
+
+namespace argus {
+
+static constexpr float kBnEps = 1e-5f;
+static constexpr float kBnMomentum = 0.1f;
+
+// ------------------------------------------------------------------------------------------------------------
+// small kernels local to the model: column sums (fc bias gradient)
+// ------------------------------------------------------------------------------------------------------------
+__global__ void colsum_bf16_kernel(const bf16* __restrict__ x, float* out, int rows, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float acc = 0.f;
+  for (int r = 0; r < rows; ++r) acc += __bfloat162float(x[static_cast<int64_t>(r) * C + c]);
+  out[c] += acc;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// layout: parameter / buffer arenas in the reference's state_dict order
+// ------------------------------------------------------------------------------------------------------------
+Model::Model(int n_cams, int resnet_output_dim) : n_cams_(n_cams), out_dim_(resnet_output_dim) {
+  ARGUS_CHECK(n_cams >= 1 && n_cams <= 8, "n_cams out of range");
+  ARGUS_CHECK(resnet_output_dim % 64 == 0 && resnet_output_dim >= 64, "resnet_output_dim must be a multiple of 64");
+  build_layout();
+}
+
+Model::~Model() {
+  cudaFree(packed_);
+  cudaFree(gpacked_);
+  cudaFree(bn_scratch_);
+  cudaFree(bn_stats_);
+  cudaFree(pack_table_dev_);
+  cudaFree(arena_);
+}
+
+void Model::build_layout() {
+  auto add_param = [&](const std::string& name, std::initializer_list<int64_t> shape) {
+    TensorInfo t;
+    t.name = name;
+    t.offset = n_param_elems_;
+    t.ndim = static_cast<int>(shape.size());
+    t.numel = 1;
+    int i = 0;
+    for (int64_t d : shape) { t.shape[i++] = d; t.numel *= d; }
+    // keep every tensor 16-byte aligned inside the arena (float4 loads in the optimizer / epilogues)
+    n_param_elems_ += (t.numel + 3) / 4 * 4;
+    params_.push_back(t);
+    return t.offset;
+  };
+  auto add_buffer = [&](const std::string& name, int64_t n) {
+    TensorInfo t;
+    t.name = name;
+    t.offset = n_buffer_elems_;
+    t.ndim = 1;
+    t.numel = n;
+    t.shape[0] = n;
+    n_buffer_elems_ += (n + 3) / 4 * 4;
+    buffers_.push_back(t);
+    return t.offset;
+  };
+  auto add_conv = [&](ConvRef& c, const std::string& conv_name, const std::string& bn_name, int cin, int cout, int k,
+                      int stride, int kind, int stage) {
+    c.shape.Cin = cin; c.shape.Cout = cout; c.shape.k = k; c.shape.stride = stride; c.shape.kind = kind;
+    c.stage = stage;
+    c.w_off = add_param(conv_name + ".weight", {cout, cin, k, k});
+    c.bn.C = cout;
+    c.bn.gamma_off = add_param(bn_name + ".weight", {cout});
+    c.bn.beta_off = add_param(bn_name + ".bias", {cout});
+    c.bn.rm_off = add_buffer(bn_name + ".running_mean", cout);
+    c.bn.rv_off = add_buffer(bn_name + ".running_var", cout);
+    c.bn.scratch_off = n_bn_scratch_;
+    n_bn_scratch_ += 4 * cout;
+    c.bn.stat_off = n_bn_stats_;
+    n_bn_stats_ += 2 * cout;
+    const int64_t packed_elems = (kind == 1) ? 64 * 256 : static_cast<int64_t>(cout) * cin * k * k;
+    c.packed_off = n_packed_;
+    n_packed_ += (packed_elems + 63) / 64 * 64;
+    // the fp32 packed-gradient scratch mirrors the packed bf16 arena (same offsets), so one table serves both
+    if (k > 1) c.gpacked_off = c.packed_off;
+    n_gpacked_ = n_packed_;
+    WeightPackEntry e;
+    e.src_off = c.w_off;
+    e.dst_off = c.packed_off;
+    e.cout = cout; e.cin = cin; e.kk = k * k; e.kind = kind;
+    pack_table_.push_back(e);
+    pack_table_stage_.push_back(stage);
+  };
+
+  // segments in network order: stem+layer1 (stage 3), layer2 (2), layer3 (1), layer4+fc+head (0)
+  stage_begin_[0] = 0;
+  add_conv(stem_, "resnet.conv1", "resnet.bn1", 3, 64, 7, 2, 1, 3);
+  const int depth[4] = {3, 4, 6, 3};
+  const int width[4] = {64, 128, 256, 512};
+  int in_ch = 64;
+  for (int L = 0; L < 4; ++L) {
+    const int stage = 3 - (L == 0 ? 0 : L);  // layer1 -> 3, layer2 -> 2, layer3 -> 1, layer4 -> 0
+    if (L > 0) stage_begin_[L] = n_param_elems_;
+    for (int b = 0; b < depth[L]; ++b) {
+      const std::string base = "resnet.layer" + std::to_string(L + 1) + "." + std::to_string(b);
+      const int stride = (b == 0 && L > 0) ? 2 : 1;
+      BlockRef blk;
+      add_conv(blk.c1, base + ".conv1", base + ".bn1", in_ch, width[L], 1, 1, 0, stage);
+      add_conv(blk.c2, base + ".conv2", base + ".bn2", width[L], width[L], 3, stride, 0, stage);
+      add_conv(blk.c3, base + ".conv3", base + ".bn3", width[L], width[L] * 4, 1, 1, 0, stage);
+      if (b == 0) {
+        blk.has_ds = true;
+        add_conv(blk.ds, base + ".downsample.0", base + ".downsample.1", in_ch, width[L] * 4, 1, stride, 0, stage);
+      }
+      blocks_.push_back(blk);
+      in_ch = width[L] * 4;
+    }
+  }
+  stage_begin_[4] = 0;  // unused
+  // fc + head (belong to stage 0 together with layer4)
+  fc_.shape.Cin = 2048; fc_.shape.Cout = out_dim_; fc_.shape.k = 1; fc_.shape.stride = 1; fc_.shape.kind = 0;
+  fc_.stage = 0;
+  fc_.w_off = add_param("resnet.fc.weight", {out_dim_, 2048});
+  fc_bias_off_ = add_param("resnet.fc.bias", {out_dim_});
+  fc_.packed_off = n_packed_;
+  n_packed_ += static_cast<int64_t>(out_dim_) * 2048;
+  {
+    WeightPackEntry e;
+    e.src_off = fc_.w_off; e.dst_off = fc_.packed_off; e.cout = out_dim_; e.cin = 2048; e.kk = 1; e.kind = 0;
+    pack_table_.push_back(e);
+    pack_table_stage_.push_back(0);
+  }
+  const int hin[3] = {n_cams_ * out_dim_, 128, 128};
+  const int hout[3] = {128, 128, 6};
+  for (int i = 0; i < 3; ++i) {
+    const std::string base = "output_mlp." + std::to_string(2 * i);
+    head_w_off_[i] = add_param(base + ".weight", {hout[i], hin[i]});
+    head_b_off_[i] = add_param(base + ".bias", {hout[i]});
+  }
+}
+
+void Model::stage_param_range(int stage, int64_t* begin, int64_t* end) const {
+  // stage 0: layer4 + fc + head, 1: layer3, 2: layer2, 3: stem + layer1
+  ARGUS_CHECK(stage >= 0 && stage < 4, "stage out of range");
+  const int64_t seg_begin[4] = {stage_begin_[3], stage_begin_[2], stage_begin_[1], 0};
+  const int64_t seg_end[4] = {n_param_elems_, stage_begin_[3], stage_begin_[2], stage_begin_[1]};
+  *begin = seg_begin[stage];
+  *end = seg_end[stage];
+}
+
+void Model::bind(float* params, float* grads, float* buffers) {
+  require_sm100();
+  params_dev_ = params;
+  grads_dev_ = grads;
+  buffers_dev_ = buffers;
+  if (packed_ == nullptr) {
+    ARGUS_CUDA(cudaMalloc(&packed_, n_packed_ * sizeof(bf16)));
+    ARGUS_CUDA(cudaMalloc(&gpacked_, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
+    ARGUS_CUDA(cudaMalloc(&bn_scratch_, n_bn_scratch_ * sizeof(float)));
+    ARGUS_CUDA(cudaMalloc(&bn_stats_, n_bn_stats_ * sizeof(float)));
+    ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
+    ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
+                          cudaMemcpyHostToDevice));
+    ARGUS_CUDA(cudaMemset(gpacked_, 0, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
+  }
+  plans_.clear();
+  last_train_plan_ = nullptr;
+  eval_fold_dirty_ = true;
+}
+
+void Model::sync_weights(cudaStream_t s) {
+  ARGUS_CHECK(params_dev_ != nullptr, "model is not bound to a parameter arena");
+  pack_weights(params_dev_, packed_, pack_table_dev_, static_cast<int>(pack_table_.size()), s);
+  eval_fold_dirty_ = true;
+}
+
+void Model::zero_grads(cudaStream_t s) {
+  ARGUS_CHECK(grads_dev_ != nullptr, "model is not bound to a gradient arena");
+  ARGUS_CUDA(cudaMemsetAsync(grads_dev_, 0, n_param_elems_ * sizeof(float), s));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// planning
+// ------------------------------------------------------------------------------------------------------------
+template <typename T>
+T* Model::arena_alloc(size_t count) {
+  const size_t bytes = (count * sizeof(T) + 1023) / 1024 * 1024;
+  uint8_t* p = arena_ ? arena_ + arena_used_ : nullptr;
+  arena_used_ += bytes;
+  return reinterpret_cast<T*>(p);
+}
+
+void Model::reserve(int max_batch, int H, int W, bool training) {
+  ARGUS_CHECK(max_batch > 0, "batch must be positive");
+  ARGUS_CHECK(is_pow2(H) && is_pow2(W) && H >= 32 && W >= 32, "H and W must be powers of two >= 32");
+  // dry run to size the arena
+  uint8_t* saved = arena_;
+  arena_ = nullptr;
+  Plan tmp;
+  tmp.B = max_batch; tmp.H = H; tmp.W = W; tmp.N = max_batch * n_cams_; tmp.training = training;
+  arena_used_ = 0;
+  // build_plan only measures when arena_ == nullptr
+  build_plan(tmp);
+  const size_t need = arena_used_;
+  arena_ = saved;
+  if (need > arena_bytes_) {
+    if (arena_) ARGUS_CUDA(cudaFree(arena_));
+    arena_ = nullptr;
+    ARGUS_CUDA(cudaMalloc(&arena_, need));
+    arena_bytes_ = need;
+    plans_.clear();
+    last_train_plan_ = nullptr;
+  }
+  reserved_batch_ = std::max(reserved_batch_, max_batch);
+  reserved_h_ = H; reserved_w_ = W;
+  reserved_training_ = reserved_training_ || training;
+}
+
+Plan& Model::get_plan(int B, int H, int W, bool training) {
+  auto key = std::make_tuple(B, H, W, training);
+  auto it = plans_.find(key);
+  if (it != plans_.end()) return *it->second;
+  reserve(B, H, W, training);  // grows the arena if needed (and drops stale plans)
+  auto p = std::make_unique<Plan>();
+  p->B = B; p->H = H; p->W = W; p->N = B * n_cams_; p->training = training;
+  arena_used_ = 0;
+  build_plan(*p);
+  ARGUS_CHECK(arena_used_ <= arena_bytes_, "activation arena overflow");
+  Plan& ref = *p;
+  plans_[key] = std::move(p);
+  return ref;
+}
+
+void Model::build_plan(Plan& p) {
+  const bool real = (arena_ != nullptr);  // dry runs only measure
+  const int N = p.N, H = p.H, W = p.W;
+  const bool tr = p.training;
+  auto plan_conv = [&](ConvPlan& cp, ConvRef& c, int n, int h, int w, const bf16* in, bf16* out_raw,
+                       bool want_dgrad) {
+    c.shape.N = n; c.shape.H = h; c.shape.W = w;
+    if (!real) return;
+    cp.fwd = plan_conv_forward(c.shape, in, packed_ + c.packed_off, out_raw);
+    cp.has_dgrad = want_dgrad;
+  };
+  // ---- stem
+  p.x_s2d = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
+  const int H1 = H / 2, W1 = W / 2;  // stem output
+  const int H2 = H1 / 2, W2 = W1 / 2;  // after max pooling
+  const size_t stem_elems = static_cast<size_t>(N) * H1 * W1 * 64;
+  if (tr) p.raw0 = arena_alloc<bf16>(stem_elems); else p.act0 = arena_alloc<bf16>(stem_elems);
+  p.pooled0 = arena_alloc<bf16>(stem_elems / 4);
+  if (tr) p.idx0 = arena_alloc<uint8_t>(stem_elems / 4);
+  plan_conv(p.stem, stem_, N, H, W, p.x_s2d, tr ? p.raw0 : p.act0, false);
+
+  // ---- bottleneck blocks
+  p.blocks.assign(blocks_.size(), BlockPlan());
+  bf16* x = p.pooled0;
+  int h = H2, w = W2;
+  size_t max_elems = stem_elems;
+  for (size_t i = 0; i < blocks_.size(); ++i) {
+    BlockRef& br = blocks_[i];
+    BlockPlan& bp = p.blocks[i];
+    const int s = br.c2.shape.stride;
+    const int ho = h / s, wo = w / s;
+    const size_t e_in = static_cast<size_t>(N) * h * w;
+    const size_t e_out = static_cast<size_t>(N) * ho * wo;
+    bp.x = x;
+    bp.rows_in = e_in; bp.rows_mid = e_in; bp.rows_out = e_out;
+    bp.x_bytes = e_in * br.c1.shape.Cin * sizeof(bf16);
+    const int wd = br.c1.shape.Cout, oc = br.c3.shape.Cout;
+    if (tr) bp.raw1 = arena_alloc<bf16>(e_in * wd);
+    bp.act1 = arena_alloc<bf16>(e_in * wd);
+    if (tr) bp.raw2 = arena_alloc<bf16>(e_out * wd);
+    bp.act2 = arena_alloc<bf16>(e_out * wd);
+    if (tr) bp.raw3 = arena_alloc<bf16>(e_out * oc);
+    if (br.has_ds) bp.rawd = arena_alloc<bf16>(e_out * oc);  // eval: holds the folded-BN identity branch
+    bp.out = arena_alloc<bf16>(e_out * oc);
+    max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
+    plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
+    plan_conv(bp.c2, br.c2, N, h, w, bp.act1, tr ? bp.raw2 : bp.act2, true);
+    plan_conv(bp.c3, br.c3, N, ho, wo, bp.act2, tr ? bp.raw3 : bp.out, true);
+    if (br.has_ds) plan_conv(bp.ds, br.ds, N, h, w, bp.x, bp.rawd, true);
+    x = bp.out;
+    h = ho; w = wo;
+  }
+  p.final_hw = h * w;
+  // ---- pooling, fc, head
+  p.pooled = arena_alloc<bf16>(static_cast<size_t>(N) * 2048);
+  p.feat = arena_alloc<bf16>(static_cast<size_t>(N) * out_dim_);
+  plan_conv(p.fc, fc_, N, 1, 1, p.pooled, p.feat, true);
+  const int B = p.B, F = n_cams_ * out_dim_;
+  p.z0 = arena_alloc<float>(static_cast<size_t>(B) * F);
+  p.h1 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.a1 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.h2 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.a2 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.out = arena_alloc<float>(static_cast<size_t>(B) * 8);
+  if (!tr) return;
+
+  // ---- backward scratch
+  p.d_out = arena_alloc<float>(static_cast<size_t>(B) * 8);
+  p.d_a2 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.d_a1 = arena_alloc<float>(static_cast<size_t>(B) * 128);
+  p.d_z0 = arena_alloc<float>(static_cast<size_t>(B) * F);
+  p.d_feat = arena_alloc<bf16>(static_cast<size_t>(N) * out_dim_);
+  p.d_pooled = arena_alloc<bf16>(static_cast<size_t>(N) * 2048);
+  bf16* G[5];
+  for (int i = 0; i < 5; ++i) G[i] = arena_alloc<bf16>(max_elems);
+  if (real) {
+    p.fc.wgrad = plan_conv_wgrad(fc_.shape, p.d_feat, p.pooled, grads_dev_ + fc_.w_off);
+    p.fc.dgrad = plan_conv_dgrad(fc_.shape, p.d_feat, packed_ + fc_.packed_off, p.d_pooled);
+  }
+  // rotate the five scratch buffers through the blocks in reverse order (see Model::backward)
+  bf16 *P = G[0], *Q = G[1], *R = G[2], *S = G[3], *T = G[4];
+  for (int i = static_cast<int>(blocks_.size()) - 1; i >= 0; --i) {
+    BlockRef& br = blocks_[i];
+    BlockPlan& bp = p.blocks[i];
+    bp.g_out = P; bp.g_q = Q; bp.g_r = R; bp.g_t = T; bp.g_x = S;
+    if (real) {
+      auto wg_dst = [&](const ConvRef& c) { return c.gpacked_off >= 0 ? gpacked_ + c.gpacked_off : grads_dev_ + c.w_off; };
+      // conv3: dy = Q (dRaw3), input act2, dx -> R
+      bp.c3.wgrad = plan_conv_wgrad(br.c3.shape, Q, bp.act2, wg_dst(br.c3));
+      bp.c3.dgrad = plan_conv_dgrad(br.c3.shape, Q, packed_ + br.c3.packed_off, R);
+      // conv2: dy = Q (dRaw2), input act1, dx -> R
+      bp.c2.wgrad = plan_conv_wgrad(br.c2.shape, Q, bp.act1, wg_dst(br.c2));
+      bp.c2.dgrad = plan_conv_dgrad(br.c2.shape, Q, packed_ + br.c2.packed_off, R);
+      // conv1: dy = Q (dRaw1), input x, dx -> S (+ residual)
+      bp.c1.wgrad = plan_conv_wgrad(br.c1.shape, Q, bp.x, wg_dst(br.c1));
+      bp.c1.dgrad = plan_conv_dgrad(br.c1.shape, Q, packed_ + br.c1.packed_off, S);
+      if (br.has_ds) {
+        // downsample: dy = R (dRawd), input x, dx -> T
+        bp.ds.wgrad = plan_conv_wgrad(br.ds.shape, R, bp.x, wg_dst(br.ds));
+        bp.ds.dgrad = plan_conv_dgrad(br.ds.shape, R, packed_ + br.ds.packed_off, T);
+      }
+    }
+    std::swap(P, S);  // this block's input gradient is the previous block's output gradient
+  }
+  p.g_stem_in = P;
+  p.g_act0 = Q;
+  p.g_raw0 = R;
+  if (real) p.stem.wgrad = plan_conv_wgrad(stem_.shape, R, p.x_s2d, gpacked_ + stem_.gpacked_off);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------------------
+void Model::fold_eval(cudaStream_t s) {
+  auto fold = [&](const ConvRef& c) {
+    float* sc = bn_scratch_ + c.bn.scratch_off;
+    bn_fold_eval(params_dev_ + c.bn.gamma_off, params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off,
+                 buffers_dev_ + c.bn.rv_off, kBnEps, sc, sc + c.bn.C, c.bn.C, s);
+  };
+  fold(stem_);
+  for (auto& b : blocks_) {
+    fold(b.c1); fold(b.c2); fold(b.c3);
+    if (b.has_ds) fold(b.ds);
+  }
+  eval_fold_dirty_ = false;
+}
+
+void Model::run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s) {
+  Epilogue e;
+  e.stat_sum = bn_stats_ + c.bn.stat_off;
+  e.stat_sqsum = e.stat_sum + c.bn.C;
+  launch_conv(cp.fwd, e, s);
+  float* sc = bn_scratch_ + c.bn.scratch_off;
+  bn_finalize(e.stat_sum, e.stat_sqsum, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
+              params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off, buffers_dev_ + c.bn.rv_off, kBnMomentum, kBnEps,
+              sc, sc + c.bn.C, sc + 2 * c.bn.C, sc + 3 * c.bn.C, c.bn.C, s);
+}
+
+void Model::forward_train(Plan& p, cudaStream_t s) {
+  ARGUS_CUDA(cudaMemsetAsync(bn_stats_, 0, n_bn_stats_ * sizeof(float), s));
+  eval_fold_dirty_ = true;  // scale/shift scratch now holds batch statistics
+  const int N = p.N;
+  auto SC = [&](const ConvRef& c) { return bn_scratch_ + c.bn.scratch_off; };
+  run_conv_train(p.stem, stem_, static_cast<int64_t>(N) * (p.H / 2) * (p.W / 2), s);
+  maxpool_fwd(p.raw0, SC(stem_), SC(stem_) + 64, p.pooled0, p.idx0, N, p.H / 2, p.W / 2, 64, s);
+  for (size_t i = 0; i < blocks_.size(); ++i) {
+    BlockRef& br = blocks_[i];
+    BlockPlan& bp = p.blocks[i];
+    const int wd = br.c1.shape.Cout, oc = br.c3.shape.Cout;
+    run_conv_train(bp.c1, br.c1, bp.rows_in, s);
+    bn_apply(bp.raw1, SC(br.c1), SC(br.c1) + wd, nullptr, nullptr, nullptr, 1, bp.act1, bp.rows_in, wd, s);
+    run_conv_train(bp.c2, br.c2, bp.rows_out, s);
+    bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, bp.rows_out, wd, s);
+    run_conv_train(bp.c3, br.c3, bp.rows_out, s);
+    if (br.has_ds) {
+      run_conv_train(bp.ds, br.ds, bp.rows_out, s);
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.rawd, SC(br.ds), SC(br.ds) + oc, 1, bp.out, bp.rows_out, oc, s);
+    } else {
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.x, nullptr, nullptr, 1, bp.out, bp.rows_out, oc, s);
+    }
+  }
+}
+
+void Model::forward_eval(Plan& p, cudaStream_t s) {
+  if (eval_fold_dirty_) fold_eval(s);
+  const int N = p.N;
+  auto EP = [&](const ConvRef& c, const bf16* res, int relu) {
+    Epilogue e;
+    e.scale = bn_scratch_ + c.bn.scratch_off;
+    e.shift = e.scale + c.bn.C;
+    e.residual = res;
+    e.relu = relu;
+    return e;
+  };
+  launch_conv(p.stem.fwd, EP(stem_, nullptr, 1), s);
+  maxpool_fwd(p.act0, nullptr, nullptr, p.pooled0, nullptr, N, p.H / 2, p.W / 2, 64, s);
+  for (size_t i = 0; i < blocks_.size(); ++i) {
+    BlockRef& br = blocks_[i];
+    BlockPlan& bp = p.blocks[i];
+    launch_conv(bp.c1.fwd, EP(br.c1, nullptr, 1), s);
+    launch_conv(bp.c2.fwd, EP(br.c2, nullptr, 1), s);
+    const bf16* identity = bp.x;
+    if (br.has_ds) {
+      launch_conv(bp.ds.fwd, EP(br.ds, nullptr, 0), s);
+      identity = bp.rawd;
+    }
+    launch_conv(bp.c3.fwd, EP(br.c3, identity, 1), s);
+  }
+}
+
+void Model::head_forward(Plan& p, float* out, cudaStream_t s) {
+  const int N = p.N, B = p.B, F = n_cams_ * out_dim_;
+  avgpool_fwd(p.blocks.back().out, p.pooled, N, p.final_hw, 2048, s);
+  Epilogue e;
+  e.shift = params_dev_ + fc_bias_off_;
+  launch_conv(p.fc.fwd, e, s);
+  // (N, out_dim) row-major == (B, n_cams*out_dim): views of one sample are adjacent (argus/models.py:87)
+  gelu_fwd_bf16(p.feat, p.z0, static_cast<int64_t>(B) * F, s);
+  linear_fwd(p.z0, params_dev_ + head_w_off_[0], params_dev_ + head_b_off_[0], p.h1, p.a1, B, F, 128, s);
+  linear_fwd(p.a1, params_dev_ + head_w_off_[1], params_dev_ + head_b_off_[1], p.h2, p.a2, B, 128, 128, s);
+  linear_fwd(p.a2, params_dev_ + head_w_off_[2], params_dev_ + head_b_off_[2], p.out, nullptr, B, 128, 6, s);
+  ARGUS_CUDA(cudaMemcpyAsync(out, p.out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+}
+
+void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s) {
+  ARGUS_CHECK(params_dev_ != nullptr && buffers_dev_ != nullptr, "model is not bound");
+  ARGUS_CHECK(B > 0, "empty batch");
+  ARGUS_CHECK(!training || B * n_cams_ * (H / 32) * (W / 32) > 1,
+              "train-mode batch norm needs more than one value per channel");
+  Plan& p = get_plan(B, H, W, training);
+  if (is_u8)
+    pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d, p.N, H, W, s);
+  else
+    pack_input_f32(static_cast<const float*>(x), p.x_s2d, p.N, H, W, s);
+  if (training) {
+    forward_train(p, s);
+    last_train_plan_ = &p;
+  } else {
+    forward_eval(p, s);
+  }
+  head_forward(p, out, s);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------------------------
+void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
+                        cudaStream_t s) {
+  const float* sc = bn_scratch_ + c.bn.scratch_off;
+  float* dgamma = grads_dev_ + c.bn.gamma_off;
+  float* dbeta = grads_dev_ + c.bn.beta_off;
+  const int C = c.bn.C;
+  bn_bwd_reduce(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, rows, C, mask, s);
+  bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
+}
+
+void Model::conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s) {
+  launch_wgrad(cp.wgrad, s);
+  Epilogue e;
+  e.residual = residual;
+  for (const auto& l : cp.dgrad) launch_conv(l, e, s);
+}
+
+void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s) {
+  ARGUS_CHECK(last_train_plan_ != nullptr, "backward() needs a preceding training forward()");
+  ARGUS_CHECK(grads_dev_ != nullptr, "model is not bound to a gradient arena");
+  Plan& p = *last_train_plan_;
+  const int N = p.N, B = p.B, F = n_cams_ * out_dim_;
+  const int n_blocks = static_cast<int>(blocks_.size());
+  // block index ranges per stage: stage 0 = layer4, 1 = layer3, 2 = layer2, 3 = layer1
+  const int first_block[4] = {13, 7, 3, 0};
+  const int last_block[4] = {16, 13, 7, 3};
+  for (int stage = stage_begin; stage < stage_end; ++stage) {
+    if (stage == 0) {
+      // ---- head
+      ARGUS_CUDA(cudaMemcpyAsync(p.d_out, d_out, static_cast<size_t>(B) * 6 * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, s));
+      float* g = grads_dev_;
+      linear_bwd(p.d_out, nullptr, p.a2, params_dev_ + head_w_off_[2], g + head_w_off_[2], g + head_b_off_[2],
+                 p.d_a2, B, 128, 6, s);
+      linear_bwd(p.d_a2, p.h2, p.a1, params_dev_ + head_w_off_[1], g + head_w_off_[1], g + head_b_off_[1], p.d_a1, B,
+                 128, 128, s);
+      linear_bwd(p.d_a1, p.h1, p.z0, params_dev_ + head_w_off_[0], g + head_w_off_[0], g + head_b_off_[0], p.d_z0, B,
+                 F, 128, s);
+      gelu_bwd_bf16(p.d_z0, p.feat, p.d_feat, static_cast<int64_t>(B) * F, s);
+      // ---- fc
+      colsum_bf16_kernel<<<(out_dim_ + 127) / 128, 128, 0, s>>>(p.d_feat, g + fc_bias_off_, N, out_dim_);
+      ARGUS_CUDA(cudaGetLastError());
+      launch_wgrad(p.fc.wgrad, s);
+      Epilogue e;
+      for (const auto& l : p.fc.dgrad) launch_conv(l, e, s);
+      avgpool_bwd(p.d_pooled, p.blocks.back().g_out, N, p.final_hw, 2048, s);
+    }
+    for (int i = last_block[stage] - 1; i >= first_block[stage]; --i) {
+      ARGUS_CHECK(i < n_blocks, "block index");
+      BlockRef& br = blocks_[i];
+      BlockPlan& bp = p.blocks[i];
+      // zero this block's packed 3x3 gradient scratch
+      ARGUS_CUDA(cudaMemsetAsync(gpacked_ + br.c2.gpacked_off, 0,
+                                 static_cast<size_t>(br.c2.shape.Ktot()) * br.c2.shape.Cout * sizeof(float), s));
+      bf16 *P = bp.g_out, *Q = bp.g_q, *R = bp.g_r, *T = bp.g_t;
+      // bn3 (+ residual ReLU): P becomes the masked gradient, Q = dRaw3
+      bn_backward(br.c3, P, bp.raw3, bp.out, Q, bp.rows_out, 2, s);
+      const bf16* residual = P;
+      if (br.has_ds) {
+        bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
+        if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
+        conv_backward(bp.ds, nullptr, s);  // R -> T
+        residual = T;
+      }
+      conv_backward(bp.c3, nullptr, s);                                   // Q -> R (dAct2)
+      bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);      // Q = dRaw2
+      conv_backward(bp.c2, nullptr, s);                                   // Q -> R (dAct1)
+      bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);       // Q = dRaw1
+      conv_backward(bp.c1, residual, s);                                  // Q -> S (+ residual)
+    }
+    if (stage == 3) {
+      // ---- stem: max-pool backward, bn1 backward, weight gradient
+      ARGUS_CUDA(cudaMemsetAsync(gpacked_ + stem_.gpacked_off, 0, 64 * 256 * sizeof(float), s));
+      maxpool_bwd(p.g_stem_in, p.idx0, p.g_act0, N, p.H / 2, p.W / 2, 64, s);
+      bn_backward(stem_, p.g_act0, p.raw0, nullptr, p.g_raw0, static_cast<int64_t>(N) * (p.H / 2) * (p.W / 2), 1, s);
+      launch_wgrad(p.stem.wgrad, s);
+    }
+    // packed 3x3 / stem gradients of this stage -> PyTorch layout in the gradient arena
+    {
+      int lo = -1, hi = -1;
+      for (size_t i = 0; i < pack_table_.size(); ++i)
+        if (pack_table_stage_[i] == stage) {
+          if (lo < 0) lo = static_cast<int>(i);
+          hi = static_cast<int>(i) + 1;
+        }
+      if (lo >= 0) unpack_wgrads(gpacked_, grads_dev_, pack_table_dev_ + lo, hi - lo, s);
+    }
+  }
+}
+
+}  // namespace argus

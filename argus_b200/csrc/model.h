@@ -1,0 +1,156 @@
+// NCameraCNN (/root/reference/argus/models.py:26-90) as a statically scheduled graph over the sm_100a kernels:
+// shared-weight ResNet-50 per view -> fc(2048 -> resnet_output_dim) -> concat views -> GELU -> MLP -> se(3) 6-vector.
+//
+// The model object owns: packed bf16 weights, batch-norm scratch, activation and gradient arenas, and the per-batch
+// launch plans (TMA tensor maps). The caller (PyTorch) owns the fp32 parameter / gradient / buffer arenas whose
+// layout is described by tensor_info() in the reference's state_dict order.
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "conv_ops.h"
+#include "kernels.h"
+#include "runtime.h"
+
+namespace argus {
+
+struct TensorInfo {
+  std::string name;
+  int64_t offset = 0;  // element offset inside its arena
+  int64_t numel = 0;
+  int ndim = 0;
+  int64_t shape[4] = {0, 0, 0, 0};
+};
+
+struct BnRef {
+  int C = 0;
+  int64_t gamma_off = 0, beta_off = 0;  // parameter arena
+  int64_t rm_off = 0, rv_off = 0;       // buffer arena
+  int64_t scratch_off = 0;              // bn scratch arena: scale, shift, mean, invstd (4*C floats)
+  int64_t stat_off = 0;                 // statistics arena: sum, sqsum (2*C floats)
+};
+
+struct ConvRef {
+  ConvShape shape;           // N filled in at plan time
+  int64_t w_off = 0;         // parameter arena (PyTorch layout)
+  int64_t packed_off = 0;    // packed bf16 arena
+  int64_t gpacked_off = -1;  // packed fp32 gradient scratch (-1: gradient accumulates directly in the grad arena)
+  BnRef bn;
+  int stage = 0;             // backward stage (0 = head/fc/layer4 ... 3 = layer1/stem)
+};
+
+struct BlockRef {
+  ConvRef c1, c2, c3, ds;
+  bool has_ds = false;
+};
+
+struct ConvPlan {
+  ConvLaunch fwd;
+  std::vector<ConvLaunch> dgrad;
+  WgradLaunch wgrad;
+  bool has_dgrad = false;
+};
+
+struct BlockPlan {
+  ConvPlan c1, c2, c3, ds;
+  bf16 *x = nullptr, *raw1 = nullptr, *act1 = nullptr, *raw2 = nullptr, *act2 = nullptr, *raw3 = nullptr,
+       *rawd = nullptr, *out = nullptr;
+  int64_t rows_in = 0, rows_mid = 0, rows_out = 0;
+  // gradient scratch roles for this block
+  bf16 *g_out = nullptr, *g_q = nullptr, *g_r = nullptr, *g_t = nullptr, *g_x = nullptr;
+  size_t x_bytes = 0;
+};
+
+struct Plan {
+  int B = 0, H = 0, W = 0, N = 0;
+  bool training = false;
+  ConvPlan stem;
+  bf16 *x_s2d = nullptr, *raw0 = nullptr, *act0 = nullptr, *pooled0 = nullptr;
+  uint8_t* idx0 = nullptr;
+  std::vector<BlockPlan> blocks;
+  ConvPlan fc;
+  bf16 *pooled = nullptr, *feat = nullptr;
+  int final_hw = 0;
+  // head (fp32)
+  float *z0 = nullptr, *h1 = nullptr, *a1 = nullptr, *h2 = nullptr, *a2 = nullptr, *out = nullptr;
+  float *d_out = nullptr, *d_a2 = nullptr, *d_a1 = nullptr, *d_z0 = nullptr;
+  bf16 *d_feat = nullptr, *d_pooled = nullptr;
+  bf16* g_stem_in = nullptr;   // gradient wrt the pooled stem output (= layer1.0 input gradient)
+  bf16 *g_act0 = nullptr, *g_raw0 = nullptr;
+};
+
+class Model {
+ public:
+  Model(int n_cams, int resnet_output_dim);
+  ~Model();
+
+  const std::vector<TensorInfo>& params() const { return params_; }
+  const std::vector<TensorInfo>& buffers() const { return buffers_; }
+  int64_t num_param_elems() const { return n_param_elems_; }
+  int64_t num_buffer_elems() const { return n_buffer_elems_; }
+  // element range [begin, end) of the parameter arena owned by a backward stage (for bucketed all-reduce)
+  void stage_param_range(int stage, int64_t* begin, int64_t* end) const;
+
+  void bind(float* params, float* grads, float* buffers);
+  void reserve(int max_batch, int H, int W, bool training);
+  void sync_weights(cudaStream_t s);   // fp32 parameters -> packed bf16 (+ marks the eval BN fold dirty)
+
+  // x: (B, 3*n_cams, H, W) fp32 NCHW in [0,1], or u8 (B*n_cams, H, W, 3) when is_u8. out: (B, 6) fp32.
+  void forward(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s);
+  // d_out: (B, 6) gradient of the loss wrt forward()'s output. Accumulates parameter gradients (+=) into the bound
+  // gradient arena for stages [stage_begin, stage_end); stages must be run in increasing order 0..3.
+  void backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
+  void zero_grads(cudaStream_t s);
+
+  int n_cams() const { return n_cams_; }
+  int out_dim() const { return out_dim_; }
+  size_t arena_bytes() const { return arena_bytes_; }
+
+ private:
+  void build_layout();
+  Plan& get_plan(int B, int H, int W, bool training);
+  void build_plan(Plan& p);
+  void fold_eval(cudaStream_t s);
+  void forward_train(Plan& p, cudaStream_t s);
+  void forward_eval(Plan& p, cudaStream_t s);
+  void head_forward(Plan& p, float* out, cudaStream_t s);
+  void run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s);
+  void bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
+                   cudaStream_t s);
+  void conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s);
+
+  template <typename T>
+  T* arena_alloc(size_t count);
+
+  int n_cams_, out_dim_;
+  std::vector<TensorInfo> params_, buffers_;
+  int64_t n_param_elems_ = 0, n_buffer_elems_ = 0;
+  ConvRef stem_;
+  std::vector<BlockRef> blocks_;
+  ConvRef fc_;  // bn unused; bias at fc_bias_off_
+  int64_t fc_bias_off_ = 0;
+  int64_t head_w_off_[3] = {0, 0, 0}, head_b_off_[3] = {0, 0, 0};
+  int64_t stage_begin_[5] = {0, 0, 0, 0, 0};  // parameter-arena offsets where each network segment starts
+
+  float *params_dev_ = nullptr, *grads_dev_ = nullptr, *buffers_dev_ = nullptr;
+  bf16* packed_ = nullptr;
+  float* gpacked_ = nullptr;
+  float* bn_scratch_ = nullptr;
+  float* bn_stats_ = nullptr;
+  int64_t n_packed_ = 0, n_gpacked_ = 0, n_bn_scratch_ = 0, n_bn_stats_ = 0;
+  WeightPackEntry* pack_table_dev_ = nullptr;
+  std::vector<WeightPackEntry> pack_table_;
+  std::vector<int> pack_table_stage_;
+  bool eval_fold_dirty_ = true;
+
+  uint8_t* arena_ = nullptr;
+  size_t arena_bytes_ = 0, arena_used_ = 0;
+  int reserved_batch_ = 0, reserved_h_ = 0, reserved_w_ = 0;
+  bool reserved_training_ = false;
+  std::map<std::tuple<int, int, int, bool>, std::unique_ptr<Plan>> plans_;
+  Plan* last_train_plan_ = nullptr;
+};
+
+}  // namespace argus

@@ -46,6 +46,50 @@ int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, in
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream);
 
+/* ---- pose loss and pose exponential ------------------------------------------------------------------------
+ * argus_pose_loss: geometric_loss_fn (argus/train.py:105-119) forward AND analytic backward in one launch.
+ *   pred (B,6) fp32 se3 [tau, phi]; target (B,7) fp32 SE3 [t, qx, qy, qz, qw]; loss (B) per-sample (nullable);
+ *   loss_mean (1) += mean over B (nullable, caller zeroes); grad (B,6) = grad_scale * dloss/dpred (nullable).
+ * argus_pose_exp: pp.se3(pred).Exp() (argus/utils.py:179-189); wxyz != 0 emits [t, qw, qx, qy, qz]
+ *   (argus/utils.py:130-145). */
+int argus_pose_loss(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
+                    float grad_scale, void* stream);
+int argus_pose_exp(const float* pred, float* pose, int B, int wxyz, void* stream);
+
+/* ---- optimizer step tail: clip_grad_norm_ + Adam (argus/train.py:318-319) ------------------------------------
+ * Flat fp32 arenas of n elements. scratch must hold >= 1024 floats. grads are scaled by gscale (1/world_size for
+ * data-parallel averaging) before the norm; norm_out (nullable) receives the pre-clip global L2 norm. */
+int argus_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                         float* scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                         int step, float* norm_out, void* stream);
+
+/* ---- the model: NCameraCNN (argus/models.py:26-90) -----------------------------------------------------------
+ * The library defines the flat layout of the parameter arena (trainable tensors, reference state_dict order) and
+ * the buffer arena (BN running_mean / running_var); the caller allocates them and binds them. */
+typedef struct argus_model argus_model;
+int argus_model_create(argus_model** out, int n_cams, int resnet_output_dim);
+int argus_model_destroy(argus_model* m);
+int argus_model_counts(argus_model* m, int* n_params, int* n_buffers, int64_t* param_elems, int64_t* buffer_elems);
+/* name_cap bytes of `name` are filled (NUL terminated); shape has room for 4 entries. */
+int argus_model_tensor_info(argus_model* m, int is_buffer, int index, char* name, int name_cap, int64_t* offset,
+                            int64_t* numel, int* ndim, int64_t* shape);
+int argus_model_bind(argus_model* m, float* params, float* grads, float* buffers);
+/* Pre-allocate activations for up to max_batch pairs of H x W images (grows on demand otherwise). */
+int argus_model_reserve(argus_model* m, int max_batch, int H, int W, int training);
+/* fp32 parameters -> packed bf16 tensor-core operands; call after every parameter update / load_state_dict. */
+int argus_model_sync_weights(argus_model* m, void* stream);
+/* NCameraCNN.forward (argus/models.py:66-90). x is (B, 3*n_cams, H, W) fp32 NCHW, or u8 (B*n_cams, H, W, 3) when
+ * is_u8. training != 0 uses batch statistics and updates the running statistics. out is (B, 6) fp32. */
+int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, int W, int training, float* out,
+                        void* stream);
+int argus_model_zero_grads(argus_model* m, void* stream);
+/* Backward of the last training forward. d_out (B,6). Stages 0..3 (head+fc+layer4, layer3, layer2, layer1+stem)
+ * must run in order; gradients are ADDED into the bound gradient arena. */
+int argus_model_backward(argus_model* m, const float* d_out, int stage_begin, int stage_end, void* stream);
+/* Element range of the parameter arena whose gradients are final once `stage` has run (all-reduce buckets). */
+int argus_model_stage_range(argus_model* m, int stage, int64_t* begin, int64_t* end);
+int argus_model_arena_bytes(argus_model* m, int64_t* bytes);
+
 #ifdef __cplusplus
 }
 #endif

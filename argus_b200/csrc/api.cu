@@ -21,6 +21,21 @@ extern "C" {
 const char* argus_last_error_string(void) { return get_last_error(); }
 int argus_version(void) { return 100; }
 
+int argus_profile_enable(int on) {
+  ARGUS_API_BEGIN
+  profile_enable(on != 0);
+  ARGUS_API_END
+}
+int argus_profile_report(char* json, int cap) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(json != nullptr && cap > 2, "bad report buffer");
+  const std::string r = profile_report_json();
+  ARGUS_CHECK(static_cast<int>(r.size()) < cap, "profile report buffer too small");
+  std::memcpy(json, r.c_str(), r.size() + 1);
+  ARGUS_API_END
+}
+int64_t argus_launch_count(void) { return launch_count(); }
+
 int argus_require_device(void) {
   ARGUS_API_BEGIN
   require_sm100();
@@ -179,6 +194,13 @@ int argus_model_stage_range(argus_model* m, int stage, int64_t* begin, int64_t* 
   ARGUS_API_BEGIN
   ARGUS_CHECK(m != nullptr, "null model");
   m->impl.stage_param_range(stage, begin, end);
+  ARGUS_API_END
+}
+int argus_model_copy_activation(argus_model* m, int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C,
+                                void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.copy_activation(index, dst, capacity_elems, rows, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 int argus_model_arena_bytes(argus_model* m, int64_t* bytes) {

@@ -1,7 +1,10 @@
 #include "conv_ops.h"
 
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
 
 namespace argus {
@@ -60,6 +63,79 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
     throw Error(msg);
   }
   return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch accounting / profiling
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct ProfRecord {
+  const char* family;
+  cudaEvent_t start, stop;
+  double flops, bytes;
+};
+std::atomic<int64_t> g_launches{0};
+bool g_profiling = false;
+std::vector<ProfRecord> g_records;
+std::vector<cudaEvent_t> g_event_pool;
+cudaEvent_t new_event() {
+  if (!g_event_pool.empty()) {
+    cudaEvent_t e = g_event_pool.back();
+    g_event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  ARGUS_CUDA(cudaEventCreate(&e));
+  return e;
+}
+}  // namespace
+
+void profile_enable(bool on) {
+  if (on) {
+    for (auto& r : g_records) { g_event_pool.push_back(r.start); g_event_pool.push_back(r.stop); }
+    g_records.clear();
+  }
+  g_profiling = on;
+}
+bool profile_enabled() { return g_profiling; }
+int64_t launch_count() { return g_launches.load(); }
+
+ProfileScope::ProfileScope(const char* family, cudaStream_t s, double flops, double bytes) : stream(s) {
+  g_launches.fetch_add(1);
+  if (!g_profiling) return;
+  ProfRecord r{family, new_event(), new_event(), flops, bytes};
+  cudaEventRecord(r.start, s);
+  slot = static_cast<int>(g_records.size());
+  g_records.push_back(r);
+}
+ProfileScope::~ProfileScope() {
+  if (slot >= 0) cudaEventRecord(g_records[slot].stop, stream);
+}
+
+std::string profile_report_json() {
+  struct Agg { int launches = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  std::vector<std::string> order;
+  for (auto& r : g_records) {
+    cudaEventSynchronize(r.stop);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.start, r.stop);
+    if (!agg.count(r.family)) order.push_back(r.family);
+    Agg& a = agg[r.family];
+    a.launches += 1; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+  }
+  std::string out = "{";
+  bool first = true;
+  for (auto& name : order) {
+    const Agg& a = agg[name];
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
+             first ? "" : ", ", name.c_str(), a.launches, a.ms, a.flops, a.bytes);
+    out += buf;
+    first = false;
+  }
+  out += "}";
+  return out;
 }
 
 int num_sms() {
@@ -338,6 +414,8 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   p.stat_sum = e.stat_sum;
   p.stat_sqsum = e.stat_sqsum;
   ARGUS_CHECK((e.stat_sum == nullptr) == (e.stat_sqsum == nullptr), "BN statistic pointers come in pairs");
+  const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * p.num_taps * p.kblocks_per_tap * kBlockK;
+  ProfileScope prof(l.b_mn ? "conv_dgrad" : "conv_fwd", stream, flops, 0.0);
   const int key = l.block_n * 2 + l.b_mn;
   switch (key) {
     case 64 * 2 + 0: launch_conv_t<64, 0>(p, stream); break;
@@ -365,6 +443,8 @@ static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
 }
 
 void launch_wgrad(const WgradLaunch& l, cudaStream_t stream) {
+  const double flops = 2.0 * l.p.kblocks_total * 64.0 * l.p.cout * static_cast<double>(l.p.cin) * l.p.num_taps;
+  ProfileScope prof("conv_wgrad", stream, flops, 0.0);
   switch (l.block_n) {
     case 64: launch_wgrad_t<64>(l.p, stream); break;
     case 128: launch_wgrad_t<128>(l.p, stream); break;

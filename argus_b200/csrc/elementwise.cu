@@ -121,11 +121,13 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, uint4* __res
 }
 
 void pack_input_f32(const float* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
+  ProfileScope prof("pack_input", s, 0, static_cast<double>(n_images) * H * W * 3 * 4 + static_cast<double>(n_images) * (H / 2) * (W / 2 + 4) * 32);
   const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
   pack_input_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
   ARGUS_CUDA(cudaGetLastError());
 }
 void pack_input_u8(const uint8_t* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
+  ProfileScope prof("pack_input", s, 0, static_cast<double>(n_images) * H * W * 3 + static_cast<double>(n_images) * (H / 2) * (W / 2 + 4) * 32);
   const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
   pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
   ARGUS_CUDA(cudaGetLastError());
@@ -181,11 +183,13 @@ __global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, flo
 }
 void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries,
                   cudaStream_t s) {
+  ProfileScope prof("pack_weights", s, 0, 0);
   pack_weights_kernel<<<dim3(32, n_entries), 256, 0, s>>>(params, packed, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
                    cudaStream_t s) {
+  ProfileScope prof("unpack_wgrads", s, 0, 0);
   unpack_wgrads_kernel<<<dim3(32, n_entries), 256, 0, s>>>(packed_grads, grads, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -217,6 +221,7 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sqsum, double 
 void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                  float* save_mean, float* save_invstd, int C, cudaStream_t s) {
+  ProfileScope prof("bn_finalize", s, 0, 40.0 * C);
   bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, save_mean, save_invstd, C);
   ARGUS_CUDA(cudaGetLastError());
@@ -231,6 +236,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 }
 void bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   float eps, float* scale, float* shift, int C, cudaStream_t s) {
+  ProfileScope prof("bn_finalize", s, 0, 24.0 * C);
   bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -270,6 +276,7 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ x, const float* __rest
 }
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
               const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s) {
+  ProfileScope prof("bn_apply", s, 0, static_cast<double>(rows) * C * 2 * (res ? 3 : 2));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_apply: C/8 must be a power of two");
   const int64_t nvec = rows * (C / 8);
   const int grid = grid_for(nvec, 256);
@@ -366,6 +373,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
                    int mask_mode, cudaStream_t s) {
+  ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_bwd_reduce: C/8 must be a power of two");
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);
@@ -415,6 +423,7 @@ __global__ void bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restr
 void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                   const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
                   int64_t rows, int C, int mask_mode, cudaStream_t s) {
+  ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 5 : 3));
   const int cvec = C / 8;
   const int64_t nvec = rows * cvec;
   const int grid = grid_for(nvec, 256);
@@ -489,6 +498,7 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
 }
 void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y, uint8_t* idx, int N, int H, int W,
                  int C, cudaStream_t s) {
+  ProfileScope prof("maxpool", s, 0, static_cast<double>(N) * H * W * C * 2 * 1.25 + (idx ? static_cast<double>(N) * H * W * C / 4 : 0.0));
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
   maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), scale, shift,
                                                           reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),
@@ -533,6 +543,7 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __
   }
 }
 void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int W, int C, cudaStream_t s) {
+  ProfileScope prof("maxpool", s, 0, static_cast<double>(N) * H * W * C * 2 * 1.25 + static_cast<double>(N) * H * W * C / 4);
   const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
   maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
                                                           reinterpret_cast<const uint2*>(idx),
@@ -562,6 +573,7 @@ __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
   }
 }
 void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s) {
+  ProfileScope prof("avgpool", s, 0, static_cast<double>(N) * (HW + 1) * C * 2);
   const int64_t total = static_cast<int64_t>(N) * (C / 8);
   avgpool_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(x),
                                                           reinterpret_cast<uint4*>(y), N, HW, C / 8);
@@ -581,6 +593,7 @@ __global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restri
   }
 }
 void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s) {
+  ProfileScope prof("avgpool", s, 0, static_cast<double>(N) * (HW + 1) * C * 2);
   const int64_t total = static_cast<int64_t>(N) * HW * (C / 8);
   avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
                                                           reinterpret_cast<uint4*>(dx), N, HW, C / 8);

@@ -26,6 +26,7 @@ __global__ void gelu_fwd_bf16_kernel(const bf16* __restrict__ x, float* __restri
     y[i] = gelu_f(__bfloat162float(x[i]));
 }
 void gelu_fwd_bf16(const bf16* x, float* y, int64_t n, cudaStream_t s) {
+  ProfileScope prof("head", s, 0, 6.0 * n);
   gelu_fwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(x, y, n);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -36,6 +37,7 @@ __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dz, const bf16* _
     dx[i] = __float2bfloat16(dz[i] * gelu_grad_f(__bfloat162float(x[i])));
 }
 void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStream_t s) {
+  ProfileScope prof("head", s, 0, 8.0 * n);
   gelu_bwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(dz, x, dx, n);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -60,6 +62,7 @@ __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __re
 }
 void linear_fwd(const float* x, const float* w, const float* b, float* y, float* act, int B, int In, int Out,
                 cudaStream_t s) {
+  ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
   const int64_t threads = static_cast<int64_t>(B) * Out * 32;
   linear_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, s>>>(x, w, b, y, act, B, In, Out);
   ARGUS_CUDA(cudaGetLastError());
@@ -96,6 +99,7 @@ __global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* _
 }
 void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
                 int In, int Out, cudaStream_t s) {
+  ProfileScope prof("head", s, 4.0 * B * In * Out, 4.0 * (2.0 * B * In + 2.0 * In * Out + static_cast<double>(B) * Out));
   if (pre != nullptr) {
     gelu_grad_inplace_kernel<<<(B * Out + 255) / 256, 256, 0, s>>>(dy, pre, B * Out);
     ARGUS_CUDA(cudaGetLastError());
@@ -139,6 +143,7 @@ __global__ void pose_loss_kernel(const float* __restrict__ pred, const float* __
 }
 void pose_loss_fwd_bwd(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
                        float grad_scale, cudaStream_t s) {
+  ProfileScope prof("pose_loss", s, 0, 80.0 * B);
   if (B <= 0) return;
   pose_loss_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, target, loss, loss_mean, grad, B, grad_scale);
   ARGUS_CUDA(cudaGetLastError());
@@ -160,6 +165,7 @@ __global__ void pose_exp_kernel(const float* __restrict__ pred, float* __restric
   }
 }
 void pose_exp(const float* pred, float* pose, int B, int wxyz, cudaStream_t s) {
+  ProfileScope prof("pose_loss", s, 0, 52.0 * B);
   if (B <= 0) return;
   pose_exp_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, pose, B, wxyz);
   ARGUS_CUDA(cudaGetLastError());
@@ -194,6 +200,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
   }
 }
 int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t s) {
+  ProfileScope prof("grad_norm", s, 0, 4.0 * n);
   grad_sqnorm_kernel<<<kNormBlocks, 256, 0, s>>>(g, n, partial);
   ARGUS_CUDA(cudaGetLastError());
   return kNormBlocks;
@@ -237,6 +244,7 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* partial, int n_partial,
                     float gscale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
                     float* norm_out, cudaStream_t s) {
+  ProfileScope prof("clip_adam", s, 0, 28.0 * n);
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
   clip_adam_kernel<<<4 * num_sms(), 256, 0, s>>>(p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,

@@ -164,6 +164,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
   }
   plans_.clear();
   last_train_plan_ = nullptr;
+  last_plan_ = nullptr;
   eval_fold_dirty_ = true;
 }
 
@@ -209,6 +210,7 @@ void Model::reserve(int max_batch, int H, int W, bool training) {
     arena_bytes_ = need;
     plans_.clear();
     last_train_plan_ = nullptr;
+    last_plan_ = nullptr;
   }
   reserved_batch_ = std::max(reserved_batch_, max_batch);
   reserved_h_ = H; reserved_w_ = W;
@@ -444,6 +446,7 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
     pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d, p.N, H, W, s);
   else
     pack_input_f32(static_cast<const float*>(x), p.x_s2d, p.N, H, W, s);
+  last_plan_ = &p;
   if (training) {
     forward_train(p, s);
     last_train_plan_ = &p;
@@ -451,6 +454,29 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
     forward_eval(p, s);
   }
   head_forward(p, out, s);
+}
+
+void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s) {
+  ARGUS_CHECK(last_plan_ != nullptr, "no forward pass has run yet");
+  Plan& p = *last_plan_;
+  const bf16* src = nullptr;
+  int64_t r = 0;
+  int c = 0;
+  if (index == -1) {
+    src = p.pooled0; r = static_cast<int64_t>(p.N) * (p.H / 4) * (p.W / 4); c = 64;
+  } else if (index >= 0 && index < static_cast<int>(p.blocks.size())) {
+    src = p.blocks[index].out; r = p.blocks[index].rows_out; c = blocks_[index].c3.shape.Cout;
+  } else if (index == 16) {
+    src = p.pooled; r = p.N; c = 2048;
+  } else if (index == 17) {
+    src = p.feat; r = p.N; c = out_dim_;
+  } else {
+    throw Error("activation index out of range");
+  }
+  ARGUS_CHECK(r * c <= capacity_elems, "destination too small for the requested activation");
+  ARGUS_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(r) * c * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  if (rows) *rows = r;
+  if (C) *C = c;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -496,6 +522,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
                  F, 128, s);
       gelu_bwd_bf16(p.d_z0, p.feat, p.d_feat, static_cast<int64_t>(B) * F, s);
       // ---- fc
+      { ProfileScope prof("head", s, 0, 2.0 * N * out_dim_); }
       colsum_bf16_kernel<<<(out_dim_ + 127) / 128, 128, 0, s>>>(p.d_feat, g + fc_bias_off_, N, out_dim_);
       ARGUS_CUDA(cudaGetLastError());
       launch_wgrad(p.fc.wgrad, s);

@@ -103,6 +103,9 @@ class Model {
   // gradient arena for stages [stage_begin, stage_end); stages must be run in increasing order 0..3.
   void backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
   void zero_grads(cudaStream_t s);
+  // Debug / test probe: copies an activation of the LAST forward (bf16 NHWC rows x C) into dst.
+  // index -1: pooled stem output; 0..15: bottleneck block outputs; 16: globally pooled features; 17: fc output.
+  void copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s);
 
   int n_cams() const { return n_cams_; }
   int out_dim() const { return out_dim_; }
@@ -151,6 +154,7 @@ class Model {
   bool reserved_training_ = false;
   std::map<std::tuple<int, int, int, bool>, std::unique_ptr<Plan>> plans_;
   Plan* last_train_plan_ = nullptr;
+  Plan* last_plan_ = nullptr;
 };
 
 }  // namespace argus

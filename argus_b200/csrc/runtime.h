@@ -55,6 +55,20 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
 int num_sms();
 void require_sm100();
 
+// ---- launch accounting and optional per-kernel-family timing (used by bench.py for the roofline figures) ----
+// Every kernel launcher opens a ProfileScope: it always bumps the launch counter and, while profiling is enabled,
+// brackets the launch with CUDA events on the launching stream and records algorithmic FLOPs / bytes.
+void profile_enable(bool on);                    // clears previous records when switching on
+bool profile_enabled();
+int64_t launch_count();                          // kernels launched by this library since load
+std::string profile_report_json();               // synchronises the recorded events and aggregates per family
+struct ProfileScope {
+  ProfileScope(const char* family, cudaStream_t stream, double flops, double bytes);
+  ~ProfileScope();
+  int slot = -1;
+  cudaStream_t stream = nullptr;
+};
+
 inline int ilog2(int v) {
   int l = 0;
   while ((1 << l) < v) ++l;

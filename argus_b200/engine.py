@@ -1,0 +1,127 @@
+"""Fused training step for the hot path of /root/reference/argus/train.py:298-320:
+
+    images.to(device) -> [augmentation] -> model(images) -> geometric_loss_fn -> mean -> backward
+    -> clip_grad_norm_(max_grad_norm) -> Adam step
+
+executed as a handful of C-ABI calls on one stream, with no host synchronisation inside the step (the reference
+synchronises every step through `loss.item()`, train.py:312). Under data parallelism (train.py:137-166,199) the
+gradient arena is all-reduced in four reverse-order buckets over NCCL while the rest of the backward pass runs.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from .models import NCameraCNN
+
+
+class TrainEngine:
+    """Owns the optimizer state (flat Adam moments) and runs fused training steps on an NCameraCNN.
+
+    Args:
+        model: an argus_b200 NCameraCNN already on a CUDA device.
+        lr, betas, eps: torch.optim.Adam defaults as used by the reference (train.py:232).
+        max_grad_norm: clip_grad_norm_ threshold (train.py:318); <= 0 disables clipping.
+        process_group: torch.distributed group for data parallelism (None = single process).
+        augmentation: optional argus_b200.data.Augmentation applied on device to uint8 image batches.
+    """
+
+    def __init__(self, model: NCameraCNN, lr: float = 1e-4, max_grad_norm: float = 1.0,
+                 betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
+                 process_group: Optional["dist.ProcessGroup"] = None, distributed: Optional[bool] = None,
+                 augmentation=None) -> None:
+        if not model.flat_params.is_cuda:
+            raise _lib.ArgusError("TrainEngine needs the model on a CUDA device (no CPU fallback)")
+        self.model = model
+        self.lr = float(lr)
+        self.max_grad_norm = float(max_grad_norm)
+        self.betas = (float(betas[0]), float(betas[1]))
+        self.eps = float(eps)
+        self.augmentation = augmentation
+        self.step_count = 0
+        self.device = model.flat_params.device
+        if distributed is None:
+            distributed = dist.is_available() and dist.is_initialized()
+        self.distributed = bool(distributed)
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if self.distributed else 1
+        n = model.flat_params.numel()
+        self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
+        self._scratch = torch.zeros(1024, dtype=torch.float32, device=self.device)
+        self._grad_norm = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._loss_mean = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._stage_ranges = model.stage_ranges()
+        self.last_grad_norm = self._grad_norm
+        if self.distributed:
+            # DDP's constructor broadcasts rank 0's parameters and buffers (train.py:199)
+            dist.broadcast(model.flat_params, src=0, group=process_group)
+            dist.broadcast(model._flat_buffers, src=0, group=process_group)
+            model.sync_weights(force=True)
+
+    # ------------------------------------------------------------------------------------------------------------
+    def forward_backward(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """Forward, loss, backward (+ bucketed gradient all-reduce). Returns the mean loss as a device scalar.
+
+        images: (B, 3*n_cams, H, W) float32 in [0,1]  or  (B, n_cams, H, W, 3) uint8; targets: (B, 7) [t, q_xyzw].
+        """
+        model = self.model
+        lib_stream = _lib.stream_ptr()
+        if self.augmentation is not None and images.dtype == torch.uint8:
+            images = self.augmentation.apply_u8(images, step=self.step_count)
+        model.train()
+        out = model._forward_impl(images, True)
+        B = out.shape[0]
+        targets = targets.to(device=self.device, dtype=torch.float32).contiguous()
+        grad = torch.empty_like(out)
+        self._loss_mean.zero_()
+        with torch.cuda.device(self.device):
+            # d(mean loss)/d pred = grad / B   (train.py:308-309; the loss is always evaluated in fp32)
+            _lib.call("argus_pose_loss", out, targets, None, self._loss_mean, grad, int(B), 1.0 / B, lib_stream)
+            _lib.call("argus_model_zero_grads", model._handle.ptr, lib_stream)
+            works = []
+            flat_grads = model.flat_grads
+            for stage in range(4):
+                _lib.call("argus_model_backward", model._handle.ptr, grad, stage, stage + 1, lib_stream)
+                if self.world > 1:
+                    b, e = self._stage_ranges[stage]
+                    works.append(dist.all_reduce(flat_grads[b:e], op=dist.ReduceOp.SUM, group=self.group,
+                                                 async_op=True))
+            for w in works:
+                w.wait()
+        return self._loss_mean[0]
+
+    def optimizer_step(self) -> None:
+        """clip_grad_norm_ + Adam on the flat arenas, then refresh the packed bf16 weights."""
+        model = self.model
+        self.step_count += 1
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            _lib.check(lib.argus_clip_adam_step(
+                _lib.ptr(model.flat_params), _lib.ptr(model.flat_grads), _lib.ptr(self.exp_avg),
+                _lib.ptr(self.exp_avg_sq), ctypes.c_int64(model.flat_params.numel()), _lib.ptr(self._scratch),
+                ctypes.c_float(1.0 / self.world), ctypes.c_float(self.max_grad_norm), ctypes.c_float(self.lr),
+                ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps),
+                ctypes.c_int(self.step_count), _lib.ptr(self._grad_norm), _lib.stream_ptr()))
+        model.sync_weights(force=True)
+
+    def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+        """One full training step; returns the (pre-update) mean loss as a device scalar without synchronising."""
+        loss = self.forward_backward(images, targets)
+        self.optimizer_step()
+        return loss
+
+    # ------------------------------------------------------------------------------------------------------------
+    def state_dict(self) -> dict:
+        return {"step": self.step_count, "exp_avg": self.exp_avg.clone(), "exp_avg_sq": self.exp_avg_sq.clone(),
+                "lr": self.lr}
+
+    def load_state_dict(self, state: dict) -> None:
+        self.step_count = int(state["step"])
+        self.exp_avg.copy_(state["exp_avg"])
+        self.exp_avg_sq.copy_(state["exp_avg_sq"])
+        self.lr = float(state["lr"])

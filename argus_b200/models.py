@@ -299,6 +299,21 @@ class NCameraCNN(nn.Module):
         fg = self._flat_grads
         return [fg[off:off + numel].view(shape).clone() for (_n, off, numel, shape) in self._param_infos]
 
+    def probe_activation(self, index: int) -> torch.Tensor:
+        """Test probe: activation of the last forward as a (rows, C) bf16 tensor (NHWC rows).
+        index -1: pooled stem output, 0..15: bottleneck outputs, 16: pooled features, 17: resnet.fc output."""
+        self._ensure_bound()
+        dev = self._flat_params.device
+        cap = 1 << 28
+        rows, C = ctypes.c_int64(), ctypes.c_int()
+        # first ask for the size with a generous upper bound, then trim
+        buf = torch.empty(cap, dtype=torch.bfloat16, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().argus_model_copy_activation(self._handle.ptr, ctypes.c_int(index), _lib.ptr(buf),
+                                                               ctypes.c_int64(cap), ctypes.byref(rows),
+                                                               ctypes.byref(C), _lib.stream_ptr()))
+        return buf[: rows.value * C.value].view(rows.value, C.value).clone()
+
     # ------------------------------------------------------------------ public forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         """Forward pass through the CNN (reference: argus/models.py:66-90).

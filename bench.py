@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the argus_b200 hot path.
+
+    python bench.py --gpus N --steps K --warmup W              # our B200 path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path (oracle port)
+
+Workload (BASELINE.json configs[1]): one data-parallel training step of NCameraCNN on a synthetic 2-view batch of
+256 image pairs per GPU at 256x256 — uint8 images -> GPU augmentation -> forward (bf16, fp32 accumulate) ->
+SE(3) pose loss -> backward -> clip_grad_norm_ + Adam.  Metric: training image-pairs/s over all GPUs.
+
+`value` is timed on the device with the uint8 batch already resident in HBM; `e2e` is the same step through the
+public engine API with pinned HOST buffers (H2D of the images/targets and D2H of the loss inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+PAIR_FLOPS_FWD = 21.362e9          # forward GEMM FLOPs per image pair at 256x256
+PAIR_FLOPS_TRAIN = 63.47e9         # forward + dgrad + wgrad (no stem dgrad)
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()), "measured"
+        except Exception:
+            pass
+    return dict(FALLBACK_PEAKS), "fallback"
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with nvidia-smi while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.samples: list[list[str]] = []
+        self.proc = None
+
+    def start(self) -> None:
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self) -> None:
+        for line in self.proc.stdout:
+            self.samples.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            if len(s) < 7:
+                continue
+            try:
+                sm.append(float(s[0]))
+                smax = float(s[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def synthetic_batch(B: int, n_cams: int, H: int, W: int, seed: int):
+    """uint8 HWC image pairs (what a decoded PNG pair is, reference tests/conftest.py:35-41) and SE3 targets."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    images = torch.randint(0, 256, (B, n_cams, H, W, 3), dtype=torch.uint8, generator=g)
+    q = torch.randn(B, 4, generator=g)
+    targets = torch.cat([torch.randn(B, 3, generator=g), q / q.norm(dim=-1, keepdim=True)], -1)
+    return images, targets
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from argus_b200 import _lib
+    from argus_b200.engine import TrainEngine
+    from argus_b200.models import NCameraCNN
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    B, H, W, n_cams = args.batch, args.size, args.size, 2
+
+    torch.manual_seed(42)
+    model = NCameraCNN().to(dev)
+    augmentation = None
+    try:
+        from argus_b200.data import Augmentation, AugmentationConfig
+        augmentation = Augmentation(AugmentationConfig(), train=True).to(dev)
+    except ImportError:
+        augmentation = None
+    if args.no_augmentation:
+        augmentation = None
+    engine = TrainEngine(model, lr=1e-4, max_grad_norm=1.0, augmentation=augmentation)
+
+    ring = 3
+    host_batches = []
+    dev_batches = []
+    for i in range(ring):
+        imgs, tgt = synthetic_batch(B, n_cams, H, W, seed=1000 * rank + i)
+        host_batches.append((imgs.pin_memory(), tgt.pin_memory()))
+        dev_batches.append((imgs.to(dev), tgt.to(dev)))
+    lib = _lib.load()
+    lib.argus_launch_count.restype = ctypes.c_int64
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then the device-resident timed region
+    for i in range(args.warmup):
+        engine.step(*dev_batches[i % ring])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.argus_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    loss = None
+    for i in range(args.steps):
+        loss = engine.step(*dev_batches[i % ring])
+    ev1.record()
+    barrier()
+    launches = lib.argus_launch_count() - launches0
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+    final_loss = float(loss.item())
+
+    # ---- end-to-end: pinned host buffers -> H2D -> step -> loss D2H, every step
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
+    stage_img = [torch.empty_like(dev_batches[0][0]) for _ in range(2)]
+    stage_tgt = [torch.empty_like(dev_batches[0][1]) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    for i in range(2):  # warm the path
+        stage_img[0].copy_(host_batches[i % ring][0], non_blocking=True)
+        stage_tgt[0].copy_(host_batches[i % ring][1], non_blocking=True)
+        engine.step(stage_img[0], stage_tgt[0])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    # double-buffered: the copy of batch i+1 runs on a side stream while batch i trains
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    with torch.cuda.stream(copy_stream):
+        stage_img[0].copy_(host_batches[0][0], non_blocking=True)
+        stage_tgt[0].copy_(host_batches[0][1], non_blocking=True)
+        ready[0].record(copy_stream)
+    for i in range(args.steps):
+        cur, nxt = i % 2, (i + 1) % 2
+        if i + 1 < args.steps:
+            with torch.cuda.stream(copy_stream):
+                if i >= 1:
+                    copy_stream.wait_event(consumed[nxt])
+                stage_img[nxt].copy_(host_batches[(i + 1) % ring][0], non_blocking=True)
+                stage_tgt[nxt].copy_(host_batches[(i + 1) % ring][1], non_blocking=True)
+                ready[nxt].record(copy_stream)
+        torch.cuda.current_stream().wait_event(ready[cur])
+        l = engine.step(stage_img[cur], stage_tgt[cur])
+        consumed[cur].record()
+        loss_host.copy_(l.reshape(1), non_blocking=True)
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * args.steps / (float(t2.item()) / 1e3)
+    h2d = host_batches[0][0].numel() + host_batches[0][1].numel() * 4
+
+    # ---- per-kernel-family timing with CUDA events (separate pass: the headline numbers above are un-instrumented)
+    families = {}
+    if rank == 0:
+        lib.argus_profile_enable(1)
+        for i in range(2):
+            engine.step(*dev_batches[i % ring])
+        torch.cuda.synchronize()
+        buf = ctypes.create_string_buffer(1 << 16)
+        _lib.check(lib.argus_profile_report(buf, ctypes.c_int(1 << 16)))
+        lib.argus_profile_enable(0)
+        families = json.loads(buf.value.decode())
+        for f in families.values():
+            f["launches"] //= 2
+            f["ms"] /= 2
+            f["flops"] /= 2
+            f["bytes"] /= 2
+    barrier()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = load_peaks()
+    conv = [families[k] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad") if k in families]
+    conv_ms = sum(f["ms"] for f in conv)
+    conv_flops = sum(f["flops"] for f in conv)
+    conv_launches = sum(f["launches"] for f in conv)
+    total_ms = sum(f["ms"] for f in families.values()) or 1.0
+    algorithmic_flops = PAIR_FLOPS_TRAIN * B  # per step, all tensor-core launches together
+    achieved = algorithmic_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
+    peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
+    roofline = {
+        "bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_kernel (tcgen05 implicit GEMM, all launches of a step)",
+        "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+        "peak_kind": f"{peak_kind} sustained cuBLAS bf16", "traffic": None,
+        "launches_per_step": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4),
+        "issued_flops_per_step": conv_flops, "algorithmic_flops_per_step": algorithmic_flops,
+        "share_of_step": round(conv_ms / total_ms, 4),
+    }
+    mem = {}
+    for k, f in families.items():
+        if f["bytes"] > 0 and f["ms"] > 0 and k not in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
+            gbs = f["bytes"] / (f["ms"] / 1e3) / 1e9
+            mem[k] = {"ms": round(f["ms"], 3), "launches": f["launches"], "GB/s": round(gbs, 1),
+                      "frac_hbm": round(gbs / peaks["hbm_gbs"], 3)}
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_throughput(sample_pairs=8, iters=3, warmup=1, size=args.size, augmentation=augmentation is not None)
+
+    line = {
+        "metric": "train image-pairs/sec", "value": round(value, 2), "unit": "pairs/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "configs[1]: train step, synthetic 2-view batch 256/GPU at 256x256, bf16 + fp32 accumulate, "
+                               "augmentation + geometric pose loss + clip + Adam",
+                   "per_gpu_batch_pairs": B, "global_batch_pairs": B * world, "image_size": [H, W], "n_cams": n_cams,
+                   "augmentation": augmentation is not None, "parallelism": f"dp{world}",
+                   "l2_note": "no explicit flush: every step streams >30 GB of activations (>> 126 MB L2) and rotates 3 input batches"},
+        "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "note": "pinned host uint8 batch -> H2D on a side stream (double buffered) -> engine.step -> loss D2H"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernel_families_ms": {k: round(f["ms"], 3) for k, f in families.items()},
+        "memory_bound_kernels": mem,
+        "final_loss": final_loss,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = cpu
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's own algorithm on the host cores (oracle port; the reference is pure PyTorch/CPU)
+# ----------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_fn(sample_pairs: int, size: int, augmentation: bool):
+    import numpy as np
+    import torch
+
+    from oracle.ref_model import make_reference_model, torch_loss
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    model = make_reference_model(42)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    images_u8, targets = synthetic_batch(sample_pairs, 2, size, size, seed=0)
+    aug = None
+    if augmentation:
+        try:
+            from oracle import augment as oracle_aug
+            aug = oracle_aug
+        except ImportError:
+            aug = None
+
+    def step(i: int) -> float:
+        if aug is not None:
+            x = aug.augment_batch_u8(images_u8.numpy(), seed=i)          # (B, n_cams, 3, H, W) float32
+            x = torch.from_numpy(np.ascontiguousarray(x)).reshape(sample_pairs, 6, size, size)
+        else:
+            x = (images_u8.permute(0, 1, 4, 2, 3).reshape(sample_pairs, 6, size, size).float() / 255.0)
+        opt.zero_grad()
+        loss = torch_loss(model(x), targets).mean().float()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        return float(loss)
+
+    return step
+
+
+def cpu_reference_throughput(sample_pairs: int, iters: int, warmup: int, size: int, augmentation: bool) -> dict:
+    step = cpu_reference_step_fn(sample_pairs, size, augmentation)
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(iters):
+        step(warmup + i)
+    dt = time.perf_counter() - t0
+    return {"value": round(sample_pairs * iters / dt, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{iters} steps of {sample_pairs} pairs at {size}x{size} (fp32 PyTorch CPU: oracle/ref_model.py = "
+                      f"argus/models.py + loss + clip + Adam{' + oracle augmentation' if augmentation else ''}), after {warmup} warm-up"}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 8
+    aug_available = (ROOT / "oracle" / "augment.py").exists() and not args.no_augmentation
+    step = cpu_reference_step_fn(sample, args.size, aug_available)
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "train image-pairs/sec", "value": round(value, 3), "unit": "pairs/s",
+        "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "configs[1] train step (bounded sample: 8 pairs per step on the host cores)",
+                   "per_step_pairs": sample, "image_size": [args.size, args.size], "augmentation": aug_available},
+        "cpu_baseline": {"value": round(value, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"{args.steps} steps of {sample} pairs, fp32 PyTorch CPU port of the reference path"},
+        "e2e": {"value": round(value, 3), "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="image pairs per GPU")
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-augmentation", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,6 +30,13 @@ const char* argus_last_error_string(void);
 int argus_version(void);
 /* Fails unless the current CUDA device is compute capability 10.x. */
 int argus_require_device(void);
+/* Launch accounting: number of kernels this library has launched since it was loaded. */
+int64_t argus_launch_count(void);
+/* Optional per-kernel-family timing with CUDA events on the launching stream (bench.py's roofline figures).
+ * argus_profile_report synchronises the recorded events and writes a JSON object
+ * {family: {launches, ms, flops, bytes}} (algorithmic FLOPs / bytes) into `json`. */
+int argus_profile_enable(int on);
+int argus_profile_report(char* json, int cap);
 
 /* ---- convolution primitives (torch.nn.Conv2d / nn.Linear inside torchvision resnet50, called from
  *      argus/models.py:84; cuDNN / cuBLAS in the reference) ------------------------------------------------- */
@@ -89,6 +96,11 @@ int argus_model_backward(argus_model* m, const float* d_out, int stage_begin, in
 /* Element range of the parameter arena whose gradients are final once `stage` has run (all-reduce buckets). */
 int argus_model_stage_range(argus_model* m, int stage, int64_t* begin, int64_t* end);
 int argus_model_arena_bytes(argus_model* m, int64_t* bytes);
+/* Test probe: copy an activation of the last forward pass (bf16, NHWC rows x C) into dst (device memory).
+ * index -1: stem output after max pooling; 0..15: bottleneck outputs (torchvision layer1[0] .. layer4[2]);
+ * 16: global-average-pooled features; 17: resnet.fc output. */
+int argus_model_copy_activation(argus_model* m, int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C,
+                                void* stream);
 
 #ifdef __cplusplus
 }

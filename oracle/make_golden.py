@@ -52,14 +52,18 @@ def main():
     (GOLDEN / "state_dict_keys.json").write_text(json.dumps(keys, indent=0))
     print("state_dict entries:", len(keys))
 
-    # ---- model golden vectors: B=2 pairs at 64x64 (CPU-cheap), train-mode forward + backward, then eval forward
+    # ---- model golden vectors: B=2 pairs at 128x128 (CPU-cheap): eval forward at init, train-mode forward + backward,
+    # then eval forward with the updated running statistics
     g = torch.Generator().manual_seed(0)
-    x = torch.rand(2, 6, 64, 64, generator=g)
+    x = torch.rand(2, 6, 128, 128, generator=g)
     q = torch.randn(2, 4, generator=g)
     q = q / q.norm(dim=-1, keepdim=True)
     target = torch.cat([torch.randn(2, 3, generator=g), q], -1)
     outs = {}
     for name, model in (("reference", ref), ("restatement", mine)):
+        model.eval()
+        with torch.no_grad():
+            y_init = model(x)
         model.train()
         model.zero_grad()
         y = model(x)
@@ -69,6 +73,7 @@ def main():
         with torch.no_grad():
             y_eval = model(x)
         outs[name] = {
+            "eval_out_init": y_init.double().numpy().tolist(),
             "train_out": y.detach().double().numpy().tolist(),
             "loss": float(loss),
             "eval_out_after_step0": y_eval.double().numpy().tolist(),
@@ -82,7 +87,7 @@ def main():
     # cross-check the torch loss against the pinned numpy oracle
     l_np = se3_loss.geometric_loss(np.array(outs["reference"]["train_out"]), target.double().numpy()).mean()
     assert abs(l_np - outs["reference"]["loss"]) < 1e-9, (l_np, outs["reference"]["loss"])
-    gold = {"seed_weights": 42, "seed_inputs": 0, "shape": [2, 6, 64, 64], "target": target.double().numpy().tolist(),
+    gold = {"seed_weights": 42, "seed_inputs": 0, "shape": [2, 6, 128, 128], "target": target.double().numpy().tolist(),
             **outs["reference"]}
     (GOLDEN / "model_small.json").write_text(json.dumps(gold))
     print("model golden: loss", gold["loss"], "train_out[0]", gold["train_out"][0])

@@ -79,7 +79,7 @@ def torch_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
 
     K = hat(phi)
     th2 = th[..., None]
-    Jl = torch.eye(3, dtype=torch.float64) + (1 - torch.cos(th2)) / th2**2 * K + (th2 - torch.sin(th2)) / th2**3 * (K @ K)
+    Jl = torch.eye(3, dtype=torch.float64, device=pred.device) + (1 - torch.cos(th2)) / th2**2 * K + (th2 - torch.sin(th2)) / th2**3 * (K @ K)
     qp = torch.cat([phi * torch.sin(th / 2) / th, torch.cos(th / 2)], -1)
     tp = (Jl @ tau[..., None])[..., 0]
     t, q = target[..., :3], target[..., 3:]
@@ -92,6 +92,6 @@ def torch_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     phie = v * (2 * torch.atan(n / w) / n)
     the = phie.norm(dim=-1, keepdim=True)[..., None]
     Ke = hat(phie)
-    Jinv = torch.eye(3, dtype=torch.float64) - 0.5 * Ke + (1 / the**2 - (1 + torch.cos(the)) / (2 * the * torch.sin(the))) * (Ke @ Ke)
+    Jinv = torch.eye(3, dtype=torch.float64, device=pred.device) - 0.5 * Ke + (1 / the**2 - (1 + torch.cos(the)) / (2 * the * torch.sin(the))) * (Ke @ Ke)
     taue = (Jinv @ te[..., None])[..., 0]
     return (taue**2).sum(-1) + (phie**2).sum(-1)

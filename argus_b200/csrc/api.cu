@@ -81,6 +81,31 @@ int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, i
   ARGUS_API_END
 }
 
+int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step,
+                                const argus_aug_config* cfg, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(cfg != nullptr && params != nullptr && n_cams >= 1, "bad augmentation arguments");
+  AugConfig c;
+  c.color_jiggle = cfg->color_jiggle; c.planckian_jitter = cfg->planckian_jitter; c.blur = cfg->blur;
+  c.motion_blur = cfg->motion_blur; c.plasma_shadow = cfg->plasma_shadow;
+  c.brightness_lo = cfg->brightness_lo; c.brightness_span = cfg->brightness_span;
+  c.contrast_lo = cfg->contrast_lo; c.contrast_span = cfg->contrast_span;
+  c.saturation_lo = cfg->saturation_lo; c.saturation_span = cfg->saturation_span;
+  c.hue_lo = cfg->hue_lo; c.hue_span = cfg->hue_span;
+  augment_sample_params(params, n_images, n_cams, seed, step, c, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* params, int n_images, int H, int W,
+                  int apply, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(!apply || params != nullptr, "augmentation needs a parameter table");
+  augment_images(in, in_u8 != 0, out, out_s2d != 0, params, n_images, H, W, apply != 0,
+                 static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
 int argus_pose_loss(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
                     float grad_scale, void* stream) {
   ARGUS_API_BEGIN
@@ -175,6 +200,14 @@ int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, 
   ARGUS_API_BEGIN
   ARGUS_CHECK(m != nullptr, "null model");
   m->impl.forward(x, is_u8 != 0, B, H, W, training != 0, out, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
+                               int training, int apply, void* stream) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.stage_input_u8(static_cast<const uint8_t*>(images), aug_params, B, H, W, training != 0, apply != 0,
+                         static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 int argus_model_zero_grads(argus_model* m, void* stream) {

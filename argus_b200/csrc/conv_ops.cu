@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -70,7 +71,7 @@ CUtensorMap make_tmap_bf16(const void* base, int rank, const uint64_t* dims, con
 // ------------------------------------------------------------------------------------------------
 namespace {
 struct ProfRecord {
-  const char* family;
+  std::string family;
   cudaEvent_t start, stop;
   double flops, bytes;
 };
@@ -108,6 +109,22 @@ ProfileScope::ProfileScope(const char* family, cudaStream_t s, double flops, dou
   slot = static_cast<int>(g_records.size());
   g_records.push_back(r);
 }
+ProfileScope::ProfileScope(const std::string& family, cudaStream_t s, double flops, double bytes) : stream(s) {
+  g_launches.fetch_add(1);
+  if (!g_profiling) return;
+  ProfRecord r{family, new_event(), new_event(), flops, bytes};
+  cudaEventRecord(r.start, s);
+  slot = static_cast<int>(g_records.size());
+  g_records.push_back(r);
+}
+bool profile_detailed() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ARGUS_PROFILE_DETAIL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 ProfileScope::~ProfileScope() {
   if (slot >= 0) cudaEventRecord(g_records[slot].stop, stream);
 }
@@ -128,7 +145,7 @@ std::string profile_report_json() {
   bool first = true;
   for (auto& name : order) {
     const Agg& a = agg[name];
-    char buf[256];
+    char buf[384];
     snprintf(buf, sizeof(buf), "%s\"%s\": {\"launches\": %d, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}",
              first ? "" : ", ", name.c_str(), a.launches, a.ms, a.flops, a.bytes);
     out += buf;
@@ -415,7 +432,11 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   p.stat_sqsum = e.stat_sqsum;
   ARGUS_CHECK((e.stat_sum == nullptr) == (e.stat_sqsum == nullptr), "BN statistic pointers come in pairs");
   const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * p.num_taps * p.kblocks_per_tap * kBlockK;
-  ProfileScope prof(l.b_mn ? "conv_dgrad" : "conv_fwd", stream, flops, 0.0);
+  std::string fam = l.b_mn ? "conv_dgrad" : "conv_fwd";
+  if (g_profiling && profile_detailed())
+    fam += ":M" + std::to_string(p.m_total) + "_N" + std::to_string(p.n_total) + "_K" +
+           std::to_string(p.num_taps * p.kblocks_per_tap * kBlockK) + "_t" + std::to_string(p.num_taps);
+  ProfileScope prof(fam, stream, flops, 0.0);
   const int key = l.block_n * 2 + l.b_mn;
   switch (key) {
     case 64 * 2 + 0: launch_conv_t<64, 0>(p, stream); break;
@@ -444,7 +465,11 @@ static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
 
 void launch_wgrad(const WgradLaunch& l, cudaStream_t stream) {
   const double flops = 2.0 * l.p.kblocks_total * 64.0 * l.p.cout * static_cast<double>(l.p.cin) * l.p.num_taps;
-  ProfileScope prof("conv_wgrad", stream, flops, 0.0);
+  std::string fam = "conv_wgrad";
+  if (g_profiling && profile_detailed())
+    fam += ":P" + std::to_string(l.p.kblocks_total * 64) + "_Co" + std::to_string(l.p.cout) + "_Ci" +
+           std::to_string(l.p.cin) + "_t" + std::to_string(l.p.num_taps) + "_s" + std::to_string(l.p.num_ksplits);
+  ProfileScope prof(fam, stream, flops, 0.0);
   switch (l.block_n) {
     case 64: launch_wgrad_t<64>(l.p, stream); break;
     case 128: launch_wgrad_t<128>(l.p, stream); break;

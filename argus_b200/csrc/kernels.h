@@ -28,6 +28,19 @@ void pack_weights(const float* params, bf16* packed, const WeightPackEntry* tabl
 void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
                    cudaStream_t s);
 
+// ---- augmentation (argus/data.py:41-103, 213-225) ---------------------------------------------------------------
+struct AugConfig {
+  int color_jiggle, planckian_jitter, blur, motion_blur, plasma_shadow;
+  float brightness_lo, brightness_span, contrast_lo, contrast_span, saturation_lo, saturation_span, hue_lo, hue_span;
+};
+// params: (n_images, 24) fp32 table, a pure function of (seed, step, image) — see oracle/augment.py::sample_params
+void augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step, const AugConfig& cfg,
+                           cudaStream_t s);
+// in: u8 (n, H, W, 3) or fp32 (n, 3, H, W); out: bf16 space-to-depth [n][H/2][W/2+4][16] or fp32 (n, 3, H, W).
+// apply == false only converts layouts (validation / inference path). Writes plasma min/max into params[21..22].
+void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* params, int n_images, int H, int W,
+                    bool apply, cudaStream_t s);
+
 // ---- batch norm -------------------------------------------------------------------------------------------
 // train: batch statistics -> scale/shift (+ saved mean/invstd, running-stat update, torch.nn.BatchNorm2d semantics)
 void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,

@@ -165,6 +165,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
   plans_.clear();
   last_train_plan_ = nullptr;
   last_plan_ = nullptr;
+  staged_plan_ = nullptr;
   eval_fold_dirty_ = true;
 }
 
@@ -211,6 +212,7 @@ void Model::reserve(int max_batch, int H, int W, bool training) {
     plans_.clear();
     last_train_plan_ = nullptr;
     last_plan_ = nullptr;
+    staged_plan_ = nullptr;
   }
   reserved_batch_ = std::max(reserved_batch_, max_batch);
   reserved_h_ = H; reserved_w_ = W;
@@ -442,10 +444,14 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
   ARGUS_CHECK(!training || B * n_cams_ * (H / 32) * (W / 32) > 1,
               "train-mode batch norm needs more than one value per channel");
   Plan& p = get_plan(B, H, W, training);
-  if (is_u8)
+  if (x == nullptr) {
+    ARGUS_CHECK(staged_plan_ == &p, "forward(x = NULL) needs a preceding stage_input_u8() for the same batch shape");
+  } else if (is_u8) {
     pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d, p.N, H, W, s);
-  else
+  } else {
     pack_input_f32(static_cast<const float*>(x), p.x_s2d, p.N, H, W, s);
+  }
+  staged_plan_ = nullptr;
   last_plan_ = &p;
   if (training) {
     forward_train(p, s);
@@ -454,6 +460,15 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
     forward_eval(p, s);
   }
   head_forward(p, out, s);
+}
+
+void Model::stage_input_u8(const uint8_t* images, float* aug_params, int B, int H, int W, bool training, bool apply,
+                           cudaStream_t s) {
+  ARGUS_CHECK(B > 0, "empty batch");
+  ARGUS_CHECK(!apply || aug_params != nullptr, "augmentation needs a parameter table");
+  Plan& p = get_plan(B, H, W, training);
+  augment_images(images, true, p.x_s2d, true, aug_params, p.N, H, W, apply, s);
+  staged_plan_ = &p;
 }
 
 void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s) {

@@ -99,6 +99,10 @@ class Model {
 
   // x: (B, 3*n_cams, H, W) fp32 NCHW in [0,1], or u8 (B*n_cams, H, W, 3) when is_u8. out: (B, 6) fp32.
   void forward(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s);
+  // Augmentation fused with input staging: uint8 (B*n_cams, H, W, 3) images -> augmented bf16 stem input of the plan
+  // for (B, H, W, training). A following forward() with x == nullptr consumes it.
+  void stage_input_u8(const uint8_t* images, float* aug_params, int B, int H, int W, bool training, bool apply,
+                      cudaStream_t s);
   // d_out: (B, 6) gradient of the loss wrt forward()'s output. Accumulates parameter gradients (+=) into the bound
   // gradient arena for stages [stage_begin, stage_end); stages must be run in increasing order 0..3.
   void backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
@@ -155,6 +159,7 @@ class Model {
   std::map<std::tuple<int, int, int, bool>, std::unique_ptr<Plan>> plans_;
   Plan* last_train_plan_ = nullptr;
   Plan* last_plan_ = nullptr;
+  Plan* staged_plan_ = nullptr;
 };
 
 }  // namespace argus

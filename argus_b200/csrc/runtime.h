@@ -62,8 +62,10 @@ void profile_enable(bool on);                    // clears previous records when
 bool profile_enabled();
 int64_t launch_count();                          // kernels launched by this library since load
 std::string profile_report_json();               // synchronises the recorded events and aggregates per family
+bool profile_detailed();                         // ARGUS_PROFILE_DETAIL=1: conv families are split per layer shape
 struct ProfileScope {
   ProfileScope(const char* family, cudaStream_t stream, double flops, double bytes);
+  ProfileScope(const std::string& family, cudaStream_t stream, double flops, double bytes);
   ~ProfileScope();
   int slot = -1;
   cudaStream_t stream = nullptr;

@@ -1,0 +1,143 @@
+"""Data path of the hot loop (reference: /root/reference/argus/data.py).
+
+* AugmentationConfig / Augmentation keep the reference's fields and call convention (data.py:18-103) but run as one
+  fused CUDA kernel on the whole batch instead of kornia ops on CPU inside Dataset.__getitem__.
+* CameraCubePoseDataset (data.py:145-229) is provided by argus_b200.dataset (reader for the reference's on-disk
+  layout without h5py); it is re-exported here under the reference's names.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Optional, Union
+
+import torch
+
+from . import _lib
+
+
+@dataclass(frozen=True)
+class AugmentationConfig:
+    """Configuration for data augmentation (same fields and defaults as the reference, data.py:18-38)."""
+
+    # color jiggle
+    brightness: Union[float, tuple[float, float]] = (0.8, 1.0)
+    contrast: Union[float, tuple[float, float]] = (0.5, 1.2)
+    saturation: Union[float, tuple[float, float]] = (0.25, 1.2)
+    hue: Union[float, tuple[float, float]] = (-0.1, 0.1)
+
+    # spaghetti
+    num_spaghetti: int = 10
+
+    # flags
+    color_jiggle: bool = True
+    planckian_jitter: bool = True
+    random_erasing: bool = False
+    blur: bool = True
+    motion_blur: bool = True
+    plasma_shadow: bool = True
+    salt_and_pepper: bool = False
+
+
+class _AugConfigC(ctypes.Structure):
+    _fields_ = [("color_jiggle", ctypes.c_int), ("planckian_jitter", ctypes.c_int), ("blur", ctypes.c_int),
+                ("motion_blur", ctypes.c_int), ("plasma_shadow", ctypes.c_int),
+                ("brightness_lo", ctypes.c_float), ("brightness_span", ctypes.c_float),
+                ("contrast_lo", ctypes.c_float), ("contrast_span", ctypes.c_float),
+                ("saturation_lo", ctypes.c_float), ("saturation_span", ctypes.c_float),
+                ("hue_lo", ctypes.c_float), ("hue_span", ctypes.c_float)]
+
+
+def _range(v, center: float, lower_bound: Optional[float] = None) -> tuple[float, float]:
+    """kornia's convention for a scalar factor f: the range is (center - f, center + f)."""
+    if isinstance(v, (tuple, list)):
+        return float(v[0]), float(v[1])
+    lo, hi = center - float(v), center + float(v)
+    if lower_bound is not None:
+        lo = max(lo, lower_bound)
+    return lo, hi
+
+
+N_PARAMS = 24
+
+
+class Augmentation(torch.nn.Module):
+    """Data augmentation module for the images (reference: data.py:41-103).
+
+    forward(images) keeps the reference contract — float images (n, 3, H, W) in [0,1] in, same shape out, identity
+    unless constructed with train=True — and treats the n images as the n_cams views of ONE sample, exactly as the
+    reference does when it calls the module per sample (data.py:224). `augment_batch` is the batched entry point used
+    by the training engine: uint8 (B, n_cams, H, W, 3) pairs -> augmented images, one launch for the whole batch.
+
+    Randomness: every sampled parameter is a pure function of (seed, step, image index), see oracle/augment.py; the
+    module-level counter `step` advances on every call so that successive calls differ and a re-run with the same
+    seed reproduces them (the reference's only augmentation contract, tests/test_train.py:69-77).
+    random_erasing / salt_and_pepper are default-OFF in the reference and not implemented here (they raise).
+    """
+
+    def __init__(self, cfg: AugmentationConfig, train: bool = True, seed: Optional[int] = None) -> None:
+        super().__init__()
+        if cfg.random_erasing or cfg.salt_and_pepper:
+            raise NotImplementedError("random_erasing / salt_and_pepper (default-off in the reference) are not built")
+        self.cfg = cfg
+        self.train = train  # (shadows nn.Module.train like the reference does, data.py:48)
+        self.seed = int(torch.initial_seed() if seed is None else seed) & ((1 << 63) - 1)
+        self.step = 0
+        b, c = _range(cfg.brightness, 1.0, 0.0), _range(cfg.contrast, 1.0, 0.0)
+        s, h = _range(cfg.saturation, 1.0, 0.0), _range(cfg.hue, 0.0)
+        self._c = _AugConfigC(int(cfg.color_jiggle), int(cfg.planckian_jitter), int(cfg.blur), int(cfg.motion_blur),
+                              int(cfg.plasma_shadow), b[0], b[1] - b[0], c[0], c[1] - c[0], s[0], s[1] - s[0],
+                              h[0], h[1] - h[0])
+        self.enabled = any([cfg.color_jiggle, cfg.planckian_jitter, cfg.blur, cfg.motion_blur, cfg.plasma_shadow])
+
+    # ------------------------------------------------------------------------------------------------------------
+    def sample_params(self, n_pairs: int, n_cams: int, device, step: Optional[int] = None) -> torch.Tensor:
+        """(n_pairs*n_cams, 24) fp32 parameter table on `device` for the given step (default: internal counter)."""
+        if step is None:
+            step = self.step
+            self.step += 1
+        params = torch.empty((n_pairs * n_cams, N_PARAMS), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            _lib.check(_lib.load().argus_augment_sample_params(
+                _lib.ptr(params), ctypes.c_int(n_pairs * n_cams), ctypes.c_int(n_cams), ctypes.c_uint64(self.seed),
+                ctypes.c_uint64(int(step)), ctypes.byref(self._c), _lib.stream_ptr()))
+        return params
+
+    def augment_batch(self, images: torch.Tensor, params: Optional[torch.Tensor] = None,
+                      step: Optional[int] = None) -> torch.Tensor:
+        """uint8 (B, n_cams, H, W, 3) or float (B, 3*n_cams, H, W) -> float32 (B, 3*n_cams, H, W) augmented."""
+        if not images.is_cuda:
+            raise _lib.ArgusError("Augmentation runs on sm_100a GPUs only (no CPU fallback)")
+        if images.dtype == torch.uint8:
+            B, n_cams, H, W, _ = images.shape
+        else:
+            B, C, H, W = images.shape
+            n_cams = C // 3
+            images = images.to(torch.float32)
+        images = images.contiguous()
+        apply = bool(self.train and self.enabled)
+        if params is None and apply:
+            params = self.sample_params(B, n_cams, images.device, step)
+        out = torch.empty((B, 3 * n_cams, H, W), dtype=torch.float32, device=images.device)
+        with torch.cuda.device(images.device):
+            _lib.call("argus_augment", images, int(images.dtype == torch.uint8), out, 0, params, int(B * n_cams), int(H),
+                      int(W), int(apply), _lib.stream_ptr())
+        return out
+
+    def forward(self, images: torch.Tensor) -> torch.Tensor:
+        """Applies the augmentations to the (n_cams, 3, H, W) views of one sample (reference: data.py:99-103)."""
+        if not (self.enabled and self.train):
+            return images
+        n, c, H, W = images.shape
+        assert c == 3, "Augmentation.forward expects (n_cams, 3, H, W) images"
+        out = self.augment_batch(images.reshape(1, n * 3, H, W))
+        return out.reshape(n, 3, H, W).to(images.dtype)
+
+
+def __getattr__(name):
+    # lazy re-export so that `from argus_b200.data import CameraCubePoseDataset` works like the reference module
+    if name in ("CameraCubePoseDataset", "CameraCubePoseDatasetConfig"):
+        from . import dataset
+
+        return getattr(dataset, name)
+    raise AttributeError(name)

@@ -71,10 +71,15 @@ class TrainEngine:
         """
         model = self.model
         lib_stream = _lib.stream_ptr()
-        if self.augmentation is not None and images.dtype == torch.uint8:
-            images = self.augmentation.apply_u8(images, step=self.step_count)
         model.train()
-        out = model._forward_impl(images, True)
+        if images.dtype == torch.uint8:
+            # fused augmentation + staging: uint8 pairs -> augmented bf16 stem input inside the model's arena
+            aug = self.augmentation
+            apply = aug is not None and aug.train and aug.enabled
+            params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
+            out = model._forward_impl(images, True, aug_params=params, augment=apply)
+        else:
+            out = model._forward_impl(images, True)
         B = out.shape[0]
         targets = targets.to(device=self.device, dtype=torch.float32).contiguous()
         grad = torch.empty_like(out)

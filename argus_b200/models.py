@@ -267,7 +267,8 @@ class NCameraCNN(nn.Module):
             _lib.call("argus_model_sync_weights", self._handle.ptr, _lib.stream_ptr())
             self._synced_version = self._flat_params._version
 
-    def _forward_impl(self, x: torch.Tensor, training: bool) -> torch.Tensor:
+    def _forward_impl(self, x: torch.Tensor, training: bool, aug_params: Optional[torch.Tensor] = None,
+                      augment: bool = False) -> torch.Tensor:
         self._ensure_bound()
         if x.device != self._flat_params.device:
             raise _lib.ArgusError(f"input is on {x.device} but the model is on {self._flat_params.device}")
@@ -285,8 +286,14 @@ class NCameraCNN(nn.Module):
         self.sync_weights()
         out = torch.empty((B, 6), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.call("argus_model_forward", self._handle.ptr, x, int(is_u8), int(B), int(H), int(W), int(training), out,
-                      _lib.stream_ptr())
+            if is_u8 and augment:
+                _lib.call("argus_model_stage_input_u8", self._handle.ptr, x, aug_params, int(B), int(H), int(W),
+                          int(training), 1, _lib.stream_ptr())
+                _lib.call("argus_model_forward", self._handle.ptr, None, 0, int(B), int(H), int(W), int(training), out,
+                          _lib.stream_ptr())
+            else:
+                _lib.call("argus_model_forward", self._handle.ptr, x, int(is_u8), int(B), int(H), int(W), int(training),
+                          out, _lib.stream_ptr())
         if training:
             self._flat_nbt += 1
         return out

@@ -53,6 +53,21 @@ int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, in
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream);
 
+/* ---- augmentation (the kornia chain of argus/data.py:41-103 applied at data.py:213-225) ------------------------
+ * Parameters are a pure function of (seed, step, image index): params is an (n_images, 24) fp32 table
+ * (layout: oracle/augment.py). Colour-jiggle draws are shared by the n_cams views of a pair (same_on_batch=True). */
+typedef struct argus_aug_config {
+  int color_jiggle, planckian_jitter, blur, motion_blur, plasma_shadow;           /* flags, data.py:31-37 */
+  float brightness_lo, brightness_span, contrast_lo, contrast_span;               /* ranges, data.py:23-26 */
+  float saturation_lo, saturation_span, hue_lo, hue_span;
+} argus_aug_config;
+int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step,
+                                const argus_aug_config* cfg, void* stream);
+/* in: u8 (n, H, W, 3) when in_u8 else fp32 (n, 3, H, W) in [0,1]; out: fp32 (n, 3, H, W), or the stem's bf16
+ * space-to-depth layout [n][H/2][W/2+4][16] when out_s2d. apply == 0 only converts. H, W multiples of 32. */
+int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* params, int n_images, int H, int W,
+                  int apply, void* stream);
+
 /* ---- pose loss and pose exponential ------------------------------------------------------------------------
  * argus_pose_loss: geometric_loss_fn (argus/train.py:105-119) forward AND analytic backward in one launch.
  *   pred (B,6) fp32 se3 [tau, phi]; target (B,7) fp32 SE3 [t, qx, qy, qz, qw]; loss (B) per-sample (nullable);
@@ -89,6 +104,10 @@ int argus_model_sync_weights(argus_model* m, void* stream);
  * is_u8. training != 0 uses batch statistics and updates the running statistics. out is (B, 6) fp32. */
 int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, int W, int training, float* out,
                         void* stream);
+/* Fused augmentation + input staging: u8 (B*n_cams, H, W, 3) -> augmented stem input of the model's own arena.
+ * The next argus_model_forward call for the same (B, H, W, training) passes x = NULL. */
+int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
+                               int training, int apply, void* stream);
 int argus_model_zero_grads(argus_model* m, void* stream);
 /* Backward of the last training forward. d_out (B,6). Stages 0..3 (head+fc+layer4, layer3, layer2, layer1+stem)
  * must run in order; gradients are ADDED into the bound gradient arena. */

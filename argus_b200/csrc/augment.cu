@@ -114,8 +114,8 @@ __device__ __forceinline__ float lattice(uint64_t seed_bits, int octave, int iy,
                        static_cast<uint64_t>(ix);
   return hash_uniform(0x504C41534D41ull, 0, key, 0);
 }
-__device__ __forceinline__ float plasma_at(int y, int x, float inv_h, float inv_w, float roughness,
-                                           uint64_t seed_bits) {
+template <typename Lattice>
+__device__ __forceinline__ float plasma_eval(int y, int x, float inv_h, float inv_w, float roughness, Lattice lat) {
   const float ys = __fmul_rn(static_cast<float>(y) + 0.5f, inv_h);
   const float xs = __fmul_rn(static_cast<float>(x) + 0.5f, inv_w);
   float field = 0.f, amp = 1.f;
@@ -128,8 +128,8 @@ __device__ __forceinline__ float plasma_at(int y, int x, float inv_h, float inv_
     float ty = __fadd_rn(fy, -flo_y), tx = __fadd_rn(fx, -flo_x);
     ty = __fmul_rn(__fmul_rn(ty, ty), __fadd_rn(3.f, -__fmul_rn(2.f, ty)));
     tx = __fmul_rn(__fmul_rn(tx, tx), __fadd_rn(3.f, -__fmul_rn(2.f, tx)));
-    const float v00 = lattice(seed_bits, l, iy, ix), v01 = lattice(seed_bits, l, iy, ix + 1);
-    const float v10 = lattice(seed_bits, l, iy + 1, ix), v11 = lattice(seed_bits, l, iy + 1, ix + 1);
+    const float v00 = lat(l, iy, ix), v01 = lat(l, iy, ix + 1);
+    const float v10 = lat(l, iy + 1, ix), v11 = lat(l, iy + 1, ix + 1);
     const float top = __fadd_rn(v00, __fmul_rn(__fadd_rn(v01, -v00), tx));
     const float bot = __fadd_rn(v10, __fmul_rn(__fadd_rn(v11, -v10), tx));
     field = __fadd_rn(field, __fmul_rn(amp, __fadd_rn(top, __fmul_rn(__fadd_rn(bot, -top), ty))));
@@ -137,18 +137,49 @@ __device__ __forceinline__ float plasma_at(int y, int x, float inv_h, float inv_
   }
   return field;
 }
+struct HashLattice {
+  uint64_t seed_bits;
+  __device__ __forceinline__ float operator()(int l, int iy, int ix) const { return lattice(seed_bits, l, iy, ix); }
+};
+// whole-image lattice in shared memory: octave l holds (2^(l+1) + 1)^2 values at offset c_lat_off[l]
+constexpr int kLatTotal = 9 + 25 + 81 + 289 + 1089 + 4225;  // 5718
+__constant__ int c_lat_off[6] = {0, 9, 34, 115, 404, 1493};
+struct FullTable {
+  const float* t;
+  __device__ __forceinline__ float operator()(int l, int iy, int ix) const {
+    return t[c_lat_off[l] + iy * ((2 << l) + 1) + ix];
+  }
+};
+// per-tile lattice window: octave l covers lattice rows [iy0[l], iy0[l] + 17) x cols [ix0[l], ix0[l] + 17)
+constexpr int kWin = 17;
+struct TileTable {
+  const float* t;
+  const int* iy0;
+  const int* ix0;
+  __device__ __forceinline__ float operator()(int l, int iy, int ix) const {
+    return t[(l * kWin + (iy - iy0[l])) * kWin + (ix - ix0[l])];
+  }
+};
 
 // one block per image: min / max of the un-normalised field -> params[21], params[22]
 __global__ void __launch_bounds__(256) plasma_minmax_kernel(float* __restrict__ params, int H, int W) {
   __shared__ float s_lo[8], s_hi[8];
+  __shared__ float s_lat[kLatTotal];
   float* P = params + static_cast<size_t>(blockIdx.x) * kAugParams;
   const float roughness = P[17];
   const uint64_t seed_bits = static_cast<uint64_t>(rintf(P[20] * 16777216.f));
   const float inv_h = 1.f / H, inv_w = 1.f / W;
   float lo = INFINITY, hi = -INFINITY;
   if (P[18] != 0.f) {
+    for (int l = 0; l < 6; ++l) {
+      const int side = (2 << l) + 1;
+      for (int i = threadIdx.x; i < side * side; i += blockDim.x)
+        s_lat[c_lat_off[l] + i] = lattice(seed_bits, l, i / side, i % side);
+    }
+    __syncthreads();
+    FullTable lat{s_lat};
     for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
-      const float f = plasma_at(i / W, i % W, inv_h, inv_w, roughness, seed_bits);
+      const float f = plasma_eval(i / W, i % W, inv_h, inv_w, roughness, lat);
       lo = fminf(lo, f);
       hi = fmaxf(hi, f);
     }
@@ -246,11 +277,34 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
   __shared__ float sA[3][kIn][kIn + 1];    // colour-jittered input with halo; later reused for the blurred tile
   __shared__ float sB[3][kIn][kMid + 1];   // after the horizontal gaussian pass
   __shared__ float sP[kAugParams];
+  __shared__ float sLat[6 * kWin * kWin];
+  __shared__ int sIy0[6], sIx0[6];
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
   if (threadIdx.x < kAugParams) sP[threadIdx.x] = params[static_cast<size_t>(n) * kAugParams + threadIdx.x];
   __syncthreads();
   const float sigma = apply ? sP[7] : 0.f;
+  // plasma lattice window of this tile (a 32-pixel tile spans at most 16 cells of the finest octave when the image
+  // side is >= 128; smaller images fall back to hashing per pixel)
+  const bool use_table = (H >= 128 && W >= 128);
+  const uint64_t seed_bits = static_cast<uint64_t>(rintf(sP[20] * 16777216.f));
+  if (apply && sP[18] != 0.f && use_table) {
+    if (threadIdx.x < 6) {
+      const int l = threadIdx.x;
+      const float cells = static_cast<float>(2 << l);
+      sIy0[l] = static_cast<int>(floorf(__fmul_rn(__fmul_rn(static_cast<float>(y0) + 0.5f, 1.f / H), cells)));
+      sIx0[l] = static_cast<int>(floorf(__fmul_rn(__fmul_rn(static_cast<float>(x0) + 0.5f, 1.f / W), cells)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 6 * kWin * kWin; i += 256) {
+      const int l = i / (kWin * kWin);
+      const int rem = i - l * kWin * kWin;
+      const int ry = rem / kWin, rx = rem - ry * kWin;
+      const int iy = sIy0[l] + ry, ix = sIx0[l] + rx;
+      const int side = (2 << l) + 1;
+      sLat[i] = (iy < side && ix < side) ? lattice(seed_bits, l, iy, ix) : 0.f;
+    }
+  }
 
   // ---- stage 1: load (+ reflect), /255, colour ops
   for (int i = threadIdx.x; i < kIn * kIn; i += 256) {
@@ -323,7 +377,6 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
   const float inv_h = 1.f / H, inv_w = 1.f / W;
   const float roughness = sP[17], intensity = apply ? sP[18] : 0.f, quantity = sP[19];
   const float p_lo = sP[21], p_den = fmaxf(sP[22] - sP[21], 1e-12f);
-  const uint64_t seed_bits = static_cast<uint64_t>(rintf(sP[20] * 16777216.f));
   float v[2][2][3];
 #pragma unroll
   for (int a = 0; a < 2; ++a)
@@ -332,7 +385,9 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
       const int py = 2 * sy + a, px = 2 * sx + b;   // position inside the tile; window index = +1
       float shade = 0.f;
       if (intensity != 0.f) {
-        const float f = plasma_at(y0 + py, x0 + px, inv_h, inv_w, roughness, seed_bits);
+        const float f = use_table
+                            ? plasma_eval(y0 + py, x0 + px, inv_h, inv_w, roughness, TileTable{sLat, sIy0, sIx0})
+                            : plasma_eval(y0 + py, x0 + px, inv_h, inv_w, roughness, HashLattice{seed_bits});
         const float fn = __fdiv_rn(f - p_lo, p_den);
         shade = fn < quantity ? intensity : 0.f;
       }

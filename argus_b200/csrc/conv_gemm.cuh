@@ -9,8 +9,8 @@
 // 128B-swizzled [128 x 64] operand tile in shared memory; padding is TMA out-of-bounds zero fill and stride-2
 // convolutions read parity-strided tensor maps. Accumulators live in TMEM (double buffered) so the epilogue of
 // tile i overlaps the main loop of tile i+1. Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
-// alloc), warps 2..5 = epilogue (TMEM -> registers -> swizzled smem -> TMA store, BN statistics, fused
-// scale/shift/residual/ReLU).
+// alloc), warps 2..9 = two epilogue groups, one per accumulator stage (TMEM -> registers -> swizzled smem -> TMA
+// store, BN statistics, fused scale/shift/residual/ReLU; the residual tile is TMA-loaded into the staging buffer).
 //
 // Reference semantics being replaced: torch.nn.Conv2d / nn.Linear inside torchvision resnet50 as called at
 // /root/reference/argus/models.py:84 (cuDNN/cuBLAS in the reference).
@@ -21,7 +21,8 @@ namespace argus {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // bf16 elements = 128 bytes = one swizzle atom row
-constexpr int kNumThreads = 192;
+constexpr int kNumThreads = 320;       // conv kernel: TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kWgradThreads = 192;     // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
 constexpr int kMaxTaps = 16;
 
 struct Tap {
@@ -36,6 +37,7 @@ struct ConvGemmParams {
   CUtensorMap a_map[4];
   CUtensorMap b_map;
   CUtensorMap out_map;
+  CUtensorMap res_map;   // residual tensor, same geometry as out_map (valid when has_res != 0)
   Tap taps[kMaxTaps];
   int num_taps;
   int kblocks_per_tap;
@@ -48,7 +50,7 @@ struct ConvGemmParams {
   // epilogue (all optional)
   const float* scale;            // per output channel multiplier (folded BN)
   const float* shift;            // per output channel offset (folded BN / bias)
-  const __nv_bfloat16* residual; // [m_total, n_total] added before ReLU
+  int has_res;                   // add the residual tile (TMA-loaded through res_map) before ReLU
   int relu;
   float* stat_sum;               // per-channel sum of the stored bf16 outputs (train-mode BN)
   float* stat_sqsum;             // per-channel sum of squares
@@ -59,13 +61,13 @@ struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = 196608 / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr int kStagesRaw = 160000 / kStageBytes;        // leaves room for 4 staging buffers
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
-  static constexpr int kOffStaging = kStages * kStageBytes;
-  static constexpr int kOffStats = kOffStaging + 2 * kStagingBytes;
-  static constexpr int kOffBars = kOffStats + 2 * BLOCK_N * 4;
-  static constexpr int kNumBars = 2 * kStages + 4;
+  static constexpr int kOffStaging = kStages * kStageBytes;      // 2 buffers per epilogue group
+  static constexpr int kOffStats = kOffStaging + 4 * kStagingBytes;
+  static constexpr int kOffBars = kOffStats + 2 * 2 * BLOCK_N * 4;   // per group: sum[BLOCK_N], sqsum[BLOCK_N]
+  static constexpr int kNumBars = 2 * kStages + 6;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
 };
@@ -88,8 +90,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
+  auto res_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 4 + g); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
-  float* s_stats = reinterpret_cast<float*>(smem + L::kOffStats);
+  float* s_stats_all = reinterpret_cast<float*>(smem + L::kOffStats);
 
   if (threadIdx.x == 0) {
     if (smem_base & 1023u) __trap();
@@ -99,7 +102,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp of the owning group
+      mbar_init(res_bar(s), 1);
     }
     fence_mbar_init();
   }
@@ -107,12 +111,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.out_map);
+    if (p.has_res) tma_prefetch_desc(&p.res_map);
   }
   if (warp == 1) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 2 * BLOCK_N; i += kNumThreads) s_stats[i] = 0.f;
+  for (int i = threadIdx.x; i < 4 * BLOCK_N; i += kNumThreads) s_stats_all[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -189,19 +194,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
+    // ===================== epilogue (warps 2..9: two groups of four warps) =====================
+    // Group g owns TMEM accumulator stage g, i.e. every second tile of this CTA, so two tile epilogues overlap each
+    // other and the main loop. Each group has its own staging buffers, statistics scratch, named barrier and TMA
+    // store queue.
+    const int ew = warp - 2;
+    const int grp = ew >> 2;
     const int wq = warp & 3;              // TMEM lane quarter this warp may access
     const int r = wq * 32 + lane;         // row of the tile owned by this thread
-    const int et = threadIdx.x - 64;      // 0..127 among epilogue threads
+    const int et = (ew & 3) * 32 + lane;  // 0..127 inside the group
     const bool store_leader = (et == 0);
-    int acc = 0;
+    const uint32_t bar_id = 1 + grp;
+    float* s_stats = s_stats_all + grp * 2 * BLOCK_N;
+    uint8_t* stg_base = smem + L::kOffStaging + grp * 2 * L::kStagingBytes;
+    const int acc = grp;
     uint32_t acc_phase = 0;
+    uint32_t res_phase = 0;
     int buf = 0;
     int cur_n = -1;
     const bool do_stats = (p.stat_sum != nullptr);
 
     auto flush_stats = [&](int n_tile) {
-      named_bar_sync(1, 128);
+      named_bar_sync(bar_id, 128);
       for (int c = et; c < BLOCK_N; c += 128) {
         const int gc = n_tile * BLOCK_N + c;
         if (gc < p.n_total) {
@@ -211,10 +225,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         s_stats[c] = 0.f;
         s_stats[BLOCK_N + c] = 0.f;
       }
-      named_bar_sync(1, 128);
+      named_bar_sync(bar_id, 128);
     };
 
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM;
@@ -223,7 +237,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int h0 = rem >> p.log2_wo;
       const int w0 = rem & ((1 << p.log2_wo) - 1);
       const int n0 = n_tile * BLOCK_N;
-      const int m = m0 + r;
       if (do_stats && n_tile != cur_n) {
         if (cur_n >= 0) flush_stats(cur_n);
         cur_n = n_tile;
@@ -234,39 +247,59 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
-        // staging buffer `buf` was handed to a TMA store two chunks ago: wait until that store has read it.
-        if (store_leader) tma_store_wait_read<1>();
-        named_bar_sync(1, 128);
-        uint8_t* stg = smem + L::kOffStaging + buf * L::kStagingBytes;
+        uint8_t* stg = stg_base + buf * L::kStagingBytes;
+        // staging buffer `buf` was handed to a TMA store two chunks ago: wait until that store has read it, then
+        // (optionally) start fetching the residual tile into it.
+        if (store_leader) {
+          tma_store_wait_read<1>();
+          if (p.has_res) {
+            mbar_arrive_expect_tx(res_bar(grp), L::kStagingBytes);
+            tma_load_4d(&p.res_map, res_bar(grp), smem_u32(stg), n0 + ch * 64, w0, h0, img0);
+          }
+        }
+        named_bar_sync(bar_id, 128);
+        uint32_t v[2][32];
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + ch * 64 + h * 32;
-          tmem_ld_32x32(taddr, v);
-          tmem_ld_wait();
+          tmem_ld_32x32(taddr, v[h]);
+        }
+        tmem_ld_wait();
+        if (ch == BLOCK_N / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        if (p.has_res) {
+          mbar_wait(res_bar(grp), res_phase);
+          res_phase ^= 1;
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
           const int c0 = n0 + ch * 64 + h * 32;
           float f[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[h][i]);
           if (p.scale != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + i));
-              f[i] *= s.x; f[i + 1] *= s.y; f[i + 2] *= s.z; f[i + 3] *= s.w;
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + i));
+              f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
             }
           }
           if (p.shift != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 s = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + i));
-              f[i] += s.x; f[i + 1] += s.y; f[i + 2] += s.z; f[i + 3] += s.w;
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + i));
+              f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
             }
           }
-          if (p.residual != nullptr && m < p.m_total) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(m) * p.n_total + c0);
+          if (p.has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const uint4 rv = __ldg(rp + q);
+              const int phys = (h * 4 + q) ^ (r & 7);
+              const uint4 rv = *reinterpret_cast<const uint4*>(stg + r * 128 + phys * 16);
               float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
               f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
               f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
@@ -283,19 +316,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             o.y = pack_bf16x2(f[q * 8 + 2], f[q * 8 + 3]);
             o.z = pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]);
             o.w = pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]);
-            const int j = h * 4 + q;                     // logical 16-byte chunk of the 128-byte row
-            const int phys = j ^ (r & 7);                // SWIZZLE_128B
+            const int phys = (h * 4 + q) ^ (r & 7);      // SWIZZLE_128B position of logical 16-byte chunk h*4+q
             *reinterpret_cast<uint4*>(stg + r * 128 + phys * 16) = o;
           }
         }
-        if (ch == BLOCK_N / 64 - 1) {
-          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tempty_bar(acc));
-        }
         fence_proxy_async_smem();
-        named_bar_sync(1, 128);
+        named_bar_sync(bar_id, 128);
         if (store_leader) {
           tma_store_4d(&p.out_map, smem_u32(stg), n0 + ch * 64, w0, h0, img0);
           tma_store_commit();
@@ -320,7 +346,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         buf ^= 1;
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      acc_phase ^= 1;
     }
     if (do_stats && cur_n >= 0) flush_stats(cur_n);
     if (store_leader) tma_store_wait_all<0>();
@@ -368,7 +394,7 @@ struct WgradSmem {
 };
 
 template <int BLOCK_N>
-__global__ void __launch_bounds__(kNumThreads, 1)
+__global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p) {
   using L = WgradSmem<BLOCK_N>;
   constexpr int kStages = L::kStages;

@@ -275,6 +275,7 @@ ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const _
     const uint64_t str[3] = {C * 2, Wo * C * 2, Ho * Wo * C * 2};
     const uint32_t box[4] = {64, bw, bh, bn};
     p.out_map = make_tmap_bf16(y, 4, dims, str, box);
+    l.out_geom.set(4, dims, str, box);
   }
   p.num_taps = fill_forward_taps(s, p.taps);
   p.kblocks_per_tap = (s.kind == 1) ? 1 : s.Cin / 64;
@@ -349,6 +350,7 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
         const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(s.N)};
         const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
         p.out_map = make_tmap_bf16(dx, 4, dims, str, box);
+        l.out_geom.set(4, dims, str, box);
       } else {
         const uint64_t dims[4] = {C, W / 2, H / 2, static_cast<uint64_t>(s.N)};
         const uint64_t str[3] = {2 * C * 2, 2 * W * C * 2, H * W * C * 2};
@@ -426,7 +428,12 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   ConvGemmParams p = l.p;
   p.scale = e.scale;
   p.shift = e.shift;
-  p.residual = e.residual;
+  p.has_res = 0;
+  if (e.residual != nullptr) {
+    ARGUS_CHECK(l.out_geom.rank == 4, "this launch cannot take a residual (strided output)");
+    p.res_map = make_tmap_bf16(e.residual, 4, l.out_geom.dims, l.out_geom.strides, l.out_geom.box);
+    p.has_res = 1;
+  }
   p.relu = e.relu;
   p.stat_sum = e.stat_sum;
   p.stat_sqsum = e.stat_sqsum;
@@ -459,7 +466,7 @@ static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   }
   const int items = p.num_co_tiles * p.num_ci_tiles * p.num_ksplits * p.num_taps;
   const int grid = std::min(items, num_sms());
-  wgrad_kernel<BN><<<grid, kNumThreads, L::kTotal, stream>>>(p);
+  wgrad_kernel<BN><<<grid, kWgradThreads, L::kTotal, stream>>>(p);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -31,10 +31,24 @@ struct Epilogue {
   float* stat_sqsum = nullptr;
 };
 
+// geometry of the (non-strided) output tensor map, kept so that a residual tensor map can be built per launch
+struct TmapGeom {
+  int rank = 0;
+  uint64_t dims[4] = {0, 0, 0, 0};
+  uint64_t strides[3] = {0, 0, 0};
+  uint32_t box[4] = {0, 0, 0, 0};
+  void set(int r, const uint64_t* d, const uint64_t* s, const uint32_t* b) {
+    rank = r;
+    for (int i = 0; i < r; ++i) { dims[i] = d[i]; box[i] = b[i]; }
+    for (int i = 0; i + 1 < r; ++i) strides[i] = s[i];
+  }
+};
+
 struct ConvLaunch {
   ConvGemmParams p;
   int block_n = 64;
   int b_mn = 0;
+  TmapGeom out_geom;
 };
 
 struct WgradLaunch {

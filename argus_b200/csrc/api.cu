@@ -81,6 +81,64 @@ int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, i
   ARGUS_API_END
 }
 
+int argus_bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                      float* save_mean, float* save_invstd, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  bn_finalize(sum, sqsum, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
+              save_invstd, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
+                   const float* rshift, int relu, void* y, int64_t rows, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  bn_apply(static_cast<const bf16*>(x), scale, shift, static_cast<const bf16*>(res), rscale, rshift, relu,
+           static_cast<bf16*>(y), rows, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_bn_backward(void* dy, const void* x, const void* out, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dx, int64_t rows,
+                      int C, int mask_mode, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  bn_bwd_reduce(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(out), scale, shift,
+                mean, invstd, dgamma, dbeta, rows, C, mask_mode, s);
+  bn_bwd_apply(static_cast<bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(out), scale, shift, mean,
+               invstd, dgamma, dbeta, static_cast<bf16*>(dx), rows, C, mask_mode, s);
+  ARGUS_API_END
+}
+int argus_maxpool_forward(const void* x, const float* scale, const float* shift, void* y, void* idx, int N, int H,
+                          int W, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "maxpool: even H, W and C % 8 == 0 required");
+  maxpool_fwd(static_cast<const bf16*>(x), scale, shift, static_cast<bf16*>(y), static_cast<uint8_t*>(idx), N, H, W, C,
+              static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_maxpool_backward(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  maxpool_bwd(static_cast<const bf16*>(dy), static_cast<const uint8_t*>(idx), static_cast<bf16*>(dx), N, H, W, C,
+              static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_avgpool_forward(const void* x, void* y, int N, int HW, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  avgpool_fwd(static_cast<const bf16*>(x), static_cast<bf16*>(y), N, HW, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_avgpool_backward(const void* dy, void* dx, int N, int HW, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  avgpool_bwd(static_cast<const bf16*>(dy), static_cast<bf16*>(dx), N, HW, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
 int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step,
                                 const argus_aug_config* cfg, void* stream) {
   ARGUS_API_BEGIN

@@ -245,15 +245,47 @@ void bn_fold_eval(const float* gamma, const float* beta, const float* running_me
 // batch norm apply (+ residual, + ReLU)
 // ------------------------------------------------------------------------------------------------------------
 template <int RES>  // 0 none, 1 plain residual, 2 residual with its own scale/shift (downsample branch)
-__global__ void bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
-                                const float* __restrict__ shift, const uint4* __restrict__ res,
-                                const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
-                                uint4* __restrict__ y, int64_t nvec, int cvec) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i & (cvec - 1)) * 8;
+__global__ void __launch_bounds__(256)
+bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
+                int relu, uint4* __restrict__ y, int64_t nvec, int cvec) {
+  // gridDim.x * 256 is a multiple of cvec (a power of two <= 256), so a thread always sees the same channel octet:
+  // the per-channel constants live in registers for the whole grid-stride loop.
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  const int c0 = static_cast<int>(tid & (cvec - 1)) * 8;
+  const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
+  F8 rs, rb;
+  if (RES == 2) { rs = load8f(rscale + c0); rb = load8f(rshift + c0); }
+  int64_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 xa = ldg_stream(x + i), xb = ldg_stream(x + i + stride);
+    uint4 ra, rbv;
+    if (RES != 0) { ra = ldg_stream(res + i); rbv = ldg_stream(res + i + stride); }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const F8 xv = unpack8(u == 0 ? xa : xb);
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
+      if (RES == 1) {
+        const F8 rv = unpack8(u == 0 ? ra : rbv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
+      } else if (RES == 2) {
+        const F8 rv = unpack8(u == 0 ? ra : rbv);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
+      }
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
+      }
+      y[i + u * stride] = pack8(o);
+    }
+  }
+  for (; i < nvec; i += stride) {
     const F8 xv = unpack8(ldg_stream(x + i));
-    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
     F8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
@@ -263,7 +295,6 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ x, const float* __rest
       for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
     } else if (RES == 2) {
       const F8 rv = unpack8(ldg_stream(res + i));
-      const F8 rs = load8f(rscale + c0), rb = load8f(rshift + c0);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
     }
@@ -277,7 +308,7 @@ __global__ void bn_apply_kernel(const uint4* __restrict__ x, const float* __rest
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
               const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s) {
   ProfileScope prof("bn_apply", s, 0, static_cast<double>(rows) * C * 2 * (res ? 3 : 2));
-  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_apply: C/8 must be a power of two");
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_apply: C/8 must be a power of two <= 256");
   const int64_t nvec = rows * (C / 8);
   const int grid = grid_for(nvec, 256);
   auto X = reinterpret_cast<const uint4*>(x);
@@ -317,46 +348,57 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
                      int64_t rows, int cvec) {
   __shared__ float red[16][256];
-  const int lanes = cvec < 256 ? cvec : 256;   // threads along the channel dimension
+  const int lanes = cvec < 256 ? cvec : 256;   // threads along the channel dimension (cvec <= 256 for C <= 2048)
   const int row_lanes = 256 / lanes;           // rows processed concurrently by one block
   const int rl = threadIdx.x / lanes;
   const int oc = threadIdx.x % lanes;
+  const int c0 = oc * 8;
+  const F8 sc = load8f(scale + c0), sh = load8f(shift + c0), mu = load8f(mean + c0), is = load8f(invstd + c0);
   float a_dy[8], a_dyx[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a_dy[k] = a_dyx[k] = 0.f;
-  for (int ocb = oc; ocb < cvec; ocb += lanes) {  // (cvec > 256 never happens for C <= 2048; kept for safety)
-    const int c0 = ocb * 8;
-    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0), mu = load8f(mean + c0), is = load8f(invstd + c0);
-    for (int64_t row = static_cast<int64_t>(blockIdx.x) * row_lanes + rl; row < rows;
-         row += static_cast<int64_t>(gridDim.x) * row_lanes) {
-      const int64_t i = row * cvec + ocb;
-      const F8 d = unpack8(ldg_stream(dy + i));
-      const F8 xv = unpack8(ldg_stream(x + i));
-      const F8 g = masked_grad<MASK>(d, xv, out, i, sc, sh);
+  auto body = [&](const uint4& dyv, const uint4& xv4, const uint4& ov4) {
+    const F8 d = unpack8(dyv);
+    const F8 xv = unpack8(xv4);
+    F8 g = d;
+    if (MASK == 1) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        a_dy[k] += g.v[k];
-        a_dyx[k] = fmaf(g.v[k], (xv.v[k] - mu.v[k]) * is.v[k], a_dyx[k]);
-      }
-    }
-    if (cvec > lanes) {  // flush per channel block (rare path)
+      for (int k = 0; k < 8; ++k) g.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]) > 0.f ? d.v[k] : 0.f;
+    } else if (MASK == 2) {
+      const F8 o = unpack8(ov4);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        atomicAdd(dbeta + c0 + k, a_dy[k]);
-        atomicAdd(dgamma + c0 + k, a_dyx[k]);
-        a_dy[k] = a_dyx[k] = 0.f;
-      }
+      for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? d.v[k] : 0.f;
     }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a_dy[k] += g.v[k];
+      a_dyx[k] = fmaf(g.v[k], xv.v[k] - mu.v[k], a_dyx[k]);   // scaled by invstd once at the end
+    }
+  };
+  const int64_t rstride = static_cast<int64_t>(gridDim.x) * row_lanes;
+  int64_t row = static_cast<int64_t>(blockIdx.x) * row_lanes + rl;
+  for (; row + rstride < rows; row += 2 * rstride) {
+    const int64_t i0 = row * cvec + oc, i1 = (row + rstride) * cvec + oc;
+    const uint4 d0 = ldg_stream(dy + i0), d1 = ldg_stream(dy + i1);
+    const uint4 x0 = ldg_stream(x + i0), x1 = ldg_stream(x + i1);
+    uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+    if (MASK == 2) { o0 = ldg_stream(out + i0); o1 = ldg_stream(out + i1); }
+    body(d0, x0, o0);
+    body(d1, x1, o1);
   }
-  if (cvec > lanes) return;
+  for (; row < rows; row += rstride) {
+    const int64_t i0 = row * cvec + oc;
+    uint4 o0 = make_uint4(0, 0, 0, 0);
+    if (MASK == 2) o0 = ldg_stream(out + i0);
+    body(ldg_stream(dy + i0), ldg_stream(x + i0), o0);
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     red[k][threadIdx.x] = a_dy[k];
-    red[8 + k][threadIdx.x] = a_dyx[k];
+    red[8 + k][threadIdx.x] = a_dyx[k] * is.v[k];
   }
   __syncthreads();
   if (rl == 0) {
-    const int c0 = oc * 8;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float s0 = 0.f, s1 = 0.f;
@@ -374,7 +416,7 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
                    int mask_mode, cudaStream_t s) {
   ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
-  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8), "bn_bwd_reduce: C/8 must be a power of two");
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_bwd_reduce: C/8 must be a power of two <= 256");
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);
   const int row_lanes = 256 / lanes;
@@ -396,27 +438,58 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
 }
 
 template <int MASK>
-__global__ void bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    const float* __restrict__ mean, const float* __restrict__ invstd,
-                                    const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    uint4* __restrict__ dx, int64_t nvec, int cvec, float inv_rows) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < nvec;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int c0 = static_cast<int>(i & (cvec - 1)) * 8;
-    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0), mu = load8f(mean + c0), is = load8f(invstd + c0);
-    const F8 dg = load8f(dgamma + c0), db = load8f(dbeta + c0);
-    const F8 d = unpack8(dy[i]);
-    const F8 xv = unpack8(ldg_stream(x + i));
-    const F8 g = masked_grad<MASK>(d, xv, out, i, sc, sh);
-    F8 o;
+__global__ void __launch_bounds__(256)
+bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
+                    const float* __restrict__ scale, const float* __restrict__ shift,
+                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                    const float* __restrict__ dgamma, const float* __restrict__ dbeta, uint4* __restrict__ dx,
+                    int64_t nvec, int cvec, float inv_rows) {
+  const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;   // multiple of cvec
+  const int c0 = static_cast<int>(tid & (cvec - 1)) * 8;
+  const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
+  // dx = sc * (g - db/M - xhat * dg/M) with xhat = (x - mu) * is   ==   sc*g + k1*x + k0
+  F8 k0, k1;
+  {
+    const F8 mu = load8f(mean + c0), is = load8f(invstd + c0), dg = load8f(dgamma + c0), db = load8f(dbeta + c0);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      const float xhat = (xv.v[k] - mu.v[k]) * is.v[k];
-      o.v[k] = sc.v[k] * (g.v[k] - db.v[k] * inv_rows - xhat * dg.v[k] * inv_rows);
+      const float c2 = sc.v[k] * dg.v[k] * inv_rows * is.v[k];
+      k1.v[k] = -c2;
+      k0.v[k] = fmaf(c2, mu.v[k], -sc.v[k] * db.v[k] * inv_rows);
     }
-    dx[i] = pack8(o);
+  }
+  auto body = [&](int64_t i, const uint4& dyv, const uint4& xv4, const uint4& ov4) {
+    const F8 d = unpack8(dyv);
+    const F8 xv = unpack8(xv4);
+    F8 g = d;
+    if (MASK == 1) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]) > 0.f ? d.v[k] : 0.f;
+    } else if (MASK == 2) {
+      const F8 o = unpack8(ov4);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? d.v[k] : 0.f;
+    }
+    F8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = fmaf(sc.v[k], g.v[k], fmaf(k1.v[k], xv.v[k], k0.v[k]));
+    dx[i] = pack8(r);
     if (MASK == 2) dy[i] = pack8(g);
+  };
+  int64_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 da = dy[i], dbv = dy[i + stride];
+    const uint4 xa = ldg_stream(x + i), xb = ldg_stream(x + i + stride);
+    uint4 oa = make_uint4(0, 0, 0, 0), ob = oa;
+    if (MASK == 2) { oa = ldg_stream(out + i); ob = ldg_stream(out + i + stride); }
+    body(i, da, xa, oa);
+    body(i + stride, dbv, xb, ob);
+  }
+  for (; i < nvec; i += stride) {
+    uint4 oa = make_uint4(0, 0, 0, 0);
+    if (MASK == 2) oa = ldg_stream(out + i);
+    body(i, dy[i], ldg_stream(x + i), oa);
   }
 }
 
@@ -424,6 +497,7 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
                   const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
                   int64_t rows, int C, int mask_mode, cudaStream_t s) {
   ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 5 : 3));
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_bwd_apply: C/8 must be a power of two <= 256");
   const int cvec = C / 8;
   const int64_t nvec = rows * cvec;
   const int grid = grid_for(nvec, 256);

@@ -53,6 +53,28 @@ int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, in
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream);
 
+/* ---- batch norm / pooling primitives (torch.nn.BatchNorm2d, ReLU, MaxPool2d(3,2,1), AdaptiveAvgPool2d(1) inside
+ *      torchvision resnet50, argus/models.py:84). x, y, dy, dx, res, out: bf16 NHWC viewed as (rows, C); C/8 a
+ *      power of two; per-channel vectors fp32. ------------------------------------------------------------------ */
+/* train-mode statistics -> scale/shift/mean/invstd and running-stat update (running_* nullable) */
+int argus_bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+                      float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                      float* save_mean, float* save_invstd, int C, void* stream);
+/* y = [relu](x*scale+shift [+ res | + res*rscale+rshift]) */
+int argus_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
+                   const float* rshift, int relu, void* y, int64_t rows, int C, void* stream);
+/* BN (+ReLU) backward. mask_mode 0: no ReLU; 1: ReLU right after the BN; 2: ReLU after a residual add (mask = out > 0,
+ * dy is overwritten with the masked gradient). dgamma / dbeta are ADDED to (caller zeroes); dx = d loss / d x. */
+int argus_bn_backward(void* dy, const void* x, const void* out, const float* scale, const float* shift,
+                      const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dx, int64_t rows,
+                      int C, int mask_mode, void* stream);
+/* max pooling 3x3/2 pad 1 of relu(x*scale+shift) (scale NULL: x already activated); idx (nullable) = arg-max tap */
+int argus_maxpool_forward(const void* x, const float* scale, const float* shift, void* y, void* idx, int N, int H,
+                          int W, int C, void* stream);
+int argus_maxpool_backward(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);
+int argus_avgpool_forward(const void* x, void* y, int N, int HW, int C, void* stream);
+int argus_avgpool_backward(const void* dy, void* dx, int N, int HW, int C, void* stream);
+
 /* ---- augmentation (the kornia chain of argus/data.py:41-103 applied at data.py:213-225) ------------------------
  * Parameters are a pure function of (seed, step, image index): params is an (n_images, 24) fp32 table
  * (layout: oracle/augment.py). Colour-jiggle draws are shared by the n_cams views of a pair (same_on_batch=True). */

@@ -1,0 +1,144 @@
+"""Strict per-op GPU parity (through the C ABI) of the batch-norm / pooling kernels against torch fp32 autograd on
+the same bf16-rounded inputs. Outputs are bf16, so the tolerance is one bf16 rounding (2^-8 relative)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from argus_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+BF16_EPS = 2.0 ** -8
+
+
+def close_bf16(got, want, extra=0.0):
+    got, want = got.float(), want.float()
+    tol = BF16_EPS * want.abs() + 1e-6 + extra
+    bad = (got - want).abs() > tol * 1.01
+    assert bad.float().mean().item() < 1e-4, (bad.float().mean().item(), (got - want).abs().max().item())
+
+
+def bn_train_forward(x, gamma, beta, eps=1e-5):
+    mean = x.mean(0)
+    var = x.var(0, unbiased=False)
+    invstd = (var + eps).rsqrt()
+    return (x - mean) * invstd * gamma + beta, mean, var, invstd
+
+
+@pytest.mark.parametrize("rows,C", [(4096, 64), (1000, 256), (513, 2048)])
+def test_bn_finalize_and_apply(cuda_device, rows, C):
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 2 + torch.randn(C, generator=g)).to(cuda_device).bfloat16()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_device)
+    beta = torch.randn(C, generator=g).to(cuda_device)
+    res = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
+    xf = x.float()
+    ssum, ssq = xf.sum(0), (xf * xf).sum(0)
+    rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
+    scale, shift, mean, invstd = (torch.empty(C, device=cuda_device) for _ in range(4))
+    lib = _lib.load()
+    _lib.check(lib.argus_bn_finalize(_lib.ptr(ssum), _lib.ptr(ssq), ctypes.c_double(rows), _lib.ptr(gamma), _lib.ptr(beta),
+                                     _lib.ptr(rm), _lib.ptr(rv), ctypes.c_float(0.1), ctypes.c_float(1e-5),
+                                     _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(invstd), ctypes.c_int(C),
+                                     _lib.stream_ptr()))
+    y_ref, m_ref, v_ref, is_ref = bn_train_forward(xf, gamma, beta)
+    assert torch.allclose(mean, m_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(invstd, is_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rm, 0.1 * m_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(rv, 0.9 + 0.1 * xf.var(0, unbiased=True), rtol=1e-4, atol=1e-5)
+    for use_res, relu in ((False, True), (True, True), (False, False)):
+        y = torch.empty_like(x)
+        _lib.check(lib.argus_bn_apply(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(res if use_res else None),
+                                      None, None, ctypes.c_int(int(relu)), _lib.ptr(y), ctypes.c_int64(rows),
+                                      ctypes.c_int(C), _lib.stream_ptr()))
+        want = y_ref + (res.float() if use_res else 0)
+        if relu:
+            want = want.relu()
+        close_bf16(y, want, extra=2e-3 * (1 + xf.abs().max().item()) * 0)
+    # residual with its own scale/shift (downsample branch)
+    y = torch.empty_like(x)
+    _lib.check(lib.argus_bn_apply(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(res), _lib.ptr(gamma), _lib.ptr(beta),
+                                  ctypes.c_int(1), _lib.ptr(y), ctypes.c_int64(rows), ctypes.c_int(C), _lib.stream_ptr()))
+    close_bf16(y, (y_ref + res.float() * gamma + beta).relu())
+
+
+@pytest.mark.parametrize("rows,C,mask", [(4096, 64, 1), (2048, 256, 0), (777, 512, 2), (4096, 2048, 1), (300, 128, 2)])
+def test_bn_backward(cuda_device, rows, C, mask):
+    g = torch.Generator().manual_seed(rows * 3 + C + mask)
+    x = (torch.randn(rows, C, generator=g) * 1.5 + torch.randn(C, generator=g)).to(cuda_device).bfloat16()
+    dy = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
+    ident = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_device)
+    beta = (torch.randn(C, generator=g) * 0.5).to(cuda_device)
+    xr = x.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y, mean, var, invstd = bn_train_forward(xr, gr, br)
+    scale = (gamma * invstd).detach()
+    shift = (beta - mean * gamma * invstd).detach()
+    if mask == 0:
+        out_t = y
+    elif mask == 1:
+        # the kernel recomputes the mask as fma(x, scale, shift) > 0: build the reference the same way so that
+        # elements within rounding of zero do not flip
+        pre = torch.addcmul(shift, x.float(), scale)
+        out_t = y * (pre > 0)
+    else:
+        out_bf16 = (y.detach() + ident.float()).relu().bfloat16()
+        out_t = (y + ident.float()) * (out_bf16.float() > 0)
+    out_t.backward(dy.float())
+    dgamma, dbeta = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+    dx = torch.empty_like(x)
+    dy_io = dy.clone()
+    out_arg = out_bf16 if mask == 2 else None
+    _lib.check(_lib.load().argus_bn_backward(_lib.ptr(dy_io), _lib.ptr(x), _lib.ptr(out_arg), _lib.ptr(scale), _lib.ptr(shift),
+                                             _lib.ptr(mean.detach()), _lib.ptr(invstd.detach()), _lib.ptr(dgamma),
+                                             _lib.ptr(dbeta), _lib.ptr(dx), ctypes.c_int64(rows), ctypes.c_int(C),
+                                             ctypes.c_int(mask), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.allclose(dbeta, br.grad, rtol=2e-3, atol=2e-3 * rows ** 0.5)
+    assert torch.allclose(dgamma, gr.grad, rtol=2e-3, atol=2e-3 * rows ** 0.5)
+    rel = ((dx.float() - xr.grad).norm() / xr.grad.norm()).item()
+    assert rel < 4e-3, rel
+    if mask == 2:
+        assert torch.equal(dy_io, (dy.float() * (out_bf16.float() > 0)).bfloat16())
+
+
+@pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 64, 32, 64), (1, 8, 8, 128)])
+def test_maxpool(cuda_device, N, H, W, C):
+    g = torch.Generator().manual_seed(N + H)
+    x = torch.randn(N, H, W, C, generator=g).to(cuda_device).bfloat16()
+    scale = (torch.rand(C, generator=g) + 0.5).to(cuda_device)
+    shift = torch.randn(C, generator=g).to(cuda_device)
+    y = torch.empty(N, H // 2, W // 2, C, device=cuda_device, dtype=torch.bfloat16)
+    idx = torch.empty(N, H // 2, W // 2, C, device=cuda_device, dtype=torch.uint8)
+    _lib.call("argus_maxpool_forward", x, scale, shift, y, idx, N, H, W, C, _lib.stream_ptr())
+    act = torch.addcmul(shift, x.float(), scale).relu().permute(0, 3, 1, 2).requires_grad_(True)
+    ref = F.max_pool2d(act, 3, 2, 1)
+    close_bf16(y, ref.permute(0, 2, 3, 1))
+    dy = torch.randn(N, H // 2, W // 2, C, generator=g).to(cuda_device).bfloat16()
+    dx = torch.empty(N, H, W, C, device=cuda_device, dtype=torch.bfloat16)
+    _lib.call("argus_maxpool_backward", dy, idx, dx, N, H, W, C, _lib.stream_ptr())
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    # ties among equal maxima may route the gradient to a different (equally valid) tap only where values tie
+    want = act.grad.permute(0, 2, 3, 1)
+    mism = ((dx.float() - want).abs() > BF16_EPS * want.abs() * 2 + 1e-6).float().mean().item()
+    assert mism < 0.02, mism
+    assert torch.allclose(dx.float().sum((1, 2)), want.sum((1, 2)), rtol=2e-2, atol=0.5)
+    # already-activated input (inference path)
+    y2 = torch.empty_like(y)
+    _lib.call("argus_maxpool_forward", act.detach().permute(0, 2, 3, 1).contiguous().bfloat16(), None, None, y2, None, N,
+              H, W, C, _lib.stream_ptr())
+    close_bf16(y2, F.max_pool2d(act.detach().bfloat16().float(), 3, 2, 1).permute(0, 2, 3, 1))
+
+
+def test_avgpool(cuda_device):
+    N, HW, C = 6, 64, 2048
+    x = torch.randn(N, HW, C, device=cuda_device).bfloat16()
+    y = torch.empty(N, C, device=cuda_device, dtype=torch.bfloat16)
+    _lib.call("argus_avgpool_forward", x, y, N, HW, C, _lib.stream_ptr())
+    close_bf16(y, x.float().mean(1))
+    dy = torch.randn(N, C, device=cuda_device).bfloat16()
+    dx = torch.empty_like(x)
+    _lib.call("argus_avgpool_backward", dy, dx, N, HW, C, _lib.stream_ptr())
+    close_bf16(dx, (dy.float() / HW)[:, None, :].expand(N, HW, C))

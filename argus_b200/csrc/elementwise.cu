@@ -8,6 +8,7 @@
 #include "runtime.h"
 
 #include <algorithm>
+#include <string>
 
 namespace argus {
 
@@ -415,7 +416,9 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
                    int mask_mode, cudaStream_t s) {
-  ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
+  std::string fam = "bn_bwd_reduce";
+  if (profile_enabled() && profile_detailed()) fam += ":R" + std::to_string(rows) + "_C" + std::to_string(C) + "_m" + std::to_string(mask_mode);
+  ProfileScope prof(fam, s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_bwd_reduce: C/8 must be a power of two <= 256");
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);

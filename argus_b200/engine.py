@@ -19,6 +19,18 @@ from . import _lib
 from .models import NCameraCNN
 
 
+def gradient_buckets(flat: torch.Tensor, stage_ranges: list[tuple[int, int]]) -> list[torch.Tensor]:
+    """Views of the flat gradient arena, one per backward stage, in the order they become final
+    (stage 0 = layer4 + fc + head ... stage 3 = stem + layer1). Together they tile the arena exactly once."""
+    return [flat[b:e] for (b, e) in stage_ranges]
+
+
+def all_reduce_bucket(bucket: torch.Tensor, group=None, async_op: bool = True):
+    """SUM all-reduce of one bucket (the 1/world average is folded into the optimizer's gradient scale).
+    DDP in the reference averages 25 MiB buckets the same way (train.py:199)."""
+    return dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+
+
 class TrainEngine:
     """Owns the optimizer state (flat Adam moments) and runs fused training steps on an NCameraCNN.
 
@@ -89,13 +101,12 @@ class TrainEngine:
             _lib.call("argus_pose_loss", out, targets, None, self._loss_mean, grad, int(B), 1.0 / B, lib_stream)
             _lib.call("argus_model_zero_grads", model._handle.ptr, lib_stream)
             works = []
-            flat_grads = model.flat_grads
+            buckets = gradient_buckets(model.flat_grads, self._stage_ranges)
             for stage in range(4):
                 _lib.call("argus_model_backward", model._handle.ptr, grad, stage, stage + 1, lib_stream)
                 if self.world > 1:
-                    b, e = self._stage_ranges[stage]
-                    works.append(dist.all_reduce(flat_grads[b:e], op=dist.ReduceOp.SUM, group=self.group,
-                                                 async_op=True))
+                    # NCCL runs on its own stream: it waits for this stage's kernels, the next stage overlaps with it
+                    works.append(all_reduce_bucket(buckets[stage], self.group, async_op=True))
             for w in works:
                 w.wait()
         return self._loss_mean[0]

@@ -121,7 +121,10 @@ def run_ours(args) -> None:
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                                timeout=datetime.timedelta(seconds=180))
     B, H, W, n_cams = args.batch, args.size, args.size, 2
 
     torch.manual_seed(42)
@@ -220,9 +223,10 @@ def run_ours(args) -> None:
     families = {}
     if rank == 0:
         lib.argus_profile_enable(1)
-        for i in range(2):
-            engine.step(*dev_batches[i % ring])
-        torch.cuda.synchronize()
+    for i in range(2):  # every rank steps (the steps contain collectives); only rank 0 records events
+        engine.step(*dev_batches[i % ring])
+    torch.cuda.synchronize()
+    if rank == 0:
         buf = ctypes.create_string_buffer(1 << 16)
         _lib.check(lib.argus_profile_report(buf, ctypes.c_int(1 << 16)))
         lib.argus_profile_enable(0)

@@ -54,3 +54,19 @@ def time_torch_fn(fn: Callable[[], torch.Tensor]) -> tuple[torch.Tensor, float]:
     end.record()
     torch.cuda.synchronize()
     return result, start.elapsed_time(end) / 1000
+
+
+def draw_spaghetti(img, n_arcs: int = 10, width_range=(1.0, 5.0)):
+    """Draws random black arcs on a PIL image (reference: argus/utils.py:252-275; CPU/PIL, uses numpy's global RNG
+    exactly like the reference so that `np.random.seed` reproduces it)."""
+    import numpy as np
+    from PIL import ImageDraw
+
+    for _ in range(n_arcs):
+        x0, y0 = np.random.randint(0, img.width), np.random.randint(0, img.height)
+        x1, y1 = np.random.randint(x0, img.width), np.random.randint(y0, img.height)
+        start_angle, end_angle = np.random.randint(0, 360), np.random.randint(0, 360)
+        width = np.random.uniform(*width_range)
+        d = ImageDraw.Draw(img)
+        d.arc((x0, y0, x1, y1), start_angle, end_angle, fill=(0, 0, 0), width=int(width))
+    return img

@@ -1,0 +1,93 @@
+"""GPU integration tests mirroring the reference's tests/test_train.py:39-77 and validate.py: one epoch on a dummy
+dataset runs, writes `<id>.pth` in the reference layout, a second run with the same seed lands on the same model,
+and validate() consumes the checkpoint."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dummy_data_path(tmp_path_factory):
+    from argus_b200.dataset import write_dataset
+
+    rng = np.random.default_rng(0)
+    root = tmp_path_factory.mktemp("data") / "dummy"
+
+    def poses(n):
+        q = rng.normal(size=(n, 4))
+        q /= np.linalg.norm(q, axis=-1, keepdims=True)
+        return np.concatenate([rng.normal(size=(n, 3)), q], -1)
+
+    yy, xx = np.mgrid[0:128, 0:128]
+    base = (np.sin(xx / 11.0) * 60 + np.cos(yy / 7.0) * 50 + 120)[None, None, :, :, None]
+    imgs = np.clip(base + rng.normal(0, 30, (24, 2, 128, 128, 3)) + rng.uniform(-50, 50, (24, 2, 1, 1, 3)), 0, 255)
+    imgs = imgs.astype(np.uint8)
+    write_dataset(str(root), imgs[:16], poses(16), imgs[16:], poses(8))
+    return str(root)
+
+
+def run_once(dummy_data_path, save_dir):
+    from argus_b200.dataset import CameraCubePoseDatasetConfig
+    from argus_b200.models import NCameraCNN
+    from argus_b200.train import TrainConfig, train
+    from argus_b200.validate import load_checkpoint
+
+    cfg = TrainConfig(dataset_config=CameraCubePoseDatasetConfig(dataset_path=dummy_data_path, center_crop=(128, 128)),
+                      batch_size=8, n_epochs=1, device="cuda", wandb_log=False, save_dir=str(save_dir), num_workers=0,
+                      num_gpus=1)
+    run_id = train(cfg)
+    path = save_dir / f"{run_id}.pth"
+    assert path.exists()
+    model = NCameraCNN()
+    load_checkpoint(model, str(path))
+    model.to("cuda").eval()
+    with torch.no_grad():
+        return model(torch.ones(1, 6, 128, 128, device="cuda")), path
+
+
+def test_train_writes_reference_layout_and_is_reproducible(cuda_device, dummy_data_path, tmp_path):
+    import json
+    from pathlib import Path
+
+    out1, path = run_once(dummy_data_path, tmp_path)
+    sd = torch.load(path, map_location="cpu", weights_only=True)
+    keys = json.loads((Path(__file__).resolve().parent / "golden" / "state_dict_keys.json").read_text())
+    assert [k["name"] for k in keys] == list(sd.keys())
+    assert all(list(sd[k["name"]].shape) == k["shape"] for k in keys)
+    assert int(sd["resnet.bn1.num_batches_tracked"]) == 2          # 16 samples / batch 8
+    assert torch.isfinite(out1).all()
+    out2, _ = run_once(dummy_data_path, tmp_path)
+    # same seed => same augmentation draws, same shuffling, same init (reference test_train.py:69-77). The reference
+    # asserts allclose at default tolerance on cuDNN; our BN statistics / weight gradients are reduced with fp32
+    # atomics (order varies run to run), so the comparison is at 2e-2 relative.
+    assert torch.allclose(out1, out2, rtol=2e-2, atol=2e-3), (out1, out2)
+
+
+def test_validate_consumes_checkpoint(cuda_device, dummy_data_path, tmp_path):
+    from argus_b200.dataset import CameraCubePoseDatasetConfig
+    from argus_b200.validate import ValConfig, validate
+
+    _, path = run_once(dummy_data_path, tmp_path)
+    res = validate(ValConfig(model_path=str(path), dataset_config=CameraCubePoseDatasetConfig(
+        dataset_path=dummy_data_path, center_crop=(128, 128))))
+    assert res["losses"].shape == (8,) and torch.isfinite(res["losses"]).all()
+    assert res["poses"].shape == (8, 7)
+    assert torch.allclose(res["poses"][:, 3:].norm(dim=-1), torch.ones(8), atol=1e-5)  # unit quaternions
+
+
+def test_loss_decreases_when_overfitting(cuda_device):
+    """A few hundred fused steps on one fixed batch drive the geometric loss down (optimizer + backward sanity)."""
+    from argus_b200.engine import TrainEngine
+    from argus_b200.models import NCameraCNN
+    from gpu_util import random_targets, structured_images
+
+    torch.manual_seed(0)
+    model = NCameraCNN().to("cuda")
+    engine = TrainEngine(model, lr=1e-3, max_grad_norm=1.0, distributed=False)
+    x = structured_images(8, 6, 64, 64, 1, "cuda")
+    t = random_targets(8, 2, "cuda")
+    losses = [engine.step(x, t).item() for _ in range(60)]
+    assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
+    assert all(np.isfinite(losses))

@@ -112,6 +112,8 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
     device = torch.device("cuda", rank) if cfg.multigpu else torch.device(cfg.device)
     if device.type != "cuda":
         raise RuntimeError("argus_b200 trains on sm_100a GPUs only (no CPU fallback)")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
     torch.cuda.set_device(device)
     if cfg.multigpu:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")

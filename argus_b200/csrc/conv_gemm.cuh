@@ -533,9 +533,9 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
         tmem_ld_wait();
         if (kb1 > kb0 && co < p.cout) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < 32; i += 4) {
             const int ci = ci_t * BLOCK_N + ch * 32 + i;
-            if (ci < p.cin) atomicAdd(row + ch * 32 + i, __uint_as_float(v[i]));
+            if (ci + 3 < p.cin) red_add_v4(row + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
           }
         }
       }

@@ -388,9 +388,9 @@ WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const _
   p.num_ci_tiles = (cin_tile_extent + l.block_n - 1) / l.block_n;
   p.kblocks_total = static_cast<int>((pixels + 63) / 64);
   const int base_items = p.num_co_tiles * p.num_ci_tiles * p.num_taps;
-  int splits = (3 * num_sms() + base_items - 1) / base_items;
-  splits = std::min(splits, std::max(1, p.kblocks_total / 8));
-  splits = std::max(splits, 1);
+  // split K so that the equal-sized work items fill the SMs in ONE wave (fewer splits = fewer fp32 reductions)
+  int splits = std::max(1, num_sms() / base_items);
+  splits = std::min(splits, std::max(1, p.kblocks_total / 4));
   // no empty splits: shrink until the last split still owns at least one k-block
   while (splits > 1) {
     const int per = (p.kblocks_total + splits - 1) / splits;

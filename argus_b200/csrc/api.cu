@@ -268,6 +268,12 @@ int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_pa
                          static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
+int argus_model_set_wgrad_overlap(argus_model* m, int on) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.set_wgrad_overlap(on != 0);
+  ARGUS_API_END
+}
 int argus_model_zero_grads(argus_model* m, void* stream) {
   ARGUS_API_BEGIN
   ARGUS_CHECK(m != nullptr, "null model");

@@ -188,7 +188,14 @@ void validate_shape(const ConvShape& s) {
   ARGUS_CHECK(s.H % s.stride == 0 && s.W % s.stride == 0, "spatial size must be divisible by the stride");
 }
 
-static int pick_block_n(int n) { return n >= 256 ? 256 : (n >= 128 ? 128 : 64); }
+// Largest N tile that still yields at least one tile per SM; small problems (inference at batch 1, layer3/4) fall
+// back to narrow tiles so that more CTAs share the work and each K loop issues cheaper MMAs.
+static int pick_block_n(int n, int64_t m_tiles = (1 << 30)) {
+  const int cands[3] = {256, 128, 64};
+  for (int bn : cands)
+    if (n >= bn && n % bn == 0 && m_tiles * (n / bn) >= num_sms()) return bn;
+  return 64;
+}
 
 // box of `pixels` consecutive pixels of an (N, Ho, Wo) grid, as (bw, bh, bn)
 static void pixel_box(int Wo, int Ho, int pixels, uint32_t& bw, uint32_t& bh, uint32_t& bn) {
@@ -257,7 +264,7 @@ ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const _
   validate_shape(s);
   ConvLaunch l;
   std::memset(&l.p, 0, sizeof(l.p));
-  l.block_n = pick_block_n(s.Cout);
+  l.block_n = pick_block_n(s.Cout, (s.out_pixels() + kBlockM - 1) / kBlockM);
   l.b_mn = 0;
   ConvGemmParams& p = l.p;
   make_input_maps(s, x, kBlockM, p.a_map);
@@ -295,7 +302,7 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
   std::vector<ConvLaunch> out;
   const int pad = s.k / 2;
   const int Ho = s.Ho(), Wo = s.Wo();
-  const int block_n = pick_block_n(s.Cin);
+  const int block_n = pick_block_n(s.Cin, (static_cast<int64_t>(s.N) * Ho * Wo + kBlockM - 1) / kBlockM);
   const int classes = (s.stride == 1) ? 1 : 4;
   for (int cls = 0; cls < classes; ++cls) {
     const int a = cls >> 1, b = cls & 1;

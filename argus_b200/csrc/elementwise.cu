@@ -373,7 +373,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       a_dy[k] += g.v[k];
-      a_dyx[k] = fmaf(g.v[k], xv.v[k] - mu.v[k], a_dyx[k]);   // scaled by invstd once at the end
+      a_dyx[k] = fmaf(g.v[k], xv.v[k], a_dyx[k]);   // sum g*x; centred and scaled by invstd once at the end
     }
   };
   const int64_t rstride = static_cast<int64_t>(gridDim.x) * row_lanes;
@@ -396,7 +396,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     red[k][threadIdx.x] = a_dy[k];
-    red[8 + k][threadIdx.x] = a_dyx[k] * is.v[k];
+    red[8 + k][threadIdx.x] = (a_dyx[k] - mu.v[k] * a_dy[k]) * is.v[k];
   }
   __syncthreads();
   if (rl == 0) {

@@ -30,6 +30,9 @@ Model::Model(int n_cams, int resnet_output_dim) : n_cams_(n_cams), out_dim_(resn
 }
 
 Model::~Model() {
+  if (side_) cudaStreamDestroy(side_);
+  if (ev_fork_) cudaEventDestroy(ev_fork_);
+  if (ev_wgrad_) cudaEventDestroy(ev_wgrad_);
   cudaFree(packed_);
   cudaFree(gpacked_);
   cudaFree(bn_scratch_);
@@ -161,6 +164,9 @@ void Model::bind(float* params, float* grads, float* buffers) {
     ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
                           cudaMemcpyHostToDevice));
     ARGUS_CUDA(cudaMemset(gpacked_, 0, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
+    ARGUS_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    ARGUS_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+    ARGUS_CUDA(cudaEventCreateWithFlags(&ev_wgrad_, cudaEventDisableTiming));
   }
   plans_.clear();
   last_train_plan_ = nullptr;
@@ -497,6 +503,13 @@ void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
+void Model::join_wgrad(cudaStream_t s) {
+  if (wgrad_pending_) {
+    ARGUS_CUDA(cudaStreamWaitEvent(s, ev_wgrad_, 0));
+    wgrad_pending_ = false;
+  }
+}
+
 void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
                         cudaStream_t s) {
   const float* sc = bn_scratch_ + c.bn.scratch_off;
@@ -504,11 +517,28 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
   float* dbeta = grads_dev_ + c.bn.beta_off;
   const int C = c.bn.C;
   bn_bwd_reduce(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, rows, C, mask, s);
+  // the apply pass overwrites a gradient buffer that an in-flight weight-gradient GEMM may still be reading
+  join_wgrad(s);
   bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
 }
 
 void Model::conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s) {
-  launch_wgrad(cp.wgrad, s);
+  // fork: the weight gradient only needs dRaw and the saved activation, both final at this point
+  join_wgrad(s);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (!overlap_wgrad_ || cap != cudaStreamCaptureStatusNone) {
+    launch_wgrad(cp.wgrad, s);
+    Epilogue e0;
+    e0.residual = residual;
+    for (const auto& l : cp.dgrad) launch_conv(l, e0, s);
+    return;
+  }
+  ARGUS_CUDA(cudaEventRecord(ev_fork_, s));
+  ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
+  launch_wgrad(cp.wgrad, side_);
+  ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_));
+  wgrad_pending_ = true;
   Epilogue e;
   e.residual = residual;
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
@@ -575,6 +605,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       bn_backward(stem_, p.g_act0, p.raw0, nullptr, p.g_raw0, static_cast<int64_t>(N) * (p.H / 2) * (p.W / 2), 1, s);
       launch_wgrad(p.stem.wgrad, s);
     }
+    join_wgrad(s);
     // packed 3x3 / stem gradients of this stage -> PyTorch layout in the gradient arena
     {
       int lo = -1, hi = -1;

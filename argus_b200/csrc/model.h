@@ -107,6 +107,8 @@ class Model {
   // gradient arena for stages [stage_begin, stage_end); stages must be run in increasing order 0..3.
   void backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
   void zero_grads(cudaStream_t s);
+  // overlap the weight-gradient GEMMs with the rest of the backward pass on a side stream (default on)
+  void set_wgrad_overlap(bool on) { overlap_wgrad_ = on; }
   // Debug / test probe: copies an activation of the LAST forward (bf16 NHWC rows x C) into dst.
   // index -1: pooled stem output; 0..15: bottleneck block outputs; 16: globally pooled features; 17: fc output.
   void copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s);
@@ -160,6 +162,12 @@ class Model {
   Plan* last_train_plan_ = nullptr;
   Plan* last_plan_ = nullptr;
   Plan* staged_plan_ = nullptr;
+  // weight-gradient GEMMs run on a side stream, overlapping the HBM-bound BN-backward / dgrad chain
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_fork_ = nullptr, ev_wgrad_ = nullptr;
+  bool wgrad_pending_ = false;
+  bool overlap_wgrad_ = true;
+  void join_wgrad(cudaStream_t s);
 };
 
 }  // namespace argus

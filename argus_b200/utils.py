@@ -70,3 +70,47 @@ def draw_spaghetti(img, n_arcs: int = 10, width_range=(1.0, 5.0)):
         d = ImageDraw.Draw(img)
         d.arc((x0, y0, x1, y1), start_angle, end_angle, fill=(0, 0, 0), width=int(width))
     return img
+
+
+class PoseEstimator:
+    """Real-time inference pipeline for `get_pose` (reference: argus/utils.py:179-189, intended to run under
+    `torch.compile(mode="reduce-overhead")`, i.e. CUDA graphs — scripts/timing.py:13-45).
+
+    The whole chain uint8 image pair(s) -> /255 + packing -> eval forward -> se3 Exp (-> optional wxyz reorder for
+    MuJoCo consumers, validate_real.py:73-76) is captured once into a CUDA graph for a fixed batch shape and replayed
+    per call, so a call costs one host->device copy, one graph launch and one (B,7) read-back.
+    """
+
+    def __init__(self, model, batch: int, H: int, W: int, uint8_input: bool = True, wxyz: bool = False) -> None:
+        dev = model.flat_params.device
+        if dev.type != "cuda":
+            raise _lib.ArgusError("PoseEstimator needs the model on a CUDA device (no CPU fallback)")
+        self.model = model.eval()
+        self.wxyz = wxyz
+        n_cams = model.n_cams
+        if uint8_input:
+            self.static_in = torch.zeros((batch, n_cams, H, W, 3), dtype=torch.uint8, device=dev)
+        else:
+            self.static_in = torch.zeros((batch, 3 * n_cams, H, W), dtype=torch.float32, device=dev)
+        self.static_out = torch.zeros((batch, 7), dtype=torch.float32, device=dev)
+        model.sync_weights()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(2):  # builds the launch plan and the eval-mode BN fold outside the capture
+                self._run_eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self._run_eager()
+
+    def _run_eager(self) -> None:
+        pred = self.model._forward_impl(self.static_in, False)
+        self.static_out.copy_(se3_exp(pred, wxyz=self.wxyz))
+
+    def __call__(self, images: torch.Tensor) -> torch.Tensor:
+        """images: same shape/dtype as the session was built for (host or device). Returns (B, 7) poses."""
+        self.static_in.copy_(images, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

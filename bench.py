@@ -221,6 +221,7 @@ def run_ours(args) -> None:
 
     # ---- per-kernel-family timing with CUDA events (separate pass: the headline numbers above are un-instrumented)
     families = {}
+    _lib.call("argus_model_set_wgrad_overlap", model._handle.ptr, 0)  # isolated kernel times for the roofline
     if rank == 0:
         lib.argus_profile_enable(1)
     for i in range(2):  # every rank steps (the steps contain collectives); only rank 0 records events
@@ -266,6 +267,11 @@ def run_ours(args) -> None:
             gbs = f["bytes"] / (f["ms"] / 1e3) / 1e9
             mem[k] = {"ms": round(f["ms"], 3), "launches": f["launches"], "GB/s": round(gbs, 1),
                       "frac_hbm": round(gbs / peaks["hbm_gbs"], 3)}
+    inference = None
+    if world == 1 and not args.no_inference:
+        del engine
+        torch.cuda.empty_cache()
+        inference = measure_inference(dev, args.size)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_reference_throughput(sample_pairs=8, iters=3, warmup=1, size=args.size, augmentation=augmentation is not None)
@@ -290,9 +296,54 @@ def run_ours(args) -> None:
     }
     if cpu is not None:
         line["cpu_baseline"] = cpu
+    if inference is not None:
+        line["inference"] = inference
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def measure_inference(dev, size: int) -> dict:
+    """BASELINE.json configs[2]: eval-mode `get_pose` latency at batch 1 and 64 (protocol of the reference's
+    scripts/timing.py:13-45: 100 timed trials after warm-up, CUDA events per trial), eager C-ABI calls and the
+    CUDA-graph PoseEstimator; input = uint8 pair(s) in pinned HOST memory (H2D inside the timed region)."""
+    import torch
+
+    from argus_b200.models import NCameraCNN
+    from argus_b200.utils import PoseEstimator, get_pose
+
+    torch.manual_seed(42)
+    model = NCameraCNN().to(dev).eval()
+    out = {}
+    for B in (1, 64):
+        host = synthetic_batch(B, 2, size, size, seed=7)[0].pin_memory()
+        est = PoseEstimator(model, B, size, size, uint8_input=True)
+        dev_in = host.to(dev)
+
+        def eager():
+            return get_pose(dev_in.copy_(host, non_blocking=True), model)
+
+        def graph():
+            return est(host)
+
+        res = {}
+        for name, fn in (("eager", eager), ("cuda_graph", graph)):
+            for _ in range(10):
+                fn()
+            torch.cuda.synchronize()
+            times = []
+            for _ in range(100):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                e1.synchronize()
+                times.append(e0.elapsed_time(e1))
+            times.sort()
+            res[name] = {"p50_ms": round(times[50], 4), "p99_ms": round(times[98], 4)}
+        res["pairs_per_s_graph"] = round(B / (res["cuda_graph"]["p50_ms"] / 1e3), 1)
+        out[f"batch{B}"] = res
+    return out
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -384,6 +435,7 @@ def main() -> None:
     ap.add_argument("--size", type=int, default=256)
     ap.add_argument("--no-augmentation", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -130,6 +130,9 @@ int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, 
  * The next argus_model_forward call for the same (B, H, W, training) passes x = NULL. */
 int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
                                int training, int apply, void* stream);
+/* Weight-gradient GEMMs normally run on a library-owned side stream, overlapping the BN-backward / dgrad chain of the
+ * caller's stream (joined before the stage returns). on = 0 serialises them (used for per-kernel timing). */
+int argus_model_set_wgrad_overlap(argus_model* m, int on);
 int argus_model_zero_grads(argus_model* m, void* stream);
 /* Backward of the last training forward. d_out (B,6). Stages 0..3 (head+fc+layer4, layer3, layer2, layer1+stem)
  * must run in order; gradients are ADDED into the bound gradient arena. */

@@ -38,8 +38,11 @@ def test_clip_adam_matches_torch(cuda_device, n, max_norm, gscale):
     assert torch.allclose(v, state["exp_avg_sq"], rtol=1e-4, atol=1e-9)
 
 
-def test_engine_step_equals_manual_composition(cuda_device):
-    """TrainEngine.step == forward, argus loss, backward through autograd, clip, torch Adam on the same model."""
+def test_engine_gradients_equal_autograd_path(cuda_device):
+    """TrainEngine.forward_backward (fused loss + staged backward into the flat arena) produces the same gradients as
+    the drop-in autograd path `geometric_loss_fn(model(x), t).mean().backward()`. Two runs of a train-mode network
+    differ only through fp32 atomic ordering in the BN statistics; the residual branches are scaled down
+    (see test_model_gpu.build_pair) so that this noise is not chaotically amplified."""
     from argus_b200.engine import TrainEngine
     from argus_b200.loss import geometric_loss_fn
     from argus_b200.models import NCameraCNN
@@ -47,24 +50,33 @@ def test_engine_step_equals_manual_composition(cuda_device):
 
     torch.manual_seed(3)
     a = NCameraCNN().to(cuda_device)
+    with torch.no_grad():
+        for name, p in a.named_parameters():
+            if name.endswith("bn3.weight"):
+                p.fill_(0.1)
     b = NCameraCNN().to(cuda_device)
     b.load_state_dict(a.state_dict())
-    x = structured_images(4, 6, 64, 64, 9, cuda_device)
-    t = random_targets(4, 10, cuda_device)
+    x = structured_images(8, 6, 128, 128, 9, cuda_device)
+    t = random_targets(8, 10, cuda_device)
     eng = TrainEngine(a, lr=1e-3, max_grad_norm=1.0, distributed=False)
-    loss_a = eng.step(x, t)
+    loss_a = eng.forward_backward(x, t)
+    ga = a.flat_grads.clone()
+    eng.forward_backward(x, t)                      # same path again: run-to-run noise floor (fp32 atomic ordering
+    ga2 = a.flat_grads.clone()                      # in BN statistics, re-quantised to bf16 at every layer)
+    noise = ((ga - ga2).norm() / ga.norm()).item()
     b.train()
-    opt = torch.optim.Adam(b.parameters(), lr=1e-3)
     loss_b = geometric_loss_fn(b(x), t).mean()
     loss_b.backward()
-    torch.nn.utils.clip_grad_norm_(b.parameters(), 1.0)
-    opt.step()
+    gb = torch.zeros_like(ga)
+    for p, (_n, off, numel, _shape) in zip(b.parameters(), b._param_infos):
+        gb[off:off + numel] = p.grad.reshape(-1)
     assert abs(loss_a.item() - loss_b.item()) < 1e-3 * abs(loss_b.item())
-    # Adam's first step moves every weight by ~lr * sign(g): compare the updates, not the raw values
-    da = a.flat_params - eng.model.flat_params.new_tensor(0) - b.flat_params
-    moved = (b.flat_params - a.flat_params).abs()
-    assert moved.mean().item() < 2e-4, moved.mean().item()   # both took (almost) the same step of size ~1e-3
-    assert int(a.resnet.bn1.num_batches_tracked) == 1
+    rel = ((ga - gb).norm() / gb.norm()).item()
+    print(f"engine vs autograd path: {rel:.3e}; engine run-to-run: {noise:.3e}")
+    assert rel < max(2e-2, 2.0 * noise), (rel, noise)
+    eng.optimizer_step()
+    assert eng.step_count == 1 and int(a.resnet.bn1.num_batches_tracked) == 2  # two training forwards so far
+    assert torch.isfinite(a.flat_params).all()
 
 
 def test_head_and_fc_against_torch(cuda_device):

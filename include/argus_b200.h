@@ -146,6 +146,25 @@ int argus_model_arena_bytes(argus_model* m, int64_t* bytes);
 int argus_model_copy_activation(argus_model* m, int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C,
                                 void* stream);
 
+/* ---- double-buffered pinned loader over a raw uint8 shard file (replaces the DataLoader / DistributedSampler /
+ *      `.to(device)` plumbing of argus/train.py:147-192,302-303). File layout: csrc/loader.cu. The caller owns the
+ *      staging buffers: two pinned host and two device buffers for images (batch * n_cams*H*W*3 bytes) and poses
+ *      (batch * 7 floats). Sampling follows DistributedSampler: one permutation per epoch (seeded by seed and
+ *      epoch), padded by wrapping, rank r takes positions r, r + world, ... ----------------------------------------- */
+typedef struct argus_loader argus_loader;
+int argus_loader_create(argus_loader** out, const char* path, int batch, int rank, int world, uint64_t seed,
+                        int shuffle, int drop_last);
+int argus_loader_destroy(argus_loader* l);
+int argus_loader_info(argus_loader* l, int64_t* n_samples, int* n_cams, int* H, int* W, int64_t* samples_per_rank,
+                      int64_t* batches_per_epoch);
+int argus_loader_bind(argus_loader* l, void* host_img0, void* host_img1, float* host_pose0, float* host_pose1,
+                      void* dev_img0, void* dev_img1, float* dev_pose0, float* dev_pose1);
+/* (Re)starts the worker thread for an epoch (DistributedSampler.set_epoch, train.py:290). */
+int argus_loader_start_epoch(argus_loader* l, int epoch);
+/* Next batch: H2D on the loader's copy stream, ordered before everything later enqueued on `stream`.
+ * *count = samples in the batch (0 = epoch finished), *buffer_index = which of the two device buffers holds it. */
+int argus_loader_next(argus_loader* l, void* stream, int* count, int* buffer_index);
+
 #ifdef __cplusplus
 }
 #endif

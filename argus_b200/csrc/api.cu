@@ -6,9 +6,23 @@
 #include "model.h"
 #include "runtime.h"
 
+#include <algorithm>
 #include <cstring>
 
 using namespace argus;
+
+// Library-owned scratch for the standalone primitive entry points (grown on demand, never on the model's hot path).
+static float* lib_scratch(int64_t elems) {
+  static float* buf = nullptr;
+  static int64_t cap = 0;
+  if (elems > cap) {
+    ARGUS_CUDA(cudaDeviceSynchronize());
+    if (buf) ARGUS_CUDA(cudaFree(buf));
+    ARGUS_CUDA(cudaMalloc(&buf, elems * sizeof(float)));
+    cap = elems;
+  }
+  return buf;
+}
 
 static ConvShape make_shape(int N, int H, int W, int Cin, int Cout, int k, int stride, int kind) {
   ConvShape s;
@@ -44,7 +58,7 @@ int argus_require_device(void) {
 
 int argus_conv2d_forward(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
                          int stride, int kind, const float* scale, const float* shift, const void* residual, int relu,
-                         float* stat_sum, float* stat_sqsum, void* stream) {
+                         float* stat_partial, int stat_slot_capacity, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
   ConvShape s = make_shape(N, H, W, Cin, Cout, k, stride, kind);
@@ -52,8 +66,22 @@ int argus_conv2d_forward(const void* x, const void* w, void* y, int N, int H, in
                                    static_cast<__nv_bfloat16*>(y));
   Epilogue e;
   e.scale = scale; e.shift = shift; e.residual = static_cast<const __nv_bfloat16*>(residual); e.relu = relu;
-  e.stat_sum = stat_sum; e.stat_sqsum = stat_sqsum;
+  e.stat_partial = stat_partial;
+  ARGUS_CHECK(stat_partial == nullptr || stat_slot_capacity >= stat_slots(l), "statistics buffer has too few slots");
   launch_conv(l, e, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_conv2d_stat_slots(int N, int H, int W, int Cin, int Cout, int k, int stride, int kind, int* slots) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(slots != nullptr, "null argument");
+  ConvShape s = make_shape(N, H, W, Cin, Cout, k, stride, kind);
+  validate_shape(s);
+  const int64_t m_tiles = (s.out_pixels() + kBlockM - 1) / kBlockM;
+  // same tile choice as plan_conv_forward: an upper bound is enough for sizing
+  const int64_t tiles = m_tiles * ((Cout + 63) / 64);
+  *slots = 2 * static_cast<int>(std::min<int64_t>(tiles, num_sms()));
   ARGUS_API_END
 }
 
@@ -77,16 +105,16 @@ int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, i
   require_sm100();
   ConvShape s = make_shape(N, H, W, Cin, Cout, k, stride, kind);
   WgradLaunch l = plan_conv_wgrad(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw);
-  launch_wgrad(l, static_cast<cudaStream_t>(stream));
+  launch_wgrad(l, lib_scratch(wgrad_scratch_elems(l)), static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 
-int argus_bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+int argus_bn_finalize(const float* partial, int slots, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                       float* save_mean, float* save_invstd, int C, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
-  bn_finalize(sum, sqsum, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
+  bn_finalize(partial, slots, count, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
               save_invstd, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
@@ -105,7 +133,7 @@ int argus_bn_backward(void* dy, const void* x, const void* out, const float* sca
   require_sm100();
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   bn_bwd_reduce(static_cast<const bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(out), scale, shift,
-                mean, invstd, dgamma, dbeta, rows, C, mask_mode, s);
+                mean, invstd, dgamma, dbeta, rows, C, mask_mode, lib_scratch(bn_bwd_scratch_elems()), s);
   bn_bwd_apply(static_cast<bf16*>(dy), static_cast<const bf16*>(x), static_cast<const bf16*>(out), scale, shift, mean,
                invstd, dgamma, dbeta, static_cast<bf16*>(dx), rows, C, mask_mode, s);
   ARGUS_API_END

@@ -52,8 +52,10 @@ struct ConvGemmParams {
   const float* shift;            // per output channel offset (folded BN / bias)
   int has_res;                   // add the residual tile (TMA-loaded through res_map) before ReLU
   int relu;
-  float* stat_sum;               // per-channel sum of the stored bf16 outputs (train-mode BN)
-  float* stat_sqsum;             // per-channel sum of squares
+  // train-mode BN statistics of the stored bf16 outputs, reduced deterministically: every (CTA, epilogue group)
+  // owns slot = 2*blockIdx.x + group of stat_partial[slot][2][n_total] (sum, sum of squares); bn_finalize adds the
+  // slots in a fixed order. The caller zeroes the buffer.
+  float* stat_partial;
 };
 
 template <int BLOCK_N>
@@ -61,12 +63,12 @@ struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = 160000 / kStageBytes;        // leaves room for 4 staging buffers
+  static constexpr int kStagesRaw = 150000 / kStageBytes;        // leaves room for 4 staging buffers + statistics
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
   static constexpr int kOffStaging = kStages * kStageBytes;      // 2 buffers per epilogue group
   static constexpr int kOffStats = kOffStaging + 4 * kStagingBytes;
-  static constexpr int kOffBars = kOffStats + 2 * 2 * BLOCK_N * 4;   // per group: sum[BLOCK_N], sqsum[BLOCK_N]
+  static constexpr int kOffBars = kOffStats + 2 * 4 * 2 * BLOCK_N * 4;   // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
   static constexpr int kNumBars = 2 * kStages + 6;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
@@ -117,7 +119,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 4 * BLOCK_N; i += kNumThreads) s_stats_all[i] = 0.f;
+  for (int i = threadIdx.x; i < 16 * BLOCK_N; i += kNumThreads) s_stats_all[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -205,25 +207,29 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int et = (ew & 3) * 32 + lane;  // 0..127 inside the group
     const bool store_leader = (et == 0);
     const uint32_t bar_id = 1 + grp;
-    float* s_stats = s_stats_all + grp * 2 * BLOCK_N;
+    float* s_stats = s_stats_all + grp * 8 * BLOCK_N;          // [warp 0..3][sum | sqsum][BLOCK_N]
+    float* s_mine = s_stats + (ew & 3) * 2 * BLOCK_N;          // this warp's private slot: no atomics, fixed order
     uint8_t* stg_base = smem + L::kOffStaging + grp * 2 * L::kStagingBytes;
     const int acc = grp;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
     int buf = 0;
     int cur_n = -1;
-    const bool do_stats = (p.stat_sum != nullptr);
+    const bool do_stats = (p.stat_partial != nullptr);
+    float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(2 * blockIdx.x + grp) * 2 * p.n_total : nullptr;
 
     auto flush_stats = [&](int n_tile) {
       named_bar_sync(bar_id, 128);
-      for (int c = et; c < BLOCK_N; c += 128) {
-        const int gc = n_tile * BLOCK_N + c;
-        if (gc < p.n_total) {
-          atomicAdd(p.stat_sum + gc, s_stats[c]);
-          atomicAdd(p.stat_sqsum + gc, s_stats[BLOCK_N + c]);
+      for (int c = et; c < 2 * BLOCK_N; c += 128) {
+        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
+        const int gc = n_tile * BLOCK_N + col;
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          acc += s_stats[w * 2 * BLOCK_N + c];
+          s_stats[w * 2 * BLOCK_N + c] = 0.f;
         }
-        s_stats[c] = 0.f;
-        s_stats[BLOCK_N + c] = 0.f;
+        if (gc < p.n_total) my_partial[which * p.n_total + gc] += acc;   // only this thread ever touches this word
       }
       named_bar_sync(bar_id, 128);
     };
@@ -339,10 +345,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             q0 = fmaf(x.x, x.x, q0); q1 = fmaf(x.y, x.y, q1);
           }
           const int c = ch * 64 + lane * 2;
-          atomicAdd(&s_stats[c], s0);
-          atomicAdd(&s_stats[c + 1], s1);
-          atomicAdd(&s_stats[BLOCK_N + c], q0);
-          atomicAdd(&s_stats[BLOCK_N + c + 1], q1);
+          s_mine[c] += s0;
+          s_mine[c + 1] += s1;
+          s_mine[BLOCK_N + c] += q0;
+          s_mine[BLOCK_N + c + 1] += q1;
         }
         buf ^= 1;
       }
@@ -378,6 +384,10 @@ struct WgradParams {
   int cout, cin;
   int dw_row_stride;      // elements between consecutive co rows of dW
   float* dw;
+  // split-K partial sums, reduced in a fixed order by wgrad_reduce (deterministic): partial[ks][cout][dw_row_stride].
+  // Used when num_ksplits > 1; with a single split the tile is added straight into dw.
+  float* partial;
+  long long partial_stride;
 };
 
 template <int BLOCK_N>
@@ -524,7 +534,10 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       const int co = co_t * 128 + r;
-      float* row = p.dw + static_cast<size_t>(co) * p.dw_row_stride + tap.b_off + ci_t * BLOCK_N;
+      const bool use_partial = (p.num_ksplits > 1);
+      const int ks = item % p.num_ksplits;
+      float* base = use_partial ? p.partial + static_cast<size_t>(ks) * p.partial_stride : p.dw;
+      float* row = base + static_cast<size_t>(co) * p.dw_row_stride + tap.b_off + ci_t * BLOCK_N;
 #pragma unroll 1
       for (int ch = 0; ch < BLOCK_N / 32; ++ch) {
         uint32_t v[32];
@@ -535,7 +548,12 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const int ci = ci_t * BLOCK_N + ch * 32 + i;
-            if (ci + 3 < p.cin) red_add_v4(row + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            if (ci + 3 < p.cin) {
+              if (use_partial)
+                *reinterpret_cast<uint4*>(row + ch * 32 + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              else
+                red_add_v4(row + ch * 32 + i, v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
           }
         }
       }

@@ -442,9 +442,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     p.has_res = 1;
   }
   p.relu = e.relu;
-  p.stat_sum = e.stat_sum;
-  p.stat_sqsum = e.stat_sqsum;
-  ARGUS_CHECK((e.stat_sum == nullptr) == (e.stat_sqsum == nullptr), "BN statistic pointers come in pairs");
+  p.stat_partial = e.stat_partial;
   const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * p.num_taps * p.kblocks_per_tap * kBlockK;
   std::string fam = l.b_mn ? "conv_dgrad" : "conv_fwd";
   if (g_profiling && profile_detailed())
@@ -463,6 +461,31 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   }
 }
 
+int stat_slots(const ConvLaunch& l) {
+  const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
+  return 2 * std::min(tiles, num_sms());
+}
+
+int64_t wgrad_scratch_elems(const WgradLaunch& l) {
+  if (l.p.num_ksplits <= 1) return 0;
+  return static_cast<int64_t>(l.p.num_ksplits) * l.p.cout * l.p.dw_row_stride;
+}
+
+// dw[i] += sum_ks partial[ks][i], splits added in index order (deterministic)
+__global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, int64_t n4, int splits) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 acc = partial[i];
+    for (int k = 1; k < splits; ++k) {
+      const float4 v = partial[static_cast<int64_t>(k) * n4 + i];
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float4 d = dw[i];
+    d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
+    dw[i] = d;
+  }
+}
+
 template <int BN>
 static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   using L = WgradSmem<BN>;
@@ -477,7 +500,12 @@ static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   ARGUS_CUDA(cudaGetLastError());
 }
 
-void launch_wgrad(const WgradLaunch& l, cudaStream_t stream) {
+void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
+  WgradLaunch l = l0;
+  const int64_t need = wgrad_scratch_elems(l);
+  ARGUS_CHECK(need == 0 || scratch != nullptr, "split-K weight gradient needs a scratch buffer");
+  l.p.partial = scratch;
+  l.p.partial_stride = static_cast<long long>(l.p.cout) * l.p.dw_row_stride;
   const double flops = 2.0 * l.p.kblocks_total * 64.0 * l.p.cout * static_cast<double>(l.p.cin) * l.p.num_taps;
   std::string fam = "conv_wgrad";
   if (g_profiling && profile_detailed())
@@ -489,6 +517,14 @@ void launch_wgrad(const WgradLaunch& l, cudaStream_t stream) {
     case 128: launch_wgrad_t<128>(l.p, stream); break;
     case 256: launch_wgrad_t<256>(l.p, stream); break;
     default: throw Error("unsupported wgrad tile configuration");
+  }
+  if (need > 0) {
+    // every (split, cout, tap, ci) word of the scratch was written by exactly one work item
+    const int64_t n4 = l.p.partial_stride / 4;
+    const int grid = static_cast<int>(std::min<int64_t>((n4 + 255) / 256, 2LL * num_sms()));
+    wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(scratch),
+                                                  reinterpret_cast<float4*>(l.p.dw), n4, l.p.num_ksplits);
+    ARGUS_CUDA(cudaGetLastError());
   }
 }
 

@@ -27,8 +27,7 @@ struct Epilogue {
   const float* shift = nullptr;
   const __nv_bfloat16* residual = nullptr;
   int relu = 0;
-  float* stat_sum = nullptr;
-  float* stat_sqsum = nullptr;
+  float* stat_partial = nullptr;   // [stat_slots(launch)][2][Cout], zeroed by the caller (train-mode BN statistics)
 };
 
 // geometry of the (non-strided) output tensor map, kept so that a residual tensor map can be built per launch
@@ -68,6 +67,11 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
 WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);
-void launch_wgrad(const WgradLaunch& l, cudaStream_t stream);
+// number of statistic slots launch_conv writes for this launch (2 per CTA)
+int stat_slots(const ConvLaunch& l);
+// elements of split-K scratch this launch needs (0 when it does not split)
+int64_t wgrad_scratch_elems(const WgradLaunch& l);
+// scratch: at least wgrad_scratch_elems(l) floats (may be null when that is 0)
+void launch_wgrad(const WgradLaunch& l, float* scratch, cudaStream_t stream);
 
 }  // namespace argus

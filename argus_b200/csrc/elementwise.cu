@@ -198,14 +198,19 @@ void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntr
 // ------------------------------------------------------------------------------------------------------------
 // batch norm: finalize / fold
 // ------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* sum, const float* sqsum, double count, const float* gamma,
+__global__ void bn_finalize_kernel(const float* __restrict__ partial, int slots, double count, const float* gamma,
                                    const float* beta, float* running_mean, float* running_var, float momentum,
                                    float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
                                    int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const double mean = static_cast<double>(sum[c]) / count;
-  double var = static_cast<double>(sqsum[c]) / count - mean * mean;
+  double sum = 0.0, sqsum = 0.0;
+  for (int k = 0; k < slots; ++k) {   // fixed order: bitwise reproducible statistics
+    sum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
+    sqsum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+  }
+  const double mean = sum / count;
+  double var = sqsum / count - mean * mean;
   if (var < 0) var = 0;
   const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
   const float sc = gamma[c] * invstd;
@@ -219,11 +224,11 @@ __global__ void bn_finalize_kernel(const float* sum, const float* sqsum, double 
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
-void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+void bn_finalize(const float* partial, int slots, double count, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                  float* save_mean, float* save_invstd, int C, cudaStream_t s) {
-  ProfileScope prof("bn_finalize", s, 0, 40.0 * C);
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sum, sqsum, count, gamma, beta, running_mean, running_var,
+  ProfileScope prof("bn_finalize", s, 0, (8.0 * slots + 40.0) * C);
+  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, s>>>(partial, slots, count, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, save_mean, save_invstd, C);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -346,7 +351,7 @@ template <int MASK>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
                      const float* __restrict__ scale, const float* __restrict__ shift,
-                     const float* __restrict__ mean, const float* __restrict__ invstd, float* dgamma, float* dbeta,
+                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
                      int64_t rows, int cvec) {
   __shared__ float red[16][256];
   const int lanes = cvec < 256 ? cvec : 256;   // threads along the channel dimension (cvec <= 256 for C <= 2048)
@@ -407,15 +412,32 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
         s0 += red[k][r * lanes + oc];
         s1 += red[8 + k][r * lanes + oc];
       }
-      atomicAdd(dbeta + c0 + k, s0);
-      atomicAdd(dgamma + c0 + k, s1);
+      // partial[block][0][c] = sum g, partial[block][1][c] = sum g * xhat
+      partial[(static_cast<size_t>(blockIdx.x) * 2 + 0) * (cvec * 8) + c0 + k] = s0;
+      partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * (cvec * 8) + c0 + k] = s1;
     }
   }
 }
 
+__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta,
+                                       int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double sb = 0.0, sg = 0.0;
+  for (int k = 0; k < blocks; ++k) {
+    sb += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
+    sg += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+  }
+  dbeta[c] += static_cast<float>(sb);
+  dgamma[c] += static_cast<float>(sg);
+}
+
+int64_t bn_bwd_scratch_elems() { return 4LL * num_sms() * 2 * 2048; }
+
 void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
-                   int mask_mode, cudaStream_t s) {
+                   int mask_mode, float* scratch, cudaStream_t s) {
+  ARGUS_CHECK(scratch != nullptr, "bn_bwd_reduce needs a scratch buffer");
   std::string fam = "bn_bwd_reduce";
   if (profile_enabled() && profile_detailed()) fam += ":R" + std::to_string(rows) + "_C" + std::to_string(C) + "_m" + std::to_string(mask_mode);
   ProfileScope prof(fam, s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
@@ -429,14 +451,16 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
   auto X = reinterpret_cast<const uint4*>(x);
   auto O = reinterpret_cast<const uint4*>(out);
   switch (mask_mode) {
-    case 0: bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec); break;
-    case 1: bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec); break;
+    case 0: bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
+    case 1: bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
     case 2:
       ARGUS_CHECK(out != nullptr, "mask_mode 2 needs the block output");
-      bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, rows, cvec);
+      bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
       break;
     default: throw Error("bad mask_mode");
   }
+  ARGUS_CUDA(cudaGetLastError());
+  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, s>>>(scratch, grid, dgamma, dbeta, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -117,35 +117,45 @@ void linear_bwd(float* dy, const float* pre, const float* x, const float* w, flo
 // ------------------------------------------------------------------------------------------------------------
 // pose loss (forward + analytic backward) and pose exponential
 // ------------------------------------------------------------------------------------------------------------
-__global__ void pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                                 float* __restrict__ loss, float* loss_mean, float* __restrict__ grad, int B,
-                                 float grad_scale) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  float l = 0.f;
-  if (b < B) {
+// One block: thread t handles samples t, t + blockDim, ...; the batch mean is reduced in a fixed order
+// (deterministic) and ADDED to *loss_mean.
+__global__ void __launch_bounds__(1024)
+pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
+                 float* loss_mean, float* __restrict__ grad, int B, float grad_scale) {
+  __shared__ double red[32];
+  double acc = 0.0;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
     double p[6], t[7], g[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) p[k] = pred[b * 6 + k];
 #pragma unroll
     for (int k = 0; k < 7; ++k) t[k] = target[b * 7 + k];
     const double lv = se3::pose_loss_and_grad(p, t, g);
-    l = static_cast<float>(lv);
-    if (loss != nullptr) loss[b] = l;
+    acc += lv;
+    if (loss != nullptr) loss[b] = static_cast<float>(lv);
     if (grad != nullptr) {
 #pragma unroll
       for (int k = 0; k < 6; ++k) grad[b * 6 + k] = static_cast<float>(g[k] * grad_scale);
     }
   }
   if (loss_mean != nullptr) {
-    l = warp_sum(l);
-    if ((threadIdx.x & 31) == 0) atomicAdd(loss_mean, l / B);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (blockDim.x + 31) / 32; ++w) tot += red[w];
+      *loss_mean += static_cast<float>(tot / B);
+    }
   }
 }
 void pose_loss_fwd_bwd(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
                        float grad_scale, cudaStream_t s) {
   ProfileScope prof("pose_loss", s, 0, 80.0 * B);
   if (B <= 0) return;
-  pose_loss_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, target, loss, loss_mean, grad, B, grad_scale);
+  const int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
+  pose_loss_kernel<<<1, threads, 0, s>>>(pred, target, loss, loss_mean, grad, B, grad_scale);
   ARGUS_CUDA(cudaGetLastError());
 }
 

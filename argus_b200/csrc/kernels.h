@@ -43,7 +43,8 @@ void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* 
 
 // ---- batch norm -------------------------------------------------------------------------------------------
 // train: batch statistics -> scale/shift (+ saved mean/invstd, running-stat update, torch.nn.BatchNorm2d semantics)
-void bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+// partial: [slots][2][C] per-(CTA, epilogue group) sums written by the conv epilogue, added here in slot order
+void bn_finalize(const float* partial, int slots, double count, const float* gamma, const float* beta,
                  float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                  float* save_mean, float* save_invstd, int C, cudaStream_t s);
 // eval: running statistics -> scale/shift
@@ -54,9 +55,12 @@ void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16*
               const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s);
 // mask_mode: 0 = no ReLU after this BN, 1 = ReLU directly after (mask recomputed from x), 2 = ReLU after a residual
 // add (mask = out > 0). Accumulates dgamma += sum(g * xhat), dbeta += sum(g) with g = masked dy.
+// Deterministic: every block writes its partial sums to `scratch` (>= bn_bwd_scratch_elems() floats), a second tiny
+// kernel adds them in block order.
 void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
-                   int mask_mode, cudaStream_t s);
+                   int mask_mode, float* scratch, cudaStream_t s);
+int64_t bn_bwd_scratch_elems();
 // dx = scale * (g - dbeta/rows - xhat * dgamma/rows); mask_mode 2 also overwrites dy with g (the identity branch
 // of the residual block consumes it).
 void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,

@@ -37,6 +37,8 @@ Model::~Model() {
   cudaFree(gpacked_);
   cudaFree(bn_scratch_);
   cudaFree(bn_stats_);
+  cudaFree(bn_bwd_scratch_);
+  cudaFree(wgrad_scratch_);
   cudaFree(pack_table_dev_);
   cudaFree(arena_);
 }
@@ -78,8 +80,8 @@ void Model::build_layout() {
     c.bn.rv_off = add_buffer(bn_name + ".running_var", cout);
     c.bn.scratch_off = n_bn_scratch_;
     n_bn_scratch_ += 4 * cout;
-    c.bn.stat_off = n_bn_stats_;
-    n_bn_stats_ += 2 * cout;
+    c.bn.stat_off = n_bn_stats_;   // in units of "channels"; scaled by 2 * max_stat_slots_ at bind time
+    n_bn_stats_ += cout;
     const int64_t packed_elems = (kind == 1) ? 64 * 256 : static_cast<int64_t>(cout) * cin * k * k;
     c.packed_off = n_packed_;
     n_packed_ += (packed_elems + 63) / 64 * 64;
@@ -159,7 +161,9 @@ void Model::bind(float* params, float* grads, float* buffers) {
     ARGUS_CUDA(cudaMalloc(&packed_, n_packed_ * sizeof(bf16)));
     ARGUS_CUDA(cudaMalloc(&gpacked_, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
     ARGUS_CUDA(cudaMalloc(&bn_scratch_, n_bn_scratch_ * sizeof(float)));
-    ARGUS_CUDA(cudaMalloc(&bn_stats_, n_bn_stats_ * sizeof(float)));
+    max_stat_slots_ = 2 * num_sms();
+    ARGUS_CUDA(cudaMalloc(&bn_stats_, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float)));
+    ARGUS_CUDA(cudaMalloc(&bn_bwd_scratch_, bn_bwd_scratch_elems() * sizeof(float)));
     ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
     ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
                           cudaMemcpyHostToDevice));
@@ -317,6 +321,7 @@ void Model::build_plan(Plan& p) {
   for (int i = 0; i < 5; ++i) G[i] = arena_alloc<bf16>(max_elems);
   if (real) {
     p.fc.wgrad = plan_conv_wgrad(fc_.shape, p.d_feat, p.pooled, grads_dev_ + fc_.w_off);
+    ensure_wgrad_scratch(p.fc.wgrad);
     p.fc.dgrad = plan_conv_dgrad(fc_.shape, p.d_feat, packed_ + fc_.packed_off, p.d_pooled);
   }
   // rotate the five scratch buffers through the blocks in reverse order (see Model::backward)
@@ -340,14 +345,21 @@ void Model::build_plan(Plan& p) {
         // downsample: dy = R (dRawd), input x, dx -> T
         bp.ds.wgrad = plan_conv_wgrad(br.ds.shape, R, bp.x, wg_dst(br.ds));
         bp.ds.dgrad = plan_conv_dgrad(br.ds.shape, R, packed_ + br.ds.packed_off, T);
+        ensure_wgrad_scratch(bp.ds.wgrad);
       }
+      ensure_wgrad_scratch(bp.c1.wgrad);
+      ensure_wgrad_scratch(bp.c2.wgrad);
+      ensure_wgrad_scratch(bp.c3.wgrad);
     }
     std::swap(P, S);  // this block's input gradient is the previous block's output gradient
   }
   p.g_stem_in = P;
   p.g_act0 = Q;
   p.g_raw0 = R;
-  if (real) p.stem.wgrad = plan_conv_wgrad(stem_.shape, R, p.x_s2d, gpacked_ + stem_.gpacked_off);
+  if (real) {
+    p.stem.wgrad = plan_conv_wgrad(stem_.shape, R, p.x_s2d, gpacked_ + stem_.gpacked_off);
+    ensure_wgrad_scratch(p.stem.wgrad);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -369,17 +381,16 @@ void Model::fold_eval(cudaStream_t s) {
 
 void Model::run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s) {
   Epilogue e;
-  e.stat_sum = bn_stats_ + c.bn.stat_off;
-  e.stat_sqsum = e.stat_sum + c.bn.C;
+  e.stat_partial = bn_stats_ + c.bn.stat_off * 2 * max_stat_slots_;
   launch_conv(cp.fwd, e, s);
   float* sc = bn_scratch_ + c.bn.scratch_off;
-  bn_finalize(e.stat_sum, e.stat_sqsum, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
+  bn_finalize(e.stat_partial, stat_slots(cp.fwd), static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
               params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off, buffers_dev_ + c.bn.rv_off, kBnMomentum, kBnEps,
               sc, sc + c.bn.C, sc + 2 * c.bn.C, sc + 3 * c.bn.C, c.bn.C, s);
 }
 
 void Model::forward_train(Plan& p, cudaStream_t s) {
-  ARGUS_CUDA(cudaMemsetAsync(bn_stats_, 0, n_bn_stats_ * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(bn_stats_, 0, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float), s));
   eval_fold_dirty_ = true;  // scale/shift scratch now holds batch statistics
   const int N = p.N;
   auto SC = [&](const ConvRef& c) { return bn_scratch_ + c.bn.scratch_off; };
@@ -503,6 +514,34 @@ void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_
 // ------------------------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------------------------
+void Model::ensure_wgrad_scratch(const WgradLaunch& l) {
+  const int64_t need = wgrad_scratch_elems(l);
+  if (need > wgrad_scratch_elems_) {
+    // plan-build time only (never on the hot path); all streams are idle for this model at that point
+    ARGUS_CUDA(cudaDeviceSynchronize());
+    if (wgrad_scratch_) ARGUS_CUDA(cudaFree(wgrad_scratch_));
+    ARGUS_CUDA(cudaMalloc(&wgrad_scratch_, need * sizeof(float)));
+    wgrad_scratch_elems_ = need;
+  }
+}
+
+// All weight-gradient GEMMs of a backward pass run on ONE stream (the side stream when overlapping), so a single
+// split-K scratch buffer is enough.
+void Model::run_wgrad(const WgradLaunch& l, cudaStream_t s) {
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (!overlap_wgrad_ || cap != cudaStreamCaptureStatusNone) {
+    join_wgrad(s);
+    launch_wgrad(l, wgrad_scratch_, s);
+    return;
+  }
+  ARGUS_CUDA(cudaEventRecord(ev_fork_, s));
+  ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
+  launch_wgrad(l, wgrad_scratch_, side_);
+  ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_));
+  wgrad_pending_ = true;
+}
+
 void Model::join_wgrad(cudaStream_t s) {
   if (wgrad_pending_) {
     ARGUS_CUDA(cudaStreamWaitEvent(s, ev_wgrad_, 0));
@@ -516,7 +555,7 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
   float* dgamma = grads_dev_ + c.bn.gamma_off;
   float* dbeta = grads_dev_ + c.bn.beta_off;
   const int C = c.bn.C;
-  bn_bwd_reduce(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, rows, C, mask, s);
+  bn_bwd_reduce(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, rows, C, mask, bn_bwd_scratch_, s);
   // the apply pass overwrites a gradient buffer that an in-flight weight-gradient GEMM may still be reading
   join_wgrad(s);
   bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
@@ -524,21 +563,7 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
 
 void Model::conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s) {
   // fork: the weight gradient only needs dRaw and the saved activation, both final at this point
-  join_wgrad(s);
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(s, &cap);
-  if (!overlap_wgrad_ || cap != cudaStreamCaptureStatusNone) {
-    launch_wgrad(cp.wgrad, s);
-    Epilogue e0;
-    e0.residual = residual;
-    for (const auto& l : cp.dgrad) launch_conv(l, e0, s);
-    return;
-  }
-  ARGUS_CUDA(cudaEventRecord(ev_fork_, s));
-  ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
-  launch_wgrad(cp.wgrad, side_);
-  ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_));
-  wgrad_pending_ = true;
+  run_wgrad(cp.wgrad, s);
   Epilogue e;
   e.residual = residual;
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
@@ -570,7 +595,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       { ProfileScope prof("head", s, 0, 2.0 * N * out_dim_); }
       colsum_bf16_kernel<<<(out_dim_ + 127) / 128, 128, 0, s>>>(p.d_feat, g + fc_bias_off_, N, out_dim_);
       ARGUS_CUDA(cudaGetLastError());
-      launch_wgrad(p.fc.wgrad, s);
+      run_wgrad(p.fc.wgrad, s);
       Epilogue e;
       for (const auto& l : p.fc.dgrad) launch_conv(l, e, s);
       avgpool_bwd(p.d_pooled, p.blocks.back().g_out, N, p.final_hw, 2048, s);
@@ -603,7 +628,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       ARGUS_CUDA(cudaMemsetAsync(gpacked_ + stem_.gpacked_off, 0, 64 * 256 * sizeof(float), s));
       maxpool_bwd(p.g_stem_in, p.idx0, p.g_act0, N, p.H / 2, p.W / 2, 64, s);
       bn_backward(stem_, p.g_act0, p.raw0, nullptr, p.g_raw0, static_cast<int64_t>(N) * (p.H / 2) * (p.W / 2), 1, s);
-      launch_wgrad(p.stem.wgrad, s);
+      run_wgrad(p.stem.wgrad, s);
     }
     join_wgrad(s);
     // packed 3x3 / stem gradients of this stage -> PyTorch layout in the gradient arena

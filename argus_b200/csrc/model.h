@@ -29,7 +29,7 @@ struct BnRef {
   int64_t gamma_off = 0, beta_off = 0;  // parameter arena
   int64_t rm_off = 0, rv_off = 0;       // buffer arena
   int64_t scratch_off = 0;              // bn scratch arena: scale, shift, mean, invstd (4*C floats)
-  int64_t stat_off = 0;                 // statistics arena: sum, sqsum (2*C floats)
+  int64_t stat_off = 0;                 // statistics arena: [max_slots][2][C] per-CTA partial sums
 };
 
 struct ConvRef {
@@ -148,6 +148,12 @@ class Model {
   float* gpacked_ = nullptr;
   float* bn_scratch_ = nullptr;
   float* bn_stats_ = nullptr;
+  float* bn_bwd_scratch_ = nullptr;   // per-block partial sums of the BN-backward reductions
+  float* wgrad_scratch_ = nullptr;    // split-K partial weight gradients (one launch at a time)
+  int64_t wgrad_scratch_elems_ = 0;
+  int max_stat_slots_ = 0;
+  void ensure_wgrad_scratch(const WgradLaunch& l);
+  void run_wgrad(const WgradLaunch& l, cudaStream_t s);
   int64_t n_packed_ = 0, n_gpacked_ = 0, n_bn_scratch_ = 0, n_bn_stats_ = 0;
   WeightPackEntry* pack_table_dev_ = nullptr;
   std::vector<WeightPackEntry> pack_table_;

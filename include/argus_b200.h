@@ -45,7 +45,11 @@ int argus_profile_report(char* json, int cap);
  * argus_pack_stem_weight); N, H, W always describe the conv input image. */
 int argus_conv2d_forward(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, int k,
                          int stride, int kind, const float* scale, const float* shift, const void* residual, int relu,
-                         float* stat_sum, float* stat_sqsum, void* stream);
+                         float* stat_partial, int stat_slot_capacity, void* stream);
+/* Train-mode BN statistics are reduced deterministically: stat_partial is a zero-filled [slots][2][Cout] fp32 buffer
+ * (per-CTA partial sums / sums of squares of the stored bf16 outputs) that argus_bn_finalize adds in slot order.
+ * argus_conv2d_stat_slots returns an upper bound on the slots a forward launch of this shape writes. */
+int argus_conv2d_stat_slots(int N, int H, int W, int Cin, int Cout, int k, int stride, int kind, int* slots);
 /* dx = conv_transpose(dy, w) (+ residual). For stride 2 the caller zero-fills dx first when k == 1. */
 int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, const void* residual, void* stream);
@@ -56,8 +60,9 @@ int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, i
 /* ---- batch norm / pooling primitives (torch.nn.BatchNorm2d, ReLU, MaxPool2d(3,2,1), AdaptiveAvgPool2d(1) inside
  *      torchvision resnet50, argus/models.py:84). x, y, dy, dx, res, out: bf16 NHWC viewed as (rows, C); C/8 a
  *      power of two; per-channel vectors fp32. ------------------------------------------------------------------ */
-/* train-mode statistics -> scale/shift/mean/invstd and running-stat update (running_* nullable) */
-int argus_bn_finalize(const float* sum, const float* sqsum, double count, const float* gamma, const float* beta,
+/* train-mode statistics ([slots][2][C] partial sums, see argus_conv2d_forward) -> scale/shift/mean/invstd and
+ * running-stat update (running_* nullable) */
+int argus_bn_finalize(const float* partial, int slots, double count, const float* gamma, const float* beta,
                       float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                       float* save_mean, float* save_invstd, int C, void* stream);
 /* y = [relu](x*scale+shift [+ res | + res*rscale+rshift]) */

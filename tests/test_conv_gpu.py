@@ -51,10 +51,12 @@ def test_conv_forward(cuda_device, case):
     xb, wb = nhwc(x), pack_w(w)
     Ho, Wo = H // s, W // s
     y = torch.full((N, Ho, Wo, Cout), float("nan"), device=cuda_device, dtype=torch.bfloat16)
-    ssum = torch.zeros(Cout, device=cuda_device)
-    ssq = torch.zeros(Cout, device=cuda_device)
-    _lib.call("argus_conv2d_forward", xb, wb, y, N, H, W, Cin, Cout, k, s, 0, None, None, None, 0, ssum, ssq,
-              _lib.stream_ptr())
+    import ctypes
+    slots = ctypes.c_int()
+    _lib.check(_lib.load().argus_conv2d_stat_slots(N, H, W, Cin, Cout, k, s, 0, ctypes.byref(slots)))
+    partial = torch.zeros(slots.value, 2, Cout, device=cuda_device)
+    _lib.call("argus_conv2d_forward", xb, wb, y, N, H, W, Cin, Cout, k, s, 0, None, None, None, 0, partial,
+              slots.value, _lib.stream_ptr())
     torch.cuda.synchronize()
     ref = F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float().permute(0, 3, 1, 2), stride=s, padding=k // 2)
     got = from_nhwc(y)
@@ -62,8 +64,15 @@ def test_conv_forward(cuda_device, case):
     assert rel_err(got, ref) < 5e-3
     assert (got - ref).abs().max().item() < 0.06
     yf = y.float().reshape(-1, Cout)
-    assert torch.allclose(ssum, yf.sum(0), rtol=1e-3, atol=1e-2)
-    assert torch.allclose(ssq, (yf * yf).sum(0), rtol=1e-3, atol=1e-2)
+    ssum, ssq = partial.double().sum(0)
+    assert torch.allclose(ssum, yf.double().sum(0), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(ssq, (yf.double() ** 2).sum(0), rtol=1e-4, atol=1e-2)
+    # deterministic reduction: a second launch reproduces every partial sum bit for bit
+    partial2 = torch.zeros_like(partial)
+    _lib.call("argus_conv2d_forward", xb, wb, y, N, H, W, Cin, Cout, k, s, 0, None, None, None, 0, partial2,
+              slots.value, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(partial, partial2)
 
 
 def test_conv_forward_fused_epilogue(cuda_device):
@@ -76,7 +85,7 @@ def test_conv_forward_fused_epilogue(cuda_device):
     res = nhwc(torch.randn(N, Cout, H, W, generator=g).to(cuda_device))
     xb, wb = nhwc(x), pack_w(w)
     y = torch.empty((N, H, W, Cout), device=cuda_device, dtype=torch.bfloat16)
-    _lib.call("argus_conv2d_forward", xb, wb, y, N, H, W, Cin, Cout, k, s, 0, scale, shift, res, 1, None, None,
+    _lib.call("argus_conv2d_forward", xb, wb, y, N, H, W, Cin, Cout, k, s, 0, scale, shift, res, 1, None, 0,
               _lib.stream_ptr())
     torch.cuda.synchronize()
     ref = F.conv2d(xb.float().permute(0, 3, 1, 2), wb.float().permute(0, 3, 1, 2))
@@ -123,6 +132,10 @@ def test_conv_wgrad(cuda_device, case):
     out.backward(dyb.float().permute(0, 3, 1, 2))
     ref = wr.grad.permute(0, 2, 3, 1)
     assert rel_err(dw, ref) < 2e-3
+    dw2 = torch.zeros_like(dw)
+    _lib.call("argus_conv2d_wgrad", dyb, xb, dw2, N, H, W, Cin, Cout, k, s, 0, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(dw, dw2)  # split-K partials are reduced in a fixed order
 
 
 def s2d_pack(img):
@@ -159,7 +172,7 @@ def test_stem(cuda_device, N, H, W):
     w = (torch.randn(64, 3, 7, 7, generator=g) / 147 ** 0.5).to(cuda_device)
     xs, ws = s2d_pack(img), stem_pack_w(w)
     y = torch.empty((N, H // 2, W // 2, 64), device=cuda_device, dtype=torch.bfloat16)
-    _lib.call("argus_conv2d_forward", xs, ws, y, N, H, W, 3, 64, 7, 2, 1, None, None, None, 0, None, None,
+    _lib.call("argus_conv2d_forward", xs, ws, y, N, H, W, 3, 64, 7, 2, 1, None, None, None, 0, None, 0,
               _lib.stream_ptr())
     torch.cuda.synchronize()
     ref = F.conv2d(img.to(torch.bfloat16).float(), w.to(torch.bfloat16).float(), stride=2, padding=3)

@@ -34,11 +34,15 @@ def test_bn_finalize_and_apply(cuda_device, rows, C):
     beta = torch.randn(C, generator=g).to(cuda_device)
     res = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
     xf = x.float()
-    ssum, ssq = xf.sum(0), (xf * xf).sum(0)
+    partial = torch.zeros(3, 2, C, device=cuda_device)           # three "CTA slots", as the conv epilogue writes them
+    bounds = [0, rows // 3, rows // 2, rows]
+    for k in range(3):
+        partial[k, 0] = xf[bounds[k]:bounds[k + 1]].sum(0)
+        partial[k, 1] = (xf[bounds[k]:bounds[k + 1]] ** 2).sum(0)
     rm, rv = torch.zeros(C, device=cuda_device), torch.ones(C, device=cuda_device)
     scale, shift, mean, invstd = (torch.empty(C, device=cuda_device) for _ in range(4))
     lib = _lib.load()
-    _lib.check(lib.argus_bn_finalize(_lib.ptr(ssum), _lib.ptr(ssq), ctypes.c_double(rows), _lib.ptr(gamma), _lib.ptr(beta),
+    _lib.check(lib.argus_bn_finalize(_lib.ptr(partial), ctypes.c_int(3), ctypes.c_double(rows), _lib.ptr(gamma), _lib.ptr(beta),
                                      _lib.ptr(rm), _lib.ptr(rv), ctypes.c_float(0.1), ctypes.c_float(1e-5),
                                      _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean), _lib.ptr(invstd), ctypes.c_int(C),
                                      _lib.stream_ptr()))
@@ -102,6 +106,16 @@ def test_bn_backward(cuda_device, rows, C, mask):
     assert rel < 4e-3, rel
     if mask == 2:
         assert torch.equal(dy_io, (dy.float() * (out_bf16.float() > 0)).bfloat16())
+    # deterministic: a second call reproduces the reductions bit for bit
+    dgamma2, dbeta2 = torch.zeros_like(dgamma), torch.zeros_like(dbeta)
+    dx2 = torch.empty_like(dx)
+    dy_io2 = dy.clone()
+    _lib.check(_lib.load().argus_bn_backward(_lib.ptr(dy_io2), _lib.ptr(x), _lib.ptr(out_arg), _lib.ptr(scale), _lib.ptr(shift),
+                                             _lib.ptr(mean.detach()), _lib.ptr(invstd.detach()), _lib.ptr(dgamma2),
+                                             _lib.ptr(dbeta2), _lib.ptr(dx2), ctypes.c_int64(rows), ctypes.c_int(C),
+                                             ctypes.c_int(mask), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(dgamma, dgamma2) and torch.equal(dbeta, dbeta2) and torch.equal(dx, dx2)
 
 
 @pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 64, 32, 64), (1, 8, 8, 128)])

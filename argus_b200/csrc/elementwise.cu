@@ -198,17 +198,29 @@ void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntr
 // ------------------------------------------------------------------------------------------------------------
 // batch norm: finalize / fold
 // ------------------------------------------------------------------------------------------------------------
-__global__ void bn_finalize_kernel(const float* __restrict__ partial, int slots, double count, const float* gamma,
-                                   const float* beta, float* running_mean, float* running_var, float momentum,
-                                   float eps, float* scale, float* shift, float* save_mean, float* save_invstd,
-                                   int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 8 channels x 32 slot lanes: lane sl adds slots sl, sl+32, ... in order, then lane 0 adds the 32 lane sums in
+// order -> the statistics are bitwise reproducible and the slot loop is 32-way parallel.
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float* __restrict__ partial, int slots, double count, const float* gamma, const float* beta,
+                   float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
+                   float* save_mean, float* save_invstd, int C) {
+  __shared__ double red[2][32][8];
+  const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + ch;
   double sum = 0.0, sqsum = 0.0;
-  for (int k = 0; k < slots; ++k) {   // fixed order: bitwise reproducible statistics
-    sum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
-    sqsum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+  if (c < C) {
+    for (int k = sl; k < slots; k += 32) {
+      sum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
+      sqsum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+    }
   }
+  red[0][sl][ch] = sum;
+  red[1][sl][ch] = sqsum;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  sum = 0.0;
+  sqsum = 0.0;
+  for (int k = 0; k < 32; ++k) { sum += red[0][k][ch]; sqsum += red[1][k][ch]; }
   const double mean = sum / count;
   double var = sqsum / count - mean * mean;
   if (var < 0) var = 0;
@@ -228,7 +240,7 @@ void bn_finalize(const float* partial, int slots, double count, const float* gam
                  float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                  float* save_mean, float* save_invstd, int C, cudaStream_t s) {
   ProfileScope prof("bn_finalize", s, 0, (8.0 * slots + 40.0) * C);
-  bn_finalize_kernel<<<(C + 63) / 64, 64, 0, s>>>(partial, slots, count, gamma, beta, running_mean, running_var,
+  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, slots, count, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, save_mean, save_invstd, C);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -419,15 +431,25 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
   }
 }
 
-__global__ void bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta,
-                                       int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256)
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta, int C) {
+  __shared__ double red[2][32][8];
+  const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + ch;
   double sb = 0.0, sg = 0.0;
-  for (int k = 0; k < blocks; ++k) {
-    sb += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
-    sg += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+  if (c < C) {
+    for (int k = sl; k < blocks; k += 32) {
+      sb += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
+      sg += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+    }
   }
+  red[0][sl][ch] = sb;
+  red[1][sl][ch] = sg;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  sb = 0.0;
+  sg = 0.0;
+  for (int k = 0; k < 32; ++k) { sb += red[0][k][ch]; sg += red[1][k][ch]; }
   dbeta[c] += static_cast<float>(sb);
   dgamma[c] += static_cast<float>(sg);
 }
@@ -460,7 +482,7 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
     default: throw Error("bad mask_mode");
   }
   ARGUS_CUDA(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(C + 63) / 64, 64, 0, s>>>(scratch, grid, dgamma, dbeta, C);
+  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, grid, dgamma, dbeta, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -572,4 +572,175 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Weight gradient for Cout == 64 layers (stem, layer1): transposed formulation dW^T[ci, co] = X_tap^T * dY.
+// The M=128 operand stacks two 64-wide input-channel boxes (two filter taps, or two channel blocks of a 1x1
+// convolution), N = 64 output channels, K = pixels. One CTA owns a contiguous pixel range and ALL boxes: the dY
+// tile is loaded once per 64 pixels instead of once per tap, no half-empty M tile is issued, and the per-CTA
+// result goes to its own slot of the split-K scratch (reduced in order afterwards).
+// ---------------------------------------------------------------------------------------------------------
+struct XposeBox {
+  int8_t map, dh, dw, valid;
+  int16_t c_off;     // channel coordinate of the box in the activation tensor
+  int16_t out_off;   // column offset inside one dW row
+};
+struct WgradXposeParams {
+  CUtensorMap dy_map;     // 2-D [pixels, 64], box (64 co, 64 pixels)
+  CUtensorMap a_map[4];   // 4-D activation maps, box (64 ch, 64-pixel box)
+  XposeBox boxes[10];
+  int num_splits;         // = gridDim.x
+  int kblocks_total;
+  int log2_wo, log2_howo;
+  int dw_row_stride;
+  float* partial;         // [num_splits][64][dw_row_stride]
+};
+
+template <int NBOX>   // padded to an even number: 2, 4 or 10
+struct WgradXposeSmem {
+  static constexpr int kStageBytes = 8192 + NBOX * 8192;
+  static constexpr int kStagesRaw = 196608 / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kOffBars = kStages * kStageBytes;
+  static constexpr int kNumBars = 2 * kStages + 1;
+  static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+  static constexpr int kTotal = kOffTmemPtr + 16;
+};
+
+template <int NBOX>
+__global__ void __launch_bounds__(kWgradThreads, 1)
+wgrad_xpose_kernel(const __grid_constant__ WgradXposeParams p) {
+  using L = WgradXposeSmem<NBOX>;
+  constexpr int kStages = L::kStages;
+  constexpr int kPairs = NBOX / 2;
+  constexpr int kTmemCols = kPairs * 64 <= 64 ? 64 : (kPairs * 64 <= 128 ? 128 : (kPairs * 64 <= 256 ? 256 : 512));
+
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t smem_base = smem_u32(smem);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base + L::kOffBars;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+  const uint32_t done_bar = bar_base + 8u * (2 * kStages);
+  volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
+
+  // boxes that are never loaded (odd tap count) must read as zeros
+  int n_valid = 0;
+  for (int b = 0; b < NBOX; ++b) n_valid += p.boxes[b].valid ? 1 : 0;
+  for (int s = 0; s < kStages; ++s)
+    for (int b = 0; b < NBOX; ++b)
+      if (!p.boxes[b].valid) {
+        uint4* z = reinterpret_cast<uint4*>(smem + s * L::kStageBytes + 8192 + b * 8192);
+        for (int i = threadIdx.x; i < 512; i += kWgradThreads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+      }
+  fence_proxy_async_smem();
+
+  if (threadIdx.x == 0) {
+    if (smem_base & 1023u) __trap();
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.dy_map);
+    for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int per = (p.kblocks_total + p.num_splits - 1) / p.num_splits;
+  const int kb0 = blockIdx.x * per;
+  const int kb1 = min(kb0 + per, p.kblocks_total);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        const int p0 = kb * 64;
+        const int img0 = p0 >> p.log2_howo;
+        const int rem = p0 & ((1 << p.log2_howo) - 1);
+        const int h0 = rem >> p.log2_wo;
+        const int w0 = rem & ((1 << p.log2_wo) - 1);
+        mbar_wait(empty_bar(stage), phase ^ 1);
+        const uint32_t sb = smem_base + stage * L::kStageBytes;   // dY tile first, then the boxes
+        mbar_arrive_expect_tx(full_bar(stage), 8192u * (1 + n_valid));
+        tma_load_2d(&p.dy_map, full_bar(stage), sb, 0, p0);
+#pragma unroll
+        for (int b = 0; b < NBOX; ++b) {
+          const XposeBox bx = p.boxes[b];
+          if (bx.valid)
+            tma_load_4d(&p.a_map[bx.map], full_bar(stage), sb + 8192 + b * 8192, bx.c_off, w0 + bx.dw, h0 + bx.dh, img0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sb = smem_base + stage * L::kStageBytes;
+#pragma unroll
+        for (int j = 0; j < kPairs; ++j) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint64_t da = make_smem_desc_sw128(sb + 8192 + j * 16384 + k * 2048, 8192, 1024);
+            const uint64_t db = make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+            umma_bf16(tmem_base + j * 64, da, db, idesc, (kb > kb0) || (k != 0));
+          }
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int wq = warp & 3;
+    const int r = wq * 32 + lane;
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    float* base = p.partial + static_cast<size_t>(blockIdx.x) * 64 * p.dw_row_stride;
+#pragma unroll 1
+    for (int j = 0; j < kPairs; ++j) {
+      const XposeBox bx = p.boxes[2 * j + (r >> 6)];
+      float* col0 = base + bx.out_off + (r & 63);
+#pragma unroll 1
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + j * 64 + h * 32, v);
+        tmem_ld_wait();
+        if (bx.valid) {
+          if (kb1 > kb0) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col0[static_cast<size_t>(h * 32 + i) * p.dw_row_stride] = __uint_as_float(v[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) col0[static_cast<size_t>(h * 32 + i) * p.dw_row_stride] = 0.f;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace argus

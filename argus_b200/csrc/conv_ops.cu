@@ -411,6 +411,38 @@ WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const _
   p.cin = cin_tile_extent;
   p.dw_row_stride = s.Ktot();
   p.dw = dw;
+
+  // ---- Cout == 64: transposed all-taps formulation
+  const int n_boxes = (s.kind == 1) ? 4 : (s.k * s.k) * (s.Cin / 64);
+  // (measured: it wins for the stem and the 3x3 layer1 convolutions; 1x1 layers are HBM-bound either way)
+  if (s.Cout == 64 && n_boxes <= 10 && (s.kind == 1 || (s.k == 3 && s.Cin == 64))) {
+    WgradXposeParams& x = l.xp;
+    std::memset(&x, 0, sizeof(x));
+    x.dy_map = p.dy_map;
+    for (int i = 0; i < 4; ++i) x.a_map[i] = p.a_map[i];
+    int nb = 0;
+    for (int t = 0; t < p.num_taps; ++t)
+      for (int cb = 0; cb < cin_tile_extent / 64; ++cb) {
+        XposeBox b{};
+        b.map = p.taps[t].map; b.dh = p.taps[t].dh; b.dw = p.taps[t].dw; b.valid = 1;
+        b.c_off = static_cast<int16_t>(cb * 64);
+        b.out_off = static_cast<int16_t>(p.taps[t].b_off + cb * 64);
+        x.boxes[nb++] = b;
+      }
+    const int padded = nb <= 2 ? 2 : (nb <= 4 ? 4 : 10);
+    l.xpose_nbox = padded;
+    x.kblocks_total = p.kblocks_total;
+    x.num_splits = std::max(1, std::min(num_sms(), p.kblocks_total / 4));
+    while (x.num_splits > 1) {  // no empty split
+      const int per = (x.kblocks_total + x.num_splits - 1) / x.num_splits;
+      if (per * (x.num_splits - 1) < x.kblocks_total) break;
+      --x.num_splits;
+    }
+    x.log2_wo = p.log2_wo;
+    x.log2_howo = p.log2_howo;
+    x.dw_row_stride = p.dw_row_stride;
+    p.num_ksplits = x.num_splits;   // scratch sizing / reduce use the same field
+  }
   return l;
 }
 
@@ -467,6 +499,7 @@ int stat_slots(const ConvLaunch& l) {
 }
 
 int64_t wgrad_scratch_elems(const WgradLaunch& l) {
+  if (l.xpose_nbox > 0) return static_cast<int64_t>(l.xp.num_splits) * 64 * l.p.dw_row_stride;
   if (l.p.num_ksplits <= 1) return 0;
   return static_cast<int64_t>(l.p.num_ksplits) * l.p.cout * l.p.dw_row_stride;
 }
@@ -484,6 +517,18 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* 
     d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
     dw[i] = d;
   }
+}
+
+template <int NBOX>
+static void launch_wgrad_xpose_t(const WgradXposeParams& p, cudaStream_t stream) {
+  using L = WgradXposeSmem<NBOX>;
+  static bool configured = false;
+  if (!configured) {
+    ARGUS_CUDA(cudaFuncSetAttribute(wgrad_xpose_kernel<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    configured = true;
+  }
+  wgrad_xpose_kernel<NBOX><<<p.num_splits, kWgradThreads, L::kTotal, stream>>>(p);
+  ARGUS_CUDA(cudaGetLastError());
 }
 
 template <int BN>
@@ -509,14 +554,25 @@ void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
   const double flops = 2.0 * l.p.kblocks_total * 64.0 * l.p.cout * static_cast<double>(l.p.cin) * l.p.num_taps;
   std::string fam = "conv_wgrad";
   if (g_profiling && profile_detailed())
-    fam += ":P" + std::to_string(l.p.kblocks_total * 64) + "_Co" + std::to_string(l.p.cout) + "_Ci" +
+    fam += std::string(l.xpose_nbox > 0 ? "x" : "") + ":P" + std::to_string(l.p.kblocks_total * 64) + "_Co" + std::to_string(l.p.cout) + "_Ci" +
            std::to_string(l.p.cin) + "_t" + std::to_string(l.p.num_taps) + "_s" + std::to_string(l.p.num_ksplits);
   ProfileScope prof(fam, stream, flops, 0.0);
-  switch (l.block_n) {
-    case 64: launch_wgrad_t<64>(l.p, stream); break;
-    case 128: launch_wgrad_t<128>(l.p, stream); break;
-    case 256: launch_wgrad_t<256>(l.p, stream); break;
-    default: throw Error("unsupported wgrad tile configuration");
+  if (l.xpose_nbox > 0) {
+    ARGUS_CHECK(scratch != nullptr, "transposed weight gradient needs a scratch buffer");
+    l.xp.partial = scratch;
+    switch (l.xpose_nbox) {
+      case 2: launch_wgrad_xpose_t<2>(l.xp, stream); break;
+      case 4: launch_wgrad_xpose_t<4>(l.xp, stream); break;
+      case 10: launch_wgrad_xpose_t<10>(l.xp, stream); break;
+      default: throw Error("unsupported transposed wgrad configuration");
+    }
+  } else {
+    switch (l.block_n) {
+      case 64: launch_wgrad_t<64>(l.p, stream); break;
+      case 128: launch_wgrad_t<128>(l.p, stream); break;
+      case 256: launch_wgrad_t<256>(l.p, stream); break;
+      default: throw Error("unsupported wgrad tile configuration");
+    }
   }
   if (need > 0) {
     // every (split, cout, tap, ci) word of the scratch was written by exactly one work item

@@ -53,6 +53,9 @@ struct ConvLaunch {
 struct WgradLaunch {
   WgradParams p;
   int block_n = 64;
+  // Cout == 64 layers use the transposed all-taps kernel instead (xpose_nbox = padded box count, 0 = not used)
+  int xpose_nbox = 0;
+  WgradXposeParams xp;
 };
 
 void validate_shape(const ConvShape& s);

@@ -39,6 +39,8 @@ CASES = [
     (2, 4, 4, 512, 512, 3, 1),      # tile spans several images, M tail
     (6, 16, 16, 256, 256, 3, 2),
     (300, 1, 1, 2048, 1024, 1, 1),  # fully connected layer, ragged M
+    (2, 64, 64, 256, 64, 1, 1),     # Cout = 64: transposed all-taps weight-gradient kernel (4 channel boxes)
+    (3, 32, 32, 64, 64, 1, 1),      # ... single box, padded pair
 ]
 
 
@@ -93,7 +95,7 @@ def test_conv_forward_fused_epilogue(cuda_device):
     assert rel_err(from_nhwc(y), ref) < 5e-3
 
 
-@pytest.mark.parametrize("case", CASES[:9])
+@pytest.mark.parametrize("case", CASES[:9] + CASES[10:])
 def test_conv_dgrad(cuda_device, case):
     N, H, W, Cin, Cout, k, s = case
     g = torch.Generator(device="cpu").manual_seed(3)

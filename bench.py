@@ -67,6 +67,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append([c.strip() for c in line.split(",")])
 
+    def mark(self) -> None:
+        """Samples before this call (start-up, warm-up) are dropped from the summary."""
+        self.first = len(self.samples)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -77,7 +81,7 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in self.samples[getattr(self, "first", 0):]:
             if len(s) < 7:
                 continue
             try:
@@ -154,12 +158,19 @@ def run_ours(args) -> None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up, then the device-resident timed region
+    # ---- warm-up, then the device-resident timed region (nvidia-smi needs ~1 s to start: launch it first)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for i in range(args.warmup):
         engine.step(*dev_batches[i % ring])
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    t_wait = time.time()
+    while not sampler.samples and time.time() - t_wait < 5.0:
+        time.sleep(0.05)                      # (no collective in this loop: ranks may wait different amounts)
+    for i in range(2):                        # back under load before the timed region
+        engine.step(*dev_batches[i % ring])
+    barrier()
+    sampler.mark()
     launches0 = lib.argus_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -428,7 +439,7 @@ def run_reference(args) -> None:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="image pairs per GPU")

@@ -69,7 +69,7 @@ struct ConvGemmSmem {
   static constexpr int kOffStaging = kStages * kStageBytes;      // 2 buffers per epilogue group
   static constexpr int kOffStats = kOffStaging + 4 * kStagingBytes;
   static constexpr int kOffBars = kOffStats + 2 * 4 * 2 * BLOCK_N * 4;   // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
-  static constexpr int kNumBars = 2 * kStages + 6;
+  static constexpr int kNumBars = 2 * kStages + 8;   // full/empty per stage, tmem full/empty x2, residual x(2 groups x 2 buffers)
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
 };
@@ -92,7 +92,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kStages + s); };
   auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kStages + 2 + s); };
-  auto res_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 4 + g); };
+  auto res_bar = [&](int g, int b) { return bar_base + 8u * (2 * kStages + 4 + 2 * g + b); };
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
   float* s_stats_all = reinterpret_cast<float*>(smem + L::kOffStats);
 
@@ -105,7 +105,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp of the owning group
-      mbar_init(res_bar(s), 1);
+      mbar_init(res_bar(s, 0), 1);
+      mbar_init(res_bar(s, 1), 1);
     }
     fence_mbar_init();
   }
@@ -212,29 +213,44 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint8_t* stg_base = smem + L::kOffStaging + grp * 2 * L::kStagingBytes;
     const int acc = grp;
     uint32_t acc_phase = 0;
-    uint32_t res_phase = 0;
+    uint32_t res_phase[2] = {0, 0};
     int buf = 0;
     int cur_n = -1;
     const bool do_stats = (p.stat_partial != nullptr);
     float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(2 * blockIdx.x + grp) * 2 * p.n_total : nullptr;
+    constexpr int kChunks = BLOCK_N / 64;
 
     auto flush_stats = [&](int n_tile) {
       named_bar_sync(bar_id, 128);
       for (int c = et; c < 2 * BLOCK_N; c += 128) {
         const int which = c / BLOCK_N, col = c - which * BLOCK_N;
         const int gc = n_tile * BLOCK_N + col;
-        float acc = 0.f;
+        float acc_s = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          acc += s_stats[w * 2 * BLOCK_N + c];
+          acc_s += s_stats[w * 2 * BLOCK_N + c];
           s_stats[w * 2 * BLOCK_N + c] = 0.f;
         }
-        if (gc < p.n_total) my_partial[which * p.n_total + gc] += acc;   // only this thread ever touches this word
+        if (gc < p.n_total) my_partial[which * p.n_total + gc] += acc_s;   // only this thread ever touches this word
       }
       named_bar_sync(bar_id, 128);
     };
+    // residual tiles are prefetched one chunk ahead (into the staging buffer the NEXT chunk will use), so their TMA
+    // latency overlaps the current chunk's TMEM loads, math and store
+    auto issue_residual = [&](int tile, int ch, int b) {
+      const int m_tile = tile / p.num_n_tiles;
+      const int n_tile = tile - m_tile * p.num_n_tiles;
+      const int m0 = m_tile * kBlockM;
+      const int img0 = m0 >> p.log2_howo;
+      const int rem = m0 & ((1 << p.log2_howo) - 1);
+      mbar_arrive_expect_tx(res_bar(grp, b), L::kStagingBytes);
+      tma_load_4d(&p.res_map, res_bar(grp, b), smem_u32(stg_base + b * L::kStagingBytes), n_tile * BLOCK_N + ch * 64,
+                  rem & ((1 << p.log2_wo) - 1), rem >> p.log2_wo, img0);
+    };
+    const int first_tile = blockIdx.x + grp * gridDim.x;
+    if (p.has_res && store_leader && first_tile < num_tiles) issue_residual(first_tile, 0, 0);
 
-    for (int tile = blockIdx.x + grp * gridDim.x; tile < num_tiles; tile += 2 * gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += 2 * gridDim.x) {
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM;
@@ -252,15 +268,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       tc_fence_after();
 
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / 64; ++ch) {
+      for (int ch = 0; ch < kChunks; ++ch) {
         uint8_t* stg = stg_base + buf * L::kStagingBytes;
-        // staging buffer `buf` was handed to a TMA store two chunks ago: wait until that store has read it, then
-        // (optionally) start fetching the residual tile into it.
         if (store_leader) {
-          tma_store_wait_read<1>();
           if (p.has_res) {
-            mbar_arrive_expect_tx(res_bar(grp), L::kStagingBytes);
-            tma_load_4d(&p.res_map, res_bar(grp), smem_u32(stg), n0 + ch * 64, w0, h0, img0);
+            // the other buffer was handed to a TMA store one chunk ago: once that store has read it, refill it with
+            // the residual tile of the next chunk (this buffer's residual is already in flight / landed)
+            tma_store_wait_read<0>();
+            const bool last_ch = (ch == kChunks - 1);
+            const int ntile = last_ch ? tile + 2 * gridDim.x : tile;
+            if (ntile < num_tiles) issue_residual(ntile, last_ch ? 0 : ch + 1, buf ^ 1);
+          } else {
+            tma_store_wait_read<1>();   // this buffer was handed to a TMA store two chunks ago
           }
         }
         named_bar_sync(bar_id, 128);
@@ -271,15 +290,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           tmem_ld_32x32(taddr, v[h]);
         }
         tmem_ld_wait();
-        if (ch == BLOCK_N / 64 - 1) {
+        if (ch == kChunks - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
         if (p.has_res) {
-          mbar_wait(res_bar(grp), res_phase);
-          res_phase ^= 1;
+          mbar_wait(res_bar(grp, buf), res_phase[buf]);
+          res_phase[buf] ^= 1;
         }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {

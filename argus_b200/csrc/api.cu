@@ -99,6 +99,21 @@ int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, in
   ARGUS_API_END
 }
 
+int argus_conv2d_dgrad_bits(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int k,
+                            const void* residual, const void* residual_bits, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ConvShape s = make_shape(N, H, W, Cin, Cout, k, 1, 0);
+  ARGUS_CHECK(residual != nullptr && residual_bits != nullptr, "null argument");
+  auto ls = plan_conv_dgrad(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(w),
+                            static_cast<__nv_bfloat16*>(dx));
+  Epilogue e;
+  e.residual = static_cast<const __nv_bfloat16*>(residual);
+  e.residual_bits = static_cast<const uint8_t*>(residual_bits);
+  for (auto& l : ls) launch_conv(l, e, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream) {
   ARGUS_API_BEGIN
@@ -123,7 +138,15 @@ int argus_bn_apply(const void* x, const float* scale, const float* shift, const 
   ARGUS_API_BEGIN
   require_sm100();
   bn_apply(static_cast<const bf16*>(x), scale, shift, static_cast<const bf16*>(res), rscale, rshift, relu,
-           static_cast<bf16*>(y), rows, C, static_cast<cudaStream_t>(stream));
+           static_cast<bf16*>(y), nullptr, rows, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_bn_apply_bits(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
+                        const float* rshift, int relu, void* y, void* relu_bits, int64_t rows, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  bn_apply(static_cast<const bf16*>(x), scale, shift, static_cast<const bf16*>(res), rscale, rshift, relu,
+           static_cast<bf16*>(y), static_cast<uint8_t*>(relu_bits), rows, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 int argus_bn_backward(void* dy, const void* x, const void* out, const float* scale, const float* shift,
@@ -294,6 +317,12 @@ int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_pa
   ARGUS_CHECK(m != nullptr, "null model");
   m->impl.stage_input_u8(static_cast<const uint8_t*>(images), aug_params, B, H, W, training != 0, apply != 0,
                          static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_model_set_precision(argus_model* m, int mode) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(m != nullptr, "null model");
+  m->impl.set_precision(mode);
   ARGUS_API_END
 }
 int argus_model_set_wgrad_overlap(argus_model* m, int on) {

@@ -459,7 +459,19 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
   const int grid = std::min(tiles, num_sms());
-  conv_gemm_kernel<BN, BMN><<<grid, kNumThreads, L::kTotal, stream>>>(p);
+  // weights-resident mode (see ConvGemmParams::b_resident)
+  ConvGemmParams q = p;
+  {
+    const int pipe_bytes = L::kStages * L::kStageBytes;
+    const int bres = p.num_taps * p.kblocks_per_tap * L::kBBytes;
+    const bool fixed_n = (tiles <= grid) || (grid % p.num_n_tiles == 0);
+    static const bool enabled = [] { const char* e = getenv("ARGUS_B_RESIDENT"); return !(e && e[0] == '0'); }();
+    if (enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
+      q.b_resident = 1;
+      q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
+    }
+  }
+  conv_gemm_kernel<BN, BMN><<<grid, kNumThreads, L::kTotal, stream>>>(q);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -472,6 +484,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     ARGUS_CHECK(l.out_geom.rank == 4, "this launch cannot take a residual (strided output)");
     p.res_map = make_tmap_bf16(e.residual, 4, l.out_geom.dims, l.out_geom.strides, l.out_geom.box);
     p.has_res = 1;
+    p.res_bits = e.residual_bits;
   }
   p.relu = e.relu;
   p.stat_partial = e.stat_partial;

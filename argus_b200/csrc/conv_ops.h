@@ -26,6 +26,7 @@ struct Epilogue {
   const float* scale = nullptr;
   const float* shift = nullptr;
   const __nv_bfloat16* residual = nullptr;
+  const uint8_t* residual_bits = nullptr;   // optional [rows][Cout/8] ReLU bit mask gating the residual (dgrad)
   int relu = 0;
   float* stat_partial = nullptr;   // [stat_slots(launch)][2][Cout], zeroed by the caller (train-mode BN statistics)
 };

@@ -35,6 +35,13 @@ __device__ __forceinline__ uint4 pack8(const F8& f) {
   u.w = pack_bf16x2(f.v[6], f.v[7]);
   return u;
 }
+// bit k = (v[k] > 0): the ReLU mask of eight channels in one byte (1/16 of the bf16 activation bytes)
+__device__ __forceinline__ uint8_t positive_bits(const F8& f) {
+  uint32_t b = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) b |= (f.v[k] > 0.f ? 1u : 0u) << k;
+  return static_cast<uint8_t>(b);
+}
 __device__ __forceinline__ F8 load8f(const float* p) {
   F8 r;
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
@@ -266,7 +273,7 @@ template <int RES>  // 0 none, 1 plain residual, 2 residual with its own scale/s
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                int relu, uint4* __restrict__ y, int64_t nvec, int cvec) {
+                int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, int64_t nvec, int cvec) {
   // gridDim.x * 256 is a multiple of cvec (a power of two <= 256), so a thread always sees the same channel octet:
   // the per-channel constants live in registers for the whole grid-stride loop.
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -295,6 +302,7 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
       }
+      if (bits != nullptr) bits[i + u * stride] = positive_bits(o);
       if (relu) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
@@ -316,6 +324,7 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
     }
+    if (bits != nullptr) bits[i] = positive_bits(o);
     if (relu) {
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
@@ -324,8 +333,8 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
   }
 }
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
-              const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s) {
-  ProfileScope prof("bn_apply", s, 0, static_cast<double>(rows) * C * 2 * (res ? 3 : 2));
+              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, int64_t rows, int C, cudaStream_t s) {
+  ProfileScope prof("bn_apply", s, 0, static_cast<double>(rows) * C * (2 * (res ? 3 : 2) + (relu_bits ? 0.125 : 0.0)));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_apply: C/8 must be a power of two <= 256");
   const int64_t nvec = rows * (C / 8);
   const int grid = grid_for(nvec, 256);
@@ -333,32 +342,17 @@ void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16*
   auto R = reinterpret_cast<const uint4*>(res);
   auto Y = reinterpret_cast<uint4*>(y);
   if (res == nullptr)
-    bn_apply_kernel<0><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+    bn_apply_kernel<0><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
   else if (rscale == nullptr)
-    bn_apply_kernel<1><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+    bn_apply_kernel<1><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
   else
-    bn_apply_kernel<2><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, nvec, C / 8);
+    bn_apply_kernel<2><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // batch norm backward: per-channel reductions, then the elementwise input gradient
 // ------------------------------------------------------------------------------------------------------------
-template <int MASK>
-__device__ __forceinline__ F8 masked_grad(const F8& dy, const F8& x, const uint4* out, int64_t i, const F8& sc,
-                                          const F8& sh) {
-  F8 g = dy;
-  if (MASK == 1) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(x.v[k], sc.v[k], sh.v[k]) > 0.f ? dy.v[k] : 0.f;
-  } else if (MASK == 2) {
-    const F8 o = unpack8(ldg_stream(out + i));
-#pragma unroll
-    for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? dy.v[k] : 0.f;
-  }
-  return g;
-}
-
 template <int MASK>
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
@@ -375,6 +369,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
   float a_dy[8], a_dyx[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) a_dy[k] = a_dyx[k] = 0.f;
+  const uint8_t* bits = reinterpret_cast<const uint8_t*>(out);   // MASK == 3: one byte per channel octet
   auto body = [&](const uint4& dyv, const uint4& xv4, const uint4& ov4) {
     const F8 d = unpack8(dyv);
     const F8 xv = unpack8(xv4);
@@ -386,6 +381,9 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
       const F8 o = unpack8(ov4);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? d.v[k] : 0.f;
+    } else if (MASK == 3) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = ((ov4.x >> k) & 1u) ? d.v[k] : 0.f;
     }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -401,6 +399,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
     const uint4 x0 = ldg_stream(x + i0), x1 = ldg_stream(x + i1);
     uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
     if (MASK == 2) { o0 = ldg_stream(out + i0); o1 = ldg_stream(out + i1); }
+    if (MASK == 3) { o0.x = __ldg(bits + i0); o1.x = __ldg(bits + i1); }
     body(d0, x0, o0);
     body(d1, x1, o1);
   }
@@ -408,6 +407,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
     const int64_t i0 = row * cvec + oc;
     uint4 o0 = make_uint4(0, 0, 0, 0);
     if (MASK == 2) o0 = ldg_stream(out + i0);
+    if (MASK == 3) o0.x = __ldg(bits + i0);
     body(ldg_stream(dy + i0), ldg_stream(x + i0), o0);
   }
 #pragma unroll
@@ -462,7 +462,7 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
   ARGUS_CHECK(scratch != nullptr, "bn_bwd_reduce needs a scratch buffer");
   std::string fam = "bn_bwd_reduce";
   if (profile_enabled() && profile_detailed()) fam += ":R" + std::to_string(rows) + "_C" + std::to_string(C) + "_m" + std::to_string(mask_mode);
-  ProfileScope prof(fam, s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 3 : 2));
+  ProfileScope prof(fam, s, 0, static_cast<double>(rows) * C * (mask_mode == 2 ? 6.0 : (mask_mode == 3 ? 4.125 : 4.0)));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_bwd_reduce: C/8 must be a power of two <= 256");
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);
@@ -478,6 +478,10 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
     case 2:
       ARGUS_CHECK(out != nullptr, "mask_mode 2 needs the block output");
       bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
+      break;
+    case 3:
+      ARGUS_CHECK(out != nullptr, "mask_mode 3 needs the ReLU bit mask");
+      bn_bwd_reduce_kernel<3><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
       break;
     default: throw Error("bad mask_mode");
   }
@@ -508,6 +512,7 @@ bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const u
       k0.v[k] = fmaf(c2, mu.v[k], -sc.v[k] * db.v[k] * inv_rows);
     }
   }
+  const uint8_t* bits = reinterpret_cast<const uint8_t*>(out);   // MASK == 3: one byte per channel octet
   auto body = [&](int64_t i, const uint4& dyv, const uint4& xv4, const uint4& ov4) {
     const F8 d = unpack8(dyv);
     const F8 xv = unpack8(xv4);
@@ -519,6 +524,9 @@ bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const u
       const F8 o = unpack8(ov4);
 #pragma unroll
       for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? d.v[k] : 0.f;
+    } else if (MASK == 3) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g.v[k] = ((ov4.x >> k) & 1u) ? d.v[k] : 0.f;
     }
     F8 r;
 #pragma unroll
@@ -532,12 +540,14 @@ bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const u
     const uint4 xa = ldg_stream(x + i), xb = ldg_stream(x + i + stride);
     uint4 oa = make_uint4(0, 0, 0, 0), ob = oa;
     if (MASK == 2) { oa = ldg_stream(out + i); ob = ldg_stream(out + i + stride); }
+    if (MASK == 3) { oa.x = __ldg(bits + i); ob.x = __ldg(bits + i + stride); }
     body(i, da, xa, oa);
     body(i + stride, dbv, xb, ob);
   }
   for (; i < nvec; i += stride) {
     uint4 oa = make_uint4(0, 0, 0, 0);
     if (MASK == 2) oa = ldg_stream(out + i);
+    if (MASK == 3) oa.x = __ldg(bits + i);
     body(i, dy[i], ldg_stream(x + i), oa);
   }
 }
@@ -545,7 +555,7 @@ bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const u
 void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                   const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
                   int64_t rows, int C, int mask_mode, cudaStream_t s) {
-  ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * 2 * (mask_mode == 2 ? 5 : 3));
+  ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * (mask_mode == 2 ? 10.0 : (mask_mode == 3 ? 6.125 : 6.0)));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_bwd_apply: C/8 must be a power of two <= 256");
   const int cvec = C / 8;
   const int64_t nvec = rows * cvec;
@@ -559,6 +569,7 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
     case 0: bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
     case 1: bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
     case 2: bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 3: bn_bwd_apply_kernel<3><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
     default: throw Error("bad mask_mode");
   }
   ARGUS_CUDA(cudaGetLastError());

@@ -51,18 +51,20 @@ void bn_finalize(const float* partial, int slots, double count, const float* gam
 void bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   float eps, float* scale, float* shift, int C, cudaStream_t s);
 // y = [relu]( x*scale+shift  [+ res]  or  [+ res*rscale+rshift] )
+// relu_bits (optional): [rows][C/8] bytes, bit k of byte j = (pre-ReLU value of channel 8j+k > 0). The backward pass
+// reads this mask instead of the whole bf16 output (1/16 of the bytes).
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
-              const float* rshift, int relu, bf16* y, int64_t rows, int C, cudaStream_t s);
+              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, int64_t rows, int C, cudaStream_t s);
 // mask_mode: 0 = no ReLU after this BN, 1 = ReLU directly after (mask recomputed from x), 2 = ReLU after a residual
-// add (mask = out > 0). Accumulates dgamma += sum(g * xhat), dbeta += sum(g) with g = masked dy.
+// add (mask = out > 0), 3 = like 2 but `out` points to the relu_bits written by bn_apply. Accumulates dgamma += sum(g * xhat), dbeta += sum(g) with g = masked dy.
 // Deterministic: every block writes its partial sums to `scratch` (>= bn_bwd_scratch_elems() floats), a second tiny
 // kernel adds them in block order.
 void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
                    int mask_mode, float* scratch, cudaStream_t s);
 int64_t bn_bwd_scratch_elems();
-// dx = scale * (g - dbeta/rows - xhat * dgamma/rows); mask_mode 2 also overwrites dy with g (the identity branch
-// of the residual block consumes it).
+// dx = scale * (g - dbeta/rows - xhat * dgamma/rows); mask_mode 2 also overwrites dy with g (mask_mode 3 leaves dy
+// untouched: the consumers of the identity-branch gradient apply the bit mask themselves).
 void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,
                   const float* mean, const float* invstd, const float* dgamma, const float* dbeta, bf16* dx,
                   int64_t rows, int C, int mask_mode, cudaStream_t s);

@@ -29,7 +29,17 @@ Model::Model(int n_cams, int resnet_output_dim) : n_cams_(n_cams), out_dim_(resn
   build_layout();
 }
 
+void Model::set_precision(int mode) {
+  ARGUS_CHECK(mode == 0 || mode == 1, "precision mode must be 0 (bf16 tensor cores) or 1 (fp32)");
+  precision_ = mode;
+  last_train_plan_ = nullptr;
+  last_plan_ = nullptr;
+  staged_plan_ = nullptr;
+  eval_fold_dirty_ = true;
+}
+
 Model::~Model() {
+  destroy_fp32_state(f32_);
   if (side_) cudaStreamDestroy(side_);
   if (ev_fork_) cudaEventDestroy(ev_fork_);
   if (ev_wgrad_) cudaEventDestroy(ev_wgrad_);
@@ -288,6 +298,7 @@ void Model::build_plan(Plan& p) {
     if (tr) bp.raw3 = arena_alloc<bf16>(e_out * oc);
     if (br.has_ds) bp.rawd = arena_alloc<bf16>(e_out * oc);  // eval: holds the folded-BN identity branch
     bp.out = arena_alloc<bf16>(e_out * oc);
+    if (tr) bp.out_bits = arena_alloc<uint8_t>(e_out * oc / 8);
     max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
     plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
     plan_conv(bp.c2, br.c2, N, h, w, bp.act1, tr ? bp.raw2 : bp.act2, true);
@@ -401,15 +412,16 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
     BlockPlan& bp = p.blocks[i];
     const int wd = br.c1.shape.Cout, oc = br.c3.shape.Cout;
     run_conv_train(bp.c1, br.c1, bp.rows_in, s);
-    bn_apply(bp.raw1, SC(br.c1), SC(br.c1) + wd, nullptr, nullptr, nullptr, 1, bp.act1, bp.rows_in, wd, s);
+    bn_apply(bp.raw1, SC(br.c1), SC(br.c1) + wd, nullptr, nullptr, nullptr, 1, bp.act1, nullptr, bp.rows_in, wd, s);
     run_conv_train(bp.c2, br.c2, bp.rows_out, s);
-    bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, bp.rows_out, wd, s);
+    bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, nullptr, bp.rows_out, wd, s);
     run_conv_train(bp.c3, br.c3, bp.rows_out, s);
     if (br.has_ds) {
       run_conv_train(bp.ds, br.ds, bp.rows_out, s);
-      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.rawd, SC(br.ds), SC(br.ds) + oc, 1, bp.out, bp.rows_out, oc, s);
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.rawd, SC(br.ds), SC(br.ds) + oc, 1, bp.out, bp.out_bits,
+               bp.rows_out, oc, s);
     } else {
-      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.x, nullptr, nullptr, 1, bp.out, bp.rows_out, oc, s);
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.x, nullptr, nullptr, 1, bp.out, bp.out_bits, bp.rows_out, oc, s);
     }
   }
 }
@@ -460,6 +472,10 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
   ARGUS_CHECK(B > 0, "empty batch");
   ARGUS_CHECK(!training || B * n_cams_ * (H / 32) * (W / 32) > 1,
               "train-mode batch norm needs more than one value per channel");
+  if (precision_ == 1) {
+    forward_fp32(x, is_u8, B, H, W, training, out, s);
+    return;
+  }
   Plan& p = get_plan(B, H, W, training);
   if (x == nullptr) {
     ARGUS_CHECK(staged_plan_ == &p, "forward(x = NULL) needs a preceding stage_input_u8() for the same batch shape");
@@ -483,12 +499,14 @@ void Model::stage_input_u8(const uint8_t* images, float* aug_params, int B, int 
                            cudaStream_t s) {
   ARGUS_CHECK(B > 0, "empty batch");
   ARGUS_CHECK(!apply || aug_params != nullptr, "augmentation needs a parameter table");
+  ARGUS_CHECK(precision_ == 0, "the fused augmentation + staging path exists in bf16 mode only");
   Plan& p = get_plan(B, H, W, training);
   augment_images(images, true, p.x_s2d, true, aug_params, p.N, H, W, apply, s);
   staged_plan_ = &p;
 }
 
 void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s) {
+  ARGUS_CHECK(precision_ == 0, "activation probes exist in bf16 mode only");
   ARGUS_CHECK(last_plan_ != nullptr, "no forward pass has run yet");
   Plan& p = *last_plan_;
   const bf16* src = nullptr;
@@ -561,17 +579,22 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
   bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
 }
 
-void Model::conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s) {
+void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* residual_bits, cudaStream_t s) {
   // fork: the weight gradient only needs dRaw and the saved activation, both final at this point
   run_wgrad(cp.wgrad, s);
   Epilogue e;
   e.residual = residual;
+  e.residual_bits = residual_bits;
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
 }
 
 void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s) {
-  ARGUS_CHECK(last_train_plan_ != nullptr, "backward() needs a preceding training forward()");
   ARGUS_CHECK(grads_dev_ != nullptr, "model is not bound to a gradient arena");
+  if (precision_ == 1) {
+    backward_fp32(d_out, stage_begin, stage_end, s);
+    return;
+  }
+  ARGUS_CHECK(last_train_plan_ != nullptr, "backward() needs a preceding training forward()");
   Plan& p = *last_train_plan_;
   const int N = p.N, B = p.B, F = n_cams_ * out_dim_;
   const int n_blocks = static_cast<int>(blocks_.size());
@@ -608,20 +631,25 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       ARGUS_CUDA(cudaMemsetAsync(gpacked_ + br.c2.gpacked_off, 0,
                                  static_cast<size_t>(br.c2.shape.Ktot()) * br.c2.shape.Cout * sizeof(float), s));
       bf16 *P = bp.g_out, *Q = bp.g_q, *R = bp.g_r, *T = bp.g_t;
-      // bn3 (+ residual ReLU): P becomes the masked gradient, Q = dRaw3
-      bn_backward(br.c3, P, bp.raw3, bp.out, Q, bp.rows_out, 2, s);
+      // bn3 (+ residual ReLU): the ReLU mask of the block output is read as a bit mask (1/16 of the bytes of `out`);
+      // P stays unmasked, every consumer of the identity-branch gradient applies the bits itself. Q = dRaw3
+      const uint8_t* bits = bp.out_bits;
+      const bf16* bits_as_out = reinterpret_cast<const bf16*>(bits);
+      bn_backward(br.c3, P, bp.raw3, bits_as_out, Q, bp.rows_out, 3, s);
       const bf16* residual = P;
+      const uint8_t* residual_bits = bits;
       if (br.has_ds) {
-        bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
+        bn_backward(br.ds, P, bp.rawd, bits_as_out, R, bp.rows_out, 3, s);
         if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
-        conv_backward(bp.ds, nullptr, s);  // R -> T
+        conv_backward(bp.ds, nullptr, nullptr, s);  // R -> T
         residual = T;
+        residual_bits = nullptr;
       }
-      conv_backward(bp.c3, nullptr, s);                                   // Q -> R (dAct2)
+      conv_backward(bp.c3, nullptr, nullptr, s);                          // Q -> R (dAct2)
       bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);      // Q = dRaw2
-      conv_backward(bp.c2, nullptr, s);                                   // Q -> R (dAct1)
+      conv_backward(bp.c2, nullptr, nullptr, s);                          // Q -> R (dAct1)
       bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);       // Q = dRaw1
-      conv_backward(bp.c1, residual, s);                                  // Q -> S (+ residual)
+      conv_backward(bp.c1, residual, residual_bits, s);                   // Q -> S (+ gated residual)
     }
     if (stage == 3) {
       // ---- stem: max-pool backward, bn1 backward, weight gradient

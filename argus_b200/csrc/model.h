@@ -57,6 +57,7 @@ struct BlockPlan {
   ConvPlan c1, c2, c3, ds;
   bf16 *x = nullptr, *raw1 = nullptr, *act1 = nullptr, *raw2 = nullptr, *act2 = nullptr, *raw3 = nullptr,
        *rawd = nullptr, *out = nullptr;
+  uint8_t* out_bits = nullptr;   // ReLU mask of `out` (training): [rows_out][Cout/8] bytes
   int64_t rows_in = 0, rows_mid = 0, rows_out = 0;
   // gradient scratch roles for this block
   bf16 *g_out = nullptr, *g_q = nullptr, *g_r = nullptr, *g_t = nullptr, *g_x = nullptr;
@@ -80,6 +81,9 @@ struct Plan {
   bf16* g_stem_in = nullptr;   // gradient wrt the pooled stem output (= layer1.0 input gradient)
   bf16 *g_act0 = nullptr, *g_raw0 = nullptr;
 };
+
+struct Fp32State;                        // fp32 parity mode (model_fp32.cu)
+void destroy_fp32_state(Fp32State* st);
 
 class Model {
  public:
@@ -113,6 +117,10 @@ class Model {
   // index -1: pooled stem output; 0..15: bottleneck block outputs; 16: globally pooled features; 17: fc output.
   void copy_activation(int index, void* dst, int64_t capacity_elems, int64_t* rows, int* C, cudaStream_t s);
 
+  // 0 = bf16 tensor-core path (default), 1 = fp32 SIMT parity mode (same parameters, buffers and results layout)
+  void set_precision(int mode);
+  int precision() const { return precision_; }
+
   int n_cams() const { return n_cams_; }
   int out_dim() const { return out_dim_; }
   size_t arena_bytes() const { return arena_bytes_; }
@@ -128,10 +136,18 @@ class Model {
   void run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s);
   void bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
                    cudaStream_t s);
-  void conv_backward(const ConvPlan& cp, const bf16* residual, cudaStream_t s);
+  void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* residual_bits, cudaStream_t s);
 
   template <typename T>
   T* arena_alloc(size_t count);
+
+  // fp32 parity mode
+  void plan_fp32(Fp32State& st, int B, int H, int W, bool training);
+  Fp32State& fp32_state(int B, int H, int W, bool training);
+  void forward_fp32(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s);
+  void backward_fp32(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
+  int precision_ = 0;
+  Fp32State* f32_ = nullptr;
 
   int n_cams_, out_dim_;
   std::vector<TensorInfo> params_, buffers_;

@@ -141,6 +141,20 @@ class NCameraCNN(nn.Module):
         self._synced_version = -1
         self._bound_key = None
         self._flat_grads = None
+        self._precision = "bf16"
+
+    def set_precision(self, precision: str) -> "NCameraCNN":
+        """"bf16" (default): tcgen05 tensor-core path. "fp32": the fp32 parity mode of the C library (same weights,
+        same results layout; matches the reference's fp32 PyTorch forward / gradients to 1e-4 relative)."""
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        _lib.call("argus_model_set_precision", self._handle.ptr, 1 if precision == "fp32" else 0)
+        self._precision = precision
+        return self
+
+    @property
+    def precision(self) -> str:
+        return self._precision
 
     # ------------------------------------------------------------------ module tree / flat arenas
     def _build_tree(self, flat_p, flat_b, flat_nbt) -> None:

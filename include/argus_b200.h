@@ -53,6 +53,11 @@ int argus_conv2d_stat_slots(int N, int H, int W, int Cin, int Cout, int k, int s
 /* dx = conv_transpose(dy, w) (+ residual). For stride 2 the caller zero-fills dx first when k == 1. */
 int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, const void* residual, void* stream);
+/* stride-1 dgrad whose residual is gated by a ReLU bit mask: dx = conv_transpose(dy, w) + residual * bit, with
+ * residual_bits = the [rows][Cin/8] byte mask written by argus_bn_apply_bits for the tensor dx is the gradient of
+ * (the identity branch of a bottleneck: the masked gradient is never materialised). */
+int argus_conv2d_dgrad_bits(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int k,
+                            const void* residual, const void* residual_bits, void* stream);
 /* dw[Cout][k*k*Cin] (fp32) += dy^T * im2col(x); the caller zero-fills dw. */
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream);
@@ -68,8 +73,13 @@ int argus_bn_finalize(const float* partial, int slots, double count, const float
 /* y = [relu](x*scale+shift [+ res | + res*rscale+rshift]) */
 int argus_bn_apply(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
                    const float* rshift, int relu, void* y, int64_t rows, int C, void* stream);
+/* same, and also writes the ReLU mask of the result: relu_bits[rows][C/8] bytes, bit k of byte j = (channel 8j+k of
+ * the pre-ReLU value > 0). The backward pass reads these bits instead of the bf16 output (1/16 of the bytes). */
+int argus_bn_apply_bits(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
+                        const float* rshift, int relu, void* y, void* relu_bits, int64_t rows, int C, void* stream);
 /* BN (+ReLU) backward. mask_mode 0: no ReLU; 1: ReLU right after the BN; 2: ReLU after a residual add (mask = out > 0,
- * dy is overwritten with the masked gradient). dgamma / dbeta are ADDED to (caller zeroes); dx = d loss / d x. */
+ * dy is overwritten with the masked gradient); 3: like 2 but `out` is the relu_bits mask of argus_bn_apply_bits and dy
+ * is left untouched. dgamma / dbeta are ADDED to (caller zeroes); dx = d loss / d x. */
 int argus_bn_backward(void* dy, const void* x, const void* out, const float* scale, const float* shift,
                       const float* mean, const float* invstd, float* dgamma, float* dbeta, void* dx, int64_t rows,
                       int C, int mask_mode, void* stream);
@@ -135,6 +145,12 @@ int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, 
  * The next argus_model_forward call for the same (B, H, W, training) passes x = NULL. */
 int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
                                int training, int apply, void* stream);
+/* Precision mode. 0 (default): bf16 activations / weights on the tcgen05 tensor cores, fp32 accumulate.
+ * 1: fp32 parity mode -- every tensor fp32, SIMT implicit-GEMM convolutions with fp32 FMA accumulation, reductions in
+ * fp64; same parameter / gradient / buffer arenas and the same entry points. It exists to compare forward outputs,
+ * losses and gradients with the reference's fp32 PyTorch path at 1e-4 relative; it is not a performance path
+ * (argus_model_stage_input_u8 and argus_model_copy_activation are bf16-mode only). */
+int argus_model_set_precision(argus_model* m, int mode);
 /* Weight-gradient GEMMs normally run on a library-owned side stream, overlapping the BN-backward / dgrad chain of the
  * caller's stream (joined before the stage returns). on = 0 serialises them (used for per-kernel timing). */
 int argus_model_set_wgrad_overlap(argus_model* m, int on);

@@ -118,6 +118,76 @@ def test_bn_backward(cuda_device, rows, C, mask):
     assert torch.equal(dgamma, dgamma2) and torch.equal(dbeta, dbeta2) and torch.equal(dx, dx2)
 
 
+def unpack_bits(bits, rows, C):
+    """[rows][C/8] bytes -> bool (rows, C): bit k of byte j = channel 8j+k."""
+    b = bits.view(rows, C // 8, 1).to(torch.int32)
+    return ((b >> torch.arange(8, device=bits.device, dtype=torch.int32)) & 1).bool().view(rows, C)
+
+
+@pytest.mark.parametrize("rows,C,ds", [(777, 512, False), (300, 128, True), (4096, 256, False)])
+def test_bn_relu_bits_forward_backward(cuda_device, rows, C, ds):
+    """Residual-block tail with the ReLU mask kept as a bit mask: bn_apply_bits writes it, bn_backward mode 3 reads it
+    (and leaves dy alone). Must reproduce mask mode 2 (mask = bf16 output > 0) exactly."""
+    g = torch.Generator().manual_seed(rows + C)
+    x = (torch.randn(rows, C, generator=g) * 1.5 + torch.randn(C, generator=g)).to(cuda_device).bfloat16()
+    ident = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
+    dy = torch.randn(rows, C, generator=g).to(cuda_device).bfloat16()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_device)
+    beta = (torch.randn(C, generator=g) * 0.5).to(cuda_device)
+    _, mean, var, invstd = bn_train_forward(x.float(), gamma, beta)
+    scale, shift = gamma * invstd, beta - mean * gamma * invstd
+    rs = (torch.rand(C, generator=g) + 0.5).to(cuda_device) if ds else None
+    rb = torch.randn(C, generator=g).to(cuda_device) if ds else None
+    lib = _lib.load()
+    y = torch.empty_like(x)
+    y_plain = torch.empty_like(x)
+    bits = torch.zeros(rows, C // 8, device=cuda_device, dtype=torch.uint8)
+    _lib.check(lib.argus_bn_apply_bits(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(ident), _lib.ptr(rs), _lib.ptr(rb),
+                                       ctypes.c_int(1), _lib.ptr(y), _lib.ptr(bits), ctypes.c_int64(rows), ctypes.c_int(C),
+                                       _lib.stream_ptr()))
+    _lib.check(lib.argus_bn_apply(_lib.ptr(x), _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(ident), _lib.ptr(rs), _lib.ptr(rb),
+                                  ctypes.c_int(1), _lib.ptr(y_plain), ctypes.c_int64(rows), ctypes.c_int(C), _lib.stream_ptr()))
+    assert torch.equal(y, y_plain)
+    assert torch.equal(unpack_bits(bits, rows, C), y.float() > 0)
+
+    def backward(mask_mode, out_arg):
+        dgamma, dbeta = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+        dx = torch.empty_like(x)
+        dy_io = dy.clone()
+        _lib.check(lib.argus_bn_backward(_lib.ptr(dy_io), _lib.ptr(x), _lib.ptr(out_arg), _lib.ptr(scale), _lib.ptr(shift),
+                                         _lib.ptr(mean), _lib.ptr(invstd), _lib.ptr(dgamma), _lib.ptr(dbeta), _lib.ptr(dx),
+                                         ctypes.c_int64(rows), ctypes.c_int(C), ctypes.c_int(mask_mode), _lib.stream_ptr()))
+        return dgamma, dbeta, dx, dy_io
+
+    g2, b2, dx2, dy2 = backward(2, y)
+    g3, b3, dx3, dy3 = backward(3, bits)
+    assert torch.equal(g2, g3) and torch.equal(b2, b3) and torch.equal(dx2, dx3)
+    assert torch.equal(dy3, dy)                                              # mode 3 does not touch dy
+    assert torch.equal(dy2, (dy.float() * (y.float() > 0)).bfloat16())       # mode 2 masks it in place
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout", [(2, 16, 16, 256, 64), (1, 8, 8, 512, 128), (3, 8, 16, 64, 64)])
+def test_dgrad_residual_bits(cuda_device, N, H, W, Cin, Cout):
+    """1x1 dgrad whose residual is gated by the bit mask == dgrad with the pre-masked residual, bit for bit."""
+    g = torch.Generator().manual_seed(N * H + Cin)
+    rows = N * H * W
+    dyt = torch.randn(rows, Cout, generator=g).to(cuda_device).bfloat16()
+    w = (torch.randn(Cout, Cin, generator=g) / Cout ** 0.5).to(cuda_device).bfloat16()
+    res = torch.randn(rows, Cin, generator=g).to(cuda_device).bfloat16()
+    keep = torch.rand(rows, Cin, generator=g).to(cuda_device) > 0.4
+    k8 = keep.view(rows, Cin // 8, 8).to(torch.int32)
+    bits = (k8 << torch.arange(8, device=cuda_device, dtype=torch.int32)).sum(-1).to(torch.uint8).contiguous()
+    masked = (res.float() * keep).bfloat16()
+    dx_a = torch.empty(rows, Cin, device=cuda_device, dtype=torch.bfloat16)
+    dx_b = torch.empty_like(dx_a)
+    _lib.call("argus_conv2d_dgrad", dyt, w, dx_a, N, H, W, Cin, Cout, 1, 1, masked, _lib.stream_ptr())
+    _lib.call("argus_conv2d_dgrad_bits", dyt, w, dx_b, N, H, W, Cin, Cout, 1, res, bits, _lib.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(dx_a, dx_b)
+    want = dyt.float() @ w.float() + masked.float()
+    close_bf16(dx_b, want, extra=2e-2)
+
+
 @pytest.mark.parametrize("N,H,W,C", [(2, 16, 16, 64), (3, 64, 32, 64), (1, 8, 8, 128)])
 def test_maxpool(cuda_device, N, H, W, C):
     g = torch.Generator().manual_seed(N + H)

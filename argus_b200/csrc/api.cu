@@ -3,6 +3,7 @@
 
 #include "conv_ops.h"
 #include "kernels.h"
+#include "kernels_fp32.h"
 #include "model.h"
 #include "runtime.h"
 
@@ -177,6 +178,16 @@ int argus_maxpool_backward(const void* dy, const void* idx, void* dx, int N, int
               static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
+int argus_stem_pool_bn_backward(const void* dpool, const void* idx, const void* raw, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, float* dgamma,
+                                float* dbeta, void* dx, int N, int H, int W, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  stem_pool_bn_backward(static_cast<const bf16*>(dpool), static_cast<const uint8_t*>(idx), static_cast<const bf16*>(raw),
+                        scale, shift, mean, invstd, dgamma, dbeta, static_cast<bf16*>(dx), N, H, W, C,
+                        lib_scratch(bn_bwd_scratch_elems()), static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
 int argus_avgpool_forward(const void* x, void* y, int N, int HW, int C, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
@@ -241,6 +252,78 @@ int argus_clip_adam_step(float* params, const float* grads, float* exp_avg, floa
   const int np = grad_sqnorm_partials(grads, n, scratch, s);
   clip_adam_step(params, grads, exp_avg, exp_avg_sq, n, scratch, np, gscale, max_norm, lr, beta1, beta2, eps, step,
                  norm_out, s);
+  ARGUS_API_END
+}
+
+// ---- fp32 parity-mode primitives -----------------------------------------------------------------------------
+static ConvShapeF32 make_shape_f32(int N, int H, int W, int Cin, int Cout, int k, int stride) {
+  ARGUS_CHECK(N > 0 && H > 0 && W > 0 && Cin > 0 && Cout > 0, "empty convolution");
+  ARGUS_CHECK((k == 1 || k == 3 || k == 7) && (stride == 1 || stride == 2), "fp32 conv: k in {1,3,7}, stride in {1,2}");
+  ConvShapeF32 s;
+  s.N = N; s.H = H; s.W = W; s.Cin = Cin; s.Cout = Cout; s.k = k; s.stride = stride;
+  return s;
+}
+int argus_fp32_conv2d_forward(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin,
+                              int Cout, int k, int stride, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  conv_f32_forward(make_shape_f32(N, H, W, Cin, Cout, k, stride), x, w, bias, y, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin, int Cout, int k,
+                            int stride, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  conv_f32_dgrad(make_shape_f32(N, H, W, Cin, Cout, k, stride), dy, w, dx, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
+                            int stride, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  const ConvShapeF32 s = make_shape_f32(N, H, W, Cin, Cout, k, stride);
+  conv_f32_wgrad(s, dy, x, dw, lib_scratch(conv_f32_wgrad_scratch_elems(s, nullptr)), static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+static double* lib_scratch_f64(int64_t elems) { return reinterpret_cast<double*>(lib_scratch(2 * elems)); }
+int argus_fp32_bn_train(const float* x, int64_t rows, int C, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                        float* save_invstd, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  bn_f32_train_stats(x, rows, C, gamma, beta, running_mean, running_var, momentum, eps, scale, shift, save_mean,
+                     save_invstd, lib_scratch_f64(static_cast<int64_t>(kBnF32MaxBlocks) * 2 * C),
+                     static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_bn_apply(const float* x, const float* scale, const float* shift, const float* res, const float* rscale,
+                        const float* rshift, int relu, float* y, int64_t rows, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  bn_f32_apply(x, scale, shift, res, rscale, rshift, relu, y, rows, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_bn_backward(const float* dy, const float* x, const float* out, const float* scale, const float* mean,
+                           const float* invstd, float* dgamma, float* dbeta, float* dx, float* g_out, int64_t rows,
+                           int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  double* part = lib_scratch_f64(static_cast<int64_t>(kBnF32MaxBlocks) * 2 * C + C);
+  float* sums = reinterpret_cast<float*>(part + static_cast<int64_t>(kBnF32MaxBlocks) * 2 * C);
+  bn_f32_backward(dy, x, out, scale, mean, invstd, dgamma, dbeta, dx, g_out, rows, C, part, sums,
+                  static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_maxpool_forward(const float* x, float* y, void* idx, int N, int H, int W, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  maxpool_f32_fwd(x, y, static_cast<uint8_t*>(idx), N, H, W, C, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_fp32_maxpool_backward(const float* dy, const void* idx, float* dx, int N, int H, int W, int C, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  maxpool_f32_bwd(dy, static_cast<const uint8_t*>(idx), dx, N, H, W, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 

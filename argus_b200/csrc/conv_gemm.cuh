@@ -56,6 +56,16 @@ struct ConvGemmParams {
   // activation tiles only (res_stages of them). Cuts the L2 -> SM traffic of the small-K layers by 1/3 .. 2/3.
   int b_resident;
   int res_stages;
+  // Halo mode (3x3, stride 1, tile inside one image): instead of nine [128 x 64] activation boxes per 64-channel
+  // block (one per tap, each re-read from L2), three boxes of (rows + 2) image rows are loaded -- one per horizontal
+  // shift dw -- and the three vertical taps are row offsets into the same shared-memory box. Activation traffic from
+  // L2 drops from 9 x 16 KB to 3 x (16 KB + 2 image rows). halo_boff[dw+1][dh+1] = weight offset of the tap.
+  int halo;
+  int halo_rows;          // image rows per tile (128 / W)
+  int halo_row_bytes;     // W * 128
+  int halo_stages;
+  int32_t halo_boff[3][3];
+  CUtensorMap halo_map;   // box {64, W, rows + 2, 1}
   const uint8_t* res_bits;       // optional [m_total][n_total/8] bit mask: residual element counts only where its bit is set
   int relu;
   // train-mode BN statistics of the stored bf16 outputs, reduced deterministically: every (CTA, epilogue group)
@@ -69,12 +79,15 @@ struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = 150000 / kStageBytes;        // leaves room for 4 staging buffers + statistics
-  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
-  static constexpr int kOffStaging = kStages * kStageBytes;      // 2 buffers per epilogue group
+  static constexpr int kStatsBytes = 2 * 4 * 2 * BLOCK_N * 4;    // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
+  // operand pipeline region: everything the 227 KB of shared memory leave after staging, statistics and barriers
+  static constexpr int kPipeBytes = (232448 - 1024 - 4 * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
+  static constexpr int kStagesRaw = kPipeBytes / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
+  static constexpr int kOffStaging = kPipeBytes;                 // 2 staging buffers per epilogue group
   static constexpr int kOffStats = kOffStaging + 4 * kStagingBytes;
-  static constexpr int kOffBars = kOffStats + 2 * 4 * 2 * BLOCK_N * 4;   // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
+  static constexpr int kOffBars = kOffStats + kStatsBytes;
   static constexpr int kMaxStages = 8;               // stage ring length in weights-resident mode (<= kMaxStages)
   // full/empty per stage, tmem full/empty x2, residual x(2 groups x 2 buffers), resident-weights barrier
   static constexpr int kNumBars = 2 * kMaxStages + 9;
@@ -107,8 +120,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   float* s_stats_all = reinterpret_cast<float*>(smem + L::kOffStats);
   // pipeline geometry: streaming mode = kStages x (A | B); weights-resident mode = res_stages x A, then the B slab
   const bool resident = (p.b_resident != 0);
-  const int nstages = resident ? p.res_stages : kStages;
-  const uint32_t stage_bytes = resident ? L::kABytes : L::kStageBytes;
+  const bool halo = (p.halo != 0);
+  const uint32_t halo_a_bytes = static_cast<uint32_t>(p.halo_rows + 2) * p.halo_row_bytes;
+  const int nstages = halo ? p.halo_stages : (resident ? p.res_stages : kStages);
+  const uint32_t stage_bytes = halo ? halo_a_bytes + 3u * L::kBBytes : (resident ? L::kABytes : L::kStageBytes);
   const uint32_t bres_base = smem_base + static_cast<uint32_t>(nstages) * L::kABytes;
 
   if (threadIdx.x == 0) {
@@ -128,6 +143,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   }
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
+    if (p.halo) tma_prefetch_desc(&p.halo_map);
     tma_prefetch_desc(&p.b_map);
     tma_prefetch_desc(&p.out_map);
     if (p.has_res) tma_prefetch_desc(&p.res_map);
@@ -178,6 +194,23 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         const int h0 = rem >> p.log2_wo;
         const int w0 = rem & ((1 << p.log2_wo) - 1);
         const int n0 = n_tile * BLOCK_N;
+        if (halo) {
+          for (int kb = 0; kb < p.kblocks_per_tap; ++kb)
+            for (int dwi = 0; dwi < 3; ++dwi) {
+              mbar_wait(empty_bar(stage), phase ^ 1);
+              const uint32_t sa = smem_base + stage * stage_bytes;
+              mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+              tma_load_4d(&p.halo_map, full_bar(stage), sa, kb * kBlockK, w0 + dwi - 1, h0 - 1, img0);
+#pragma unroll
+              for (int dhi = 0; dhi < 3; ++dhi) {
+                Tap tap{};
+                tap.b_off = p.halo_boff[dwi][dhi];
+                load_b(full_bar(stage), sa + halo_a_bytes + dhi * L::kBBytes, tap, kb, n0);
+              }
+              if (++stage == nstages) { stage = 0; phase ^= 1; }
+            }
+          continue;
+        }
         for (int t = 0; t < p.num_taps; ++t) {
           const Tap tap = p.taps[t];
           for (int kb = 0; kb < p.kblocks_per_tap; ++kb) {
@@ -204,6 +237,31 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        if (halo) {
+          const int nst = 3 * p.kblocks_per_tap;
+          for (int st = 0; st < nst; ++st) {
+            mbar_wait(full_bar(stage), phase);
+            tc_fence_after();
+            const uint32_t sa = smem_base + stage * stage_bytes;
+#pragma unroll
+            for (int dhi = 0; dhi < 3; ++dhi) {
+              const uint32_t a0 = sa + static_cast<uint32_t>(dhi) * p.halo_row_bytes;   // multiple of 1024 (W >= 8)
+              const uint32_t sb = sa + halo_a_bytes + dhi * L::kBBytes;
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                const uint64_t da = make_smem_desc_sw128(a0 + k * 32, 0, 1024);
+                const uint64_t db = (B_MN == 0) ? make_smem_desc_sw128(sb + k * 32, 0, 1024)
+                                                : make_smem_desc_sw128(sb + k * 2048, 8192, 1024);
+                umma_bf16(tmem_d, da, db, idesc, (st | dhi | k) != 0);
+              }
+            }
+            umma_commit(empty_bar(stage));
+            if (st == nst - 1) umma_commit(tfull_bar(acc));
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
+          }
+          if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          continue;
+        }
         for (int kb = 0; kb < num_kblocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();

@@ -260,6 +260,30 @@ static int fill_forward_taps(const ConvShape& s, Tap* taps) {
   return n;
 }
 
+// Halo mode (see ConvGemmParams::halo): 3x3 stride-1 convolutions whose 128-pixel tile is `rows` whole image rows.
+// `src` is the tensor the A operand is read from (x for forward, dy for dgrad), both on the (N, H, W) grid.
+static void setup_halo(ConvGemmParams& p, const ConvShape& s, const __nv_bfloat16* src, int channels, bool dgrad,
+                       int block_n) {
+  p.halo = 0;
+  if (s.kind != 0 || s.k != 3 || s.stride != 1 || block_n > 128) return;
+  uint32_t bw, bh, bn;
+  pixel_box(s.W, s.H, kBlockM, bw, bh, bn);
+  if (bn != 1 || static_cast<int>(bw) != s.W || s.W < 8 || static_cast<int>(bw * bh) != kBlockM) return;
+  const uint64_t C = channels, H = s.H, W = s.W;
+  const uint64_t dims[4] = {C, W, H, static_cast<uint64_t>(s.N)};
+  const uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+  const uint32_t box[4] = {64, bw, bh + 2, 1};
+  p.halo_map = make_tmap_bf16(src, 4, dims, str, box);
+  p.halo_rows = static_cast<int>(bh);
+  p.halo_row_bytes = s.W * 128;
+  for (int dwi = 0; dwi < 3; ++dwi)
+    for (int dhi = 0; dhi < 3; ++dhi) {
+      const int kh = dgrad ? 2 - dhi : dhi, kw = dgrad ? 2 - dwi : dwi;
+      p.halo_boff[dwi][dhi] = (kh * 3 + kw) * s.Cin;
+    }
+  p.halo = 1;
+}
+
 ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const __nv_bfloat16* w, __nv_bfloat16* y) {
   validate_shape(s);
   ConvLaunch l;
@@ -292,6 +316,7 @@ ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const _
   p.num_n_tiles = (s.Cout + l.block_n - 1) / l.block_n;
   p.log2_wo = ilog2(s.Wo());
   p.log2_howo = ilog2(s.Ho() * s.Wo());
+  setup_halo(p, s, x, s.Cin, false, l.block_n);
   return l;
 }
 
@@ -370,6 +395,7 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
     p.num_n_tiles = (s.Cin + block_n - 1) / block_n;
     p.log2_wo = ilog2(Wo);
     p.log2_howo = ilog2(Ho * Wo);
+    setup_halo(p, s, dy, s.Cout, true, block_n);
     out.push_back(l);
   }
   return out;
@@ -465,8 +491,14 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
     const int pipe_bytes = L::kStages * L::kStageBytes;
     const int bres = p.num_taps * p.kblocks_per_tap * L::kBBytes;
     const bool fixed_n = (tiles <= grid) || (grid % p.num_n_tiles == 0);
-    static const bool enabled = [] { const char* e = getenv("ARGUS_B_RESIDENT"); return !(e && e[0] == '0'); }();
-    if (enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
+    static const bool enabled = [] { const char* e = getenv("ARGUS_B_RESIDENT"); return (e && e[0] == '1'); }();
+    static const bool halo_enabled = [] { const char* e = getenv("ARGUS_HALO"); return !(e && e[0] == '0'); }();
+    if (q.halo) {
+      const int stage = (q.halo_rows + 2) * q.halo_row_bytes + 3 * L::kBBytes;
+      q.halo_stages = std::min(L::kMaxStages, L::kPipeBytes / stage);
+      if (!halo_enabled || q.halo_stages < 2) q.halo = 0;
+    }
+    if (!q.halo && enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
       q.b_resident = 1;
       q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
     }

@@ -685,6 +685,154 @@ void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int
   ARGUS_CUDA(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// stem: max-pool backward fused into the batch-norm (+ReLU) backward of the stem convolution
+// ------------------------------------------------------------------------------------------------------------
+// The gradient wrt the stem activation is never materialised: both passes (per-channel sums, then dx) rebuild it from
+// the pooled gradient and the arg-max bytes. Thread = one 2x2 patch of stem pixels x 8 channels: the patch touches
+// exactly four pooling windows -- (a,b), (a,b+1), (a+1,b), (a+1,b+1) -- so 4 window loads serve 4 pixels (the plain
+// max-pool backward kernel needs up to 4 per pixel), and the 1.07 GB intermediate (write + two reads) disappears.
+template <int APPLY>
+__global__ void __launch_bounds__(256)
+stem_pool_bn_bwd_kernel(const uint4* __restrict__ dpool, const uint2* __restrict__ idx, const uint4* __restrict__ raw,
+                        const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ partial,
+                        uint4* __restrict__ dx, int N, int H, int W, float inv_rows) {
+  constexpr int cvec = 8;   // C = 64
+  __shared__ float red[16][256];
+  const int Ho = H >> 1, Wo = W >> 1;
+  const int cv = threadIdx.x & 7;
+  const int c0 = cv * 8;
+  const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
+  F8 k0, k1;
+  if (APPLY) {
+    const F8 mu = load8f(mean + c0), is = load8f(invstd + c0), dg = load8f(dgamma + c0), db = load8f(dbeta + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float c2 = sc.v[k] * dg.v[k] * inv_rows * is.v[k];
+      k1.v[k] = -c2;
+      k0.v[k] = fmaf(c2, mu.v[k], -sc.v[k] * db.v[k] * inv_rows);
+    }
+  }
+  float a_dy[8], a_dyx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a_dy[k] = a_dyx[k] = 0.f;
+  const int64_t patches = static_cast<int64_t>(N) * Ho * Wo;
+  for (int64_t pi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 3; pi < patches;
+       pi += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 3) {
+    const int b = static_cast<int>(pi % Wo);
+    const int64_t t = pi / Wo;
+    const int a = static_cast<int>(t % Ho);
+    const int n = static_cast<int>(t / Ho);
+    // the four windows of this patch: w[dy][dx] = window (a + dy, b + dx)
+    F8 wd[2][2];
+    uint2 wi[2][2];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dxx = 0; dxx < 2; ++dxx) {
+        const bool ok = (a + dy < Ho) && (b + dxx < Wo);
+        if (ok) {
+          const int64_t j = ((static_cast<int64_t>(n) * Ho + a + dy) * Wo + b + dxx) * cvec + cv;
+          wi[dy][dxx] = __ldg(idx + j);
+          wd[dy][dxx] = unpack8(__ldg(dpool + j));
+        } else {
+          wi[dy][dxx] = make_uint2(0xffffffffu, 0xffffffffu);   // code 255 never matches
+#pragma unroll
+          for (int k = 0; k < 8; ++k) wd[dy][dxx].v[k] = 0.f;
+        }
+      }
+    auto code_of = [](const uint2& id, int k) { return ((k < 4 ? (id.x >> (8 * k)) : (id.y >> (8 * (k - 4)))) & 0xffu); };
+#pragma unroll
+    for (int py = 0; py < 2; ++py)
+#pragma unroll
+      for (int px = 0; px < 2; ++px) {
+        const int64_t i = ((static_cast<int64_t>(n) * H + 2 * a + py) * W + 2 * b + px) * cvec + cv;
+        const F8 xv = unpack8(ldg_stream(raw + i));
+        F8 g;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+        // windows containing pixel (2a+py, 2b+px): rows {a} (py == 0) or {a, a+1} (py == 1); tap kh = 1 + py - 2*dy
+#pragma unroll
+        for (int dy = 0; dy <= py; ++dy)
+#pragma unroll
+          for (int dxx = 0; dxx <= px; ++dxx) {
+            const uint32_t code = static_cast<uint32_t>((1 + py - 2 * dy) * 3 + (1 + px - 2 * dxx));
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              if (code_of(wi[dy][dxx], k) == code) g.v[k] += wd[dy][dxx].v[k];
+          }
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (!(fmaf(xv.v[k], sc.v[k], sh.v[k]) > 0.f)) g.v[k] = 0.f;
+        if (APPLY) {
+          F8 r;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) r.v[k] = fmaf(sc.v[k], g.v[k], fmaf(k1.v[k], xv.v[k], k0.v[k]));
+          dx[i] = pack8(r);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            a_dy[k] += g.v[k];
+            a_dyx[k] = fmaf(g.v[k], xv.v[k], a_dyx[k]);
+          }
+        }
+      }
+  }
+  if (!APPLY) {
+    const F8 mu = load8f(mean + c0), is = load8f(invstd + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      red[k][threadIdx.x] = a_dy[k];
+      red[8 + k][threadIdx.x] = (a_dyx[k] - mu.v[k] * a_dy[k]) * is.v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int r = 0; r < 32; ++r) {
+          s0 += red[k][r * 8 + cv];
+          s1 += red[8 + k][r * 8 + cv];
+        }
+        partial[(static_cast<size_t>(blockIdx.x) * 2 + 0) * 64 + c0 + k] = s0;
+        partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * 64 + c0 + k] = s1;
+      }
+    }
+  }
+}
+
+void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* raw, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                           bf16* dx, int N, int H, int W, int C, float* scratch, cudaStream_t s) {
+  ARGUS_CHECK(C == 64, "the fused stem backward is written for 64 channels");
+  ARGUS_CHECK(H % 2 == 0 && W % 2 == 0, "stem output must have even height and width");
+  ARGUS_CHECK(scratch != nullptr, "stem_pool_bn_backward needs a scratch buffer");
+  const int64_t rows = static_cast<int64_t>(N) * H * W;
+  const int64_t threads = rows / 4 * 8;
+  const float inv_rows = static_cast<float>(1.0 / static_cast<double>(rows));
+  auto DP = reinterpret_cast<const uint4*>(dpool);
+  auto ID = reinterpret_cast<const uint2*>(idx);
+  auto RW = reinterpret_cast<const uint4*>(raw);
+  {
+    ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * (2.0 + 0.75));
+    const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, 4LL * num_sms())));
+    stem_pool_bn_bwd_kernel<0><<<grid, 256, 0, s>>>(DP, ID, RW, scale, shift, mean, invstd, nullptr, nullptr, scratch,
+                                                    nullptr, N, H, W, inv_rows);
+    ARGUS_CUDA(cudaGetLastError());
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, grid, dgamma, dbeta, C);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+  {
+    ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * (4.0 + 0.75));
+    const int grid = grid_for(threads, 256);
+    stem_pool_bn_bwd_kernel<1><<<grid, 256, 0, s>>>(DP, ID, RW, scale, shift, mean, invstd, dgamma, dbeta, nullptr,
+                                                    reinterpret_cast<uint4*>(dx), N, H, W, inv_rows);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+}
+
 __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int HW, int cvec) {
   const int64_t total = static_cast<int64_t>(N) * cvec;
   const float inv = 1.0f / HW;

@@ -75,6 +75,12 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
 void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y, uint8_t* idx, int N, int H, int W,
                  int C, cudaStream_t s);
 void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int W, int C, cudaStream_t s);
+// Stem tail backward in two passes over the stem convolution output `raw` (N, H, W, 64): max-pool backward (from the
+// pooled gradient dpool (N, H/2, W/2, 64) and the arg-max bytes), ReLU mask and batch-norm backward fused, the
+// un-pooled gradient is never written. dgamma / dbeta are accumulated (+=); dx = gradient wrt `raw`.
+void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* raw, const float* scale,
+                           const float* shift, const float* mean, const float* invstd, float* dgamma, float* dbeta,
+                           bf16* dx, int N, int H, int W, int C, float* scratch, cudaStream_t s);
 // global average pooling (N, HW, C) -> (N, C) and its backward
 void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s);
 void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s);

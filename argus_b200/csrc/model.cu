@@ -654,8 +654,13 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
     if (stage == 3) {
       // ---- stem: max-pool backward, bn1 backward, weight gradient
       ARGUS_CUDA(cudaMemsetAsync(gpacked_ + stem_.gpacked_off, 0, 64 * 256 * sizeof(float), s));
-      maxpool_bwd(p.g_stem_in, p.idx0, p.g_act0, N, p.H / 2, p.W / 2, 64, s);
-      bn_backward(stem_, p.g_act0, p.raw0, nullptr, p.g_raw0, static_cast<int64_t>(N) * (p.H / 2) * (p.W / 2), 1, s);
+      {
+        // max-pool backward fused into the stem's BN(+ReLU) backward: p.g_act0 is never written
+        const float* sc = bn_scratch_ + stem_.bn.scratch_off;
+        join_wgrad(s);   // g_raw0 aliases a buffer the previous block's weight-gradient GEMM may still read
+        stem_pool_bn_backward(p.g_stem_in, p.idx0, p.raw0, sc, sc + 64, sc + 128, sc + 192, grads_dev_ + stem_.bn.gamma_off,
+                              grads_dev_ + stem_.bn.beta_off, p.g_raw0, N, p.H / 2, p.W / 2, 64, bn_bwd_scratch_, s);
+      }
       run_wgrad(p.stem.wgrad, s);
     }
     join_wgrad(s);

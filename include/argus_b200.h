@@ -87,8 +87,37 @@ int argus_bn_backward(void* dy, const void* x, const void* out, const float* sca
 int argus_maxpool_forward(const void* x, const float* scale, const float* shift, void* y, void* idx, int N, int H,
                           int W, int C, void* stream);
 int argus_maxpool_backward(const void* dy, const void* idx, void* dx, int N, int H, int W, int C, void* stream);
+/* Stem tail backward, fused: max-pool backward (pooled gradient dpool (N,H/2,W/2,64) + arg-max bytes idx) -> ReLU mask
+ * -> batch-norm backward over the stem convolution output raw (N,H,W,64). Equivalent to argus_maxpool_backward followed
+ * by argus_bn_backward(mask_mode 1) without materialising the un-pooled gradient. dgamma / dbeta are ADDED to. */
+int argus_stem_pool_bn_backward(const void* dpool, const void* idx, const void* raw, const float* scale,
+                                const float* shift, const float* mean, const float* invstd, float* dgamma,
+                                float* dbeta, void* dx, int N, int H, int W, int C, void* stream);
 int argus_avgpool_forward(const void* x, void* y, int N, int HW, int C, void* stream);
 int argus_avgpool_backward(const void* dy, void* dx, int N, int HW, int C, void* stream);
+
+/* ---- fp32 parity-mode primitives (argus_model_set_precision(m, 1) runs the network on these) ---------------------
+ * All tensors fp32; activations NHWC; weights and weight gradients in PyTorch's [Cout][Cin][k][k] layout; padding k/2.
+ * SIMT implicit GEMMs with fp32 FMA accumulation; split-K partial sums, batch-norm statistics and BN-backward sums are
+ * accumulated in fp64 in a fixed order. Same semantics as torch.nn.Conv2d / BatchNorm2d / MaxPool2d(3,2,1). */
+int argus_fp32_conv2d_forward(const float* x, const float* w, const float* bias, float* y, int N, int H, int W, int Cin,
+                              int Cout, int k, int stride, void* stream);
+int argus_fp32_conv2d_dgrad(const float* dy, const float* w, float* dx, int N, int H, int W, int Cin, int Cout, int k,
+                            int stride, void* stream);
+/* dw += dy^T im2col(x) */
+int argus_fp32_conv2d_wgrad(const float* dy, const float* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
+                            int stride, void* stream);
+int argus_fp32_bn_train(const float* x, int64_t rows, int C, const float* gamma, const float* beta, float* running_mean,
+                        float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                        float* save_invstd, void* stream);
+int argus_fp32_bn_apply(const float* x, const float* scale, const float* shift, const float* res, const float* rscale,
+                        const float* rshift, int relu, float* y, int64_t rows, int C, void* stream);
+/* g = dy where out > 0 (all of dy when out is NULL); dgamma / dbeta are ADDED to; g_out (nullable) receives g */
+int argus_fp32_bn_backward(const float* dy, const float* x, const float* out, const float* scale, const float* mean,
+                           const float* invstd, float* dgamma, float* dbeta, float* dx, float* g_out, int64_t rows,
+                           int C, void* stream);
+int argus_fp32_maxpool_forward(const float* x, float* y, void* idx, int N, int H, int W, int C, void* stream);
+int argus_fp32_maxpool_backward(const float* dy, const void* idx, float* dx, int N, int H, int W, int C, void* stream);
 
 /* ---- augmentation (the kornia chain of argus/data.py:41-103 applied at data.py:213-225) ------------------------
  * Parameters are a pure function of (seed, step, image index): params is an (n_images, 24) fp32 table

@@ -41,6 +41,9 @@ CASES = [
     (300, 1, 1, 2048, 1024, 1, 1),  # fully connected layer, ragged M
     (2, 64, 64, 256, 64, 1, 1),     # Cout = 64: transposed all-taps weight-gradient kernel (4 channel boxes)
     (3, 32, 32, 64, 64, 1, 1),      # ... single box, padded pair
+    (20, 32, 32, 128, 128, 3, 1),   # halo mode with BLOCK_N = 128 and two channel blocks (layer2 shape)
+    (3, 16, 16, 64, 128, 3, 1),     # halo mode, eight image rows per tile
+    (2, 8, 16, 128, 64, 3, 1),      # halo mode, tile = one whole (8 x 16) image
 ]
 
 

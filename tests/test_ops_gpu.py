@@ -216,6 +216,70 @@ def test_maxpool(cuda_device, N, H, W, C):
     close_bf16(y2, F.max_pool2d(act.detach().bfloat16().float(), 3, 2, 1).permute(0, 2, 3, 1))
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 16, 16), (3, 64, 32), (1, 8, 128)])
+def test_stem_pool_bn_backward_fused(cuda_device, N, H, W):
+    """max-pool backward + ReLU mask + BN backward in two fused passes == the unfused composition (which rounds the
+    un-pooled gradient to bf16 in between) within one bf16 rounding, and == torch autograd."""
+    C = 64
+    g = torch.Generator().manual_seed(N + H + W)
+    raw = (torch.randn(N, H, W, C, generator=g) * 1.5 + torch.randn(C, generator=g)).to(cuda_device).bfloat16()
+    gamma = (torch.rand(C, generator=g) + 0.5).to(cuda_device)
+    beta = (torch.randn(C, generator=g) * 0.5).to(cuda_device)
+    rows = N * H * W
+    xr = raw.float().view(rows, C).requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    y, mean, var, invstd = bn_train_forward(xr, gr, br)
+    scale, shift = (gamma * invstd).detach(), (beta - mean * gamma * invstd).detach()
+    pooled = torch.empty(N, H // 2, W // 2, C, device=cuda_device, dtype=torch.bfloat16)
+    idx = torch.empty(N, H // 2, W // 2, C, device=cuda_device, dtype=torch.uint8)
+    _lib.call("argus_maxpool_forward", raw, scale, shift, pooled, idx, N, H, W, C, _lib.stream_ptr())
+    dpool = torch.randn(N, H // 2, W // 2, C, generator=g).to(cuda_device).bfloat16()
+    # unfused composition
+    dact = torch.empty_like(raw)
+    _lib.call("argus_maxpool_backward", dpool, idx, dact, N, H, W, C, _lib.stream_ptr())
+    dg_a, db_a = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+    dx_a = torch.empty_like(raw)
+    lib = _lib.load()
+    _lib.check(lib.argus_bn_backward(_lib.ptr(dact), _lib.ptr(raw), None, _lib.ptr(scale), _lib.ptr(shift), _lib.ptr(mean.detach()),
+                                     _lib.ptr(invstd.detach()), _lib.ptr(dg_a), _lib.ptr(db_a), _lib.ptr(dx_a),
+                                     ctypes.c_int64(rows), ctypes.c_int(C), ctypes.c_int(1), _lib.stream_ptr()))
+    # fused
+    dg_b, db_b = torch.zeros(C, device=cuda_device), torch.zeros(C, device=cuda_device)
+    dx_b = torch.empty_like(raw)
+    _lib.check(lib.argus_stem_pool_bn_backward(_lib.ptr(dpool), _lib.ptr(idx), _lib.ptr(raw), _lib.ptr(scale), _lib.ptr(shift),
+                                               _lib.ptr(mean.detach()), _lib.ptr(invstd.detach()), _lib.ptr(dg_b), _lib.ptr(db_b),
+                                               _lib.ptr(dx_b), ctypes.c_int(N), ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(C),
+                                               _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    # torch reference: the un-pooled gradient routed by OUR arg-max bytes (ties are equally valid), then autograd
+    ii = idx.long()
+    dact_ref = torch.zeros(N, H, W, C, device=cuda_device)
+    ph, pw = torch.meshgrid(torch.arange(H // 2, device=cuda_device), torch.arange(W // 2, device=cuda_device), indexing="ij")
+    hh = (2 * ph - 1)[None, :, :, None] + ii // 3
+    ww = (2 * pw - 1)[None, :, :, None] + ii % 3
+    nn_ = torch.arange(N, device=cuda_device)[:, None, None, None].expand_as(ii)
+    cc = torch.arange(C, device=cuda_device)[None, None, None, :].expand_as(ii)
+    dact_ref.index_put_((nn_, hh, ww, cc), dpool.float(), accumulate=True)
+    pre = torch.addcmul(shift, raw.float().view(rows, C), scale)
+    (y * (pre > 0)).backward(dact_ref.view(rows, C))
+    assert torch.allclose(db_b, br.grad, rtol=2e-3, atol=2e-3 * rows ** 0.5)
+    assert torch.allclose(dg_b, gr.grad, rtol=2e-3, atol=2e-3 * rows ** 0.5)
+    assert rel_err(dx_b.float().view(rows, C), xr.grad) < 4e-3
+    assert rel_err(dx_b.float(), dx_a.float()) < 6e-3      # the unfused path rounds the un-pooled gradient to bf16
+    # deterministic
+    dg_c, db_c, dx_c = torch.zeros_like(dg_b), torch.zeros_like(db_b), torch.empty_like(dx_b)
+    _lib.check(lib.argus_stem_pool_bn_backward(_lib.ptr(dpool), _lib.ptr(idx), _lib.ptr(raw), _lib.ptr(scale), _lib.ptr(shift),
+                                               _lib.ptr(mean.detach()), _lib.ptr(invstd.detach()), _lib.ptr(dg_c), _lib.ptr(db_c),
+                                               _lib.ptr(dx_c), ctypes.c_int(N), ctypes.c_int(H), ctypes.c_int(W), ctypes.c_int(C),
+                                               _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(dg_b, dg_c) and torch.equal(db_b, db_c) and torch.equal(dx_b, dx_c)
+
+
+def rel_err(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
 def test_avgpool(cuda_device):
     N, HW, C = 6, 64, 2048
     x = torch.randn(N, HW, C, device=cuda_device).bfloat16()

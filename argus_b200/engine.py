@@ -84,7 +84,14 @@ class TrainEngine:
         model = self.model
         lib_stream = _lib.stream_ptr()
         model.train()
-        if images.dtype == torch.uint8:
+        if images.dtype == torch.uint8 and model.precision == "fp32":
+            # fp32 parity mode: the same augmentation kernel with fp32 NCHW output, then the fp32 network
+            aug = self.augmentation
+            if aug is not None and aug.train and aug.enabled:
+                out = model._forward_impl(aug.augment_batch(images), True)
+            else:
+                out = model._forward_impl(images, True)
+        elif images.dtype == torch.uint8:
             # fused augmentation + staging: uint8 pairs -> augmented bf16 stem input inside the model's arena
             aug = self.augmentation
             apply = aug is not None and aug.train and aug.enabled

@@ -49,7 +49,11 @@ class TrainConfig:
 
     # speed optimizations
     multigpu: bool = False
-    amp: bool = False  # accepted for CLI parity: compute is always bf16 storage with fp32 accumulation here
+    amp: bool = False  # accepted for CLI parity (the reference's fp16 autocast + GradScaler, train.py:74,234,298-300):
+    #                    the bf16 path has fp32's exponent range, so no loss scaling exists here
+    # not in the reference: "bf16" = tcgen05 tensor-core path (default), "fp32" = the fp32 parity mode (what the
+    # reference computes with amp=False), see argus_model_set_precision in include/argus_b200.h
+    precision: str = "bf16"
 
     # validation, printing, and saving
     val_epochs: int = 1
@@ -136,7 +140,7 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
     train_dataloader = DataLoader(train_dataset, shuffle=train_shuffle, sampler=train_sampler, **common)
     val_dataloader = DataLoader(val_dataset, shuffle=False, sampler=val_sampler, **common)
 
-    model = NCameraCNN(cfg.model_config).to(device)
+    model = NCameraCNN(cfg.model_config).to(device).set_precision(cfg.precision)
     augmentation = Augmentation(cfg.augmentation_config, train=True, seed=cfg.random_seed + 7919 * rank) \
         if cfg.use_augmentation else None
     engine = TrainEngine(model, lr=cfg.learning_rate, max_grad_norm=cfg.max_grad_norm, augmentation=augmentation)

@@ -90,3 +90,27 @@ def test_loss_decreases_when_overfitting(cuda_device):
     losses = [engine.step(x, t).item() for _ in range(60)]
     assert losses[-1] < 0.5 * losses[0], (losses[0], losses[-1])
     assert all(np.isfinite(losses))
+
+
+def test_loss_curve_tracks_reference(cuda_device):
+    """North star: "a matching ... loss curve". 300 steps of the bf16 product path against the same 300 steps of the
+    reference (PyTorch fp32, TF32 off) from identical weights on an identical batch sequence (profiles/loss_curve.py;
+    the committed 1000-step run is profiles/r1_loss_curve_1k.json). The trajectories separate chaotically after ~100
+    steps -- torch's own bf16 autocast run of the reference deviates from its fp32 run by up to 50 % per window -- so
+    the assertion is on the trend: every 100-step window mean within 2x of the reference's, and the same descent."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "profiles"))
+    from loss_curve import make_task, run_ours, run_reference, window_means
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    images, targets = make_task(size=128)
+    ref = window_means(run_reference(images, targets, 300, 8, autocast=False), 100)
+    ours = window_means(run_ours(images, targets, 300, 8, "bf16"), 100)
+    print("loss windows: reference fp32", ref, " ours bf16", ours)
+    assert abs(ours[0] - ref[0]) / ref[0] < 0.1          # the first 100 steps still coincide closely
+    for a, b in zip(ours, ref):
+        assert 0.5 < a / b < 2.0, (ours, ref)
+    assert ours[-1] < 0.35 * ours[0] and ref[-1] < 0.35 * ref[0]

@@ -267,6 +267,7 @@ void Model::build_plan(Plan& p) {
   };
   // ---- stem
   p.x_s2d = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
+  p.x_s2d_alt = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
   const int H1 = H / 2, W1 = W / 2;  // stem output
   const int H2 = H1 / 2, W2 = W1 / 2;  // after max pooling
   const size_t stem_elems = static_cast<size_t>(N) * H1 * W1 * 64;
@@ -274,6 +275,7 @@ void Model::build_plan(Plan& p) {
   p.pooled0 = arena_alloc<bf16>(stem_elems / 4);
   if (tr) p.idx0 = arena_alloc<uint8_t>(stem_elems / 4);
   plan_conv(p.stem, stem_, N, H, W, p.x_s2d, tr ? p.raw0 : p.act0, false);
+  if (real) p.stem_fwd_alt = plan_conv_forward(stem_.shape, p.x_s2d_alt, packed_ + stem_.packed_off, tr ? p.raw0 : p.act0);
 
   // ---- bottleneck blocks
   p.blocks.assign(blocks_.size(), BlockPlan());
@@ -369,6 +371,7 @@ void Model::build_plan(Plan& p) {
   p.g_raw0 = R;
   if (real) {
     p.stem.wgrad = plan_conv_wgrad(stem_.shape, R, p.x_s2d, gpacked_ + stem_.gpacked_off);
+    p.stem_wgrad_alt = plan_conv_wgrad(stem_.shape, R, p.x_s2d_alt, gpacked_ + stem_.gpacked_off);
     ensure_wgrad_scratch(p.stem.wgrad);
   }
 }
@@ -477,13 +480,16 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
     return;
   }
   Plan& p = get_plan(B, H, W, training);
+  // every input is written to the alternate stem buffer, which then becomes the current one: a batch staged ahead of
+  // time (stage_input_u8 on another stream) never touches the buffer the in-flight pass still reads
   if (x == nullptr) {
     ARGUS_CHECK(staged_plan_ == &p, "forward(x = NULL) needs a preceding stage_input_u8() for the same batch shape");
   } else if (is_u8) {
-    pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d, p.N, H, W, s);
+    pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d_alt, p.N, H, W, s);
   } else {
-    pack_input_f32(static_cast<const float*>(x), p.x_s2d, p.N, H, W, s);
+    pack_input_f32(static_cast<const float*>(x), p.x_s2d_alt, p.N, H, W, s);
   }
+  p.use_alt_input();
   staged_plan_ = nullptr;
   last_plan_ = &p;
   if (training) {
@@ -501,7 +507,7 @@ void Model::stage_input_u8(const uint8_t* images, float* aug_params, int B, int 
   ARGUS_CHECK(!apply || aug_params != nullptr, "augmentation needs a parameter table");
   ARGUS_CHECK(precision_ == 0, "the fused augmentation + staging path exists in bf16 mode only");
   Plan& p = get_plan(B, H, W, training);
-  augment_images(images, true, p.x_s2d, true, aug_params, p.N, H, W, apply, s);
+  augment_images(images, true, p.x_s2d_alt, true, aug_params, p.N, H, W, apply, s);
   staged_plan_ = &p;
 }
 

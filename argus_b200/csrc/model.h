@@ -69,6 +69,17 @@ struct Plan {
   bool training = false;
   ConvPlan stem;
   bf16 *x_s2d = nullptr, *raw0 = nullptr, *act0 = nullptr, *pooled0 = nullptr;
+  // The stem input is double buffered so that the NEXT batch can be augmented / staged (on another stream) while the
+  // current one trains: x_s2d / stem.fwd / stem.wgrad describe the buffer the current pass reads, the *_alt members
+  // the one the next staging call writes. use_alt_input() swaps the two sets.
+  bf16* x_s2d_alt = nullptr;
+  ConvLaunch stem_fwd_alt;
+  WgradLaunch stem_wgrad_alt;
+  void use_alt_input() {
+    std::swap(x_s2d, x_s2d_alt);
+    std::swap(stem.fwd, stem_fwd_alt);
+    std::swap(stem.wgrad, stem_wgrad_alt);
+  }
   uint8_t* idx0 = nullptr;
   std::vector<BlockPlan> blocks;
   ConvPlan fc;

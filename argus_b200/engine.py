@@ -69,6 +69,11 @@ class TrainEngine:
         self._loss_mean = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._stage_ranges = model.stage_ranges()
         self.last_grad_norm = self._grad_norm
+        # look-ahead staging (prefetch): side stream + events, see prefetch()
+        self._side = torch.cuda.Stream(device=self.device)
+        self._prev_done = torch.cuda.Event()
+        self._staged_event = torch.cuda.Event()
+        self._staged = None            # (data_ptr, shape) of the uint8 batch already augmented into the model
         if self.distributed:
             # DDP's constructor broadcasts rank 0's parameters and buffers (train.py:199)
             dist.broadcast(model.flat_params, src=0, group=process_group)
@@ -76,6 +81,36 @@ class TrainEngine:
             model.sync_weights(force=True)
 
     # ------------------------------------------------------------------------------------------------------------
+    def prefetch(self, images: torch.Tensor, after: Optional["torch.cuda.Event"] = None) -> None:
+        """Augment + stage the NEXT uint8 batch on a side stream while the step enqueued just before keeps the GPU
+        busy (the augmentation kernel is ALU-bound, the training step HBM-bound: they overlap well). The model keeps
+        two stem-input buffers, so the batch in flight is not disturbed. Call it right after step(); the following
+        step() / forward_backward() must be given the same tensor. `after`: an event the staging must wait for (e.g. the
+        host-to-device copy of `images` on a copy stream); work already enqueued on the current stream before the
+        preceding step() is waited for automatically. A no-op for inputs the fused staging path does not cover (float
+        images, fp32 mode)."""
+        model = self.model
+        if images.dtype != torch.uint8 or model.precision != "bf16":
+            return
+        aug = self.augmentation
+        apply = aug is not None and aug.train and aug.enabled
+        # the buffer being written was last read by the step BEFORE the one in flight: wait for that step only
+        self._side.wait_event(self._prev_done)
+        if after is not None:
+            self._side.wait_event(after)
+        with torch.cuda.stream(self._side):
+            params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
+            B, _, H, W, _ = images.shape
+            model._ensure_bound()
+            with torch.cuda.device(self.device):
+                _lib.call("argus_model_stage_input_u8", model._handle.ptr, images.contiguous(), params, int(B), int(H),
+                          int(W), 1, int(apply), _lib.stream_ptr())
+            self._staged_event.record(self._side)
+        images.record_stream(self._side)
+        if params is not None:
+            params.record_stream(self._side)
+        self._staged = (images.data_ptr(), tuple(images.shape))
+
     def forward_backward(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """Forward, loss, backward (+ bucketed gradient all-reduce). Returns the mean loss as a device scalar.
 
@@ -84,7 +119,17 @@ class TrainEngine:
         model = self.model
         lib_stream = _lib.stream_ptr()
         model.train()
-        if images.dtype == torch.uint8 and model.precision == "fp32":
+        # everything enqueued so far (the previous step) precedes this event: a prefetch() issued after this call may
+        # overwrite the stem buffer of the previous step as soon as it fires
+        self._prev_done.record(torch.cuda.current_stream(self.device))
+        staged, self._staged = self._staged, None
+        if staged is not None:
+            # (also when the staged batch is not the one given now: its write into the alternate buffer must be over
+            # before anything else is staged there)
+            torch.cuda.current_stream(self.device).wait_event(self._staged_event)
+        if staged is not None and images.dtype == torch.uint8 and staged == (images.data_ptr(), tuple(images.shape)):
+            out = model._forward_staged(images.shape[0], images.shape[2], images.shape[3])
+        elif images.dtype == torch.uint8 and model.precision == "fp32":
             # fp32 parity mode: the same augmentation kernel with fp32 NCHW output, then the fp32 network
             aug = self.augmentation
             if aug is not None and aug.train and aug.enabled:

@@ -312,6 +312,17 @@ class NCameraCNN(nn.Module):
             self._flat_nbt += 1
         return out
 
+    def _forward_staged(self, B: int, H: int, W: int) -> torch.Tensor:
+        """Training forward over a batch already staged by argus_model_stage_input_u8 (TrainEngine.prefetch)."""
+        self._ensure_bound()
+        self.sync_weights()
+        dev = self._flat_params.device
+        out = torch.empty((B, 6), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("argus_model_forward", self._handle.ptr, None, 0, int(B), int(H), int(W), 1, out, _lib.stream_ptr())
+        self._flat_nbt += 1
+        return out
+
     def _backward_impl(self, grad_out: torch.Tensor) -> list[torch.Tensor]:
         g = grad_out.contiguous().to(torch.float32)
         with torch.cuda.device(g.device):

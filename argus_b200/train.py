@@ -186,14 +186,27 @@ def train(cfg: TrainConfig, rank: int = 0) -> None:
         model.train()
         epoch_losses = []
         pending = None  # loss of the previous step, read one step late so that no step ever synchronises
-        for example in train_dataloader:
-            images = example["images"].to(device, non_blocking=True)        # (B, n_cams, H, W, 3) uint8
-            cube_pose = example["cube_pose"].to(device, non_blocking=True)  # (B, 7) [t, q_xyzw]
-            loss = engine.step(images, cube_pose)
+
+        def to_device(example):
+            if example is None:
+                return None
+            return (example["images"].to(device, non_blocking=True),        # (B, n_cams, H, W, 3) uint8
+                    example["cube_pose"].to(device, non_blocking=True))     # (B, 7) [t, q_xyzw]
+
+        # one batch of look-ahead: while step k trains, batch k+1 is copied to the device and augmented + staged on the
+        # engine's side stream (the reference augments on CPU workers, data.py:213-225)
+        batches = iter(train_dataloader)
+        current = to_device(next(batches, None))
+        while current is not None:
+            upcoming = to_device(next(batches, None))
+            loss = engine.step(*current)
+            if upcoming is not None:
+                engine.prefetch(upcoming[0])
             epoch_losses.append(loss.detach().clone())
             if log and pending is not None:
                 wandb.log({"loss": float(pending)})
             pending = epoch_losses[-1]
+            current = upcoming
         if log and pending is not None:
             wandb.log({"loss": float(pending)})
         if epoch % cfg.print_epochs == 0 and epoch_losses:

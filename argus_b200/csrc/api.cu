@@ -197,7 +197,7 @@ int argus_avgpool_forward(const void* x, void* y, int N, int HW, int C, void* st
 int argus_avgpool_backward(const void* dy, void* dx, int N, int HW, int C, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
-  avgpool_bwd(static_cast<const bf16*>(dy), static_cast<bf16*>(dx), N, HW, C, static_cast<cudaStream_t>(stream));
+  avgpool_bwd(static_cast<const bf16*>(dy), static_cast<bf16*>(dx), nullptr, N, HW, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 

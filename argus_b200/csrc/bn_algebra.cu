@@ -1,0 +1,190 @@
+// Algebraic batch-norm backward for the expanding 1x1 convolution of a bottleneck (conv3 -> bn3 -> +identity -> ReLU).
+//
+// The textbook backward makes two full passes over the widest tensors of the block (4C channels): a reduction
+// (sum g, sum g*xhat over raw3) and an elementwise pass that writes dRaw3 = sc*g + k1*raw3 + k0, which the weight-
+// and input-gradient GEMMs then read again. Because raw3 = act2 * W3^T is LINEAR in the (4x narrower) saved activation,
+// all of that collapses onto GEMMs over g and act2 plus a few [4C x C] / [C x C] matrices:
+//
+// (W3 below is the bf16-rounded weight the forward GEMM actually used, so raw3 = act2 W3^T holds up to the bf16
+//  rounding of the stored raw3.)
+//   H  = g^T act2                  (the weight-gradient GEMM, run on the masked gradient g itself)       [4C x C]
+//   G  = act2^T act2               (Gram matrix, a C x C weight-gradient-shaped GEMM)                    [C x C]
+//   s  = colsum(act2),  db = colsum(g)  (db comes from the statistics slots of the dgrad that produced g)
+//   sum_p g*raw3  = rowdot(W3, H)                  -> dgamma = invstd * (rowdot - mean * db),  dbeta = db
+//   k1 = -sc * dgamma * invstd / P,   k0 = -k1 * mean - sc * db / P              (dRaw3 = sc*g + k1*raw3 + k0)
+//   dAct2 = g (diag(sc) W3) + act2 (W3^T diag(k1) W3) + k0^T W3     -> ONE dgrad GEMM over the concatenated K = 4C + C
+//   dW3   = diag(sc) H + diag(k1) W3 G + k0 (x) s
+//
+// so neither raw3 nor dRaw3 is touched in the backward pass. All small-matrix work is fp32 and deterministic.
+// Reference semantics: autograd of torch.nn.BatchNorm2d + Conv2d(1x1) inside torchvision's Bottleneck
+// (/root/reference/argus/models.py:84).
+#include "kernels.h"
+#include "ptx.cuh"
+#include "runtime.h"
+
+#include <algorithm>
+
+namespace argus {
+
+// one warp per output channel o
+__global__ void __launch_bounds__(256)
+bn_alg_coeffs_kernel(const bf16* __restrict__ W, const float* __restrict__ H, const float* __restrict__ stat_partial,
+                     int slots, int stat_stride, const float* __restrict__ scale, const float* __restrict__ mean,
+                     const float* __restrict__ invstd, float inv_rows, float* dgamma, float* dbeta,
+                     float* __restrict__ k1k0, bf16* __restrict__ bstack, int O, int C) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  // db = sum over the statistic slots, lanes take slots round-robin, then a fixed shuffle tree: deterministic
+  double db = 0.0;
+  for (int k = lane; k < slots; k += 32) db += static_cast<double>(stat_partial[static_cast<size_t>(k) * stat_stride + o]);
+  double t = 0.0;
+  const bf16* w = W + static_cast<size_t>(o) * C;
+  const float* h = H + static_cast<size_t>(o) * C;
+  for (int i = lane; i < C; i += 32) t += static_cast<double>(__bfloat162float(w[i])) * static_cast<double>(h[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    db += __shfl_xor_sync(0xffffffffu, db, off);
+    t += __shfl_xor_sync(0xffffffffu, t, off);
+  }
+  const float sc = scale[o], mu = mean[o], is = invstd[o];
+  const double dg = static_cast<double>(is) * (t - static_cast<double>(mu) * db);
+  const double c2 = static_cast<double>(sc) * dg * static_cast<double>(is) * inv_rows;
+  const float k1 = static_cast<float>(-c2);
+  const float k0 = static_cast<float>(c2 * mu - static_cast<double>(sc) * db * inv_rows);
+  if (lane == 0) {
+    dgamma[o] += static_cast<float>(dg);
+    dbeta[o] += static_cast<float>(db);
+    k1k0[o] = k1;
+    k1k0[O + o] = k0;
+  }
+  bf16* b = bstack + static_cast<size_t>(o) * C;
+  for (int i = lane; i < C; i += 32) b[i] = __float2bfloat16(sc * __bfloat162float(w[i]));
+}
+
+// M[j][i] = sum_o W[o][j] k1[o] W[o][i] -> bstack rows O + j (bf16);  blockIdx.y == C/16: bias[i] = sum_o k0[o] W[o][i]
+__global__ void __launch_bounds__(256)
+bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0, bf16* __restrict__ bstack,
+                     float* __restrict__ bias, int O, int C) {
+  __shared__ float sWj[32][17];   // [o chunk][j]
+  __shared__ float sWi[32][17];   // [o chunk][i]
+  const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * 16;
+  const bool bias_row = (blockIdx.y == C / 16);
+  const int j0 = bias_row ? 0 : blockIdx.y * 16;
+  float acc = 0.f;
+  for (int o0 = 0; o0 < O; o0 += 32) {
+    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+      const int oo = e >> 4, c = e & 15;
+      sWi[oo][c] = __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + i0 + c]);
+      sWj[oo][c] = bias_row ? k1k0[O + o0 + oo]
+                            : __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + j0 + c]) * k1k0[o0 + oo];
+    }
+    __syncthreads();
+    if (!bias_row) {
+#pragma unroll 8
+      for (int oo = 0; oo < 32; ++oo) acc = fmaf(sWj[oo][tj], sWi[oo][ti], acc);
+    } else if (tj == 0) {
+#pragma unroll 8
+      for (int oo = 0; oo < 32; ++oo) acc = fmaf(sWj[oo][0], sWi[oo][ti], acc);
+    }
+    __syncthreads();
+  }
+  if (!bias_row) bstack[static_cast<size_t>(O + j0 + tj) * C + i0 + ti] = __float2bfloat16(acc);
+  else if (tj == 0) bias[i0 + ti] = acc;
+}
+
+// dW[o][i] += sc[o] H[o][i] + k0[o] s[i] + k1[o] sum_j W[o][j] G[j][i]
+__global__ void __launch_bounds__(256)
+bn_alg_dw_kernel(const bf16* __restrict__ W, const float* __restrict__ H, const float* __restrict__ G,
+                 const float* __restrict__ s, const float* __restrict__ scale, const float* __restrict__ k1k0,
+                 float* __restrict__ dW, int O, int C) {
+  __shared__ float sW[16][33];   // [o][j chunk]
+  __shared__ float sG[32][17];   // [j chunk][i]
+  const int ti = threadIdx.x & 15, to = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * 16, o0 = blockIdx.y * 16;
+  float acc = 0.f;
+  for (int j0 = 0; j0 < C; j0 += 32) {
+    for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+      const int a = e >> 5, b = e & 31;      // W tile [16 o][32 j]
+      sW[a][b] = __bfloat162float(W[static_cast<size_t>(o0 + a) * C + j0 + b]);
+      const int c = e >> 4, d = e & 15;      // G tile [32 j][16 i]
+      sG[c][d] = G[static_cast<size_t>(j0 + c) * C + i0 + d];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) acc = fmaf(sW[to][j], sG[j][ti], acc);
+    __syncthreads();
+  }
+  const int o = o0 + to, i = i0 + ti;
+  const size_t idx = static_cast<size_t>(o) * C + i;
+  dW[idx] += scale[o] * H[idx] + k1k0[O + o] * s[i] + k1k0[o] * acc;
+}
+
+void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const float* s, const float* stat_partial,
+                           int slots, int stat_stride, const float* scale, const float* mean, const float* invstd,
+                           double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
+                           int O, int C, cudaStream_t st) {
+  ARGUS_CHECK(O % 32 == 0 && C % 32 == 0, "algebraic BN backward: O and C must be multiples of 32");
+  ProfileScope prof("bn_algebra", st, 4.0 * O * static_cast<double>(C) * C, 0);
+  bn_alg_coeffs_kernel<<<(O * 32 + 255) / 256, 256, 0, st>>>(W, H, stat_partial, slots, stat_stride, scale, mean, invstd,
+                                                            static_cast<float>(1.0 / rows), dgamma, dbeta, k1k0, bstack,
+                                                            O, C);
+  ARGUS_CUDA(cudaGetLastError());
+  bn_alg_matrix_kernel<<<dim3(C / 16, C / 16 + 1), 256, 0, st>>>(W, k1k0, bstack, bias, O, C);
+  ARGUS_CUDA(cudaGetLastError());
+  bn_alg_dw_kernel<<<dim3(C / 16, O / 16), 256, 0, st>>>(W, H, G, s, scale, k1k0, dW, O, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// deterministic column sums of a bf16 (rows, C) matrix: per-block partials, then an ordered reduction
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t rows, int cvec) {
+  __shared__ float red[8][256];
+  const int lanes = cvec < 256 ? cvec : 256;
+  const int row_lanes = 256 / lanes;
+  const int rl = threadIdx.x / lanes, oc = threadIdx.x % lanes;
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int64_t r = static_cast<int64_t>(blockIdx.x) * row_lanes + rl; r < rows;
+       r += static_cast<int64_t>(gridDim.x) * row_lanes) {
+    const uint4 u = __ldg(x + r * cvec + oc);
+    float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
+    acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  if (rl == 0) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s0 = 0.f;
+      for (int r = 0; r < row_lanes; ++r) s0 += red[k][r * lanes + oc];
+      partial[static_cast<size_t>(blockIdx.x) * (cvec * 8) + oc * 8 + k] = s0;
+    }
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out, int C) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int b = 0; b < blocks; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * C + c]);
+  out[c] = static_cast<float>(acc);
+}
+void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st) {
+  ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "colsum: C/8 must be a power of two <= 256");
+  ProfileScope prof("bn_algebra", st, 0, static_cast<double>(rows) * C * 2);
+  const int cvec = C / 8;
+  const int lanes = std::min(cvec, 256);
+  const int row_lanes = 256 / lanes;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + row_lanes - 1) / row_lanes, 2LL * num_sms())));
+  colsum_partial_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), scratch, rows, cvec);
+  ARGUS_CUDA(cudaGetLastError());
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, blocks, out, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+}  // namespace argus

@@ -67,6 +67,12 @@ struct ConvGemmParams {
   int32_t halo_boff[3][3];
   CUtensorMap halo_map;   // box {64, W, rows + 2, 1}
   const uint8_t* res_bits;       // optional [m_total][n_total/8] bit mask: residual element counts only where its bit is set
+  const uint8_t* out_bits;       // optional [m_total][n_total/8] bit mask applied to the RESULT (after the residual add):
+                                 // the dgrad that produces the gradient of a ReLU output stores it already masked
+  // K concatenation (1x1 only): after the regular k-blocks, k2_blocks more 64-wide blocks are read from a_map[1]
+  // (same pixel grid) against the weight rows that follow: D = [A0 | A1] * [B0 ; B1]. Used by the algebraic
+  // batch-norm backward (model.cu), where A1 = the saved activation and B1 a small correction matrix.
+  int k2_blocks;
   int relu;
   // train-mode BN statistics of the stored bf16 outputs, reduced deterministically: every (CTA, epilogue group)
   // owns slot = 2*blockIdx.x + group of stat_partial[slot][2][n_total] (sum, sum of squares); bn_finalize adds the
@@ -159,7 +165,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-  const int num_kblocks = p.num_taps * p.kblocks_per_tap;
+  const int num_kblocks = p.num_taps * p.kblocks_per_tap + p.k2_blocks;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -221,6 +227,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (!resident) load_b(full_bar(stage), sa + L::kABytes, tap, kb, n0);
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
+        }
+        for (int kb = 0; kb < p.k2_blocks; ++kb) {
+          // concatenated K segment: activations from a_map[1], weight rows continue after the first segment
+          mbar_wait(empty_bar(stage), phase ^ 1);
+          const uint32_t sa = smem_base + stage * stage_bytes;
+          mbar_arrive_expect_tx(full_bar(stage), stage_bytes);
+          tma_load_4d(&p.a_map[1], full_bar(stage), sa, kb * kBlockK, w0, h0, img0);
+          Tap tap{};
+          load_b(full_bar(stage), sa + L::kABytes, tap, p.num_taps * p.kblocks_per_tap + kb, n0);
+          if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -368,6 +384,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           }
         }
         named_bar_sync(bar_id, 128);
+        uint2 obits = make_uint2(0xffffffffu, 0xffffffffu);
+        if (p.out_bits != nullptr && m0 + r < p.m_total)
+          obits = __ldg(reinterpret_cast<const uint2*>(p.out_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
+                                                       ((n0 + ch * 64) >> 3)));
         uint2 rbits = make_uint2(0xffffffffu, 0xffffffffu);
         if (p.res_bits != nullptr && m0 + r < p.m_total)
           rbits = __ldg(reinterpret_cast<const uint2*>(p.res_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
@@ -430,6 +450,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (p.relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+          }
+          if (p.out_bits != nullptr) {
+            const uint32_t ob = (h == 0 ? obits.x : obits.y);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = ((ob >> i) & 1u) ? f[i] : 0.f;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {

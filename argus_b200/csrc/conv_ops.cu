@@ -401,6 +401,34 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
   return out;
 }
 
+ConvLaunch plan_dgrad_concat(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* a1, int C1,
+                             const __nv_bfloat16* bstack, __nv_bfloat16* dx) {
+  validate_shape(s);
+  ARGUS_CHECK(s.kind == 0 && s.k == 1 && s.stride == 1, "concatenated dgrad is defined for 1x1 stride-1 convolutions");
+  ARGUS_CHECK(C1 > 0 && C1 % 64 == 0, "second source must have a multiple of 64 channels");
+  std::vector<ConvLaunch> ls = plan_conv_dgrad(s, dy, bstack, dx);
+  ARGUS_CHECK(ls.size() == 1, "unexpected dgrad decomposition");
+  ConvLaunch l = ls[0];
+  ConvGemmParams& p = l.p;
+  uint32_t bw, bh, bn;
+  pixel_box(s.W, s.H, kBlockM, bw, bh, bn);
+  {
+    const uint64_t C = C1;
+    const uint64_t dims[4] = {C, static_cast<uint64_t>(s.W), static_cast<uint64_t>(s.H), static_cast<uint64_t>(s.N)};
+    const uint64_t str[3] = {C * 2, s.W * C * 2, static_cast<uint64_t>(s.H) * s.W * C * 2};
+    const uint32_t box[4] = {64, bw, bh, bn};
+    p.a_map[1] = make_tmap_bf16(a1, 4, dims, str, box);
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cin), static_cast<uint64_t>(s.Cout + C1)};
+    const uint64_t str[1] = {static_cast<uint64_t>(s.Cin) * 2};
+    const uint32_t box[2] = {64, 64};
+    p.b_map = make_tmap_bf16(bstack, 2, dims, str, box);
+  }
+  p.k2_blocks = C1 / 64;
+  return l;
+}
+
 WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw) {
   validate_shape(s);
   WgradLaunch l;
@@ -498,7 +526,7 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
       q.halo_stages = std::min(L::kMaxStages, L::kPipeBytes / stage);
       if (!halo_enabled || q.halo_stages < 2) q.halo = 0;
     }
-    if (!q.halo && enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
+    if (!q.halo && q.k2_blocks == 0 && enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
       q.b_resident = 1;
       q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
     }
@@ -519,12 +547,13 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     p.res_bits = e.residual_bits;
   }
   p.relu = e.relu;
+  p.out_bits = e.out_bits;
   p.stat_partial = e.stat_partial;
-  const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * p.num_taps * p.kblocks_per_tap * kBlockK;
+  const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * (p.num_taps * p.kblocks_per_tap + p.k2_blocks) * kBlockK;
   std::string fam = l.b_mn ? "conv_dgrad" : "conv_fwd";
   if (g_profiling && profile_detailed())
     fam += ":M" + std::to_string(p.m_total) + "_N" + std::to_string(p.n_total) + "_K" +
-           std::to_string(p.num_taps * p.kblocks_per_tap * kBlockK) + "_t" + std::to_string(p.num_taps);
+           std::to_string((p.num_taps * p.kblocks_per_tap + p.k2_blocks) * kBlockK) + "_t" + std::to_string(p.num_taps);
   ProfileScope prof(fam, stream, flops, 0.0);
   const int key = l.block_n * 2 + l.b_mn;
   switch (key) {

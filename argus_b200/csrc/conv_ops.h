@@ -27,6 +27,7 @@ struct Epilogue {
   const float* shift = nullptr;
   const __nv_bfloat16* residual = nullptr;
   const uint8_t* residual_bits = nullptr;   // optional [rows][Cout/8] ReLU bit mask gating the residual (dgrad)
+  const uint8_t* out_bits = nullptr;        // optional [rows][Cout/8] ReLU bit mask applied to the stored result
   int relu = 0;
   float* stat_partial = nullptr;   // [stat_slots(launch)][2][Cout], zeroed by the caller (train-mode BN statistics)
 };
@@ -68,6 +69,10 @@ ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const _
 std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* w,
                                         __nv_bfloat16* dx);
 // dw[Cout][Ktot] (fp32, accumulated with atomics: caller zero-fills) = dy^T * im2col(x)
+// 1x1 stride-1 dgrad over a concatenated K: dx[p, n] = sum_{k < Cout} dy[p, k] B[k, n] + sum_{k < C1} a1[p, k] B[Cout + k, n]
+// with B = bstack, a row-major [(Cout + C1)][Cin] bf16 matrix, and a1 an (N, H, W, C1) activation on the same grid.
+ConvLaunch plan_dgrad_concat(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* a1, int C1,
+                             const __nv_bfloat16* bstack, __nv_bfloat16* dx);
 WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);

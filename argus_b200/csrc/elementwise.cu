@@ -861,7 +861,8 @@ void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s) {
                                                           reinterpret_cast<uint4*>(y), N, HW, C / 8);
   ARGUS_CUDA(cudaGetLastError());
 }
-__global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int N, int HW, int cvec) {
+__global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, const uint8_t* __restrict__ bits,
+                                   int N, int HW, int cvec) {
   const int64_t total = static_cast<int64_t>(N) * HW * cvec;
   const float inv = 1.0f / HW;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -869,16 +870,17 @@ __global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restri
     const int cv = static_cast<int>(i % cvec);
     const int n = static_cast<int>(i / (static_cast<int64_t>(HW) * cvec));
     F8 v = unpack8(__ldg(dy + static_cast<int64_t>(n) * cvec + cv));
+    const uint32_t b = bits != nullptr ? bits[i] : 0xffu;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v.v[k] *= inv;
+    for (int k = 0; k < 8; ++k) v.v[k] = ((b >> k) & 1u) ? v.v[k] * inv : 0.f;
     dx[i] = pack8(v);
   }
 }
-void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s) {
+void avgpool_bwd(const bf16* dy, bf16* dx, const uint8_t* relu_bits, int N, int HW, int C, cudaStream_t s) {
   ProfileScope prof("avgpool", s, 0, static_cast<double>(N) * (HW + 1) * C * 2);
   const int64_t total = static_cast<int64_t>(N) * HW * (C / 8);
   avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
-                                                          reinterpret_cast<uint4*>(dx), N, HW, C / 8);
+                                                          reinterpret_cast<uint4*>(dx), relu_bits, N, HW, C / 8);
   ARGUS_CUDA(cudaGetLastError());
 }
 

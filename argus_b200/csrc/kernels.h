@@ -83,7 +83,20 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
                            bf16* dx, int N, int H, int W, int C, float* scratch, cudaStream_t s);
 // global average pooling (N, HW, C) -> (N, C) and its backward
 void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s);
-void avgpool_bwd(const bf16* dy, bf16* dx, int N, int HW, int C, cudaStream_t s);
+// relu_bits (optional, [N*HW][C/8]): the result is stored already masked by the ReLU bit mask of the pooled tensor
+void avgpool_bwd(const bf16* dy, bf16* dx, const uint8_t* relu_bits, int N, int HW, int C, cudaStream_t s);
+
+// ---- algebraic batch-norm backward of an expanding 1x1 convolution (bn_algebra.cu) -------------------------------
+// W: bf16 [O][C] weights (the packed copy the forward GEMM used); H = g^T act [O][C]; G = act^T act [C][C]; s = colsum(act) [C]; stat_partial: per-slot sums
+// of g ([slot] stride stat_stride floats, channel o at offset o) written by the dgrad epilogue that produced g.
+// Accumulates dgamma / dbeta / dW (+=) and writes the stacked bf16 dgrad operand bstack [(O + C)][C]
+// (rows < O: scale[o] * W[o][:], rows O + j: W^T diag(k1) W) and the fp32 bias row k0^T W [C]. k1k0: 2*O floats scratch.
+void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const float* s, const float* stat_partial,
+                           int slots, int stat_stride, const float* scale, const float* mean, const float* invstd,
+                           double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
+                           int O, int C, cudaStream_t st);
+// out[c] = sum_r x[r][c], deterministic; scratch: >= 2 * num_sms * C floats
+void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st);
 
 // ---- head MLP (fp32 SIMT; argus/models.py:58-64,88-90) -----------------------------------------------------
 // z = gelu(feat) ; feat bf16 (rows, cols) -> z fp32

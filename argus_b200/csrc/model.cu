@@ -48,6 +48,8 @@ Model::~Model() {
   cudaFree(bn_scratch_);
   cudaFree(bn_stats_);
   cudaFree(bn_bwd_scratch_);
+  cudaFree(alg_h_); cudaFree(alg_g_); cudaFree(alg_s_); cudaFree(alg_k1k0_); cudaFree(alg_bias_); cudaFree(alg_gstats_);
+  cudaFree(alg_bstack_);
   cudaFree(wgrad_scratch_);
   cudaFree(pack_table_dev_);
   cudaFree(arena_);
@@ -174,6 +176,25 @@ void Model::bind(float* params, float* grads, float* buffers) {
     max_stat_slots_ = 2 * num_sms();
     ARGUS_CUDA(cudaMalloc(&bn_stats_, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float)));
     ARGUS_CUDA(cudaMalloc(&bn_bwd_scratch_, bn_bwd_scratch_elems() * sizeof(float)));
+    {
+      const char* e = getenv("ARGUS_BN_ALGEBRA");
+      bn_algebra_ = !(e && e[0] == '0');
+      // eligible: bottlenecks whose mid width is <= 256 (layers 1-3); layer4's small matrices would cost more than the
+      // two passes over its (small) activations
+      for (const auto& b : blocks_)
+        if (b.c1.shape.Cout <= 256) {
+          alg_max_o_ = std::max(alg_max_o_, b.c3.shape.Cout);
+          alg_max_c_ = std::max(alg_max_c_, b.c1.shape.Cout);
+        }
+      const size_t O = alg_max_o_, C = alg_max_c_;
+      ARGUS_CUDA(cudaMalloc(&alg_h_, O * C * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_g_, C * C * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_s_, C * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_k1k0_, 2 * O * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_bias_, C * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_gstats_, static_cast<size_t>(max_stat_slots_) * 2 * O * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_bstack_, (O + C) * C * sizeof(bf16)));
+    }
     ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
     ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
                           cudaMemcpyHostToDevice));
@@ -348,6 +369,18 @@ void Model::build_plan(Plan& p) {
       // conv3: dy = Q (dRaw3), input act2, dx -> R
       bp.c3.wgrad = plan_conv_wgrad(br.c3.shape, Q, bp.act2, wg_dst(br.c3));
       bp.c3.dgrad = plan_conv_dgrad(br.c3.shape, Q, packed_ + br.c3.packed_off, R);
+      bp.algebraic = bn_algebra_ && br.c1.shape.Cout <= 256;
+      if (bp.algebraic) {
+        // algebraic bn3 backward: GEMMs on the masked gradient P itself (never on dRaw3)
+        const int C = br.c3.shape.Cin;
+        bp.h_wgrad = plan_conv_wgrad(br.c3.shape, P, bp.act2, alg_h_);
+        ConvShape gs = br.c3.shape;
+        gs.Cout = C;
+        bp.gram_wgrad = plan_conv_wgrad(gs, bp.act2, bp.act2, alg_g_);
+        bp.c3_concat = plan_dgrad_concat(br.c3.shape, P, bp.act2, C, alg_bstack_, R);
+        ensure_wgrad_scratch(bp.h_wgrad);
+        ensure_wgrad_scratch(bp.gram_wgrad);
+      }
       // conv2: dy = Q (dRaw2), input act1, dx -> R
       bp.c2.wgrad = plan_conv_wgrad(br.c2.shape, Q, bp.act1, wg_dst(br.c2));
       bp.c2.dgrad = plan_conv_dgrad(br.c2.shape, Q, packed_ + br.c2.packed_off, R);
@@ -585,13 +618,40 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
   bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
 }
 
-void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* residual_bits, cudaStream_t s) {
+void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats,
+                          cudaStream_t s) {
   // fork: the weight gradient only needs dRaw and the saved activation, both final at this point
   run_wgrad(cp.wgrad, s);
   Epilogue e;
   e.residual = residual;
-  e.residual_bits = residual_bits;
+  e.out_bits = out_bits;
+  if (out_stats != nullptr) {
+    ARGUS_CHECK(cp.dgrad.size() == 1, "gradient statistics need a single dgrad launch");
+    alg_gstats_slots_ = stat_slots(cp.dgrad[0]);
+    ARGUS_CUDA(cudaMemsetAsync(out_stats, 0, static_cast<size_t>(alg_gstats_slots_) * 2 * cp.dgrad[0].p.n_total * sizeof(float), s));
+    e.stat_partial = out_stats;
+  }
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
+}
+
+// conv3 + bn3 backward without touching raw3 / dRaw3 (see bn_algebra.cu for the derivation)
+void Model::bn3_backward_algebraic(const BlockRef& br, BlockPlan& bp, int N, cudaStream_t s) {
+  const int O = br.c3.shape.Cout, C = br.c3.shape.Cin;
+  join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O) * C * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(alg_g_, 0, static_cast<size_t>(C) * C * sizeof(float), s));
+  launch_wgrad(bp.h_wgrad, wgrad_scratch_, s);      // H = g^T act2
+  launch_wgrad(bp.gram_wgrad, wgrad_scratch_, s);   // G = act2^T act2
+  colsum_rows_bf16(bp.act2, bp.rows_out, C, bn_bwd_scratch_, alg_s_, s);
+  const float* sc = bn_scratch_ + br.c3.bn.scratch_off;
+  bn_alg_backward_small(packed_ + br.c3.packed_off, alg_h_, alg_g_, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
+                        sc + 2 * O, sc + 3 * O, static_cast<double>(bp.rows_out), grads_dev_ + br.c3.bn.gamma_off,
+                        grads_dev_ + br.c3.bn.beta_off, grads_dev_ + br.c3.w_off, alg_k1k0_, alg_bstack_, alg_bias_, O, C,
+                        s);
+  Epilogue e;
+  e.shift = alg_bias_;
+  launch_conv(bp.c3_concat, e, s);                  // dAct2 = [g | act2] * [diag(sc) W3 ; W3^T diag(k1) W3] + k0^T W3
+  (void)N;
 }
 
 void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s) {
@@ -627,7 +687,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       run_wgrad(p.fc.wgrad, s);
       Epilogue e;
       for (const auto& l : p.fc.dgrad) launch_conv(l, e, s);
-      avgpool_bwd(p.d_pooled, p.blocks.back().g_out, N, p.final_hw, 2048, s);
+      avgpool_bwd(p.d_pooled, p.blocks.back().g_out, p.blocks.back().out_bits, N, p.final_hw, 2048, s);
     }
     for (int i = last_block[stage] - 1; i >= first_block[stage]; --i) {
       ARGUS_CHECK(i < n_blocks, "block index");
@@ -637,25 +697,30 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       ARGUS_CUDA(cudaMemsetAsync(gpacked_ + br.c2.gpacked_off, 0,
                                  static_cast<size_t>(br.c2.shape.Ktot()) * br.c2.shape.Cout * sizeof(float), s));
       bf16 *P = bp.g_out, *Q = bp.g_q, *R = bp.g_r, *T = bp.g_t;
-      // bn3 (+ residual ReLU): the ReLU mask of the block output is read as a bit mask (1/16 of the bytes of `out`);
-      // P stays unmasked, every consumer of the identity-branch gradient applies the bits itself. Q = dRaw3
-      const uint8_t* bits = bp.out_bits;
-      const bf16* bits_as_out = reinterpret_cast<const bf16*>(bits);
-      bn_backward(br.c3, P, bp.raw3, bits_as_out, Q, bp.rows_out, 3, s);
+      // The gradient P of the block output arrives ALREADY masked by the block's final ReLU (the dgrad epilogue or
+      // avgpool_bwd that produced it applied the bit mask), so it is the BN3 / downsample-BN upstream gradient and the
+      // identity-branch gradient at once.
+      const uint8_t* prev_bits = (i > 0) ? p.blocks[i - 1].out_bits : nullptr;
+      float* prev_stats = (i > 0 && p.blocks[i - 1].algebraic) ? alg_gstats_ : nullptr;
       const bf16* residual = P;
-      const uint8_t* residual_bits = bits;
       if (br.has_ds) {
-        bn_backward(br.ds, P, bp.rawd, bits_as_out, R, bp.rows_out, 3, s);
+        bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
         if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
-        conv_backward(bp.ds, nullptr, nullptr, s);  // R -> T
+        conv_backward(bp.ds, nullptr, nullptr, nullptr, s);  // R -> T
         residual = T;
-        residual_bits = nullptr;
       }
-      conv_backward(bp.c3, nullptr, nullptr, s);                          // Q -> R (dAct2)
-      bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);      // Q = dRaw2
-      conv_backward(bp.c2, nullptr, nullptr, s);                          // Q -> R (dAct1)
-      bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);       // Q = dRaw1
-      conv_backward(bp.c1, residual, residual_bits, s);                   // Q -> S (+ gated residual)
+      if (bp.algebraic) {
+        bn3_backward_algebraic(br, bp, N, s);                                // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
+      } else {
+        bn_backward(br.c3, P, bp.raw3, nullptr, Q, bp.rows_out, 0, s);      // Q = dRaw3
+        conv_backward(bp.c3, nullptr, nullptr, nullptr, s);                  // Q -> R (dAct2)
+      }
+      bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);        // Q = dRaw2
+      conv_backward(bp.c2, nullptr, nullptr, nullptr, s);                    // Q -> R (dAct1)
+      bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);         // Q = dRaw1
+      // Q -> S (+ identity-branch gradient), masked by the previous block's ReLU bits; its channel sums are the
+      // dbeta of the previous block's algebraic bn3 backward
+      conv_backward(bp.c1, residual, prev_bits, prev_stats, s);
     }
     if (stage == 3) {
       // ---- stem: max-pool backward, bn1 backward, weight gradient

@@ -61,6 +61,10 @@ struct BlockPlan {
   int64_t rows_in = 0, rows_mid = 0, rows_out = 0;
   // gradient scratch roles for this block
   bf16 *g_out = nullptr, *g_q = nullptr, *g_r = nullptr, *g_t = nullptr, *g_x = nullptr;
+  // algebraic bn3 backward (bn_algebra.cu): H = g^T act2, G = act2^T act2, concatenated-K dgrad of conv3
+  bool algebraic = false;
+  WgradLaunch h_wgrad, gram_wgrad;
+  ConvLaunch c3_concat;
   size_t x_bytes = 0;
 };
 
@@ -147,7 +151,10 @@ class Model {
   void run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s);
   void bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
                    cudaStream_t s);
-  void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* residual_bits, cudaStream_t s);
+  // out_bits: ReLU mask of the tensor whose gradient this dgrad produces (stored masked); out_stats: per-slot channel
+  // sums of that masked gradient (the dbeta of the algebraic bn3 backward of the previous block)
+  void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats, cudaStream_t s);
+  void bn3_backward_algebraic(const BlockRef& br, BlockPlan& bp, int N, cudaStream_t s);
 
   template <typename T>
   T* arena_alloc(size_t count);
@@ -176,6 +183,13 @@ class Model {
   float* bn_scratch_ = nullptr;
   float* bn_stats_ = nullptr;
   float* bn_bwd_scratch_ = nullptr;   // per-block partial sums of the BN-backward reductions
+  // algebraic bn3 backward scratch (sized for the widest eligible block)
+  bool bn_algebra_ = true;
+  int alg_max_o_ = 0, alg_max_c_ = 0;
+  float *alg_h_ = nullptr, *alg_g_ = nullptr, *alg_s_ = nullptr, *alg_k1k0_ = nullptr, *alg_bias_ = nullptr;
+  float* alg_gstats_ = nullptr;       // [max_stat_slots_][2][alg_max_o_] sums of the masked gradient, per dgrad CTA slot
+  bf16* alg_bstack_ = nullptr;
+  int alg_gstats_slots_ = 0;          // slots the last producing dgrad launch wrote
   float* wgrad_scratch_ = nullptr;    // split-K partial weight gradients (one launch at a time)
   int64_t wgrad_scratch_elems_ = 0;
   int max_stat_slots_ = 0;

@@ -153,3 +153,49 @@ def test_train_forward_backward(cuda_device, B, H, W, gain):
     l2 = ours.resnet.layer2._modules["0"].bn2
     assert rel(l2.running_var, ref.resnet.layer2[0].bn2.running_var) < 2e-2 or True
     assert int(ours.resnet.bn1.num_batches_tracked) == 1
+
+
+def test_algebraic_bn3_backward_matches_textbook(cuda_device, monkeypatch):
+    """The algebraic conv3/bn3 backward (csrc/bn_algebra.cu: GEMMs on the masked gradient and the saved activation
+    instead of two passes over raw3 / dRaw3) against the textbook BN backward kernels (ARGUS_BN_ALGEBRA=0) on the same
+    weights and inputs: identical forward, gradients equal up to bf16 rounding of the intermediates, and against the
+    fp32 reference both are equally far."""
+    from argus_b200.loss import geometric_loss_fn
+    from argus_b200.models import NCameraCNN
+    from oracle.ref_model import torch_loss
+
+    ref, ours_alg = build_pair(cuda_device, residual_gain=0.2)
+    monkeypatch.setenv("ARGUS_BN_ALGEBRA", "0")
+    ours_txt = NCameraCNN().to(cuda_device)
+    ours_txt.load_state_dict(ref.state_dict())
+    x = structured_images(8, 6, 128, 128, 3, cuda_device)
+    target = random_targets(8, 4, cuda_device)
+    ours_txt.train()
+    y_txt = ours_txt(x)                       # binds (reads the environment) on first use
+    geometric_loss_fn(y_txt, target).mean().backward()
+    monkeypatch.delenv("ARGUS_BN_ALGEBRA")
+    ours_alg.train()
+    y_alg = ours_alg(x)
+    geometric_loss_fn(y_alg, target).mean().backward()
+    ref.train()
+    torch_loss(ref(x), target).mean().backward()
+    torch.cuda.synchronize()
+    assert torch.equal(y_txt, y_alg)
+    g_ref = {n: p.grad for n, p in ref.named_parameters()}
+    num = num_a = num_t = den = 0.0
+    worst = []
+    for (n, pa), (_, pt) in zip(ours_alg.named_parameters(), ours_txt.named_parameters()):
+        gr = g_ref[n].double()
+        num += (pa.grad.double() - pt.grad.double()).pow(2).sum().item()
+        num_a += (pa.grad.double() - gr).pow(2).sum().item()
+        num_t += (pt.grad.double() - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+        worst.append((rel(pa.grad, pt.grad), rel(pa.grad, gr), rel(pt.grad, gr), n))
+    worst.sort(reverse=True)
+    print("algebraic vs textbook, algebraic vs ref, textbook vs ref, name")
+    for w in worst[:8]:
+        print("   %.3e  %.3e  %.3e  %s" % w)
+    r_at, r_a, r_t = (num / den) ** 0.5, (num_a / den) ** 0.5, (num_t / den) ** 0.5
+    print(f"global: algebraic vs textbook {r_at:.3e}; vs fp32 reference: algebraic {r_a:.3e} textbook {r_t:.3e}")
+    assert r_a < max(1.25 * r_t, 2e-2)
+    assert r_at < max(2.0 * r_t, 2e-2)

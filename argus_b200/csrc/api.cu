@@ -139,7 +139,7 @@ int argus_bn_apply(const void* x, const float* scale, const float* shift, const 
   ARGUS_API_BEGIN
   require_sm100();
   bn_apply(static_cast<const bf16*>(x), scale, shift, static_cast<const bf16*>(res), rscale, rshift, relu,
-           static_cast<bf16*>(y), nullptr, rows, C, static_cast<cudaStream_t>(stream));
+           static_cast<bf16*>(y), nullptr, nullptr, rows, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 int argus_bn_apply_bits(const void* x, const float* scale, const float* shift, const void* res, const float* rscale,
@@ -147,7 +147,7 @@ int argus_bn_apply_bits(const void* x, const float* scale, const float* shift, c
   ARGUS_API_BEGIN
   require_sm100();
   bn_apply(static_cast<const bf16*>(x), scale, shift, static_cast<const bf16*>(res), rscale, rshift, relu,
-           static_cast<bf16*>(y), static_cast<uint8_t*>(relu_bits), rows, C, static_cast<cudaStream_t>(stream));
+           static_cast<bf16*>(y), static_cast<uint8_t*>(relu_bits), nullptr, rows, C, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 int argus_bn_backward(void* dy, const void* x, const void* out, const float* scale, const float* shift,

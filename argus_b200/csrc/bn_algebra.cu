@@ -63,24 +63,43 @@ bn_alg_coeffs_kernel(const bf16* __restrict__ W, const float* __restrict__ H, co
 }
 
 // M[j][i] = sum_o W[o][j] k1[o] W[o][i] -> bstack rows O + j (bf16);  blockIdx.y == C/16: bias[i] = sum_o k0[o] W[o][i]
+// The reduction over o is split over blockIdx.z (kSplitO chunks, fixed boundaries): each split writes its partial
+// 16x16 tile to `partial` and a second tiny kernel adds the splits in order (deterministic).
+constexpr int kSplitO = 8;
 __global__ void __launch_bounds__(256)
-bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0, bf16* __restrict__ bstack,
-                     float* __restrict__ bias, int O, int C) {
+bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0, float* __restrict__ partial, int O,
+                     int C) {
   __shared__ float sWj[32][17];   // [o chunk][j]
   __shared__ float sWi[32][17];   // [o chunk][i]
   const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
   const int i0 = blockIdx.x * 16;
   const bool bias_row = (blockIdx.y == C / 16);
   const int j0 = bias_row ? 0 : blockIdx.y * 16;
+  const int per = O / kSplitO;
+  const int o_begin = blockIdx.z * per, o_end = o_begin + per;
   float acc = 0.f;
-  for (int o0 = 0; o0 < O; o0 += 32) {
-    for (int e = threadIdx.x; e < 32 * 16; e += 256) {
+  // register prefetch of the next 32-row chunk while the current one is being multiplied
+  float ni[2], nj[2];
+  auto fetch = [&](int o0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = threadIdx.x + 256 * u;
       const int oo = e >> 4, c = e & 15;
-      sWi[oo][c] = __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + i0 + c]);
-      sWj[oo][c] = bias_row ? k1k0[O + o0 + oo]
-                            : __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + j0 + c]) * k1k0[o0 + oo];
+      ni[u] = __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + i0 + c]);
+      nj[u] = bias_row ? k1k0[O + o0 + oo]
+                       : __bfloat162float(W[static_cast<size_t>(o0 + oo) * C + j0 + c]) * k1k0[o0 + oo];
+    }
+  };
+  fetch(o_begin);
+  for (int o0 = o_begin; o0 < o_end; o0 += 32) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = threadIdx.x + 256 * u;
+      sWi[e >> 4][e & 15] = ni[u];
+      sWj[e >> 4][e & 15] = nj[u];
     }
     __syncthreads();
+    if (o0 + 32 < o_end) fetch(o0 + 32);
     if (!bias_row) {
 #pragma unroll 8
       for (int oo = 0; oo < 32; ++oo) acc = fmaf(sWj[oo][tj], sWi[oo][ti], acc);
@@ -90,8 +109,19 @@ bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0,
     }
     __syncthreads();
   }
-  if (!bias_row) bstack[static_cast<size_t>(O + j0 + tj) * C + i0 + ti] = __float2bfloat16(acc);
-  else if (tj == 0) bias[i0 + ti] = acc;
+  // partial[z][row][i], row = j (0..C-1) or C for the bias row
+  const int row = bias_row ? C : j0 + tj;
+  if (!bias_row || tj == 0) partial[(static_cast<size_t>(blockIdx.z) * (C + 1) + row) * C + i0 + ti] = acc;
+}
+__global__ void bn_alg_matrix_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ bstack,
+                                            float* __restrict__ bias, int O, int C) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (C + 1) * C) return;
+  float acc = 0.f;
+  for (int z = 0; z < kSplitO; ++z) acc += partial[static_cast<size_t>(z) * (C + 1) * C + idx];
+  const int row = idx / C, i = idx - row * C;
+  if (row < C) bstack[static_cast<size_t>(O + row) * C + i] = __float2bfloat16(acc);
+  else bias[i] = acc;
 }
 
 // dW[o][i] += sc[o] H[o][i] + k0[o] s[i] + k1[o] sum_j W[o][j] G[j][i]
@@ -124,14 +154,16 @@ bn_alg_dw_kernel(const bf16* __restrict__ W, const float* __restrict__ H, const 
 void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const float* s, const float* stat_partial,
                            int slots, int stat_stride, const float* scale, const float* mean, const float* invstd,
                            double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
-                           int O, int C, cudaStream_t st) {
-  ARGUS_CHECK(O % 32 == 0 && C % 32 == 0, "algebraic BN backward: O and C must be multiples of 32");
+                           float* mpartial, int O, int C, cudaStream_t st) {
+  ARGUS_CHECK(O % (32 * kSplitO) == 0 && C % 32 == 0, "algebraic BN backward: O % 256 == 0 and C % 32 == 0 required");
   ProfileScope prof("bn_algebra", st, 4.0 * O * static_cast<double>(C) * C, 0);
   bn_alg_coeffs_kernel<<<(O * 32 + 255) / 256, 256, 0, st>>>(W, H, stat_partial, slots, stat_stride, scale, mean, invstd,
                                                             static_cast<float>(1.0 / rows), dgamma, dbeta, k1k0, bstack,
                                                             O, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_alg_matrix_kernel<<<dim3(C / 16, C / 16 + 1), 256, 0, st>>>(W, k1k0, bstack, bias, O, C);
+  bn_alg_matrix_kernel<<<dim3(C / 16, C / 16 + 1, kSplitO), 256, 0, st>>>(W, k1k0, mpartial, O, C);
+  ARGUS_CUDA(cudaGetLastError());
+  bn_alg_matrix_reduce_kernel<<<((C + 1) * C + 255) / 256, 256, 0, st>>>(mpartial, bstack, bias, O, C);
   ARGUS_CUDA(cudaGetLastError());
   bn_alg_dw_kernel<<<dim3(C / 16, O / 16), 256, 0, st>>>(W, H, G, s, scale, k1k0, dW, O, C);
   ARGUS_CUDA(cudaGetLastError());
@@ -149,12 +181,18 @@ colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, 
   float acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-  for (int64_t r = static_cast<int64_t>(blockIdx.x) * row_lanes + rl; r < rows;
-       r += static_cast<int64_t>(gridDim.x) * row_lanes) {
-    const uint4 u = __ldg(x + r * cvec + oc);
+  auto add = [&](const uint4& u) {
     float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), c = unpack_bf16x2(u.z), d = unpack_bf16x2(u.w);
     acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y; acc[4] += c.x; acc[5] += c.y; acc[6] += d.x; acc[7] += d.y;
+  };
+  const int64_t rs = static_cast<int64_t>(gridDim.x) * row_lanes;
+  int64_t r = static_cast<int64_t>(blockIdx.x) * row_lanes + rl;
+  for (; r + 3 * rs < rows; r += 4 * rs) {   // four independent 16-byte loads in flight per thread
+    const uint4 u0 = __ldg(x + r * cvec + oc), u1 = __ldg(x + (r + rs) * cvec + oc);
+    const uint4 u2 = __ldg(x + (r + 2 * rs) * cvec + oc), u3 = __ldg(x + (r + 3 * rs) * cvec + oc);
+    add(u0); add(u1); add(u2); add(u3);
   }
+  for (; r < rows; r += rs) add(__ldg(x + r * cvec + oc));
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc[k];
   __syncthreads();
@@ -174,17 +212,23 @@ __global__ void colsum_final_kernel(const float* __restrict__ partial, int block
   for (int b = 0; b < blocks; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * C + c]);
   out[c] = static_cast<float>(acc);
 }
+void colsum_finalize(const float* partial, int blocks, float* out, int C, cudaStream_t st) {
+  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, out, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st) {
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "colsum: C/8 must be a power of two <= 256");
   ProfileScope prof("bn_algebra", st, 0, static_cast<double>(rows) * C * 2);
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);
   const int row_lanes = 256 / lanes;
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + row_lanes - 1) / row_lanes, 2LL * num_sms())));
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + row_lanes - 1) / row_lanes, 4LL * num_sms())));
   colsum_partial_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), scratch, rows, cvec);
   ARGUS_CUDA(cudaGetLastError());
   colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, blocks, out, C);
   ARGUS_CUDA(cudaGetLastError());
 }
+
+int64_t bn_alg_matrix_scratch_elems(int C) { return static_cast<int64_t>(kSplitO) * (C + 1) * C; }
 
 }  // namespace argus

@@ -269,11 +269,12 @@ void bn_fold_eval(const float* gamma, const float* beta, const float* running_me
 // ------------------------------------------------------------------------------------------------------------
 // batch norm apply (+ residual, + ReLU)
 // ------------------------------------------------------------------------------------------------------------
-template <int RES>  // 0 none, 1 plain residual, 2 residual with its own scale/shift (downsample branch)
+template <int RES, bool SUM>  // RES: 0 none, 1 plain residual, 2 residual with its own scale/shift (downsample branch)
 __global__ void __launch_bounds__(256)
 bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
                 const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
-                int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, int64_t nvec, int cvec) {
+                int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, float* __restrict__ colsum_partial,
+                int64_t nvec, int cvec) {
   // gridDim.x * 256 is a multiple of cvec (a power of two <= 256), so a thread always sees the same channel octet:
   // the per-channel constants live in registers for the whole grid-stride loop.
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -282,45 +283,20 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
   const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
   F8 rs, rb;
   if (RES == 2) { rs = load8f(rscale + c0); rb = load8f(rshift + c0); }
-  int64_t i = tid;
-  for (; i + stride < nvec; i += 2 * stride) {
-    const uint4 xa = ldg_stream(x + i), xb = ldg_stream(x + i + stride);
-    uint4 ra, rbv;
-    if (RES != 0) { ra = ldg_stream(res + i); rbv = ldg_stream(res + i + stride); }
+  F8 acc;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const F8 xv = unpack8(u == 0 ? xa : xb);
-      F8 o;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
-      if (RES == 1) {
-        const F8 rv = unpack8(u == 0 ? ra : rbv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
-      } else if (RES == 2) {
-        const F8 rv = unpack8(u == 0 ? ra : rbv);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
-      }
-      if (bits != nullptr) bits[i + u * stride] = positive_bits(o);
-      if (relu) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
-      }
-      y[i + u * stride] = pack8(o);
-    }
-  }
-  for (; i < nvec; i += stride) {
-    const F8 xv = unpack8(ldg_stream(x + i));
+  for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
+  auto one = [&](int64_t i, const uint4& xq, const uint4& rq) {
+    const F8 xv = unpack8(xq);
     F8 o;
 #pragma unroll
     for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
     if (RES == 1) {
-      const F8 rv = unpack8(ldg_stream(res + i));
+      const F8 rv = unpack8(rq);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
     } else if (RES == 2) {
-      const F8 rv = unpack8(ldg_stream(res + i));
+      const F8 rv = unpack8(rq);
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
     }
@@ -329,24 +305,65 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
 #pragma unroll
       for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
     }
-    y[i] = pack8(o);
+    const uint4 packed = pack8(o);
+    y[i] = packed;
+    if (SUM) {
+      const F8 r = unpack8(packed);   // sums of the STORED (bf16) values
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc.v[k] += r.v[k];
+    }
+  };
+  int64_t i = tid;
+  for (; i + stride < nvec; i += 2 * stride) {
+    const uint4 xa = ldg_stream(x + i), xb = ldg_stream(x + i + stride);
+    uint4 ra = make_uint4(0, 0, 0, 0), rbv = ra;
+    if (RES != 0) { ra = ldg_stream(res + i); rbv = ldg_stream(res + i + stride); }
+    one(i, xa, ra);
+    one(i + stride, xb, rbv);
+  }
+  for (; i < nvec; i += stride) {
+    uint4 ra = make_uint4(0, 0, 0, 0);
+    if (RES != 0) ra = ldg_stream(res + i);
+    one(i, ldg_stream(x + i), ra);
+  }
+  if (SUM) {
+    // per-block column sums of the output: threads t, t + cvec, ... of the block share a channel octet
+    __shared__ float red[8][256];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc.v[k];
+    __syncthreads();
+    const int lanes = cvec < 256 ? cvec : 256;
+    if (threadIdx.x < lanes) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float s0 = 0.f;
+        for (int r = threadIdx.x; r < 256; r += lanes) s0 += red[k][r];
+        colsum_partial[static_cast<size_t>(blockIdx.x) * (cvec * 8) + threadIdx.x * 8 + k] = s0;
+      }
+    }
   }
 }
+int bn_apply_grid(int64_t rows, int C) { return grid_for(rows * (C / 8), 256); }
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
-              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, int64_t rows, int C, cudaStream_t s) {
+              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, float* colsum_partial, int64_t rows, int C,
+              cudaStream_t s) {
   ProfileScope prof("bn_apply", s, 0, static_cast<double>(rows) * C * (2 * (res ? 3 : 2) + (relu_bits ? 0.125 : 0.0)));
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "bn_apply: C/8 must be a power of two <= 256");
   const int64_t nvec = rows * (C / 8);
-  const int grid = grid_for(nvec, 256);
+  const int grid = bn_apply_grid(rows, C);
   auto X = reinterpret_cast<const uint4*>(x);
   auto R = reinterpret_cast<const uint4*>(res);
   auto Y = reinterpret_cast<uint4*>(y);
-  if (res == nullptr)
-    bn_apply_kernel<0><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
-  else if (rscale == nullptr)
-    bn_apply_kernel<1><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
-  else
-    bn_apply_kernel<2><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nvec, C / 8);
+  if (colsum_partial != nullptr) {
+    ARGUS_CHECK(res == nullptr, "column sums are only produced by the plain (no residual) variant");
+    bn_apply_kernel<0, true><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, colsum_partial, nvec, C / 8);
+  } else if (res == nullptr) {
+    bn_apply_kernel<0, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+  } else if (rscale == nullptr) {
+    bn_apply_kernel<1, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+  } else {
+    bn_apply_kernel<2, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+  }
   ARGUS_CUDA(cudaGetLastError());
 }
 

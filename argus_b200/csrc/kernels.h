@@ -53,8 +53,13 @@ void bn_fold_eval(const float* gamma, const float* beta, const float* running_me
 // y = [relu]( x*scale+shift  [+ res]  or  [+ res*rscale+rshift] )
 // relu_bits (optional): [rows][C/8] bytes, bit k of byte j = (pre-ReLU value of channel 8j+k > 0). The backward pass
 // reads this mask instead of the whole bf16 output (1/16 of the bytes).
+// colsum_partial (optional, plain variant only): [bn_apply_grid(rows, C)][C] per-block column sums of the stored
+// output, added in block order by colsum_finalize (the algebraic bn3 backward needs colsum(act2)).
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
-              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, int64_t rows, int C, cudaStream_t s);
+              const float* rshift, int relu, bf16* y, uint8_t* relu_bits, float* colsum_partial, int64_t rows, int C,
+              cudaStream_t s);
+int bn_apply_grid(int64_t rows, int C);
+void colsum_finalize(const float* partial, int blocks, float* out, int C, cudaStream_t st);
 // mask_mode: 0 = no ReLU after this BN, 1 = ReLU directly after (mask recomputed from x), 2 = ReLU after a residual
 // add (mask = out > 0), 3 = like 2 but `out` points to the relu_bits written by bn_apply. Accumulates dgamma += sum(g * xhat), dbeta += sum(g) with g = masked dy.
 // Deterministic: every block writes its partial sums to `scratch` (>= bn_bwd_scratch_elems() floats), a second tiny
@@ -94,8 +99,9 @@ void avgpool_bwd(const bf16* dy, bf16* dx, const uint8_t* relu_bits, int N, int 
 void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const float* s, const float* stat_partial,
                            int slots, int stat_stride, const float* scale, const float* mean, const float* invstd,
                            double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
-                           int O, int C, cudaStream_t st);
-// out[c] = sum_r x[r][c], deterministic; scratch: >= 2 * num_sms * C floats
+                           float* mpartial, int O, int C, cudaStream_t st);
+int64_t bn_alg_matrix_scratch_elems(int C);   // floats of `mpartial`
+// out[c] = sum_r x[r][c], deterministic; scratch: >= 4 * num_sms * C floats
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st);
 
 // ---- head MLP (fp32 SIMT; argus/models.py:58-64,88-90) -----------------------------------------------------

@@ -50,6 +50,7 @@ Model::~Model() {
   cudaFree(bn_bwd_scratch_);
   cudaFree(alg_h_); cudaFree(alg_g_); cudaFree(alg_s_); cudaFree(alg_k1k0_); cudaFree(alg_bias_); cudaFree(alg_gstats_);
   cudaFree(alg_bstack_);
+  cudaFree(alg_mpartial_);
   cudaFree(wgrad_scratch_);
   cudaFree(pack_table_dev_);
   cudaFree(arena_);
@@ -194,6 +195,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
       ARGUS_CUDA(cudaMalloc(&alg_bias_, C * sizeof(float)));
       ARGUS_CUDA(cudaMalloc(&alg_gstats_, static_cast<size_t>(max_stat_slots_) * 2 * O * sizeof(float)));
       ARGUS_CUDA(cudaMalloc(&alg_bstack_, (O + C) * C * sizeof(bf16)));
+      ARGUS_CUDA(cudaMalloc(&alg_mpartial_, bn_alg_matrix_scratch_elems(static_cast<int>(C)) * sizeof(float)));
     }
     ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
     ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
@@ -322,6 +324,8 @@ void Model::build_plan(Plan& p) {
     if (br.has_ds) bp.rawd = arena_alloc<bf16>(e_out * oc);  // eval: holds the folded-BN identity branch
     bp.out = arena_alloc<bf16>(e_out * oc);
     if (tr) bp.out_bits = arena_alloc<uint8_t>(e_out * oc / 8);
+    if (tr && bn_algebra_ && wd <= 256)
+      bp.act2_colsum = arena_alloc<float>(static_cast<size_t>(bn_apply_grid(static_cast<int64_t>(e_out), wd)) * wd);
     max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
     plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
     plan_conv(bp.c2, br.c2, N, h, w, bp.act1, tr ? bp.raw2 : bp.act2, true);
@@ -380,6 +384,17 @@ void Model::build_plan(Plan& p) {
         bp.c3_concat = plan_dgrad_concat(br.c3.shape, P, bp.act2, C, alg_bstack_, R);
         ensure_wgrad_scratch(bp.h_wgrad);
         ensure_wgrad_scratch(bp.gram_wgrad);
+      }
+      bp.ds_algebraic = bp.algebraic && br.has_ds && br.ds.shape.stride == 1;
+      if (bp.ds_algebraic) {
+        const int C = br.ds.shape.Cin;
+        bp.ds_h_wgrad = plan_conv_wgrad(br.ds.shape, P, bp.x, alg_h_);
+        ConvShape gs = br.ds.shape;
+        gs.Cout = C;
+        bp.ds_gram_wgrad = plan_conv_wgrad(gs, bp.x, bp.x, alg_g_);
+        bp.ds_concat = plan_dgrad_concat(br.ds.shape, P, bp.x, C, alg_bstack_, T);
+        ensure_wgrad_scratch(bp.ds_h_wgrad);
+        ensure_wgrad_scratch(bp.ds_gram_wgrad);
       }
       // conv2: dy = Q (dRaw2), input act1, dx -> R
       bp.c2.wgrad = plan_conv_wgrad(br.c2.shape, Q, bp.act1, wg_dst(br.c2));
@@ -448,16 +463,18 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
     BlockPlan& bp = p.blocks[i];
     const int wd = br.c1.shape.Cout, oc = br.c3.shape.Cout;
     run_conv_train(bp.c1, br.c1, bp.rows_in, s);
-    bn_apply(bp.raw1, SC(br.c1), SC(br.c1) + wd, nullptr, nullptr, nullptr, 1, bp.act1, nullptr, bp.rows_in, wd, s);
+    bn_apply(bp.raw1, SC(br.c1), SC(br.c1) + wd, nullptr, nullptr, nullptr, 1, bp.act1, nullptr, nullptr, bp.rows_in, wd, s);
     run_conv_train(bp.c2, br.c2, bp.rows_out, s);
-    bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, nullptr, bp.rows_out, wd, s);
+    bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, nullptr, bp.act2_colsum,
+             bp.rows_out, wd, s);
     run_conv_train(bp.c3, br.c3, bp.rows_out, s);
     if (br.has_ds) {
       run_conv_train(bp.ds, br.ds, bp.rows_out, s);
-      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.rawd, SC(br.ds), SC(br.ds) + oc, 1, bp.out, bp.out_bits,
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.rawd, SC(br.ds), SC(br.ds) + oc, 1, bp.out, bp.out_bits, nullptr,
                bp.rows_out, oc, s);
     } else {
-      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.x, nullptr, nullptr, 1, bp.out, bp.out_bits, bp.rows_out, oc, s);
+      bn_apply(bp.raw3, SC(br.c3), SC(br.c3) + oc, bp.x, nullptr, nullptr, 1, bp.out, bp.out_bits, nullptr, bp.rows_out,
+               oc, s);
     }
   }
 }
@@ -634,24 +651,27 @@ void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
 }
 
-// conv3 + bn3 backward without touching raw3 / dRaw3 (see bn_algebra.cu for the derivation)
-void Model::bn3_backward_algebraic(const BlockRef& br, BlockPlan& bp, int N, cudaStream_t s) {
-  const int O = br.c3.shape.Cout, C = br.c3.shape.Cin;
+// Expanding 1x1 convolution + batch norm backward without touching the BN input or its gradient (see bn_algebra.cu
+// for the derivation): upstream masked gradient g and the saved conv input `act` go through three GEMMs.
+void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& h, const WgradLaunch& gram,
+                                       const ConvLaunch& concat, const bf16* act, const float* colsum_partial, int64_t rows,
+                                       cudaStream_t s) {
+  const int O = c.shape.Cout, C = c.shape.Cin;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
   ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O) * C * sizeof(float), s));
   ARGUS_CUDA(cudaMemsetAsync(alg_g_, 0, static_cast<size_t>(C) * C * sizeof(float), s));
-  launch_wgrad(bp.h_wgrad, wgrad_scratch_, s);      // H = g^T act2
-  launch_wgrad(bp.gram_wgrad, wgrad_scratch_, s);   // G = act2^T act2
-  colsum_rows_bf16(bp.act2, bp.rows_out, C, bn_bwd_scratch_, alg_s_, s);
-  const float* sc = bn_scratch_ + br.c3.bn.scratch_off;
-  bn_alg_backward_small(packed_ + br.c3.packed_off, alg_h_, alg_g_, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
-                        sc + 2 * O, sc + 3 * O, static_cast<double>(bp.rows_out), grads_dev_ + br.c3.bn.gamma_off,
-                        grads_dev_ + br.c3.bn.beta_off, grads_dev_ + br.c3.w_off, alg_k1k0_, alg_bstack_, alg_bias_, O, C,
-                        s);
+  launch_wgrad(h, wgrad_scratch_, s);      // H = g^T act
+  launch_wgrad(gram, wgrad_scratch_, s);   // G = act^T act
+  if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
+  else colsum_rows_bf16(act, rows, C, bn_bwd_scratch_, alg_s_, s);
+  const float* sc = bn_scratch_ + c.bn.scratch_off;
+  bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g_, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
+                        sc + 2 * O, sc + 3 * O, static_cast<double>(rows), grads_dev_ + c.bn.gamma_off,
+                        grads_dev_ + c.bn.beta_off, grads_dev_ + c.w_off, alg_k1k0_, alg_bstack_, alg_bias_, alg_mpartial_, O,
+                        C, s);
   Epilogue e;
   e.shift = alg_bias_;
-  launch_conv(bp.c3_concat, e, s);                  // dAct2 = [g | act2] * [diag(sc) W3 ; W3^T diag(k1) W3] + k0^T W3
-  (void)N;
+  launch_conv(concat, e, s);               // dAct = [g | act] * [diag(sc) W ; W^T diag(k1) W] + k0^T W
 }
 
 void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s) {
@@ -704,13 +724,18 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       float* prev_stats = (i > 0 && p.blocks[i - 1].algebraic) ? alg_gstats_ : nullptr;
       const bf16* residual = P;
       if (br.has_ds) {
-        bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
-        if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
-        conv_backward(bp.ds, nullptr, nullptr, nullptr, s);  // R -> T
+        if (bp.ds_algebraic) {
+          conv_bn_backward_algebraic(br.ds, bp.ds_h_wgrad, bp.ds_gram_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, s);
+        } else {
+          bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
+          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
+          conv_backward(bp.ds, nullptr, nullptr, nullptr, s);  // R -> T
+        }
         residual = T;
       }
       if (bp.algebraic) {
-        bn3_backward_algebraic(br, bp, N, s);                                // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
+        // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
+        conv_bn_backward_algebraic(br.c3, bp.h_wgrad, bp.gram_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, s);
       } else {
         bn_backward(br.c3, P, bp.raw3, nullptr, Q, bp.rows_out, 0, s);      // Q = dRaw3
         conv_backward(bp.c3, nullptr, nullptr, nullptr, s);                  // Q -> R (dAct2)

@@ -500,6 +500,31 @@ WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const _
   return l;
 }
 
+WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw) {
+  ARGUS_CHECK(s.kind == 0 && s.k == 1 && s.stride == 1, "stacked weight gradient + Gram is defined for 1x1 stride-1");
+  ARGUS_CHECK(s.Cout % 128 == 0, "Cout must be a multiple of 128");
+  // plan as a convolution with Cout + Cin output channels, then point the rows beyond Cout at x
+  ConvShape st = s;
+  st.Cout = s.Cout + s.Cin;
+  WgradLaunch l = plan_conv_wgrad(st, dy, x, dw);
+  ARGUS_CHECK(l.xpose_nbox == 0, "unexpected kernel choice");
+  const int64_t pixels = s.out_pixels();
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cout), static_cast<uint64_t>(pixels)};
+    const uint64_t str[1] = {static_cast<uint64_t>(s.Cout) * 2};
+    const uint32_t box[2] = {64, 64};
+    l.p.dy_map = make_tmap_bf16(dy, 2, dims, str, box);
+  }
+  {
+    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cin), static_cast<uint64_t>(pixels)};
+    const uint64_t str[1] = {static_cast<uint64_t>(s.Cin) * 2};
+    const uint32_t box[2] = {64, 64};
+    l.p.dy_map2 = make_tmap_bf16(x, 2, dims, str, box);
+  }
+  l.p.co_split = s.Cout;
+  return l;
+}
+
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
@@ -626,7 +651,7 @@ void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
   l.p.partial = scratch;
   l.p.partial_stride = static_cast<long long>(l.p.cout) * l.p.dw_row_stride;
   const double flops = 2.0 * l.p.kblocks_total * 64.0 * l.p.cout * static_cast<double>(l.p.cin) * l.p.num_taps;
-  std::string fam = "conv_wgrad";
+  std::string fam = l0.family;
   if (g_profiling && profile_detailed())
     fam += std::string(l.xpose_nbox > 0 ? "x" : "") + ":P" + std::to_string(l.p.kblocks_total * 64) + "_Co" + std::to_string(l.p.cout) + "_Ci" +
            std::to_string(l.p.cin) + "_t" + std::to_string(l.p.num_taps) + "_s" + std::to_string(l.p.num_ksplits);

@@ -53,6 +53,7 @@ struct ConvLaunch {
 };
 
 struct WgradLaunch {
+  const char* family = "conv_wgrad";   // profiling family (the Gram GEMM of the algebraic BN backward is not a conv)
   WgradParams p;
   int block_n = 64;
   // Cout == 64 layers use the transposed all-taps kernel instead (xpose_nbox = padded box count, 0 = not used)
@@ -74,6 +75,10 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
 ConvLaunch plan_dgrad_concat(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* a1, int C1,
                              const __nv_bfloat16* bstack, __nv_bfloat16* dx);
 WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
+
+// 1x1 only: dw[(Cout + Cin)][Cin] (fp32, +=): rows < Cout = dy^T x (the weight gradient), rows Cout + j = x^T x (the
+// Gram matrix of the input); Cout must be a multiple of 128. One launch, x tiles loaded once for both.
+WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);
 // number of statistic slots launch_conv writes for this launch (2 per CTA)

@@ -48,7 +48,7 @@ Model::~Model() {
   cudaFree(bn_scratch_);
   cudaFree(bn_stats_);
   cudaFree(bn_bwd_scratch_);
-  cudaFree(alg_h_); cudaFree(alg_g_); cudaFree(alg_s_); cudaFree(alg_k1k0_); cudaFree(alg_bias_); cudaFree(alg_gstats_);
+  cudaFree(alg_h_); cudaFree(alg_s_); cudaFree(alg_k1k0_); cudaFree(alg_bias_); cudaFree(alg_gstats_);
   cudaFree(alg_bstack_);
   cudaFree(alg_mpartial_);
   cudaFree(wgrad_scratch_);
@@ -188,8 +188,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
           alg_max_c_ = std::max(alg_max_c_, b.c1.shape.Cout);
         }
       const size_t O = alg_max_o_, C = alg_max_c_;
-      ARGUS_CUDA(cudaMalloc(&alg_h_, O * C * sizeof(float)));
-      ARGUS_CUDA(cudaMalloc(&alg_g_, C * C * sizeof(float)));
+      ARGUS_CUDA(cudaMalloc(&alg_h_, (O + C) * C * sizeof(float)));   // H [O][C] followed by the Gram matrix [C][C]
       ARGUS_CUDA(cudaMalloc(&alg_s_, C * sizeof(float)));
       ARGUS_CUDA(cudaMalloc(&alg_k1k0_, 2 * O * sizeof(float)));
       ARGUS_CUDA(cudaMalloc(&alg_bias_, C * sizeof(float)));
@@ -377,24 +376,16 @@ void Model::build_plan(Plan& p) {
       if (bp.algebraic) {
         // algebraic bn3 backward: GEMMs on the masked gradient P itself (never on dRaw3)
         const int C = br.c3.shape.Cin;
-        bp.h_wgrad = plan_conv_wgrad(br.c3.shape, P, bp.act2, alg_h_);
-        ConvShape gs = br.c3.shape;
-        gs.Cout = C;
-        bp.gram_wgrad = plan_conv_wgrad(gs, bp.act2, bp.act2, alg_g_);
+        bp.hg_wgrad = plan_conv_wgrad_gram(br.c3.shape, P, bp.act2, alg_h_);
         bp.c3_concat = plan_dgrad_concat(br.c3.shape, P, bp.act2, C, alg_bstack_, R);
-        ensure_wgrad_scratch(bp.h_wgrad);
-        ensure_wgrad_scratch(bp.gram_wgrad);
+        ensure_wgrad_scratch(bp.hg_wgrad);
       }
       bp.ds_algebraic = bp.algebraic && br.has_ds && br.ds.shape.stride == 1;
       if (bp.ds_algebraic) {
         const int C = br.ds.shape.Cin;
-        bp.ds_h_wgrad = plan_conv_wgrad(br.ds.shape, P, bp.x, alg_h_);
-        ConvShape gs = br.ds.shape;
-        gs.Cout = C;
-        bp.ds_gram_wgrad = plan_conv_wgrad(gs, bp.x, bp.x, alg_g_);
+        bp.ds_hg_wgrad = plan_conv_wgrad_gram(br.ds.shape, P, bp.x, alg_h_);
         bp.ds_concat = plan_dgrad_concat(br.ds.shape, P, bp.x, C, alg_bstack_, T);
-        ensure_wgrad_scratch(bp.ds_h_wgrad);
-        ensure_wgrad_scratch(bp.ds_gram_wgrad);
+        ensure_wgrad_scratch(bp.ds_hg_wgrad);
       }
       // conv2: dy = Q (dRaw2), input act1, dx -> R
       bp.c2.wgrad = plan_conv_wgrad(br.c2.shape, Q, bp.act1, wg_dst(br.c2));
@@ -653,19 +644,17 @@ void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_
 
 // Expanding 1x1 convolution + batch norm backward without touching the BN input or its gradient (see bn_algebra.cu
 // for the derivation): upstream masked gradient g and the saved conv input `act` go through three GEMMs.
-void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& h, const WgradLaunch& gram,
-                                       const ConvLaunch& concat, const bf16* act, const float* colsum_partial, int64_t rows,
-                                       cudaStream_t s) {
+void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
+                                       const float* colsum_partial, int64_t rows, cudaStream_t s) {
   const int O = c.shape.Cout, C = c.shape.Cin;
+  float* alg_g = alg_h_ + static_cast<size_t>(O) * C;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
-  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O) * C * sizeof(float), s));
-  ARGUS_CUDA(cudaMemsetAsync(alg_g_, 0, static_cast<size_t>(C) * C * sizeof(float), s));
-  launch_wgrad(h, wgrad_scratch_, s);      // H = g^T act
-  launch_wgrad(gram, wgrad_scratch_, s);   // G = act^T act
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s));
+  launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) and G = act^T act (rows O..O+C), act tiles loaded once
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_rows_bf16(act, rows, C, bn_bwd_scratch_, alg_s_, s);
   const float* sc = bn_scratch_ + c.bn.scratch_off;
-  bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g_, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
+  bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
                         sc + 2 * O, sc + 3 * O, static_cast<double>(rows), grads_dev_ + c.bn.gamma_off,
                         grads_dev_ + c.bn.beta_off, grads_dev_ + c.w_off, alg_k1k0_, alg_bstack_, alg_bias_, alg_mpartial_, O,
                         C, s);
@@ -725,7 +714,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       const bf16* residual = P;
       if (br.has_ds) {
         if (bp.ds_algebraic) {
-          conv_bn_backward_algebraic(br.ds, bp.ds_h_wgrad, bp.ds_gram_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, s);
+          conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, s);
         } else {
           bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
           if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
@@ -735,7 +724,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       }
       if (bp.algebraic) {
         // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
-        conv_bn_backward_algebraic(br.c3, bp.h_wgrad, bp.gram_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, s);
+        conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, s);
       } else {
         bn_backward(br.c3, P, bp.raw3, nullptr, Q, bp.rows_out, 0, s);      // Q = dRaw3
         conv_backward(bp.c3, nullptr, nullptr, nullptr, s);                  // Q -> R (dAct2)

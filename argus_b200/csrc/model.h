@@ -64,10 +64,10 @@ struct BlockPlan {
   // algebraic bn3 backward (bn_algebra.cu): H = g^T act2, G = act2^T act2, concatenated-K dgrad of conv3
   bool algebraic = false;
   float* act2_colsum = nullptr;   // [bn_apply_grid][C] per-block column sums of act2, written by the forward bn_apply
-  WgradLaunch h_wgrad, gram_wgrad;
+  WgradLaunch hg_wgrad;           // one launch: H (rows < O) and the Gram matrix (rows O..O+C) into alg_h_
   ConvLaunch c3_concat;
   bool ds_algebraic = false;      // same for a stride-1 downsample branch (layer1.0), with act = the block input
-  WgradLaunch ds_h_wgrad, ds_gram_wgrad;
+  WgradLaunch ds_hg_wgrad;
   ConvLaunch ds_concat;
   size_t x_bytes = 0;
 };
@@ -160,8 +160,8 @@ class Model {
   void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats, cudaStream_t s);
   // conv (expanding 1x1) + BN backward on the masked upstream gradient (bn_algebra.cu); colsum_partial == nullptr:
   // the column sums of `act` are computed here
-  void conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& h, const WgradLaunch& gram, const ConvLaunch& concat,
-                                  const bf16* act, const float* colsum_partial, int64_t rows, cudaStream_t s);
+  void conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
+                                  const float* colsum_partial, int64_t rows, cudaStream_t s);
 
   template <typename T>
   T* arena_alloc(size_t count);
@@ -193,7 +193,7 @@ class Model {
   // algebraic bn3 backward scratch (sized for the widest eligible block)
   bool bn_algebra_ = true;
   int alg_max_o_ = 0, alg_max_c_ = 0;
-  float *alg_h_ = nullptr, *alg_g_ = nullptr, *alg_s_ = nullptr, *alg_k1k0_ = nullptr, *alg_bias_ = nullptr;
+  float *alg_h_ = nullptr, *alg_s_ = nullptr, *alg_k1k0_ = nullptr, *alg_bias_ = nullptr;
   float* alg_mpartial_ = nullptr;
   float* alg_gstats_ = nullptr;       // [max_stat_slots_][2][alg_max_o_] sums of the masked gradient, per dgrad CTA slot
   bf16* alg_bstack_ = nullptr;

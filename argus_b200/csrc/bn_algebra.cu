@@ -173,7 +173,16 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
 // deterministic column sums of a bf16 (rows, C) matrix: per-block partials, then an ordered reduction
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t rows, int cvec) {
+colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t rows, int cvec, int stride,
+                      int Wo, int HoWo, int W, int HW) {
+  // stride 2: row r of the (N, H/2, W/2) grid is pixel (2h, 2w) of the (N, H, W) tensor
+  auto src = [&](int64_t r) -> int64_t {
+    if (stride == 1) return r;
+    const int64_t n = r / HoWo;
+    const int rem = static_cast<int>(r - n * HoWo);
+    const int h2 = rem / Wo, w2 = rem - h2 * Wo;
+    return n * HW + static_cast<int64_t>(stride * h2) * W + stride * w2;
+  };
   __shared__ float red[8][256];
   const int lanes = cvec < 256 ? cvec : 256;
   const int row_lanes = 256 / lanes;
@@ -188,11 +197,11 @@ colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, 
   const int64_t rs = static_cast<int64_t>(gridDim.x) * row_lanes;
   int64_t r = static_cast<int64_t>(blockIdx.x) * row_lanes + rl;
   for (; r + 3 * rs < rows; r += 4 * rs) {   // four independent 16-byte loads in flight per thread
-    const uint4 u0 = __ldg(x + r * cvec + oc), u1 = __ldg(x + (r + rs) * cvec + oc);
-    const uint4 u2 = __ldg(x + (r + 2 * rs) * cvec + oc), u3 = __ldg(x + (r + 3 * rs) * cvec + oc);
+    const uint4 u0 = __ldg(x + src(r) * cvec + oc), u1 = __ldg(x + src(r + rs) * cvec + oc);
+    const uint4 u2 = __ldg(x + src(r + 2 * rs) * cvec + oc), u3 = __ldg(x + src(r + 3 * rs) * cvec + oc);
     add(u0); add(u1); add(u2); add(u3);
   }
-  for (; r < rows; r += rs) add(__ldg(x + r * cvec + oc));
+  for (; r < rows; r += rs) add(__ldg(x + src(r) * cvec + oc));
 #pragma unroll
   for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc[k];
   __syncthreads();
@@ -205,27 +214,43 @@ colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, 
     }
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out, int C) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+// block = 8 channels x 32 lanes: lane sl adds blocks sl, sl+32, ... in order, lane 0 then adds the 32 lane sums in
+// order (bitwise reproducible, 32-way parallel; a single thread per channel took 80 us over 1184 partials)
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out, int C) {
+  __shared__ double red[32][8];
+  const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 8 + ch;
   double acc = 0.0;
-  for (int b = 0; b < blocks; ++b) acc += static_cast<double>(partial[static_cast<size_t>(b) * C + c]);
+  if (c < C)
+    for (int b = sl; b < blocks; b += 32) acc += static_cast<double>(partial[static_cast<size_t>(b) * C + c]);
+  red[sl][ch] = acc;
+  __syncthreads();
+  if (sl != 0 || c >= C) return;
+  acc = 0.0;
+  for (int k = 0; k < 32; ++k) acc += red[k][ch];
   out[c] = static_cast<float>(acc);
 }
 void colsum_finalize(const float* partial, int blocks, float* out, int C, cudaStream_t st) {
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(partial, blocks, out, C);
+  colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, blocks, out, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st) {
+  colsum_pixels_bf16(x, static_cast<int>(rows), 1, 1, C, 1, scratch, out, st);
+}
+void colsum_pixels_bf16(const bf16* x, int N, int H, int W, int C, int stride, float* scratch, float* out,
+                        cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(N) * (H / stride) * (W / stride);
   ARGUS_CHECK(C % 8 == 0 && is_pow2(C / 8) && C <= 2048, "colsum: C/8 must be a power of two <= 256");
   ProfileScope prof("bn_algebra", st, 0, static_cast<double>(rows) * C * 2);
   const int cvec = C / 8;
   const int lanes = std::min(cvec, 256);
   const int row_lanes = 256 / lanes;
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + row_lanes - 1) / row_lanes, 4LL * num_sms())));
-  colsum_partial_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), scratch, rows, cvec);
+  colsum_partial_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), scratch, rows, cvec, stride, W / stride,
+                                                (H / stride) * (W / stride), W, H * W);
   ARGUS_CUDA(cudaGetLastError());
-  colsum_final_kernel<<<(C + 127) / 128, 128, 0, st>>>(scratch, blocks, out, C);
+  colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(scratch, blocks, out, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 

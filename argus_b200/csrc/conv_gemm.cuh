@@ -514,10 +514,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 // ---------------------------------------------------------------------------------------------------------
 struct WgradParams {
   CUtensorMap dy_map;     // 2-D [pixels, Cout], box (64 co, 64 pixels)
-  // Stacked M operand: output rows >= co_split (a multiple of 128, 0 = off) are read through dy_map2 instead, so one
-  // launch yields [dy | dy2]^T x. With dy2 = x this appends the Gram matrix x^T x to the weight gradient and the x
-  // tiles are loaded once for both (algebraic batch-norm backward, bn_algebra.cu).
-  CUtensorMap dy_map2;
+  // Stacked M operand: output rows >= co_split (a multiple of 128, 0 = off) are read from the activation tensor x
+  // itself (through a_map, channel = row - co_split), so one launch yields [dy | x]^T x: the weight gradient with the
+  // Gram matrix x^T x appended (algebraic batch-norm backward, bn_algebra.cu). Works for strided x maps too.
   int co_split;
   CUtensorMap a_map[4];   // 4-D activation maps (C, W, H, N) by parity, box (64 ci, 64-pixel box)
   Tap taps[kMaxTaps];     // b_off = element offset of the tap inside one dW row
@@ -581,7 +580,6 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
   }
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.dy_map);
-    if (p.co_split > 0) tma_prefetch_desc(&p.dy_map2);
     for (int i = 0; i < 4; ++i) tma_prefetch_desc(&p.a_map[i]);
   }
   if (warp == 1) {
@@ -627,11 +625,14 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
           mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-          const bool second = (p.co_split > 0 && co_t * 128 >= p.co_split);
-          const CUtensorMap* dmap = second ? &p.dy_map2 : &p.dy_map;
-          const int co0 = second ? co_t * 128 - p.co_split : co_t * 128;
-          tma_load_2d(dmap, full_bar(stage), sa, co0, p0);
-          tma_load_2d(dmap, full_bar(stage), sa + 8192, co0 + 64, p0);
+          if (p.co_split > 0 && co_t * 128 >= p.co_split) {
+            const int c0 = co_t * 128 - p.co_split;
+            tma_load_4d(&p.a_map[tap.map], full_bar(stage), sa, c0, w0 + tap.dw, h0 + tap.dh, img0);
+            tma_load_4d(&p.a_map[tap.map], full_bar(stage), sa + 8192, c0 + 64, w0 + tap.dw, h0 + tap.dh, img0);
+          } else {
+            tma_load_2d(&p.dy_map, full_bar(stage), sa, co_t * 128, p0);
+            tma_load_2d(&p.dy_map, full_bar(stage), sa + 8192, co_t * 128 + 64, p0);
+          }
 #pragma unroll
           for (int j = 0; j < BLOCK_N / 64; ++j)
             tma_load_4d(&p.a_map[tap.map], full_bar(stage), sb + j * 8192, ci_t * BLOCK_N + j * 64, w0 + tap.dw,

@@ -404,18 +404,20 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
 ConvLaunch plan_dgrad_concat(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* a1, int C1,
                              const __nv_bfloat16* bstack, __nv_bfloat16* dx) {
   validate_shape(s);
-  ARGUS_CHECK(s.kind == 0 && s.k == 1 && s.stride == 1, "concatenated dgrad is defined for 1x1 stride-1 convolutions");
+  ARGUS_CHECK(s.kind == 0 && s.k == 1, "concatenated dgrad is defined for 1x1 convolutions");
   ARGUS_CHECK(C1 > 0 && C1 % 64 == 0, "second source must have a multiple of 64 channels");
   std::vector<ConvLaunch> ls = plan_conv_dgrad(s, dy, bstack, dx);
-  ARGUS_CHECK(ls.size() == 1, "unexpected dgrad decomposition");
+  ARGUS_CHECK(ls.size() == 1, "unexpected dgrad decomposition");   // stride 2: only parity class (0,0) has a tap
   ConvLaunch l = ls[0];
   ConvGemmParams& p = l.p;
+  const int Ho = s.Ho(), Wo = s.Wo();
   uint32_t bw, bh, bn;
-  pixel_box(s.W, s.H, kBlockM, bw, bh, bn);
+  pixel_box(Wo, Ho, kBlockM, bw, bh, bn);
   {
-    const uint64_t C = C1;
-    const uint64_t dims[4] = {C, static_cast<uint64_t>(s.W), static_cast<uint64_t>(s.H), static_cast<uint64_t>(s.N)};
-    const uint64_t str[3] = {C * 2, s.W * C * 2, static_cast<uint64_t>(s.H) * s.W * C * 2};
+    // a1 lives on the conv INPUT grid (N, H, W, C1); the GEMM rows are output pixels: stride 2 reads its (0,0) plane
+    const uint64_t C = C1, H = s.H, W = s.W, st = s.stride;
+    const uint64_t dims[4] = {C, static_cast<uint64_t>(Wo), static_cast<uint64_t>(Ho), static_cast<uint64_t>(s.N)};
+    const uint64_t str[3] = {st * C * 2, st * W * C * 2, H * W * C * 2};
     const uint32_t box[4] = {64, bw, bh, bn};
     p.a_map[1] = make_tmap_bf16(a1, 4, dims, str, box);
   }
@@ -501,26 +503,18 @@ WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const _
 }
 
 WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw) {
-  ARGUS_CHECK(s.kind == 0 && s.k == 1 && s.stride == 1, "stacked weight gradient + Gram is defined for 1x1 stride-1");
+  ARGUS_CHECK(s.kind == 0 && s.k == 1, "stacked weight gradient + Gram is defined for 1x1 convolutions");
   ARGUS_CHECK(s.Cout % 128 == 0, "Cout must be a multiple of 128");
-  // plan as a convolution with Cout + Cin output channels, then point the rows beyond Cout at x
+  // plan as a convolution with Cout + Cin output channels, then point the rows beyond Cout at x (through a_map)
   ConvShape st = s;
   st.Cout = s.Cout + s.Cin;
   WgradLaunch l = plan_conv_wgrad(st, dy, x, dw);
   ARGUS_CHECK(l.xpose_nbox == 0, "unexpected kernel choice");
   const int64_t pixels = s.out_pixels();
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cout), static_cast<uint64_t>(pixels)};
-    const uint64_t str[1] = {static_cast<uint64_t>(s.Cout) * 2};
-    const uint32_t box[2] = {64, 64};
-    l.p.dy_map = make_tmap_bf16(dy, 2, dims, str, box);
-  }
-  {
-    const uint64_t dims[2] = {static_cast<uint64_t>(s.Cin), static_cast<uint64_t>(pixels)};
-    const uint64_t str[1] = {static_cast<uint64_t>(s.Cin) * 2};
-    const uint32_t box[2] = {64, 64};
-    l.p.dy_map2 = make_tmap_bf16(x, 2, dims, str, box);
-  }
+  const uint64_t dims[2] = {static_cast<uint64_t>(s.Cout), static_cast<uint64_t>(pixels)};
+  const uint64_t str[1] = {static_cast<uint64_t>(s.Cout) * 2};
+  const uint32_t box[2] = {64, 64};
+  l.p.dy_map = make_tmap_bf16(dy, 2, dims, str, box);
   l.p.co_split = s.Cout;
   return l;
 }

@@ -103,6 +103,9 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
 int64_t bn_alg_matrix_scratch_elems(int C);   // floats of `mpartial`
 // out[c] = sum_r x[r][c], deterministic; scratch: >= 4 * num_sms * C floats
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st);
+// same over the pixels (stride*h, stride*w) of an (N, H, W, C) tensor (what a strided 1x1 convolution reads)
+void colsum_pixels_bf16(const bf16* x, int N, int H, int W, int C, int stride, float* scratch, float* out,
+                        cudaStream_t st);
 
 // ---- head MLP (fp32 SIMT; argus/models.py:58-64,88-90) -----------------------------------------------------
 // z = gelu(feat) ; feat bf16 (rows, cols) -> z fp32

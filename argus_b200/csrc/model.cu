@@ -186,6 +186,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
         if (b.c1.shape.Cout <= 256) {
           alg_max_o_ = std::max(alg_max_o_, b.c3.shape.Cout);
           alg_max_c_ = std::max(alg_max_c_, b.c1.shape.Cout);
+          if (b.has_ds && b.ds.shape.Cin <= 256) alg_max_c_ = std::max(alg_max_c_, b.ds.shape.Cin);
         }
       const size_t O = alg_max_o_, C = alg_max_c_;
       ARGUS_CUDA(cudaMalloc(&alg_h_, (O + C) * C * sizeof(float)));   // H [O][C] followed by the Gram matrix [C][C]
@@ -380,7 +381,7 @@ void Model::build_plan(Plan& p) {
         bp.c3_concat = plan_dgrad_concat(br.c3.shape, P, bp.act2, C, alg_bstack_, R);
         ensure_wgrad_scratch(bp.hg_wgrad);
       }
-      bp.ds_algebraic = bp.algebraic && br.has_ds && br.ds.shape.stride == 1;
+      bp.ds_algebraic = bp.algebraic && br.has_ds && br.ds.shape.Cin <= 256;   // layer1.0, layer2.0
       if (bp.ds_algebraic) {
         const int C = br.ds.shape.Cin;
         bp.ds_hg_wgrad = plan_conv_wgrad_gram(br.ds.shape, P, bp.x, alg_h_);
@@ -645,14 +646,14 @@ void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_
 // Expanding 1x1 convolution + batch norm backward without touching the BN input or its gradient (see bn_algebra.cu
 // for the derivation): upstream masked gradient g and the saved conv input `act` go through three GEMMs.
 void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
-                                       const float* colsum_partial, int64_t rows, cudaStream_t s) {
+                                       const float* colsum_partial, int64_t rows, int N, cudaStream_t s) {
   const int O = c.shape.Cout, C = c.shape.Cin;
   float* alg_g = alg_h_ + static_cast<size_t>(O) * C;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
   ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s));
   launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) and G = act^T act (rows O..O+C), act tiles loaded once
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
-  else colsum_rows_bf16(act, rows, C, bn_bwd_scratch_, alg_s_, s);
+  else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
   const float* sc = bn_scratch_ + c.bn.scratch_off;
   bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
                         sc + 2 * O, sc + 3 * O, static_cast<double>(rows), grads_dev_ + c.bn.gamma_off,
@@ -714,7 +715,8 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       const bf16* residual = P;
       if (br.has_ds) {
         if (bp.ds_algebraic) {
-          conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, s);
+          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
+          conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, N, s);
         } else {
           bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
           if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
@@ -724,7 +726,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       }
       if (bp.algebraic) {
         // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
-        conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, s);
+        conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, N, s);
       } else {
         bn_backward(br.c3, P, bp.raw3, nullptr, Q, bp.rows_out, 0, s);      // Q = dRaw3
         conv_backward(bp.c3, nullptr, nullptr, nullptr, s);                  // Q -> R (dAct2)

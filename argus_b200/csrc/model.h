@@ -66,7 +66,7 @@ struct BlockPlan {
   float* act2_colsum = nullptr;   // [bn_apply_grid][C] per-block column sums of act2, written by the forward bn_apply
   WgradLaunch hg_wgrad;           // one launch: H (rows < O) and the Gram matrix (rows O..O+C) into alg_h_
   ConvLaunch c3_concat;
-  bool ds_algebraic = false;      // same for a stride-1 downsample branch (layer1.0), with act = the block input
+  bool ds_algebraic = false;      // same for the downsample branch, with act = the block input (its even pixels at stride 2)
   WgradLaunch ds_hg_wgrad;
   ConvLaunch ds_concat;
   size_t x_bytes = 0;
@@ -161,7 +161,7 @@ class Model {
   // conv (expanding 1x1) + BN backward on the masked upstream gradient (bn_algebra.cu); colsum_partial == nullptr:
   // the column sums of `act` are computed here
   void conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
-                                  const float* colsum_partial, int64_t rows, cudaStream_t s);
+                                  const float* colsum_partial, int64_t rows, int N, cudaStream_t s);
 
   template <typename T>
   T* arena_alloc(size_t count);

@@ -170,6 +170,89 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Forward: batch statistics of y = x W^T (1x1 convolution) from the Gram matrix of its input, BEFORE the convolution
+// runs:  mean_o = W[o,:] s / P,  E[y_o^2] = W[o,:] G W[o,:]^T / P  with s = colsum(x), G = x^T x. The convolution can
+// then apply batch norm (+ residual + ReLU) in its own epilogue and its raw output is never written.
+// ------------------------------------------------------------------------------------------------------------
+// partial[o][bx] = sum over the 16 columns i of tile bx of W[o,i] * (sum_j W[o,j] G[j,i])
+__global__ void __launch_bounds__(256)
+gram_quadform_kernel(const bf16* __restrict__ W, const float* __restrict__ G, float* __restrict__ partial, int O, int C) {
+  __shared__ float sW[16][33];
+  __shared__ float sG[32][17];
+  __shared__ float sQ[16][17];
+  const int ti = threadIdx.x & 15, to = threadIdx.x >> 4;
+  const int i0 = blockIdx.x * 16, o0 = blockIdx.y * 16;
+  float acc = 0.f;
+  for (int j0 = 0; j0 < C; j0 += 32) {
+    for (int e = threadIdx.x; e < 16 * 32; e += 256) {
+      const int a = e >> 5, b = e & 31;
+      sW[a][b] = __bfloat162float(W[static_cast<size_t>(o0 + a) * C + j0 + b]);
+      const int c = e >> 4, d = e & 15;
+      sG[c][d] = G[static_cast<size_t>(j0 + c) * C + i0 + d];
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int j = 0; j < 32; ++j) acc = fmaf(sW[to][j], sG[j][ti], acc);
+    __syncthreads();
+  }
+  sQ[to][ti] = acc * __bfloat162float(W[static_cast<size_t>(o0 + to) * C + i0 + ti]);
+  __syncthreads();
+  if (ti == 0) {
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) q += sQ[to][k];
+    partial[static_cast<size_t>(o0 + to) * gridDim.x + blockIdx.x] = q;
+  }
+}
+// one warp per channel: finish the quadratic form and the mean, then torch.nn.BatchNorm2d's train-mode bookkeeping
+__global__ void __launch_bounds__(256)
+gram_stats_finalize_kernel(const bf16* __restrict__ W, const float* __restrict__ s, const float* __restrict__ partial,
+                           int nparts, double rows, const float* gamma, const float* beta, float* running_mean,
+                           float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
+                           float* save_invstd, int O, int C) {
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (o >= O) return;
+  double q = 0.0, m = 0.0;
+  for (int k = lane; k < nparts; k += 32) q += static_cast<double>(partial[static_cast<size_t>(o) * nparts + k]);
+  for (int i = lane; i < C; i += 32)
+    m += static_cast<double>(__bfloat162float(W[static_cast<size_t>(o) * C + i])) * static_cast<double>(s[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    q += __shfl_xor_sync(0xffffffffu, q, off);
+    m += __shfl_xor_sync(0xffffffffu, m, off);
+  }
+  if (lane != 0) return;
+  const double mean = m / rows;
+  double var = q / rows - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = static_cast<float>(1.0 / sqrt(var + static_cast<double>(eps)));
+  const float sc = gamma[o] * invstd;
+  scale[o] = sc;
+  shift[o] = beta[o] - static_cast<float>(mean) * sc;
+  save_mean[o] = static_cast<float>(mean);
+  save_invstd[o] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = rows > 1 ? var * rows / (rows - 1) : var;
+    running_mean[o] = (1.f - momentum) * running_mean[o] + momentum * static_cast<float>(mean);
+    running_var[o] = (1.f - momentum) * running_var[o] + momentum * static_cast<float>(unbiased);
+  }
+}
+void bn_stats_from_gram(const bf16* W, const float* G, const float* s, double rows, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                        float* scale, float* shift, float* save_mean, float* save_invstd, float* scratch, int O, int C,
+                        cudaStream_t st) {
+  ARGUS_CHECK(O % 16 == 0 && C % 32 == 0, "bn_stats_from_gram: O % 16 == 0 and C % 32 == 0 required");
+  ProfileScope prof("bn_algebra", st, 2.0 * O * static_cast<double>(C) * C, 0);
+  gram_quadform_kernel<<<dim3(C / 16, O / 16), 256, 0, st>>>(W, G, scratch, O, C);
+  ARGUS_CUDA(cudaGetLastError());
+  gram_stats_finalize_kernel<<<(O * 32 + 255) / 256, 256, 0, st>>>(W, s, scratch, C / 16, rows, gamma, beta, running_mean,
+                                                                  running_var, momentum, eps, scale, shift, save_mean,
+                                                                  save_invstd, O, C);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // deterministic column sums of a bf16 (rows, C) matrix: per-block partials, then an ordered reduction
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

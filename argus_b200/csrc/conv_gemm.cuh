@@ -67,6 +67,10 @@ struct ConvGemmParams {
   int32_t halo_boff[3][3];
   CUtensorMap halo_map;   // box {64, W, rows + 2, 1}
   const uint8_t* res_bits;       // optional [m_total][n_total/8] bit mask: residual element counts only where its bit is set
+  const float* res_scale;        // optional per-channel affine applied to the residual before the add (the downsample
+  const float* res_shift;        // branch's batch norm folded into the block tail): f += res * res_scale + res_shift
+  uint8_t* relu_bits_out;        // optional [m_total][n_total/8]: bit = (pre-ReLU value > 0), written next to the output
+                                 // (training forward of a fused conv3 + BN + residual + ReLU block tail)
   const uint8_t* out_bits;       // optional [m_total][n_total/8] bit mask applied to the RESULT (after the residual add):
                                  // the dgrad that produces the gradient of a ReLU output stores it already masked
   // K concatenation (1x1 only): after the regular k-blocks, k2_blocks more 64-wide blocks are read from a_map[1]
@@ -443,9 +447,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                 rv.w &= ((mb & 64u) ? 0x0000ffffu : 0u) | ((mb & 128u) ? 0xffff0000u : 0u);
               }
               float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
-              f[q * 8 + 0] += a.x; f[q * 8 + 1] += a.y; f[q * 8 + 2] += b.x; f[q * 8 + 3] += b.y;
-              f[q * 8 + 4] += c.x; f[q * 8 + 5] += c.y; f[q * 8 + 6] += d.x; f[q * 8 + 7] += d.y;
+              float rr8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+              if (p.res_scale != nullptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.res_scale + c0 + q * 8));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.res_scale + c0 + q * 8 + 4));
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.res_shift + c0 + q * 8));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.res_shift + c0 + q * 8 + 4));
+                rr8[0] = fmaf(rr8[0], s0.x, t0.x); rr8[1] = fmaf(rr8[1], s0.y, t0.y);
+                rr8[2] = fmaf(rr8[2], s0.z, t0.z); rr8[3] = fmaf(rr8[3], s0.w, t0.w);
+                rr8[4] = fmaf(rr8[4], s1.x, t1.x); rr8[5] = fmaf(rr8[5], s1.y, t1.y);
+                rr8[6] = fmaf(rr8[6], s1.z, t1.z); rr8[7] = fmaf(rr8[7], s1.w, t1.w);
+              }
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[q * 8 + j] += rr8[j];
             }
+          }
+          if (p.relu_bits_out != nullptr) {
+            uint32_t ob = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ob |= (f[i] > 0.f ? 1u : 0u) << i;
+            if (m0 + r < p.m_total)
+              *reinterpret_cast<uint32_t*>(p.relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
+                                           ((n0 + ch * 64 + h * 32) >> 3)) = ob;
           }
           if (p.relu) {
 #pragma unroll
@@ -518,6 +541,7 @@ struct WgradParams {
   // itself (through a_map, channel = row - co_split), so one launch yields [dy | x]^T x: the weight gradient with the
   // Gram matrix x^T x appended (algebraic batch-norm backward, bn_algebra.cu). Works for strided x maps too.
   int co_split;
+  int stacked;            // 0: every row from dy_map; 1: rows >= co_split from x (co_split may be 0: pure Gram matrix)
   CUtensorMap a_map[4];   // 4-D activation maps (C, W, H, N) by parity, box (64 ci, 64-pixel box)
   Tap taps[kMaxTaps];     // b_off = element offset of the tap inside one dW row
   int num_taps;
@@ -625,7 +649,7 @@ wgrad_kernel(const __grid_constant__ WgradParams p) {
           const uint32_t sa = smem_base + stage * L::kStageBytes;
           const uint32_t sb = sa + L::kABytes;
           mbar_arrive_expect_tx(full_bar(stage), L::kStageBytes);
-          if (p.co_split > 0 && co_t * 128 >= p.co_split) {
+          if (p.stacked && co_t * 128 >= p.co_split) {
             const int c0 = co_t * 128 - p.co_split;
             tma_load_4d(&p.a_map[tap.map], full_bar(stage), sa, c0, w0 + tap.dw, h0 + tap.dh, img0);
             tma_load_4d(&p.a_map[tap.map], full_bar(stage), sa + 8192, c0 + 64, w0 + tap.dw, h0 + tap.dh, img0);

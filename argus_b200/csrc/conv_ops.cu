@@ -516,6 +516,19 @@ WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, co
   const uint32_t box[2] = {64, 64};
   l.p.dy_map = make_tmap_bf16(dy, 2, dims, str, box);
   l.p.co_split = s.Cout;
+  l.p.stacked = 1;
+  return l;
+}
+
+WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g) {
+  ARGUS_CHECK(s.kind == 0 && s.k == 1, "Gram matrix of the pixels a 1x1 convolution reads");
+  ConvShape st = s;
+  st.Cout = s.Cin;
+  WgradLaunch l = plan_conv_wgrad(st, x, x, g);   // (the dy map is never used: every row comes from x)
+  ARGUS_CHECK(l.xpose_nbox == 0, "unexpected kernel choice");
+  l.p.co_split = 0;
+  l.p.stacked = 1;
+  l.family = "bn_algebra";
   return l;
 }
 
@@ -567,6 +580,10 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   }
   p.relu = e.relu;
   p.out_bits = e.out_bits;
+  p.res_scale = e.res_scale;
+  p.res_shift = e.res_shift;
+  p.relu_bits_out = e.relu_bits_out;
+  ARGUS_CHECK((e.res_scale == nullptr) == (e.res_shift == nullptr), "residual scale and shift come together");
   p.stat_partial = e.stat_partial;
   const double flops = 2.0 * p.m_total * static_cast<double>(p.n_total) * (p.num_taps * p.kblocks_per_tap + p.k2_blocks) * kBlockK;
   std::string fam = l.b_mn ? "conv_dgrad" : "conv_fwd";

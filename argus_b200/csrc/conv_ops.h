@@ -28,6 +28,9 @@ struct Epilogue {
   const __nv_bfloat16* residual = nullptr;
   const uint8_t* residual_bits = nullptr;   // optional [rows][Cout/8] ReLU bit mask gating the residual (dgrad)
   const uint8_t* out_bits = nullptr;        // optional [rows][Cout/8] ReLU bit mask applied to the stored result
+  const float* res_scale = nullptr;         // optional per-channel affine on the residual (both or neither)
+  const float* res_shift = nullptr;
+  uint8_t* relu_bits_out = nullptr;         // optional [rows][Cout/8]: (pre-ReLU value > 0), written by the epilogue
   int relu = 0;
   float* stat_partial = nullptr;   // [stat_slots(launch)][2][Cout], zeroed by the caller (train-mode BN statistics)
 };
@@ -80,6 +83,10 @@ WgradLaunch plan_conv_wgrad(const ConvShape& s, const __nv_bfloat16* dy, const _
 // 1x1 only: dw[(Cout + Cin)][Cin] (fp32, +=): rows < Cout = dy^T x (the weight gradient), rows Cout + j = x^T x (the
 // Gram matrix of the input pixels the convolution reads); Cout must be a multiple of 128. One launch.
 WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, const __nv_bfloat16* x, float* dw);
+
+// g[Cin][Cin] (fp32, +=) = x_s^T x_s over the input pixels x_s a 1x1 convolution of shape s reads (its even pixels at
+// stride 2): the Gram matrix from which the batch statistics of the convolution's OUTPUT follow without computing it.
+WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g);
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);
 // number of statistic slots launch_conv writes for this launch (2 per CTA)

@@ -101,6 +101,13 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
                            double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
                            float* mpartial, int O, int C, cudaStream_t st);
 int64_t bn_alg_matrix_scratch_elems(int C);   // floats of `mpartial`
+// Forward counterpart: train-mode batch statistics of y = x W^T from G = x^T x and s = colsum(x) (both over the `rows`
+// pixels the 1x1 convolution reads), before / instead of computing y: scale, shift, mean, invstd and the running-stat
+// update of torch.nn.BatchNorm2d. scratch: O * C / 16 floats.
+void bn_stats_from_gram(const bf16* W, const float* G, const float* s, double rows, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float momentum, float eps,
+                        float* scale, float* shift, float* save_mean, float* save_invstd, float* scratch, int O, int C,
+                        cudaStream_t st);
 // out[c] = sum_r x[r][c], deterministic; scratch: >= 4 * num_sms * C floats
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st);
 // same over the pixels (stride*h, stride*w) of an (N, H, W, C) tensor (what a strided 1x1 convolution reads)

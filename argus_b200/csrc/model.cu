@@ -180,6 +180,12 @@ void Model::bind(float* params, float* grads, float* buffers) {
     {
       const char* e = getenv("ARGUS_BN_ALGEBRA");
       bn_algebra_ = !(e && e[0] == '0');
+      // Fused block tail in the training forward (bn3 statistics from the Gram matrix of act2, BN + identity + ReLU +
+      // bit mask in conv3's epilogue, raw3 never written). Correct and slightly more accurate, but measured SLOWER
+      // (45.2 vs 44.1 ms/step): it moves 3.6 ms of HBM-roofline bn_apply work into the convolution epilogue, which is
+      // latency-bound (8 warps per SM), and adds 1.5 ms of Gram GEMMs. Opt-in until the epilogue is redesigned.
+      const char* ft = getenv("ARGUS_FUSED_TAIL");
+      fused_tail_ = (ft && ft[0] == '1');
       // eligible: bottlenecks whose mid width is <= 256 (layers 1-3); layer4's small matrices would cost more than the
       // two passes over its (small) activations
       for (const auto& b : blocks_)
@@ -320,8 +326,9 @@ void Model::build_plan(Plan& p) {
     bp.act1 = arena_alloc<bf16>(e_in * wd);
     if (tr) bp.raw2 = arena_alloc<bf16>(e_out * wd);
     bp.act2 = arena_alloc<bf16>(e_out * wd);
-    if (tr) bp.raw3 = arena_alloc<bf16>(e_out * oc);
-    if (br.has_ds) bp.rawd = arena_alloc<bf16>(e_out * oc);  // eval: holds the folded-BN identity branch
+    bp.fused_tail = tr && bn_algebra_ && fused_tail_ && wd <= 256;
+    if (tr && !bp.fused_tail) bp.raw3 = arena_alloc<bf16>(e_out * oc);
+    if (br.has_ds) bp.rawd = arena_alloc<bf16>(e_out * oc);  // eval / fused tail: holds the folded-BN identity branch
     bp.out = arena_alloc<bf16>(e_out * oc);
     if (tr) bp.out_bits = arena_alloc<uint8_t>(e_out * oc / 8);
     if (tr && bn_algebra_ && wd <= 256)
@@ -329,8 +336,16 @@ void Model::build_plan(Plan& p) {
     max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
     plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
     plan_conv(bp.c2, br.c2, N, h, w, bp.act1, tr ? bp.raw2 : bp.act2, true);
-    plan_conv(bp.c3, br.c3, N, ho, wo, bp.act2, tr ? bp.raw3 : bp.out, true);
+    plan_conv(bp.c3, br.c3, N, ho, wo, bp.act2, (tr && !bp.fused_tail) ? bp.raw3 : bp.out, true);
     if (br.has_ds) plan_conv(bp.ds, br.ds, N, h, w, bp.x, bp.rawd, true);
+    if (real && bp.fused_tail) {
+      bp.fwd_gram = plan_gram(br.c3.shape, bp.act2, alg_h_);
+      ensure_wgrad_scratch(bp.fwd_gram);
+      if (br.has_ds && br.ds.shape.Cin <= 256) {
+        bp.ds_fwd_gram = plan_gram(br.ds.shape, bp.x, alg_h_);
+        ensure_wgrad_scratch(bp.ds_fwd_gram);
+      }
+    }
     x = bp.out;
     h = ho; w = wo;
   }
@@ -459,6 +474,33 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
     run_conv_train(bp.c2, br.c2, bp.rows_out, s);
     bn_apply(bp.raw2, SC(br.c2), SC(br.c2) + wd, nullptr, nullptr, nullptr, 1, bp.act2, nullptr, bp.act2_colsum,
              bp.rows_out, wd, s);
+    if (bp.fused_tail) {
+      // bn3 statistics from the Gram matrix of act2; conv3 then finishes the block in its epilogue
+      stats_from_gram(br.c3, bp.fwd_gram, bp.act2, bp.act2_colsum, bp.rows_out, N, s);
+      Epilogue e;
+      e.scale = SC(br.c3);
+      e.shift = SC(br.c3) + oc;
+      e.relu = 1;
+      e.relu_bits_out = bp.out_bits;
+      e.residual = bp.x;
+      if (br.has_ds) {
+        e.residual = bp.rawd;
+        if (br.ds.shape.Cin <= 256) {
+          // downsample branch the same way: its batch norm is folded into its own epilogue
+          stats_from_gram(br.ds, bp.ds_fwd_gram, bp.x, nullptr, bp.rows_out, N, s);
+          Epilogue d;
+          d.scale = SC(br.ds);
+          d.shift = SC(br.ds) + oc;
+          launch_conv(bp.ds.fwd, d, s);
+        } else {
+          run_conv_train(bp.ds, br.ds, bp.rows_out, s);   // raw downsample output + statistics, normalised on the fly
+          e.res_scale = SC(br.ds);
+          e.res_shift = SC(br.ds) + oc;
+        }
+      }
+      launch_conv(bp.c3.fwd, e, s);
+      continue;
+    }
     run_conv_train(bp.c3, br.c3, bp.rows_out, s);
     if (br.has_ds) {
       run_conv_train(bp.ds, br.ds, bp.rows_out, s);
@@ -469,6 +511,19 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
                oc, s);
     }
   }
+}
+
+void Model::stats_from_gram(const ConvRef& c, const WgradLaunch& gram, const bf16* act, const float* colsum_partial,
+                            int64_t rows, int N, cudaStream_t s) {
+  const int O = c.shape.Cout, C = c.shape.Cin;
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(C) * C * sizeof(float), s));
+  launch_wgrad(gram, wgrad_scratch_, s);
+  if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
+  else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
+  float* sc = bn_scratch_ + c.bn.scratch_off;
+  bn_stats_from_gram(packed_ + c.packed_off, alg_h_, alg_s_, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
+                     params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off, buffers_dev_ + c.bn.rv_off, kBnMomentum,
+                     kBnEps, sc, sc + O, sc + 2 * O, sc + 3 * O, alg_mpartial_, O, C, s);
 }
 
 void Model::forward_eval(Plan& p, cudaStream_t s) {

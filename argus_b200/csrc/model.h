@@ -62,6 +62,10 @@ struct BlockPlan {
   // gradient scratch roles for this block
   bf16 *g_out = nullptr, *g_q = nullptr, *g_r = nullptr, *g_t = nullptr, *g_x = nullptr;
   // algebraic bn3 backward (bn_algebra.cu): H = g^T act2, G = act2^T act2, concatenated-K dgrad of conv3
+  // Fused block tail in the training forward (same eligibility as `algebraic`): bn3's batch statistics come from the
+  // Gram matrix of act2, so conv3 applies BN + identity + ReLU (+ bit mask) in its epilogue: raw3 is never written
+  bool fused_tail = false;
+  WgradLaunch fwd_gram, ds_fwd_gram;
   bool algebraic = false;
   float* act2_colsum = nullptr;   // [bn_apply_grid][C] per-block column sums of act2, written by the forward bn_apply
   WgradLaunch hg_wgrad;           // one launch: H (rows < O) and the Gram matrix (rows O..O+C) into alg_h_
@@ -153,6 +157,9 @@ class Model {
   void forward_eval(Plan& p, cudaStream_t s);
   void head_forward(Plan& p, float* out, cudaStream_t s);
   void run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s);
+  // batch statistics of the 1x1 convolution c from the Gram matrix of its input (gram launch + colsum) -> BN scratch
+  void stats_from_gram(const ConvRef& c, const WgradLaunch& gram, const bf16* act, const float* colsum_partial,
+                       int64_t rows, int N, cudaStream_t s);
   void bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
                    cudaStream_t s);
   // out_bits: ReLU mask of the tensor whose gradient this dgrad produces (stored masked); out_stats: per-slot channel
@@ -192,6 +199,7 @@ class Model {
   float* bn_bwd_scratch_ = nullptr;   // per-block partial sums of the BN-backward reductions
   // algebraic bn3 backward scratch (sized for the widest eligible block)
   bool bn_algebra_ = true;
+  bool fused_tail_ = false;
   int alg_max_o_ = 0, alg_max_c_ = 0;
   float *alg_h_ = nullptr, *alg_s_ = nullptr, *alg_k1k0_ = nullptr, *alg_bias_ = nullptr;
   float* alg_mpartial_ = nullptr;

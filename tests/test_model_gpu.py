@@ -158,8 +158,9 @@ def test_train_forward_backward(cuda_device, B, H, W, gain):
 def test_algebraic_bn3_backward_matches_textbook(cuda_device, monkeypatch):
     """The algebraic conv3/bn3 backward (csrc/bn_algebra.cu: GEMMs on the masked gradient and the saved activation
     instead of two passes over raw3 / dRaw3) against the textbook BN backward kernels (ARGUS_BN_ALGEBRA=0) on the same
-    weights and inputs: identical forward, gradients equal up to bf16 rounding of the intermediates, and against the
-    fp32 reference both are equally far."""
+    weights and inputs. The two forwards differ only in rounding (the fused block tail normalises the fp32 accumulator,
+    the textbook path the bf16-rounded raw3), the gradients up to bf16 rounding of the intermediates; against the fp32
+    reference both are equally far."""
     from argus_b200.loss import geometric_loss_fn
     from argus_b200.models import NCameraCNN
     from oracle.ref_model import torch_loss
@@ -180,7 +181,10 @@ def test_algebraic_bn3_backward_matches_textbook(cuda_device, monkeypatch):
     ref.train()
     torch_loss(ref(x), target).mean().backward()
     torch.cuda.synchronize()
-    assert torch.equal(y_txt, y_alg)
+    y_ref = ref(x).detach()
+    r_y_alg, r_y_txt = rel(y_alg.detach(), y_ref), rel(y_txt.detach(), y_ref)
+    print(f"output vs fp32 reference: fused/algebraic {r_y_alg:.3e}  textbook {r_y_txt:.3e}")
+    assert r_y_alg < max(1.25 * r_y_txt, 2e-2)
     g_ref = {n: p.grad for n, p in ref.named_parameters()}
     num = num_a = num_t = den = 0.0
     worst = []
@@ -199,3 +203,46 @@ def test_algebraic_bn3_backward_matches_textbook(cuda_device, monkeypatch):
     print(f"global: algebraic vs textbook {r_at:.3e}; vs fp32 reference: algebraic {r_a:.3e} textbook {r_t:.3e}")
     assert r_a < max(1.25 * r_t, 2e-2)
     assert r_at < max(2.0 * r_t, 2e-2)
+
+
+def test_fused_block_tail_forward(cuda_device, monkeypatch):
+    """ARGUS_FUSED_TAIL=1 (opt-in, csrc/model.cu): bn3's batch statistics are derived from the Gram matrix of act2
+    before conv3 runs, and conv3 applies BN + identity + ReLU + the bit mask in its epilogue (raw3 never exists). Same
+    network: outputs, BN running statistics and gradients must agree with the default path up to bf16 rounding, and
+    be at least as close to the fp32 reference."""
+    from argus_b200.loss import geometric_loss_fn
+    from argus_b200.models import NCameraCNN
+    from oracle.ref_model import torch_loss
+
+    ref, ours_def = build_pair(cuda_device, residual_gain=0.2)
+    monkeypatch.setenv("ARGUS_FUSED_TAIL", "1")
+    ours_fused = NCameraCNN().to(cuda_device)
+    ours_fused.load_state_dict(ref.state_dict())
+    x = structured_images(8, 6, 128, 128, 3, cuda_device)
+    target = random_targets(8, 4, cuda_device)
+    ours_fused.train()
+    y_f = ours_fused(x)
+    geometric_loss_fn(y_f, target).mean().backward()
+    monkeypatch.delenv("ARGUS_FUSED_TAIL")
+    ours_def.train()
+    y_d = ours_def(x)
+    geometric_loss_fn(y_d, target).mean().backward()
+    ref.train()
+    y_ref = ref(x)
+    torch_loss(y_ref, target).mean().backward()
+    torch.cuda.synchronize()
+    r_f, r_d = rel(y_f.detach(), y_ref.detach()), rel(y_d.detach(), y_ref.detach())
+    print(f"output vs fp32 reference: fused tail {r_f:.3e}  default {r_d:.3e}")
+    assert r_f < max(1.25 * r_d, 2e-2)
+    for name in ("resnet.layer1.0.bn3.running_var", "resnet.layer2.0.downsample.1.running_mean", "resnet.layer3.5.bn3.running_var"):
+        a, b = ours_fused.state_dict()[name], ref.state_dict()[name]
+        assert rel(a, b) < 3e-2, (name, rel(a, b))
+    g_ref = {n: p.grad for n, p in ref.named_parameters()}
+    num_f = num_d = den = 0.0
+    for (n, pf), (_, pd) in zip(ours_fused.named_parameters(), ours_def.named_parameters()):
+        gr = g_ref[n].double()
+        num_f += (pf.grad.double() - gr).pow(2).sum().item()
+        num_d += (pd.grad.double() - gr).pow(2).sum().item()
+        den += gr.pow(2).sum().item()
+    print(f"global gradient error vs fp32 reference: fused tail {(num_f / den) ** 0.5:.3e}  default {(num_d / den) ** 0.5:.3e}")
+    assert (num_f / den) ** 0.5 < max(1.25 * (num_d / den) ** 0.5, 2e-2)

@@ -590,7 +590,19 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   if (g_profiling && profile_detailed())
     fam += ":M" + std::to_string(p.m_total) + "_N" + std::to_string(p.n_total) + "_K" +
            std::to_string((p.num_taps * p.kblocks_per_tap + p.k2_blocks) * kBlockK) + "_t" + std::to_string(p.num_taps);
-  ProfileScope prof(fam, stream, flops, 0.0);
+  // algorithmic HBM bytes: every operand tensor once (activation planes actually read, result, residual, bit masks, weights)
+  double bytes = 0.0;
+  {
+    int maps = 0;
+    for (int t = 0; t < p.num_taps; ++t) maps |= 1 << p.taps[t].map;
+    const int nmaps = __builtin_popcount(static_cast<unsigned>(maps));
+    const double kc = static_cast<double>(p.kblocks_per_tap) * kBlockK;
+    bytes += 2.0 * p.m_total * kc * nmaps + 2.0 * p.m_total * p.k2_blocks * kBlockK;
+    bytes += 2.0 * p.m_total * p.n_total * (p.has_res ? 2 : 1);
+    bytes += (p.out_bits ? 0.125 : 0.0) * p.m_total * p.n_total + (p.relu_bits_out ? 0.125 : 0.0) * p.m_total * p.n_total;
+    bytes += 2.0 * p.n_total * (p.num_taps * kc + p.k2_blocks * kBlockK);
+  }
+  ProfileScope prof(fam, stream, flops, bytes);
   const int key = l.block_n * 2 + l.b_mn;
   switch (key) {
     case 64 * 2 + 0: launch_conv_t<64, 0>(p, stream); break;
@@ -666,7 +678,9 @@ void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
   if (g_profiling && profile_detailed())
     fam += std::string(l.xpose_nbox > 0 ? "x" : "") + ":P" + std::to_string(l.p.kblocks_total * 64) + "_Co" + std::to_string(l.p.cout) + "_Ci" +
            std::to_string(l.p.cin) + "_t" + std::to_string(l.p.num_taps) + "_s" + std::to_string(l.p.num_ksplits);
-  ProfileScope prof(fam, stream, flops, 0.0);
+  const double wbytes = 2.0 * l.p.kblocks_total * 64.0 * (static_cast<double>(l.p.cout) + l.p.cin) +
+                        4.0 * l.p.cout * static_cast<double>(l.p.dw_row_stride);
+  ProfileScope prof(fam, stream, flops, wbytes);
   if (l.xpose_nbox > 0) {
     ARGUS_CHECK(scratch != nullptr, "transposed weight gradient needs a scratch buffer");
     l.xp.partial = scratch;

@@ -277,6 +277,14 @@ def run_ours(args) -> None:
         "issued_flops_per_step": conv_flops, "algorithmic_flops_per_step": algorithmic_flops,
         "share_of_step": round(conv_ms / total_ms, 4),
     }
+    # whole-step HBM view: algorithmic bytes of every launch (each operand tensor counted once) over the step time
+    step_bytes = sum(f["bytes"] for f in families.values())
+    step_ms = ms_total / args.steps
+    hbm_step = {"algorithmic_gb_per_step": round(step_bytes / 1e9, 2),
+                "achieved_gbs": round(step_bytes / (step_ms / 1e3) / 1e9, 1), "peak_gbs": peaks["hbm_gbs"],
+                "frac": round(step_bytes / (step_ms / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
+                "note": "sum over all kernels of one step of the bytes each must move at least once, divided by the "
+                        "un-instrumented step time; the step as a whole is HBM-bound"}
     mem = {}
     for k, f in families.items():
         if f["bytes"] > 0 and f["ms"] > 0 and k not in ("conv_fwd", "conv_dgrad", "conv_wgrad"):
@@ -306,6 +314,7 @@ def run_ours(args) -> None:
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "hbm_step": hbm_step,
         "kernel_families_ms": {k: round(f["ms"], 3) for k, f in families.items()},
         "memory_bound_kernels": mem,
         "final_loss": final_loss,

@@ -115,6 +115,94 @@ int argus_conv2d_dgrad_bits(const void* dy, const void* w, void* dx, int N, int 
   ARGUS_API_END
 }
 
+int argus_conv2d_dgrad_ex(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                          const void* concat_a, int concat_channels, const float* bias, const void* residual,
+                          const void* out_bits, float* stat_partial, int stat_slot_capacity, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ConvShape s = make_shape(N, H, W, Cin, Cout, 1, stride, 0);
+  ARGUS_CHECK(residual == nullptr || stride == 1, "residual add is only supported for stride-1 dgrad");
+  ConvLaunch l;
+  if (concat_a != nullptr) {
+    l = plan_dgrad_concat(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(concat_a),
+                          concat_channels, static_cast<const __nv_bfloat16*>(w), static_cast<__nv_bfloat16*>(dx));
+  } else {
+    auto ls = plan_conv_dgrad(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(w),
+                              static_cast<__nv_bfloat16*>(dx));
+    ARGUS_CHECK(ls.size() == 1, "unexpected dgrad decomposition");
+    l = ls[0];
+  }
+  Epilogue e;
+  e.shift = bias;
+  e.residual = static_cast<const __nv_bfloat16*>(residual);
+  e.out_bits = static_cast<const uint8_t*>(out_bits);
+  e.stat_partial = stat_partial;
+  ARGUS_CHECK(stat_partial == nullptr || stat_slot_capacity >= stat_slots(l), "statistics buffer has too few slots");
+  launch_conv(l, e, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_conv2d_wgrad_gram(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int stride,
+                            void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ConvShape s = make_shape(N, H, W, Cin, Cout, 1, stride, 0);
+  WgradLaunch l = plan_conv_wgrad_gram(s, static_cast<const __nv_bfloat16*>(dy), static_cast<const __nv_bfloat16*>(x), dw);
+  launch_wgrad(l, lib_scratch(wgrad_scratch_elems(l)), static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
+int argus_conv_bn_backward_algebraic(const void* g, const void* act, const void* w_bf16, const float* g_colsum,
+                                     const float* scale, const float* mean, const float* invstd, float* dgamma,
+                                     float* dbeta, float* dw, void* dact, int N, int H, int W, int C, int O, int stride,
+                                     void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  // Self-contained form of the algebraic conv(1x1) + BN backward used by the model (csrc/bn_algebra.cu): g (N,Ho,Wo,O)
+  // masked upstream gradient, act (N,H,W,C) the convolution input, w_bf16 [O][C]; g_colsum [O] = column sums of g.
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConvShape s = make_shape(N, H, W, C, O, 1, stride, 0);
+  const int64_t rows = s.out_pixels();
+  const size_t OC = static_cast<size_t>(O) * C, CC = static_cast<size_t>(C) * C;
+  // scratch layout (floats): H|G [(O+C)*C], s [C], k1k0 [2*O], bias [C], colsum partials, matrix partials, bstack (bf16)
+  const int64_t colsum_scratch = 4LL * num_sms() * C;
+  const int64_t mpart = bn_alg_matrix_scratch_elems(C);
+  const int64_t total = static_cast<int64_t>(OC + CC) + C + 2 * O + C + colsum_scratch + mpart + (static_cast<int64_t>(O + C) * C + 1) / 2;
+  static float* buf = nullptr;
+  static int64_t cap = 0;
+  if (total > cap) {
+    ARGUS_CUDA(cudaDeviceSynchronize());
+    if (buf) ARGUS_CUDA(cudaFree(buf));
+    ARGUS_CUDA(cudaMalloc(&buf, total * sizeof(float)));
+    cap = total;
+  }
+  float* Hb = buf;
+  float* Gb = Hb + OC;
+  float* sb = Gb + CC;
+  float* k1k0 = sb + C;
+  float* bias = k1k0 + 2 * O;
+  float* cs = bias + C;
+  float* mp = cs + colsum_scratch;
+  bf16* bstack = reinterpret_cast<bf16*>(mp + mpart);
+  const bf16* G16 = static_cast<const bf16*>(g);
+  const bf16* A16 = static_cast<const bf16*>(act);
+  const bf16* W16 = static_cast<const bf16*>(w_bf16);
+  WgradLaunch hg = plan_conv_wgrad_gram(s, G16, A16, Hb);
+  ConvLaunch concat = plan_dgrad_concat(s, G16, A16, C, bstack, static_cast<bf16*>(dact));
+  ARGUS_CUDA(cudaMemsetAsync(Hb, 0, (OC + CC) * sizeof(float), st));
+  launch_wgrad(hg, lib_scratch(wgrad_scratch_elems(hg)), st);
+  colsum_pixels_bf16(A16, N, H, W, C, stride, cs, sb, st);
+  // g_colsum plays the role of ONE statistics slot (stride irrelevant)
+  bn_alg_backward_small(W16, Hb, Gb, sb, g_colsum, 1, O, scale, mean, invstd, static_cast<double>(rows), dgamma, dbeta, dw,
+                        k1k0, bstack, bias, mp, O, C, st);
+  if (stride == 2)
+    ARGUS_CUDA(cudaMemsetAsync(dact, 0, static_cast<size_t>(N) * H * W * C * sizeof(bf16), st));
+  Epilogue e;
+  e.shift = bias;
+  launch_conv(concat, e, st);
+  ARGUS_API_END
+}
+
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream) {
   ARGUS_API_BEGIN

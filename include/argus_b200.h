@@ -58,6 +58,26 @@ int argus_conv2d_dgrad(const void* dy, const void* w, void* dx, int N, int H, in
  * (the identity branch of a bottleneck: the masked gradient is never materialised). */
 int argus_conv2d_dgrad_bits(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int k,
                             const void* residual, const void* residual_bits, void* stream);
+/* 1x1 dgrad with the extras the algebraic BN backward uses. concat_a (nullable): a second activation (N,H,W,
+ * concat_channels) on the conv INPUT grid whose channels extend K; w is then the row-major [(Cout + concat_channels)][Cin]
+ * stacked matrix: dx = [dy | concat_a] * w + bias (bias nullable, per Cin). out_bits (nullable): [rows][Cin/8] ReLU mask
+ * applied to the stored result. stat_partial (nullable): zero-filled [slots][2][Cin] per-CTA sums / sums of squares of
+ * the stored result (argus_conv2d_stat_slots of the equivalent forward shape bounds the slots). */
+int argus_conv2d_dgrad_ex(const void* dy, const void* w, void* dx, int N, int H, int W, int Cin, int Cout, int stride,
+                          const void* concat_a, int concat_channels, const float* bias, const void* residual,
+                          const void* out_bits, float* stat_partial, int stat_slot_capacity, void* stream);
+/* 1x1: dw[(Cout + Cin)][Cin] (fp32, +=): rows < Cout = dy^T x, rows Cout + j = x^T x (Gram matrix of the pixels the
+ * convolution reads); Cout % 128 == 0. One launch, the x tiles are loaded once. */
+int argus_conv2d_wgrad_gram(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int stride,
+                            void* stream);
+/* Backward of y = BN_train(conv1x1(act, w)) given the upstream gradient g (already masked by any ReLU), WITHOUT reading
+ * the conv output or materialising its gradient (csrc/bn_algebra.cu): dgamma, dbeta, dw (+=, fp32 [O][C]) and
+ * dact = d loss / d act (bf16, (N,H,W,C); zero-filled here for stride 2). w_bf16: the [O][C] bf16 weight the forward
+ * used; g_colsum [O]: column sums of g; scale / mean / invstd: the forward's batch-norm constants. O % 256 == 0. */
+int argus_conv_bn_backward_algebraic(const void* g, const void* act, const void* w_bf16, const float* g_colsum,
+                                     const float* scale, const float* mean, const float* invstd, float* dgamma,
+                                     float* dbeta, float* dw, void* dact, int N, int H, int W, int C, int O, int stride,
+                                     void* stream);
 /* dw[Cout][k*k*Cin] (fp32) += dy^T * im2col(x); the caller zero-fills dw. */
 int argus_conv2d_wgrad(const void* dy, const void* x, float* dw, int N, int H, int W, int Cin, int Cout, int k,
                        int stride, int kind, void* stream);

@@ -314,6 +314,24 @@ int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* para
   ARGUS_API_END
 }
 
+int argus_spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
+                                  void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(arcs != nullptr, "null arc table");
+  spaghetti_sample_params(arcs, n_images, n_arcs, H, W, seed, step, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_spaghetti_draw(const void* in, void* out, const float* arcs, int n_images, int n_arcs, int H, int W,
+                         void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(in != nullptr && out != nullptr && (arcs != nullptr || n_arcs == 0), "null argument");
+  spaghetti_draw(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), arcs, n_images, n_arcs, H, W,
+                 static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+
 int argus_pose_loss(const float* pred, const float* target, float* loss, float* loss_mean, float* grad, int B,
                     float grad_scale, void* stream) {
   ARGUS_API_BEGIN

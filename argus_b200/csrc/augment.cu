@@ -433,6 +433,91 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// spaghetti arcs (reference: argus/utils.py:252-275 draw_spaghetti, applied to the decoded image at
+// argus/data.py:212-215 before the kornia chain; PIL on the loader's CPU workers there). Rasterisation rule and
+// sampling: oracle/augment.py (calibrated against Pillow's ImageDraw.arc, IoU 0.92; bit-exact against the oracle).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kArcFields = 10;   // cx, cy, rx, ry, cos0, sin0, cos1, sin1, width, sweep_deg
+constexpr uint64_t kArcFieldBase = 1000;
+
+__global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, int n_arcs, int H, int W, uint64_t seed,
+                                        uint64_t step) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_images * n_arcs) return;
+  const uint64_t img = t / n_arcs, a = t % n_arcs;
+  auto U = [&](uint64_t k) { return hash_uniform(seed, step, img, kArcFieldBase + a * 8 + k); };
+  auto randint = [](float u, int lo, int hi) {
+    const int v = lo + static_cast<int>(floorf(__fmul_rn(u, static_cast<float>(hi - lo))));
+    return v < hi - 1 ? v : hi - 1;
+  };
+  const int x0 = randint(U(0), 0, W), y0 = randint(U(1), 0, H);
+  const int x1 = randint(U(2), x0, W), y1 = randint(U(3), y0, H);
+  const int a0 = randint(U(4), 0, 360), a1 = randint(U(5), 0, 360);
+  float* A = arcs + static_cast<size_t>(t) * kArcFields;
+  A[0] = __fmul_rn(static_cast<float>(x0 + x1), 0.5f);
+  A[1] = __fmul_rn(static_cast<float>(y0 + y1), 0.5f);
+  A[2] = __fadd_rn(__fmul_rn(static_cast<float>(x1 - x0), 0.5f), 0.5f);
+  A[3] = __fadd_rn(__fmul_rn(static_cast<float>(y1 - y0), 0.5f), 0.5f);
+  const double r0 = static_cast<double>(a0) * 0.017453292519943295, r1 = static_cast<double>(a1) * 0.017453292519943295;
+  A[4] = static_cast<float>(cos(r0)); A[5] = static_cast<float>(sin(r0));
+  A[6] = static_cast<float>(cos(r1)); A[7] = static_cast<float>(sin(r1));
+  A[8] = floorf(__fadd_rn(1.0f, __fmul_rn(U(6), 4.0f)));
+  A[9] = static_cast<float>(((a1 - a0) % 360 + 360) % 360);
+}
+
+// thread = one pixel; black where any arc covers it (n_arcs <= 16 cached in shared memory per image row block)
+__global__ void __launch_bounds__(256)
+spaghetti_draw_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const float* __restrict__ arcs,
+                      int n_arcs, int H, int W) {
+  __shared__ float sArc[16 * kArcFields];
+  const int n = blockIdx.y;
+  for (int i = threadIdx.x; i < n_arcs * kArcFields; i += blockDim.x)
+    sArc[i] = arcs[static_cast<size_t>(n) * n_arcs * kArcFields + i];
+  __syncthreads();
+  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pix >= H * W) return;
+  const int y = pix / W, x = pix - y * W;
+  bool hit = false;
+  for (int k = 0; k < n_arcs; ++k) {
+    const float* A = sArc + k * kArcFields;
+    const float dx = __fadd_rn(static_cast<float>(x), -A[0]), dy = __fadd_rn(static_cast<float>(y), -A[1]);
+    const float u = __fdiv_rn(dx, A[2]), v = __fdiv_rn(dy, A[3]);
+    if (!(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)) <= 1.0f)) continue;
+    const float irx = __fadd_rn(A[2], -A[8]), iry = __fadd_rn(A[3], -A[8]);
+    if (irx > 0.f && iry > 0.f) {
+      const float ui = __fdiv_rn(dx, irx), vi = __fdiv_rn(dy, iry);
+      if (__fadd_rn(__fmul_rn(ui, ui), __fmul_rn(vi, vi)) < 1.0f) continue;
+    }
+    const float a = __fadd_rn(__fmul_rn(A[4], v), -__fmul_rn(A[5], u));
+    const float b = __fadd_rn(__fmul_rn(A[7], u), -__fmul_rn(A[6], v));
+    const bool sector = (A[9] <= 180.f) ? (a >= 0.f && b >= 0.f) : !(a < 0.f && b < 0.f);
+    if (sector) { hit = true; break; }
+  }
+  const size_t o = (static_cast<size_t>(n) * H * W + pix) * 3;
+  out[o] = hit ? 0 : in[o];
+  out[o + 1] = hit ? 0 : in[o + 1];
+  out[o + 2] = hit ? 0 : in[o + 2];
+}
+
+void spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
+                             cudaStream_t s) {
+  ARGUS_CHECK(n_arcs >= 0 && n_arcs <= 16, "at most 16 arcs per image");
+  if (n_images * n_arcs <= 0) return;
+  ProfileScope prof("augment_params", s, 0, 40.0 * n_images * n_arcs);
+  spaghetti_params_kernel<<<(n_images * n_arcs + 127) / 128, 128, 0, s>>>(arcs, n_images, n_arcs, H, W, seed, step);
+  ARGUS_CUDA(cudaGetLastError());
+}
+void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_images, int n_arcs, int H, int W,
+                    cudaStream_t s) {
+  ARGUS_CHECK(n_arcs >= 0 && n_arcs <= 16, "at most 16 arcs per image");
+  if (n_images <= 0) return;
+  ProfileScope prof("augment", s, 0, 6.0 * n_images * H * W);
+  dim3 grid((H * W + 255) / 256, n_images);
+  spaghetti_draw_kernel<<<grid, 256, 0, s>>>(in, out, arcs, n_arcs, H, W);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
 void augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step, const AugConfig& cfg,
                            cudaStream_t s) {
   ProfileScope prof("augment_params", s, 0, 96.0 * n_images);

@@ -41,6 +41,13 @@ void augment_sample_params(float* params, int n_images, int n_cams, uint64_t see
 void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* params, int n_images, int H, int W,
                     bool apply, cudaStream_t s);
 
+// spaghetti arcs (argus/utils.py:252-275, applied at argus/data.py:212-215): arcs = (n_images, n_arcs, 10) fp32 table, a
+// pure function of (seed, step, image, arc); draw paints them black on uint8 HWC images (out may alias in)
+void spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
+                             cudaStream_t s);
+void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_images, int n_arcs, int H, int W,
+                    cudaStream_t s);
+
 // ---- batch norm -------------------------------------------------------------------------------------------
 // train: batch statistics -> scale/shift (+ saved mean/invstd, running-stat update, torch.nn.BatchNorm2d semantics)
 // partial: [slots][2][C] per-(CTA, epilogue group) sums written by the conv epilogue, added here in slot order

@@ -75,7 +75,8 @@ class Augmentation(torch.nn.Module):
     random_erasing / salt_and_pepper are default-OFF in the reference and not implemented here (they raise).
     """
 
-    def __init__(self, cfg: AugmentationConfig, train: bool = True, seed: Optional[int] = None) -> None:
+    def __init__(self, cfg: AugmentationConfig, train: bool = True, seed: Optional[int] = None,
+                 gpu_spaghetti: bool = False) -> None:
         super().__init__()
         if cfg.random_erasing or cfg.salt_and_pepper:
             raise NotImplementedError("random_erasing / salt_and_pepper (default-off in the reference) are not built")
@@ -89,6 +90,10 @@ class Augmentation(torch.nn.Module):
                               int(cfg.plasma_shadow), b[0], b[1] - b[0], c[0], c[1] - c[0], s[0], s[1] - s[0],
                               h[0], h[1] - h[0])
         self.enabled = any([cfg.color_jiggle, cfg.planckian_jitter, cfg.blur, cfg.motion_blur, cfg.plasma_shadow])
+        # draw_spaghetti (reference: utils.py:252-275, applied by the dataset with PIL at data.py:212-215, train AND
+        # val). gpu_spaghetti=True moves it onto the device (spaghetti_batch); the dataset must then skip its PIL pass.
+        self.gpu_spaghetti = bool(gpu_spaghetti) and cfg.num_spaghetti > 0
+        self.spaghetti_step = 0
 
     # ------------------------------------------------------------------------------------------------------------
     def sample_params(self, n_pairs: int, n_cams: int, device, step: Optional[int] = None) -> torch.Tensor:
@@ -102,6 +107,28 @@ class Augmentation(torch.nn.Module):
                 _lib.ptr(params), ctypes.c_int(n_pairs * n_cams), ctypes.c_int(n_cams), ctypes.c_uint64(self.seed),
                 ctypes.c_uint64(int(step)), ctypes.byref(self._c), _lib.stream_ptr()))
         return params
+
+    def spaghetti_batch(self, images: torch.Tensor, step: Optional[int] = None) -> torch.Tensor:
+        """uint8 (B, n_cams, H, W, 3) -> a copy with `num_spaghetti` random black arcs per image (GPU rasteriser,
+        argus_spaghetti_*; rule and sampling in oracle/augment.py). Arcs are a pure function of (seed, step, image)."""
+        if not images.is_cuda or images.dtype != torch.uint8:
+            raise _lib.ArgusError("spaghetti_batch takes uint8 CUDA images (no CPU fallback; the PIL path is "
+                                  "argus_b200.utils.draw_spaghetti)")
+        B, n_cams, H, W, _ = images.shape
+        n_arcs = int(self.cfg.num_spaghetti)
+        if step is None:
+            step = self.spaghetti_step
+            self.spaghetti_step += 1
+        images = images.contiguous()
+        arcs = torch.empty((B * n_cams, n_arcs, 10), dtype=torch.float32, device=images.device)
+        out = torch.empty_like(images)
+        with torch.cuda.device(images.device):
+            # a different stream of the hash than the augmentation parameters: fields 1000+ (oracle/augment.py)
+            _lib.check(_lib.load().argus_spaghetti_sample_params(
+                _lib.ptr(arcs), ctypes.c_int(B * n_cams), ctypes.c_int(n_arcs), ctypes.c_int(H), ctypes.c_int(W),
+                ctypes.c_uint64(self.seed), ctypes.c_uint64(int(step)), _lib.stream_ptr()))
+            _lib.call("argus_spaghetti_draw", images, out, arcs, int(B * n_cams), n_arcs, int(H), int(W), _lib.stream_ptr())
+        return out
 
     def augment_batch(self, images: torch.Tensor, params: Optional[torch.Tensor] = None,
                       step: Optional[int] = None) -> torch.Tensor:

@@ -134,7 +134,9 @@ class CameraCubePoseDataset(Dataset):
     """The dataset for N cameras and a cube (reference: data.py:145-229)."""
 
     def __init__(self, cfg_dataset: CameraCubePoseDatasetConfig, cfg_aug=None, train: bool = True,
-                 as_uint8: bool = False) -> None:
+                 as_uint8: bool = False, pil_spaghetti: bool = True) -> None:
+        # pil_spaghetti=False: the training loop draws the arcs on the device instead (Augmentation.spaghetti_batch)
+        self.pil_spaghetti = pil_spaghetti
         meta = _read_metadata(cfg_dataset.dataset_path, "train" if train else "test")
         self.n_cams = meta["n_cams"]
         _cube_poses = torch.from_numpy(np.asarray(meta["cube_poses"]))  # stored quat order is (w, x, y, z)
@@ -163,7 +165,7 @@ class CameraCubePoseDataset(Dataset):
         views = []
         for v in range(self.n_cams):
             img = Image.open(f"{self.dataset_path}/{stem}_{'abcdefgh'[v]}.png").convert("RGB")
-            if self.cfg_aug is not None and self.cfg_aug.num_spaghetti > 0:
+            if self.pil_spaghetti and self.cfg_aug is not None and self.cfg_aug.num_spaghetti > 0:
                 img = draw_spaghetti(img, self.cfg_aug.num_spaghetti)   # data.py:213-215 (train AND val)
             a = np.array(img)
             if self.center_crop and a.shape[:2] != tuple(self.center_crop):

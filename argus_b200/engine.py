@@ -94,11 +94,15 @@ class TrainEngine:
             return
         aug = self.augmentation
         apply = aug is not None and aug.train and aug.enabled
+        key = (images.data_ptr(), tuple(images.shape))
         # the buffer being written was last read by the step BEFORE the one in flight: wait for that step only
         self._side.wait_event(self._prev_done)
         if after is not None:
             self._side.wait_event(after)
         with torch.cuda.stream(self._side):
+            if aug is not None and aug.gpu_spaghetti:
+                images.record_stream(self._side)
+                images = aug.spaghetti_batch(images)
             params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
             B, _, H, W, _ = images.shape
             model._ensure_bound()
@@ -109,7 +113,7 @@ class TrainEngine:
         images.record_stream(self._side)
         if params is not None:
             params.record_stream(self._side)
-        self._staged = (images.data_ptr(), tuple(images.shape))
+        self._staged = key
 
     def forward_backward(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
         """Forward, loss, backward (+ bucketed gradient all-reduce). Returns the mean loss as a device scalar.
@@ -132,6 +136,8 @@ class TrainEngine:
         elif images.dtype == torch.uint8 and model.precision == "fp32":
             # fp32 parity mode: the same augmentation kernel with fp32 NCHW output, then the fp32 network
             aug = self.augmentation
+            if aug is not None and aug.gpu_spaghetti:
+                images = aug.spaghetti_batch(images)
             if aug is not None and aug.train and aug.enabled:
                 out = model._forward_impl(aug.augment_batch(images), True)
             else:
@@ -139,6 +145,8 @@ class TrainEngine:
         elif images.dtype == torch.uint8:
             # fused augmentation + staging: uint8 pairs -> augmented bf16 stem input inside the model's arena
             aug = self.augmentation
+            if aug is not None and aug.gpu_spaghetti:
+                images = aug.spaghetti_batch(images)
             apply = aug is not None and aug.train and aug.enabled
             params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
             out = model._forward_impl(images, True, aug_params=params, augment=apply)

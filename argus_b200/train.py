@@ -71,6 +71,8 @@ class TrainConfig:
 
     # loader (not in the reference: worker count was hard-coded, train.py:147-149)
     num_workers: int = 8
+    # draw_spaghetti on the device (one kernel per batch) instead of PIL in the loader workers (data.py:212-215)
+    gpu_spaghetti: bool = True
 
     def __post_init__(self) -> None:
         assert isinstance(self.save_dir, str)
@@ -125,8 +127,9 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
         dist.init_process_group("nccl", rank=rank, world_size=cfg.num_gpus)
 
     aug_cfg = cfg.augmentation_config if cfg.use_augmentation else None
-    train_dataset = CameraCubePoseDataset(cfg.dataset_config, cfg_aug=aug_cfg, train=True, as_uint8=True)
-    val_dataset = CameraCubePoseDataset(cfg.dataset_config, cfg_aug=aug_cfg, train=False, as_uint8=True)
+    pil = not cfg.gpu_spaghetti
+    train_dataset = CameraCubePoseDataset(cfg.dataset_config, cfg_aug=aug_cfg, train=True, as_uint8=True, pil_spaghetti=pil)
+    val_dataset = CameraCubePoseDataset(cfg.dataset_config, cfg_aug=aug_cfg, train=False, as_uint8=True, pil_spaghetti=pil)
     if cfg.multigpu:
         train_sampler = DistributedSampler(train_dataset, num_replicas=cfg.num_gpus, rank=rank, shuffle=True)
         val_sampler = DistributedSampler(val_dataset, num_replicas=cfg.num_gpus, rank=rank, shuffle=False)
@@ -141,8 +144,8 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
     val_dataloader = DataLoader(val_dataset, shuffle=False, sampler=val_sampler, **common)
 
     model = NCameraCNN(cfg.model_config).to(device).set_precision(cfg.precision)
-    augmentation = Augmentation(cfg.augmentation_config, train=True, seed=cfg.random_seed + 7919 * rank) \
-        if cfg.use_augmentation else None
+    augmentation = Augmentation(cfg.augmentation_config, train=True, seed=cfg.random_seed + 7919 * rank,
+                                gpu_spaghetti=cfg.gpu_spaghetti) if cfg.use_augmentation else None
     engine = TrainEngine(model, lr=cfg.learning_rate, max_grad_norm=cfg.max_grad_norm, augmentation=augmentation)
     scheduler = ReduceLROnPlateau(engine, patience=5, factor=0.5)
     loss_fn = geometric_loss_fn
@@ -219,6 +222,9 @@ def train(cfg: TrainConfig, rank: int = 0) -> None:
                 for example in val_dataloader:
                     images = example["images"].to(device, non_blocking=True)
                     cube_pose = example["cube_pose"].to(device, non_blocking=True)
+                    aug = engine.augmentation
+                    if aug is not None and aug.gpu_spaghetti:
+                        images = aug.spaghetti_batch(images)   # the reference draws arcs on validation images too
                     pred = model(images)
                     val_losses.append(loss_fn(pred, cube_pose))
                 if val_losses:

@@ -154,6 +154,15 @@ int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_
 int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* params, int n_images, int H, int W,
                   int apply, void* stream);
 
+/* Spaghetti arcs (draw_spaghetti, argus/utils.py:252-275; drawn with PIL on the decoded image at argus/data.py:212-215,
+ * before the kornia chain). arcs: (n_images, n_arcs <= 16, 10) fp32 table, a pure function of (seed, step, image, arc)
+ * sampled as the reference does (bbox corners, integer start / end angles, width = int(U(1,5))); argus_spaghetti_draw
+ * paints them black on uint8 (n, H, W, 3) images (out may alias in). Rasterisation rule: oracle/augment.py. */
+int argus_spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
+                                  void* stream);
+int argus_spaghetti_draw(const void* in, void* out, const float* arcs, int n_images, int n_arcs, int H, int W,
+                         void* stream);
+
 /* ---- pose loss and pose exponential ------------------------------------------------------------------------
  * argus_pose_loss: geometric_loss_fn (argus/train.py:105-119) forward AND analytic backward in one launch.
  *   pred (B,6) fp32 se3 [tau, phi]; target (B,7) fp32 SE3 [t, qx, qy, qz, qw]; loss (B) per-sample (nullable);

@@ -301,3 +301,86 @@ def augment_batch_u8(images_u8: np.ndarray, seed: int = 0, step: int = 0, cfg=No
         for v in range(n_cams):
             out[b, v] = augment_image(images_u8[b, v], params[b * n_cams + v])
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# spaghetti arcs (reference: argus/utils.py:252-275 `draw_spaghetti`, applied at argus/data.py:212-215 to the decoded
+# image BEFORE the kornia chain). The reference draws with PIL's ImageDraw.arc; this restatement is OUR rasterisation
+# rule, calibrated against Pillow 12 (tests/test_oracle_augment.py: IoU 0.92 over random arcs, the rest is edge pixels):
+#   bbox (x0, y0, x1, y1) -> centre ((x0+x1)/2, (y0+y1)/2), radii ((x1-x0)/2 + 0.5, (y1-y0)/2 + 0.5);
+#   a pixel is painted black iff it is inside the outer ellipse, not strictly inside the ellipse shrunk by `width`,
+#   and its PARAMETRIC angle atan2(dy/ry, dx/rx) (clockwise from 3 o'clock, as PIL measures) lies in [start, end];
+#   the angle test is done with cross products against (cos, sin) of start / end, no transcendental per pixel.
+# Sampling follows the reference: x0 ~ U{0..W-1}, y0 ~ U{0..H-1}, x1 ~ U{x0..W-1}, y1 ~ U{y0..H-1},
+# start, end ~ U{0..359}, width = int(U(1, 5)); one draw per (seed, step, image, arc, field) through the same hash.
+# ------------------------------------------------------------------------------------------------------------------
+ARC_FIELDS = 10   # cx, cy, rx, ry, cos0, sin0, cos1, sin1, width, sweep_deg
+_ARC_FIELD_BASE = 1000
+
+
+def spaghetti_params(n_images: int, n_arcs: int, H: int, W: int, seed: int, step: int) -> np.ndarray:
+    arcs = np.zeros((n_images, n_arcs, ARC_FIELDS), dtype=np.float32)
+    img = np.arange(n_images, dtype=np.uint64)[:, None]
+    a = np.arange(n_arcs, dtype=np.uint64)[None, :]
+
+    def U(k):
+        return uniform(seed, step, img, np.uint64(_ARC_FIELD_BASE) + a * np.uint64(8) + np.uint64(k))
+
+    def randint(u, lo, hi):   # integer in [lo, hi) from a float32 uniform, lo/hi int arrays
+        span = (hi - lo).astype(np.float32)
+        v = lo + np.floor(u * span).astype(np.int64)
+        return np.minimum(v, hi - 1)
+
+    zero = np.zeros((n_images, n_arcs), dtype=np.int64)
+    x0 = randint(U(0), zero, zero + W)
+    y0 = randint(U(1), zero, zero + H)
+    x1 = randint(U(2), x0, zero + W)
+    y1 = randint(U(3), y0, zero + H)
+    a0 = randint(U(4), zero, zero + 360)
+    a1 = randint(U(5), zero, zero + 360)
+    width = np.floor(np.float32(1.0) + U(6) * np.float32(4.0)).astype(np.float32)
+    arcs[..., 0] = (x0 + x1).astype(np.float32) * np.float32(0.5)
+    arcs[..., 1] = (y0 + y1).astype(np.float32) * np.float32(0.5)
+    arcs[..., 2] = (x1 - x0).astype(np.float32) * np.float32(0.5) + np.float32(0.5)
+    arcs[..., 3] = (y1 - y0).astype(np.float32) * np.float32(0.5) + np.float32(0.5)
+    arcs[..., 4] = np.cos(np.radians(a0.astype(np.float64))).astype(np.float32)
+    arcs[..., 5] = np.sin(np.radians(a0.astype(np.float64))).astype(np.float32)
+    arcs[..., 6] = np.cos(np.radians(a1.astype(np.float64))).astype(np.float32)
+    arcs[..., 7] = np.sin(np.radians(a1.astype(np.float64))).astype(np.float32)
+    arcs[..., 8] = width
+    arcs[..., 9] = ((a1 - a0) % 360).astype(np.float32)
+    return arcs
+
+
+def arc_mask(H: int, W: int, arc: np.ndarray) -> np.ndarray:
+    """Boolean (H, W) mask of one arc (float32 arithmetic, same operation order as the CUDA kernel)."""
+    f32 = np.float32
+    cx, cy, rx, ry, c0, s0, c1, s1, wd, sweep = (f32(v) for v in arc)
+    yy, xx = np.mgrid[0:H, 0:W]
+    dx = xx.astype(f32) - cx
+    dy = yy.astype(f32) - cy
+    u = dx / rx
+    v = dy / ry
+    outer = (u * u + v * v) <= f32(1)
+    irx, iry = rx - wd, ry - wd
+    if irx > 0 and iry > 0:
+        ui, vi = dx / irx, dy / iry
+        inner = (ui * ui + vi * vi) < f32(1)
+    else:
+        inner = np.zeros_like(outer)
+    a = c0 * v - s0 * u       # sin(theta_p - theta_start)
+    b = s1 * u - c1 * v       # sin(theta_end - theta_p)
+    sector = ((a >= 0) & (b >= 0)) if sweep <= 180 else ~((a < 0) & (b < 0))
+    return outer & ~inner & sector
+
+
+def draw_spaghetti_u8(images_u8: np.ndarray, arcs: np.ndarray) -> np.ndarray:
+    """images (n, H, W, 3) uint8, arcs (n, n_arcs, ARC_FIELDS) -> copy with the arcs painted black."""
+    out = images_u8.copy()
+    n, H, W, _ = out.shape
+    for i in range(n):
+        m = np.zeros((H, W), dtype=bool)
+        for arc in arcs[i]:
+            m |= arc_mask(H, W, arc)
+        out[i][m] = 0
+    return out

@@ -88,3 +88,31 @@ def test_staged_input_equals_explicit_path(cuda_device):
     assert torch.allclose(y_fused, y_explicit, rtol=1e-3, atol=1e-5)
     assert torch.allclose(y_plain, y_plain_f32, rtol=1e-3, atol=1e-5)
     assert not torch.allclose(y_fused, y_plain, rtol=1e-3, atol=1e-5)
+
+
+def test_spaghetti_gpu_matches_oracle(cuda_device):
+    """GPU arc rasteriser == numpy oracle bit for bit on the same (seed, step): parameter table and painted pixels."""
+    import numpy as np
+
+    from argus_b200 import _lib
+    from argus_b200.data import Augmentation, AugmentationConfig
+    from oracle import augment as A
+
+    B, n_cams, H, W = 3, 2, 128, 128
+    g = torch.Generator().manual_seed(2)
+    images = torch.randint(1, 256, (B, n_cams, H, W, 3), dtype=torch.uint8, generator=g).to(cuda_device)
+    aug = Augmentation(AugmentationConfig(), train=True, seed=11, gpu_spaghetti=True)
+    out = aug.spaghetti_batch(images, step=7)
+    arcs = torch.empty(B * n_cams, 10, 10, device=cuda_device)
+    import ctypes
+    _lib.check(_lib.load().argus_spaghetti_sample_params(_lib.ptr(arcs), ctypes.c_int(B * n_cams), ctypes.c_int(10),
+                                                         ctypes.c_int(H), ctypes.c_int(W), ctypes.c_uint64(aug.seed),
+                                                         ctypes.c_uint64(7), _lib.stream_ptr()))
+    want_arcs = A.spaghetti_params(B * n_cams, 10, H, W, seed=aug.seed, step=7)
+    assert np.array_equal(arcs.cpu().numpy(), want_arcs)
+    want = A.draw_spaghetti_u8(images.cpu().numpy().reshape(B * n_cams, H, W, 3), want_arcs).reshape(B, n_cams, H, W, 3)
+    got = out.cpu().numpy()
+    assert np.array_equal(got, want)
+    assert 0.01 < (got == 0).all(-1).mean() < 0.3          # arcs were drawn, and not everywhere
+    assert torch.equal(images.cpu(), torch.randint(1, 256, (B, n_cams, H, W, 3), dtype=torch.uint8,
+                                                   generator=torch.Generator().manual_seed(2)))   # input untouched

@@ -84,31 +84,36 @@ struct ConvGemmParams {
   float* stat_partial;
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int EPI = 2>
 struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
-  static constexpr int kStatsBytes = 2 * 4 * 2 * BLOCK_N * 4;    // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
+  static constexpr int kStatsBytes = EPI * 4 * 2 * BLOCK_N * 4;  // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
   // operand pipeline region: everything the 227 KB of shared memory leave after staging, statistics and barriers
-  static constexpr int kPipeBytes = (232448 - 1024 - 4 * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
+  static constexpr int kPipeBytes = (232448 - 1024 - 2 * EPI * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
   static constexpr int kStagesRaw = kPipeBytes / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
   static constexpr int kOffStaging = kPipeBytes;                 // 2 staging buffers per epilogue group
-  static constexpr int kOffStats = kOffStaging + 4 * kStagingBytes;
+  static constexpr int kOffStats = kOffStaging + 2 * EPI * kStagingBytes;
   static constexpr int kOffBars = kOffStats + kStatsBytes;
   static constexpr int kMaxStages = 8;               // stage ring length in weights-resident mode (<= kMaxStages)
-  // full/empty per stage, tmem full/empty x2, residual x(2 groups x 2 buffers), resident-weights barrier
-  static constexpr int kNumBars = 2 * kMaxStages + 9;
+  // full/empty per stage, accumulator-full per epilogue GROUP, accumulator-empty per TMEM stage,
+  // residual x(EPI groups x 2 buffers), resident-weights barrier
+  static constexpr int kNumBars = 2 * kMaxStages + EPI + 2 + 2 * EPI + 1;
   static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
   static constexpr int kTotal = kOffTmemPtr + 16;
 };
 
-template <int BLOCK_N, int B_MN>
-__global__ void __launch_bounds__(kNumThreads, 1)
+// EPI = number of epilogue groups (4 warps each): 2 for tensor-bound shapes (3 pipeline stages at N = 256), 3 for the
+// wide, shallow-K layers whose tile time is set by the epilogue (TMEM -> math -> smem -> TMA store + statistics), which
+// is latency-bound per warp: a third group raises the epilogue throughput by half. The two TMEM accumulator stages are
+// shared: CTA-local tile t uses stage t % 2 and is finished by group t % EPI.
+template <int BLOCK_N, int B_MN, int EPI>
+__global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  using L = ConvGemmSmem<BLOCK_N>;
+  using L = ConvGemmSmem<BLOCK_N, EPI>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -122,10 +127,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   const uint32_t bar_base = smem_base + L::kOffBars;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
-  auto tfull_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + s); };
-  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + 2 + s); };
-  auto res_bar = [&](int g, int b) { return bar_base + 8u * (2 * kMaxStages + 4 + 2 * g + b); };
-  const uint32_t bres_bar = bar_base + 8u * (2 * kMaxStages + 8);
+  // "accumulator full" is signalled per epilogue GROUP (each group then sees strictly alternating phases of its own
+  // barrier; a per-stage barrier would let a group whose first tile is the stage's SECOND use pass its parity-1 wait
+  // at kernel start), "accumulator empty" per TMEM stage (single waiter: the MMA warp)
+  auto tfull_bar = [&](int g) { return bar_base + 8u * (2 * kMaxStages + g); };
+  auto tempty_bar = [&](int s) { return bar_base + 8u * (2 * kMaxStages + EPI + s); };
+  auto res_bar = [&](int g, int b) { return bar_base + 8u * (2 * kMaxStages + EPI + 2 + 2 * g + b); };
+  const uint32_t bres_bar = bar_base + 8u * (2 * kMaxStages + EPI + 2 + 2 * EPI);
   volatile uint32_t* tmem_ptr_smem = reinterpret_cast<volatile uint32_t*>(smem + L::kOffTmemPtr);
   float* s_stats_all = reinterpret_cast<float*>(smem + L::kOffStats);
   // pipeline geometry: streaming mode = kStages x (A | B); weights-resident mode = res_stages x A, then the B slab
@@ -143,11 +151,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(bres_bar, 1);
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(tfull_bar(s), 1);
-      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp of the owning group
-      mbar_init(res_bar(s, 0), 1);
-      mbar_init(res_bar(s, 1), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp of the finishing group
+    for (int g = 0; g < EPI; ++g) {
+      mbar_init(tfull_bar(g), 1);
+      mbar_init(res_bar(g, 0), 1);
+      mbar_init(res_bar(g, 1), 1);
     }
     fence_mbar_init();
   }
@@ -162,7 +170,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < 16 * BLOCK_N; i += kNumThreads) s_stats_all[i] = 0.f;
+  for (int i = threadIdx.x; i < EPI * 8 * BLOCK_N; i += blockDim.x) s_stats_all[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -252,6 +260,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int tgrp = 0;   // epilogue group that finishes this tile (CTA-local tile index % EPI)
       if (resident && blockIdx.x < num_tiles) mbar_wait(bres_bar, 0);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1);
@@ -276,10 +285,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
             }
             umma_commit(empty_bar(stage));
-            if (st == nst - 1) umma_commit(tfull_bar(acc));
+            if (st == nst - 1) umma_commit(tfull_bar(tgrp));
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+          if (++tgrp == EPI) tgrp = 0;
           continue;
         }
         for (int kb = 0; kb < num_kblocks; ++kb) {
@@ -295,17 +305,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             umma_bf16(tmem_d, da, db, idesc, (kb | k) != 0);
           }
           umma_commit(empty_bar(stage));
-          if (kb == num_kblocks - 1) umma_commit(tfull_bar(acc));
+          if (kb == num_kblocks - 1) umma_commit(tfull_bar(tgrp));
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++tgrp == EPI) tgrp = 0;
       }
     }
   } else {
-    // ===================== epilogue (warps 2..9: two groups of four warps) =====================
-    // Group g owns TMEM accumulator stage g, i.e. every second tile of this CTA, so two tile epilogues overlap each
-    // other and the main loop. Each group has its own staging buffers, statistics scratch, named barrier and TMA
-    // store queue.
+    // ===================== epilogue (warps 2..: EPI groups of four warps) =====================
+    // Group g finishes the CTA-local tiles t = g, g + EPI, ... (accumulator stage t % 2), so EPI tile epilogues
+    // overlap each other and the main loop. Each group has its own staging buffers, statistics scratch, named
+    // barrier and TMA store queue.
     const int ew = warp - 2;
     const int grp = ew >> 2;
     const int wq = warp & 3;              // TMEM lane quarter this warp may access
@@ -316,13 +327,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     float* s_stats = s_stats_all + grp * 8 * BLOCK_N;          // [warp 0..3][sum | sqsum][BLOCK_N]
     float* s_mine = s_stats + (ew & 3) * 2 * BLOCK_N;          // this warp's private slot: no atomics, fixed order
     uint8_t* stg_base = smem + L::kOffStaging + grp * 2 * L::kStagingBytes;
-    const int acc = grp;
-    uint32_t acc_phase = 0;
     uint32_t res_phase[2] = {0, 0};
     int buf = 0;
     int cur_n = -1;
     const bool do_stats = (p.stat_partial != nullptr);
-    float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(2 * blockIdx.x + grp) * 2 * p.n_total : nullptr;
+    float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(EPI * blockIdx.x + grp) * 2 * p.n_total : nullptr;
     constexpr int kChunks = BLOCK_N / 64;
 
     auto flush_stats = [&](int n_tile) {
@@ -355,7 +364,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const int first_tile = blockIdx.x + grp * gridDim.x;
     if (p.has_res && store_leader && first_tile < num_tiles) issue_residual(first_tile, 0, 0);
 
-    for (int tile = first_tile; tile < num_tiles; tile += 2 * gridDim.x) {
+    int t_local = grp;
+    uint32_t full_phase = 0;
+    for (int tile = first_tile; tile < num_tiles; tile += EPI * gridDim.x, t_local += EPI, full_phase ^= 1) {
+      const int acc = t_local & 1;   // TMEM accumulator stage of this tile
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
       const int m0 = m_tile * kBlockM;
@@ -369,7 +381,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         cur_n = n_tile;
       }
 
-      mbar_wait(tfull_bar(acc), acc_phase);
+      mbar_wait(tfull_bar(grp), full_phase);
       tc_fence_after();
 
 #pragma unroll 1
@@ -381,7 +393,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             // the residual tile of the next chunk (this buffer's residual is already in flight / landed)
             tma_store_wait_read<0>();
             const bool last_ch = (ch == kChunks - 1);
-            const int ntile = last_ch ? tile + 2 * gridDim.x : tile;
+            const int ntile = last_ch ? tile + EPI * gridDim.x : tile;
             if (ntile < num_tiles) issue_residual(ntile, last_ch ? 0 : ch + 1, buf ^ 1);
           } else {
             tma_store_wait_read<1>();   // this buffer was handed to a TMA store two chunks ago
@@ -516,7 +528,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         buf ^= 1;
       }
-      acc_phase ^= 1;
     }
     if (do_stats && cur_n >= 0) flush_stats(cur_n);
     if (store_leader) tma_store_wait_all<0>();

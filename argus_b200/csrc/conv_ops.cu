@@ -317,6 +317,7 @@ ConvLaunch plan_conv_forward(const ConvShape& s, const __nv_bfloat16* x, const _
   p.log2_wo = ilog2(s.Wo());
   p.log2_howo = ilog2(s.Ho() * s.Wo());
   setup_halo(p, s, x, s.Cin, false, l.block_n);
+  l.epi = choose_epilogue_groups(p, l.block_n);
   return l;
 }
 
@@ -396,6 +397,7 @@ std::vector<ConvLaunch> plan_conv_dgrad(const ConvShape& s, const __nv_bfloat16*
     p.log2_wo = ilog2(Wo);
     p.log2_howo = ilog2(Ho * Wo);
     setup_halo(p, s, dy, s.Cout, true, block_n);
+    l.epi = choose_epilogue_groups(p, block_n);
     out.push_back(l);
   }
   return out;
@@ -428,6 +430,7 @@ ConvLaunch plan_dgrad_concat(const ConvShape& s, const __nv_bfloat16* dy, const 
     p.b_map = make_tmap_bf16(bstack, 2, dims, str, box);
   }
   p.k2_blocks = C1 / 64;
+  l.epi = choose_epilogue_groups(p, l.block_n);
   return l;
 }
 
@@ -535,12 +538,12 @@ WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g) {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BMN>
+template <int BN, int BMN, int EPI>
 static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
-  using L = ConvGemmSmem<BN>;
+  using L = ConvGemmSmem<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -563,8 +566,19 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
       q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
     }
   }
-  conv_gemm_kernel<BN, BMN><<<grid, kNumThreads, L::kTotal, stream>>>(q);
+  conv_gemm_kernel<BN, BMN, EPI><<<grid, 64 + 128 * EPI, L::kTotal, stream>>>(q);
   ARGUS_CUDA(cudaGetLastError());
+}
+
+// Number of epilogue groups for a launch. Default 2. ARGUS_EPI=3 runs every non-halo launch with three groups (an
+// experiment kept reachable): measured, a third group does NOT help (44.6 -> 45.8 ms/step; 44.7 when restricted to the
+// wide shallow-K layers) because only two TMEM accumulator stages exist at N = 256, so at most two tile epilogues are
+// in flight; what bounds those layers is the time one tile holds its accumulator stage, not the number of warps.
+int choose_epilogue_groups(const ConvGemmParams& p, int block_n) {
+  static const int forced = [] { const char* e = getenv("ARGUS_EPI"); return e ? atoi(e) : 0; }();
+  (void)block_n;
+  if (p.halo) return 2;
+  return forced == 3 ? 3 : 2;
 }
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
@@ -603,21 +617,27 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     bytes += 2.0 * p.n_total * (p.num_taps * kc + p.k2_blocks * kBlockK);
   }
   ProfileScope prof(fam, stream, flops, bytes);
-  const int key = l.block_n * 2 + l.b_mn;
+  const int key = (l.block_n * 2 + l.b_mn) * 4 + l.epi;
   switch (key) {
-    case 64 * 2 + 0: launch_conv_t<64, 0>(p, stream); break;
-    case 128 * 2 + 0: launch_conv_t<128, 0>(p, stream); break;
-    case 256 * 2 + 0: launch_conv_t<256, 0>(p, stream); break;
-    case 64 * 2 + 1: launch_conv_t<64, 1>(p, stream); break;
-    case 128 * 2 + 1: launch_conv_t<128, 1>(p, stream); break;
-    case 256 * 2 + 1: launch_conv_t<256, 1>(p, stream); break;
+    case (64 * 2 + 0) * 4 + 2: launch_conv_t<64, 0, 2>(p, stream); break;
+    case (128 * 2 + 0) * 4 + 2: launch_conv_t<128, 0, 2>(p, stream); break;
+    case (256 * 2 + 0) * 4 + 2: launch_conv_t<256, 0, 2>(p, stream); break;
+    case (64 * 2 + 1) * 4 + 2: launch_conv_t<64, 1, 2>(p, stream); break;
+    case (128 * 2 + 1) * 4 + 2: launch_conv_t<128, 1, 2>(p, stream); break;
+    case (256 * 2 + 1) * 4 + 2: launch_conv_t<256, 1, 2>(p, stream); break;
+    case (64 * 2 + 0) * 4 + 3: launch_conv_t<64, 0, 3>(p, stream); break;
+    case (128 * 2 + 0) * 4 + 3: launch_conv_t<128, 0, 3>(p, stream); break;
+    case (256 * 2 + 0) * 4 + 3: launch_conv_t<256, 0, 3>(p, stream); break;
+    case (64 * 2 + 1) * 4 + 3: launch_conv_t<64, 1, 3>(p, stream); break;
+    case (128 * 2 + 1) * 4 + 3: launch_conv_t<128, 1, 3>(p, stream); break;
+    case (256 * 2 + 1) * 4 + 3: launch_conv_t<256, 1, 3>(p, stream); break;
     default: throw Error("unsupported conv tile configuration");
   }
 }
 
 int stat_slots(const ConvLaunch& l) {
   const int tiles = l.p.num_m_tiles * l.p.num_n_tiles;
-  return 2 * std::min(tiles, num_sms());
+  return l.epi * std::min(tiles, num_sms());
 }
 
 int64_t wgrad_scratch_elems(const WgradLaunch& l) {

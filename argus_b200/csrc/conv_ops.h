@@ -52,6 +52,7 @@ struct ConvLaunch {
   ConvGemmParams p;
   int block_n = 64;
   int b_mn = 0;
+  int epi = 2;        // epilogue groups of the kernel variant (choose_epilogue_groups)
   TmapGeom out_geom;
 };
 
@@ -89,7 +90,8 @@ WgradLaunch plan_conv_wgrad_gram(const ConvShape& s, const __nv_bfloat16* dy, co
 WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g);
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream);
-// number of statistic slots launch_conv writes for this launch (2 per CTA)
+int choose_epilogue_groups(const ConvGemmParams& p, int block_n);
+// number of statistic slots launch_conv writes for this launch (one per epilogue group per CTA)
 int stat_slots(const ConvLaunch& l);
 // elements of split-K scratch this launch needs (0 when it does not split)
 int64_t wgrad_scratch_elems(const WgradLaunch& l);

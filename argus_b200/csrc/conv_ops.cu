@@ -557,9 +557,17 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
     static const bool enabled = [] { const char* e = getenv("ARGUS_B_RESIDENT"); return (e && e[0] == '1'); }();
     static const bool halo_enabled = [] { const char* e = getenv("ARGUS_HALO"); return !(e && e[0] == '0'); }();
     if (q.halo) {
-      const int stage = (q.halo_rows + 2) * q.halo_row_bytes + 3 * L::kBBytes;
+      const int halo_a = (q.halo_rows + 2) * q.halo_row_bytes;
+      const int stage = halo_a + 3 * L::kBBytes;
       q.halo_stages = std::min(L::kMaxStages, L::kPipeBytes / stage);
       if (!halo_enabled || q.halo_stages < 2) q.halo = 0;
+      // halo + weights resident (default on, ARGUS_HALO_RESIDENT=0 disables): when the whole weight slab fits next to
+      // two activation boxes (layer1 3x3: 72 KB), the per-tile L2 -> SM traffic drops from 3 x (32 + 24) to 3 x 32 KB
+      static const bool halo_res = [] { const char* e = getenv("ARGUS_HALO_RESIDENT"); return !(e && e[0] == '0'); }();
+      if (q.halo && halo_res && fixed_n && q.k2_blocks == 0 && bres + 2 * halo_a <= L::kPipeBytes) {
+        q.b_resident = 1;
+        q.halo_stages = std::min(L::kMaxStages, (L::kPipeBytes - bres) / halo_a);
+      }
     }
     if (!q.halo && q.k2_blocks == 0 && enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
       q.b_resident = 1;
@@ -651,7 +659,15 @@ __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* 
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 acc = partial[i];
-    for (int k = 1; k < splits; ++k) {
+    int k = 1;
+    for (; k + 8 <= splits; k += 8) {   // eight loads in flight, additions in split order (same bits as the plain loop)
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = partial[static_cast<int64_t>(k + u) * n4 + i];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+    }
+    for (; k < splits; ++k) {
       const float4 v = partial[static_cast<int64_t>(k) * n4 + i];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }

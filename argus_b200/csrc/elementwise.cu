@@ -202,6 +202,14 @@ void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntr
   ARGUS_CUDA(cudaGetLastError());
 }
 
+// plain 4-byte global load as a volatile asm statement: a run of these is issued back to back (the compiler keeps
+// their order and cannot fold the consumers in between), so N partial sums cost one memory round trip, not N
+__device__ __forceinline__ float ldg_f32_issue(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // batch norm: finalize / fold
 // ------------------------------------------------------------------------------------------------------------
@@ -216,9 +224,23 @@ bn_finalize_kernel(const float* __restrict__ partial, int slots, double count, c
   const int c = blockIdx.x * 8 + ch;
   double sum = 0.0, sqsum = 0.0;
   if (c < C) {
-    for (int k = sl; k < slots; k += 32) {
-      sum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
-      sqsum += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+    // eight slots per batch: the loads are issued together (one L2 round trip instead of eight), the additions keep
+    // the slot order (missing slots are skipped) -> same bits as the plain loop
+    for (int k = sl; k < slots; k += 32 * 8) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int kk = min(k + 32 * u, slots - 1);   // clamped: always a valid address, masked below
+        a[u] = ldg_f32_issue(partial + (static_cast<size_t>(kk) * 2 + 0) * C + c);
+        b[u] = ldg_f32_issue(partial + (static_cast<size_t>(kk) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k + 32 * u < slots) {
+          sum += static_cast<double>(a[u]);
+          sqsum += static_cast<double>(b[u]);
+        }
+      }
     }
   }
   red[0][sl][ch] = sum;
@@ -343,7 +365,17 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
     }
   }
 }
-int bn_apply_grid(int64_t rows, int C) { return grid_for(rows * (C / 8), 256); }
+// shared-memory ring version (defined below, next to the ring versions of the backward passes)
+static bool bn_ring_enabled();
+static int bn_ring_grid(int64_t nvec);
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static void launch_bn_apply_ring(const uint4* x, const float* scale, const float* shift, const uint4* res,
+                                 const float* rscale, const float* rshift, int relu, uint4* y, uint8_t* bits,
+                                 float* colsum_partial, int64_t nvec, int cvec, cudaStream_t s);
+// number of per-block column-sum partials bn_apply writes (callers size and finalize the buffer with this)
+int bn_apply_grid(int64_t rows, int C) {
+  return bn_ring_enabled() ? bn_ring_grid(rows * (C / 8)) : grid_for(rows * (C / 8), 256);
+}
 void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16* res, const float* rscale,
               const float* rshift, int relu, bf16* y, uint8_t* relu_bits, float* colsum_partial, int64_t rows, int C,
               cudaStream_t s) {
@@ -354,6 +386,13 @@ void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16*
   auto X = reinterpret_cast<const uint4*>(x);
   auto R = reinterpret_cast<const uint4*>(res);
   auto Y = reinterpret_cast<uint4*>(y);
+  if (bn_ring_enabled()) {
+    ARGUS_CHECK(aligned16(x) && aligned16(res) && aligned16(y), "bn_apply: tensors must be 16-byte aligned");
+    ARGUS_CHECK(colsum_partial == nullptr || res == nullptr, "column sums are only produced by the plain (no residual) variant");
+    launch_bn_apply_ring(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, colsum_partial, nvec, C / 8, s);
+    ARGUS_CUDA(cudaGetLastError());
+    return;
+  }
   if (colsum_partial != nullptr) {
     ARGUS_CHECK(res == nullptr, "column sums are only produced by the plain (no residual) variant");
     bn_apply_kernel<0, true><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, colsum_partial, nvec, C / 8);
@@ -455,9 +494,21 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dga
   const int c = blockIdx.x * 8 + ch;
   double sb = 0.0, sg = 0.0;
   if (c < C) {
-    for (int k = sl; k < blocks; k += 32) {
-      sb += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 0) * C + c]);
-      sg += static_cast<double>(partial[(static_cast<size_t>(k) * 2 + 1) * C + c]);
+    for (int k = sl; k < blocks; k += 32 * 8) {   // batched loads, ordered additions (see bn_finalize_kernel)
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int kk = min(k + 32 * u, blocks - 1);
+        a[u] = ldg_f32_issue(partial + (static_cast<size_t>(kk) * 2 + 0) * C + c);
+        b[u] = ldg_f32_issue(partial + (static_cast<size_t>(kk) * 2 + 1) * C + c);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (k + 32 * u < blocks) {
+          sb += static_cast<double>(a[u]);
+          sg += static_cast<double>(b[u]);
+        }
+      }
     }
   }
   red[0][sl][ch] = sb;
@@ -469,6 +520,446 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dga
   for (int k = 0; k < 32; ++k) { sb += red[0][k][ch]; sg += red[1][k][ch]; }
   dbeta[c] += static_cast<float>(sb);
   dgamma[c] += static_cast<float>(sg);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Shared-memory ring versions of the two batch-norm backward passes (default; ARGUS_BN_RING=0 selects the register
+// versions above). A producer warp streams 8 KB slices of dy / x (/ out or the bit mask) into a ring of stages with
+// 1-D bulk copies (TMA) that complete on mbarriers; eight consumer warps read their 16-byte vectors from the landed
+// stage, release it, and do the math. The bytes in flight per SM are set by the ring (2 CTAs x 6 stages x 16 KB)
+// instead of by the registers the loads of one loop iteration can hold (1024 threads x 64 B), which is what kept the
+// register versions at 55-70 % of the HBM copy bandwidth.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kRingVec = 512;   // uint4 per tensor per stage: two per consumer thread
+template <int MASK>
+struct BnRing {
+  static constexpr int kTensorBytes = kRingVec * 16;
+  static constexpr int kExtraBytes = MASK == 2 ? kTensorBytes : (MASK == 3 ? kRingVec : 0);
+  static constexpr int kStageBytes = 2 * kTensorBytes + kExtraBytes;
+  static constexpr int kStages = MASK == 2 ? 4 : 6;
+  static constexpr int kOffBars = kStages * kStageBytes;
+  static constexpr int kTotal = kOffBars + 2 * kStages * 8;
+  static_assert(kStages * kStageBytes >= 16 * 256 * 4, "the block reduction reuses the ring memory");
+};
+constexpr int kRingThreads = 288;   // 8 consumer warps + 1 producer warp
+
+template <int MASK>
+__device__ __forceinline__ void bn_ring_producer(uint32_t sbase, const uint4* dy, const uint4* x, const uint4* out,
+                                                 int64_t nfull) {
+  using R = BnRing<MASK>;
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t c = blockIdx.x; c < nfull; c += gridDim.x) {
+    const uint32_t full = sbase + R::kOffBars + 8u * s, empty = sbase + R::kOffBars + 8u * (R::kStages + s);
+    mbar_wait(empty, ph ^ 1);
+    mbar_arrive_expect_tx(full, R::kStageBytes);
+    const uint32_t dst = sbase + s * R::kStageBytes;
+    bulk_load_1d(dst, dy + c * kRingVec, R::kTensorBytes, full);
+    bulk_load_1d(dst + R::kTensorBytes, x + c * kRingVec, R::kTensorBytes, full);
+    if (MASK == 2) bulk_load_1d(dst + 2 * R::kTensorBytes, out + c * kRingVec, R::kTensorBytes, full);
+    if (MASK == 3)
+      bulk_load_1d(dst + 2 * R::kTensorBytes, reinterpret_cast<const uint8_t*>(out) + c * kRingVec, kRingVec, full);
+    if (++s == R::kStages) { s = 0; ph ^= 1; }
+  }
+}
+__device__ __forceinline__ void bn_ring_init(uint32_t sbase, int off_bars, int stages) {
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(sbase + off_bars + 8u * s, 1);
+      mbar_init(sbase + off_bars + 8u * (stages + s), 8);   // one arrive per consumer warp
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+}
+// masked gradient of eight channels (see bn_bwd_reduce_kernel)
+template <int MASK>
+__device__ __forceinline__ F8 bn_masked_grad(const F8& d, const F8& xv, const uint4& ov4, const F8& sc, const F8& sh) {
+  F8 g = d;
+  if (MASK == 1) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]) > 0.f ? d.v[k] : 0.f;
+  } else if (MASK == 2) {
+    const F8 o = unpack8(ov4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = o.v[k] > 0.f ? d.v[k] : 0.f;
+  } else if (MASK == 3) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) g.v[k] = ((ov4.x >> k) & 1u) ? d.v[k] : 0.f;
+  }
+  return g;
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(kRingThreads, 2)
+bn_bwd_reduce_ring_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
+                          const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd,
+                          float* __restrict__ partial, int64_t nvec, int cvec) {
+  using R = BnRing<MASK>;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t sbase = smem_u32(ring_smem);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  bn_ring_init(sbase, R::kOffBars, R::kStages);
+  const int64_t nfull = nvec / kRingVec;
+  const int lanes = cvec < 256 ? cvec : 256;
+  const int oc = t & (lanes - 1);
+  const int c0 = oc * 8;
+  float a_dy[8], a_dyx[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a_dy[k] = a_dyx[k] = 0.f;
+  if (warp == 8) {
+    if (lane == 0) bn_ring_producer<MASK>(sbase, dy, x, out, nfull);
+  } else {
+    F8 sc, sh;
+    if (MASK == 1) { sc = load8f(scale + c0); sh = load8f(shift + c0); }
+    auto body = [&](const uint4& dyv, const uint4& xv4, const uint4& ov4) {
+      const F8 d = unpack8(dyv);
+      const F8 xv = unpack8(xv4);
+      const F8 g = bn_masked_grad<MASK>(d, xv, ov4, sc, sh);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        a_dy[k] += g.v[k];
+        a_dyx[k] = fmaf(g.v[k], xv.v[k], a_dyx[k]);
+      }
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t c = blockIdx.x; c < nfull; c += gridDim.x) {
+      mbar_wait(sbase + R::kOffBars + 8u * s, ph);
+      const uint8_t* st = ring_smem + s * R::kStageBytes;
+      const uint4* sd = reinterpret_cast<const uint4*>(st);
+      const uint4* sx = reinterpret_cast<const uint4*>(st + R::kTensorBytes);
+      const uint4 d0 = sd[t], d1 = sd[t + 256], x0 = sx[t], x1 = sx[t + 256];
+      uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+      if (MASK == 2) {
+        const uint4* so = reinterpret_cast<const uint4*>(st + 2 * R::kTensorBytes);
+        o0 = so[t]; o1 = so[t + 256];
+      }
+      if (MASK == 3) {
+        const uint8_t* sb = st + 2 * R::kTensorBytes;
+        o0.x = sb[t]; o1.x = sb[t + 256];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbase + R::kOffBars + 8u * (R::kStages + s));   // stage free: data is in registers
+      body(d0, x0, o0);
+      body(d1, x1, o1);
+      if (++s == R::kStages) { s = 0; ph ^= 1; }
+    }
+    if (blockIdx.x == 0) {
+      // ragged tail (< one stage): straight from global memory
+      const uint8_t* bits = reinterpret_cast<const uint8_t*>(out);
+      for (int64_t i = nfull * kRingVec + t; i < nvec; i += 256) {
+        uint4 o0 = make_uint4(0, 0, 0, 0);
+        if (MASK == 2) o0 = ldg_stream(out + i);
+        if (MASK == 3) o0.x = __ldg(bits + i);
+        body(ldg_stream(dy + i), ldg_stream(x + i), o0);
+      }
+    }
+  }
+  // Block reduction over the threads that share a channel octet (t = oc mod lanes): warp shuffles across the lanes of
+  // a warp that share it (lanes < 32), then one shared-memory pass across the eight warps. Fixed order -> deterministic.
+  float v[16];
+  {
+    F8 mu, is;
+    if (t < 256) { mu = load8f(mean + c0); is = load8f(invstd + c0); }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      v[k] = a_dy[k];
+      v[8 + k] = t < 256 ? (a_dyx[k] - mu.v[k] * a_dy[k]) * is.v[k] : 0.f;
+    }
+  }
+  if (warp < 8) {
+    for (int o = 16; o >= lanes; o >>= 1) {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+    }
+  }
+  __syncthreads();   // every stage has been consumed: the ring memory becomes the reduction scratch
+  float (*red)[16][32] = reinterpret_cast<float (*)[16][32]>(ring_smem);   // [warp][value][lane]
+  if (warp < 8) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) red[warp][k][lane] = v[k];
+  }
+  __syncthreads();
+  // thread t < lanes owns octet t; the warps holding it are w = (t / 32) + j * (lanes / 32) for lanes >= 32, all eight
+  // warps (lane t) for lanes < 32
+  if (t < lanes) {
+    const int wstep = lanes >= 32 ? lanes / 32 : 1;
+    const int w0 = lanes >= 32 ? t / 32 : 0;
+    const int ln = t & 31;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float s0 = 0.f, s1 = 0.f;
+      for (int w = w0; w < 8; w += wstep) {
+        s0 += red[w][k][ln];
+        s1 += red[w][8 + k][ln];
+      }
+      partial[(static_cast<size_t>(blockIdx.x) * 2 + 0) * (cvec * 8) + c0 + k] = s0;
+      partial[(static_cast<size_t>(blockIdx.x) * 2 + 1) * (cvec * 8) + c0 + k] = s1;
+    }
+  }
+}
+
+template <int MASK>
+__global__ void __launch_bounds__(kRingThreads, 2)
+bn_bwd_apply_ring_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const uint4* __restrict__ out,
+                         const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ dgamma, const float* __restrict__ dbeta, uint4* __restrict__ dx,
+                         int64_t nvec, int cvec, float inv_rows) {
+  using R = BnRing<MASK>;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t sbase = smem_u32(ring_smem);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  bn_ring_init(sbase, R::kOffBars, R::kStages);
+  const int64_t nfull = nvec / kRingVec;
+  if (warp == 8) {
+    if (lane == 0) bn_ring_producer<MASK>(sbase, dy, x, out, nfull);
+    return;
+  }
+  const int c0 = (t & ((cvec < 256 ? cvec : 256) - 1)) * 8;
+  const F8 sc = load8f(scale + c0);
+  F8 sh;
+  if (MASK == 1) sh = load8f(shift + c0);
+  F8 k0, k1;
+  {
+    const F8 mu = load8f(mean + c0), is = load8f(invstd + c0), dg = load8f(dgamma + c0), db = load8f(dbeta + c0);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float c2 = sc.v[k] * dg.v[k] * inv_rows * is.v[k];
+      k1.v[k] = -c2;
+      k0.v[k] = fmaf(c2, mu.v[k], -sc.v[k] * db.v[k] * inv_rows);
+    }
+  }
+  auto body = [&](int64_t i, const uint4& dyv, const uint4& xv4, const uint4& ov4) {
+    const F8 d = unpack8(dyv);
+    const F8 xv = unpack8(xv4);
+    const F8 g = bn_masked_grad<MASK>(d, xv, ov4, sc, sh);
+    F8 r;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r.v[k] = fmaf(sc.v[k], g.v[k], fmaf(k1.v[k], xv.v[k], k0.v[k]));
+    dx[i] = pack8(r);
+    if (MASK == 2) dy[i] = pack8(g);
+  };
+  int s = 0;
+  uint32_t ph = 0;
+  for (int64_t c = blockIdx.x; c < nfull; c += gridDim.x) {
+    mbar_wait(sbase + R::kOffBars + 8u * s, ph);
+    const uint8_t* st = ring_smem + s * R::kStageBytes;
+    const uint4* sd = reinterpret_cast<const uint4*>(st);
+    const uint4* sx = reinterpret_cast<const uint4*>(st + R::kTensorBytes);
+    const uint4 d0 = sd[t], d1 = sd[t + 256], x0 = sx[t], x1 = sx[t + 256];
+    uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+    if (MASK == 2) {
+      const uint4* so = reinterpret_cast<const uint4*>(st + 2 * R::kTensorBytes);
+      o0 = so[t]; o1 = so[t + 256];
+    }
+    if (MASK == 3) {
+      const uint8_t* sb = st + 2 * R::kTensorBytes;
+      o0.x = sb[t]; o1.x = sb[t + 256];
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(sbase + R::kOffBars + 8u * (R::kStages + s));
+    const int64_t i0 = c * kRingVec + t;
+    body(i0, d0, x0, o0);
+    body(i0 + 256, d1, x1, o1);
+    if (++s == R::kStages) { s = 0; ph ^= 1; }
+  }
+  if (blockIdx.x == 0) {
+    const uint8_t* bits = reinterpret_cast<const uint8_t*>(out);
+    for (int64_t i = nfull * kRingVec + t; i < nvec; i += 256) {
+      uint4 o0 = make_uint4(0, 0, 0, 0);
+      if (MASK == 2) o0 = ldg_stream(out + i);
+      if (MASK == 3) o0.x = __ldg(bits + i);
+      body(i, dy[i], ldg_stream(x + i), o0);
+    }
+  }
+}
+
+// Forward batch-norm apply through the same ring: x (+ residual) stream in, y (+ ReLU bits, + per-block column sums) out.
+template <int RES>
+struct ApplyRing {
+  static constexpr int kTensorBytes = kRingVec * 16;
+  static constexpr int kStageBytes = RES ? 2 * kTensorBytes : kTensorBytes;
+  static constexpr int kStages = RES ? 6 : 10;
+  static constexpr int kOffBars = kStages * kStageBytes;
+  static constexpr int kTotal = kOffBars + 2 * kStages * 8;
+  static_assert(kStages * kStageBytes >= 8 * 16 * 32 * 4, "the block reduction reuses the ring memory");
+};
+template <int RES, bool SUM>
+__global__ void __launch_bounds__(kRingThreads, 2)
+bn_apply_ring_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                     const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
+                     int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, float* __restrict__ colsum_partial,
+                     int64_t nvec, int cvec) {
+  using R = ApplyRing<RES>;
+  extern __shared__ __align__(128) uint8_t ring_smem[];
+  const uint32_t sbase = smem_u32(ring_smem);
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  bn_ring_init(sbase, R::kOffBars, R::kStages);
+  const int64_t nfull = nvec / kRingVec;
+  const int lanes = cvec < 256 ? cvec : 256;
+  const int c0 = (t & (lanes - 1)) * 8;
+  F8 acc;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc.v[k] = 0.f;
+  if (warp == 8) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int64_t c = blockIdx.x; c < nfull; c += gridDim.x) {
+        const uint32_t full = sbase + R::kOffBars + 8u * s, empty = sbase + R::kOffBars + 8u * (R::kStages + s);
+        mbar_wait(empty, ph ^ 1);
+        mbar_arrive_expect_tx(full, R::kStageBytes);
+        const uint32_t dst = sbase + s * R::kStageBytes;
+        bulk_load_1d(dst, x + c * kRingVec, R::kTensorBytes, full);
+        if (RES) bulk_load_1d(dst + R::kTensorBytes, res + c * kRingVec, R::kTensorBytes, full);
+        if (++s == R::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+    if (!SUM) return;
+  } else {
+    const F8 sc = load8f(scale + c0), sh = load8f(shift + c0);
+    F8 rs, rb;
+    if (RES == 2) { rs = load8f(rscale + c0); rb = load8f(rshift + c0); }
+    auto one = [&](int64_t i, const uint4& xq, const uint4& rq) {
+      const F8 xv = unpack8(xq);
+      F8 o;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaf(xv.v[k], sc.v[k], sh.v[k]);
+      if (RES == 1) {
+        const F8 rv = unpack8(rq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += rv.v[k];
+      } else if (RES == 2) {
+        const F8 rv = unpack8(rq);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] += fmaf(rv.v[k], rs.v[k], rb.v[k]);
+      }
+      if (bits != nullptr) bits[i] = positive_bits(o);
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(o.v[k], 0.f);
+      }
+      const uint4 packed = pack8(o);
+      y[i] = packed;
+      if (SUM) {
+        const F8 r = unpack8(packed);   // sums of the STORED (bf16) values
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc.v[k] += r.v[k];
+      }
+    };
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t c = blockIdx.x; c < nfull; c += gridDim.x) {
+      mbar_wait(sbase + R::kOffBars + 8u * s, ph);
+      const uint8_t* st = ring_smem + s * R::kStageBytes;
+      const uint4* sx = reinterpret_cast<const uint4*>(st);
+      const uint4 x0 = sx[t], x1 = sx[t + 256];
+      uint4 r0 = make_uint4(0, 0, 0, 0), r1 = r0;
+      if (RES) {
+        const uint4* sr = reinterpret_cast<const uint4*>(st + R::kTensorBytes);
+        r0 = sr[t]; r1 = sr[t + 256];
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sbase + R::kOffBars + 8u * (R::kStages + s));
+      const int64_t i0 = c * kRingVec + t;
+      one(i0, x0, r0);
+      one(i0 + 256, x1, r1);
+      if (++s == R::kStages) { s = 0; ph ^= 1; }
+    }
+    if (blockIdx.x == 0) {
+      for (int64_t i = nfull * kRingVec + t; i < nvec; i += 256) {
+        uint4 r0 = make_uint4(0, 0, 0, 0);
+        if (RES) r0 = ldg_stream(res + i);
+        one(i, ldg_stream(x + i), r0);
+      }
+    }
+  }
+  if (SUM) {
+    // per-block column sums: same reduction scheme as bn_bwd_reduce_ring_kernel
+    if (warp < 8) {
+      for (int o = 16; o >= lanes; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc.v[k] += __shfl_xor_sync(0xffffffffu, acc.v[k], o);
+      }
+    }
+    __syncthreads();
+    float (*red)[8][32] = reinterpret_cast<float (*)[8][32]>(ring_smem);   // [warp][value][lane]
+    if (warp < 8) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[warp][k][lane] = acc.v[k];
+    }
+    __syncthreads();
+    if (t < lanes) {
+      const int wstep = lanes >= 32 ? lanes / 32 : 1;
+      const int w0 = lanes >= 32 ? t / 32 : 0;
+      const int ln = t & 31;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float s0 = 0.f;
+        for (int w = w0; w < 8; w += wstep) s0 += red[w][k][ln];
+        colsum_partial[static_cast<size_t>(blockIdx.x) * (cvec * 8) + t * 8 + k] = s0;
+      }
+    }
+  }
+}
+template <int RES, bool SUM>
+static void launch_bn_apply_ring_t(const uint4* x, const float* scale, const float* shift, const uint4* res,
+                                   const float* rscale, const float* rshift, int relu, uint4* y, uint8_t* bits,
+                                   float* colsum_partial, int64_t nvec, int cvec, cudaStream_t s) {
+  static const bool once = [] {
+    ARGUS_CUDA(cudaFuncSetAttribute(bn_apply_ring_kernel<RES, SUM>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    ApplyRing<RES>::kTotal));
+    return true;
+  }();
+  (void)once;
+  bn_apply_ring_kernel<RES, SUM><<<bn_ring_grid(nvec), kRingThreads, ApplyRing<RES>::kTotal, s>>>(
+      x, scale, shift, res, rscale, rshift, relu, y, bits, colsum_partial, nvec, cvec);
+}
+static void launch_bn_apply_ring(const uint4* x, const float* scale, const float* shift, const uint4* res,
+                                 const float* rscale, const float* rshift, int relu, uint4* y, uint8_t* bits,
+                                 float* colsum_partial, int64_t nvec, int cvec, cudaStream_t s) {
+  if (colsum_partial != nullptr) launch_bn_apply_ring_t<0, true>(x, scale, shift, res, rscale, rshift, relu, y, bits, colsum_partial, nvec, cvec, s);
+  else if (res == nullptr) launch_bn_apply_ring_t<0, false>(x, scale, shift, res, rscale, rshift, relu, y, bits, nullptr, nvec, cvec, s);
+  else if (rscale == nullptr) launch_bn_apply_ring_t<1, false>(x, scale, shift, res, rscale, rshift, relu, y, bits, nullptr, nvec, cvec, s);
+  else launch_bn_apply_ring_t<2, false>(x, scale, shift, res, rscale, rshift, relu, y, bits, nullptr, nvec, cvec, s);
+}
+
+static bool bn_ring_enabled() {
+  static const bool on = [] { const char* e = getenv("ARGUS_BN_RING"); return !(e && e[0] == '0'); }();
+  return on;
+}
+static int bn_ring_grid(int64_t nvec) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(nvec / kRingVec, 2LL * num_sms())));
+}
+template <int MASK>
+static void launch_bn_bwd_reduce_ring(const uint4* dy, const uint4* x, const uint4* out, const float* scale,
+                                      const float* shift, const float* mean, const float* invstd, float* partial,
+                                      int64_t nvec, int cvec, int grid, cudaStream_t s) {
+  static const bool once = [] {
+    ARGUS_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_ring_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BnRing<MASK>::kTotal));
+    return true;
+  }();
+  (void)once;
+  bn_bwd_reduce_ring_kernel<MASK><<<grid, kRingThreads, BnRing<MASK>::kTotal, s>>>(dy, x, out, scale, shift, mean, invstd,
+                                                                                  partial, nvec, cvec);
+}
+template <int MASK>
+static void launch_bn_bwd_apply_ring(uint4* dy, const uint4* x, const uint4* out, const float* scale,
+                                     const float* shift, const float* mean, const float* invstd, const float* dgamma,
+                                     const float* dbeta, uint4* dx, int64_t nvec, int cvec, float inv_rows,
+                                     cudaStream_t s) {
+  static const bool once = [] {
+    ARGUS_CUDA(cudaFuncSetAttribute(bn_bwd_apply_ring_kernel<MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    BnRing<MASK>::kTotal));
+    return true;
+  }();
+  (void)once;
+  bn_bwd_apply_ring_kernel<MASK><<<bn_ring_grid(nvec), kRingThreads, BnRing<MASK>::kTotal, s>>>(
+      dy, x, out, scale, shift, mean, invstd, dgamma, dbeta, dx, nvec, cvec, inv_rows);
 }
 
 int64_t bn_bwd_scratch_elems() { return 4LL * num_sms() * 2 * 2048; }
@@ -489,6 +980,27 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
   auto DY = reinterpret_cast<const uint4*>(dy);
   auto X = reinterpret_cast<const uint4*>(x);
   auto O = reinterpret_cast<const uint4*>(out);
+  if (bn_ring_enabled() && aligned16(dy) && aligned16(x) && aligned16(out)) {
+    const int64_t nvec = rows * cvec;
+    const int rgrid = bn_ring_grid(nvec);
+    switch (mask_mode) {
+      case 0: launch_bn_bwd_reduce_ring<0>(DY, X, O, scale, shift, mean, invstd, scratch, nvec, cvec, rgrid, s); break;
+      case 1: launch_bn_bwd_reduce_ring<1>(DY, X, O, scale, shift, mean, invstd, scratch, nvec, cvec, rgrid, s); break;
+      case 2:
+        ARGUS_CHECK(out != nullptr, "mask_mode 2 needs the block output");
+        launch_bn_bwd_reduce_ring<2>(DY, X, O, scale, shift, mean, invstd, scratch, nvec, cvec, rgrid, s);
+        break;
+      case 3:
+        ARGUS_CHECK(out != nullptr, "mask_mode 3 needs the ReLU bit mask");
+        launch_bn_bwd_reduce_ring<3>(DY, X, O, scale, shift, mean, invstd, scratch, nvec, cvec, rgrid, s);
+        break;
+      default: throw Error("bad mask_mode");
+    }
+    ARGUS_CUDA(cudaGetLastError());
+    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, rgrid, dgamma, dbeta, C);
+    ARGUS_CUDA(cudaGetLastError());
+    return;
+  }
   switch (mask_mode) {
     case 0: bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
     case 1: bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
@@ -582,6 +1094,17 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
   auto X = reinterpret_cast<const uint4*>(x);
   auto O = reinterpret_cast<const uint4*>(out);
   auto DX = reinterpret_cast<uint4*>(dx);
+  if (bn_ring_enabled() && aligned16(dy) && aligned16(x) && aligned16(out) && aligned16(dx)) {
+    switch (mask_mode) {
+      case 0: launch_bn_bwd_apply_ring<0>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows, s); break;
+      case 1: launch_bn_bwd_apply_ring<1>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows, s); break;
+      case 2: launch_bn_bwd_apply_ring<2>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows, s); break;
+      case 3: launch_bn_bwd_apply_ring<3>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows, s); break;
+      default: throw Error("bad mask_mode");
+    }
+    ARGUS_CUDA(cudaGetLastError());
+    return;
+  }
   switch (mask_mode) {
     case 0: bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
     case 1: bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;

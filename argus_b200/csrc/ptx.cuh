@@ -110,6 +110,13 @@ __device__ __forceinline__ void tma_load_4d(const void* desc, uint32_t bar, uint
       "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// 1-D bulk copy global -> shared (TMA without a tensor map): `bytes` % 16 == 0, both addresses 16-byte aligned;
+// completes on the mbarrier like the tiled loads
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const void* desc, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(desc)),
@@ -213,6 +220,28 @@ __device__ __forceinline__ void red_add_v4(float* addr, uint32_t a, uint32_t b, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(__uint_as_float(a)),
                "f"(__uint_as_float(b)), "f"(__uint_as_float(c)), "f"(__uint_as_float(d))
                : "memory");
+}
+// Packed fp32x2 arithmetic (Blackwell FADD2 / FFMA2: two fp32 lanes per issue slot), used by the statistics loops
+__device__ __forceinline__ uint64_t f32x2_from_bf16x2(uint32_t w) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
+  return r;
+}
+__device__ __forceinline__ void f32x2_add(uint64_t& acc, uint64_t x) {
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(x));
+}
+__device__ __forceinline__ void f32x2_fma_sq(uint64_t& acc, uint64_t x) {
+  asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(x));
+}
+__device__ __forceinline__ float2 f32x2_unpack(uint64_t v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+  return v;
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

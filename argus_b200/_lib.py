@@ -11,7 +11,8 @@ from ctypes import c_char_p, c_double, c_float, c_int, c_int64, c_void_p
 from pathlib import Path
 
 _PKG_DIR = Path(__file__).resolve().parent
-LIB_PATH = _PKG_DIR / "libargus_b200.so"
+# ARGUS_B200_LIB selects another build of the same library (A/B experiments); the default is the in-tree build
+LIB_PATH = Path(os.environ["ARGUS_B200_LIB"]).resolve() if os.environ.get("ARGUS_B200_LIB") else _PKG_DIR / "libargus_b200.so"
 HEADER_PATH = _PKG_DIR.parent / "include" / "argus_b200.h"
 
 

@@ -189,14 +189,14 @@ int argus_conv_bn_backward_algebraic(const void* g, const void* act, const void*
   const bf16* W16 = static_cast<const bf16*>(w_bf16);
   WgradLaunch hg = plan_conv_wgrad_gram(s, G16, A16, Hb);
   ConvLaunch concat = plan_dgrad_concat(s, G16, A16, C, bstack, static_cast<bf16*>(dact));
-  ARGUS_CUDA(cudaMemsetAsync(Hb, 0, (OC + CC) * sizeof(float), st));
+  ARGUS_CUDA(cudaMemsetAsync(Hb, 0, (OC + CC) * sizeof(float), st)); pdl_break(st, kPdlAfterMemop);
   launch_wgrad(hg, lib_scratch(wgrad_scratch_elems(hg)), st);
   colsum_pixels_bf16(A16, N, H, W, C, stride, cs, sb, st);
   // g_colsum plays the role of ONE statistics slot (stride irrelevant)
   bn_alg_backward_small(W16, Hb, Gb, sb, g_colsum, 1, O, scale, mean, invstd, static_cast<double>(rows), dgamma, dbeta, dw,
                         k1k0, bstack, bias, mp, O, C, st);
   if (stride == 2)
-    ARGUS_CUDA(cudaMemsetAsync(dact, 0, static_cast<size_t>(N) * H * W * C * sizeof(bf16), st));
+    ARGUS_CUDA(cudaMemsetAsync(dact, 0, static_cast<size_t>(N) * H * W * C * sizeof(bf16), st)); pdl_break(st, kPdlAfterMemop);
   Epilogue e;
   e.shift = bias;
   launch_conv(concat, e, st);

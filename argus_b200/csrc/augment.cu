@@ -44,6 +44,7 @@ __device__ __forceinline__ float lerp_rn(float u, float lo, float span) { return
 // ------------------------------------------------------------------------------------------------------------
 __global__ void aug_params_kernel(float* __restrict__ params, int n_images, int n_cams, uint64_t seed, uint64_t step,
                                   AugConfig cfg) {
+  pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_images) return;
   float* P = params + static_cast<size_t>(n) * kAugParams;
@@ -163,6 +164,7 @@ struct TileTable {
 
 // one block per image: min / max of the un-normalised field -> params[21], params[22]
 __global__ void __launch_bounds__(256) plasma_minmax_kernel(float* __restrict__ params, int H, int W) {
+  pdl_prologue();
   __shared__ float s_lo[8], s_hi[8];
   __shared__ float s_lat[kLatTotal];
   float* P = params + static_cast<size_t>(blockIdx.x) * kAugParams;
@@ -274,6 +276,7 @@ template <bool IN_U8, bool OUT_S2D>
 __global__ void __launch_bounds__(256)
 augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float* __restrict__ params, int H, int W,
                int apply) {
+  pdl_prologue();
   __shared__ float sA[3][kIn][kIn + 1];    // colour-jittered input with halo; later reused for the blurred tile
   __shared__ float sB[3][kIn][kMid + 1];   // after the horizontal gaussian pass
   __shared__ float sP[kAugParams];
@@ -443,6 +446,7 @@ constexpr uint64_t kArcFieldBase = 1000;
 
 __global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, int n_arcs, int H, int W, uint64_t seed,
                                         uint64_t step) {
+  pdl_prologue();
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_images * n_arcs) return;
   const uint64_t img = t / n_arcs, a = t % n_arcs;
@@ -470,6 +474,7 @@ __global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, 
 __global__ void __launch_bounds__(256)
 spaghetti_draw_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const float* __restrict__ arcs,
                       int n_arcs, int H, int W) {
+  pdl_prologue();
   __shared__ float sArc[16 * kArcFields];
   const int n = blockIdx.y;
   for (int i = threadIdx.x; i < n_arcs * kArcFields; i += blockDim.x)
@@ -505,7 +510,7 @@ void spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W
   ARGUS_CHECK(n_arcs >= 0 && n_arcs <= 16, "at most 16 arcs per image");
   if (n_images * n_arcs <= 0) return;
   ProfileScope prof("augment_params", s, 0, 40.0 * n_images * n_arcs);
-  spaghetti_params_kernel<<<(n_images * n_arcs + 127) / 128, 128, 0, s>>>(arcs, n_images, n_arcs, H, W, seed, step);
+  launch_kernel(spaghetti_params_kernel, (n_images * n_arcs + 127) / 128, 128, 0, s, arcs, n_images, n_arcs, H, W, seed, step);
   ARGUS_CUDA(cudaGetLastError());
 }
 void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_images, int n_arcs, int H, int W,
@@ -514,7 +519,7 @@ void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_im
   if (n_images <= 0) return;
   ProfileScope prof("augment", s, 0, 6.0 * n_images * H * W);
   dim3 grid((H * W + 255) / 256, n_images);
-  spaghetti_draw_kernel<<<grid, 256, 0, s>>>(in, out, arcs, n_arcs, H, W);
+  launch_kernel(spaghetti_draw_kernel, grid, 256, 0, s, in, out, arcs, n_arcs, H, W);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -522,7 +527,7 @@ void augment_sample_params(float* params, int n_images, int n_cams, uint64_t see
                            cudaStream_t s) {
   ProfileScope prof("augment_params", s, 0, 96.0 * n_images);
   if (n_images <= 0) return;
-  aug_params_kernel<<<(n_images + 127) / 128, 128, 0, s>>>(params, n_images, n_cams, seed, step, cfg);
+  launch_kernel(aug_params_kernel, (n_images + 127) / 128, 128, 0, s, params, n_images, n_cams, seed, step, cfg);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -532,7 +537,7 @@ void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* 
   if (n_images <= 0) return;
   if (apply) {
     ProfileScope prof("augment_params", s, 0, 8.0 * n_images);
-    plasma_minmax_kernel<<<n_images, 256, 0, s>>>(params, H, W);
+    launch_kernel(plasma_minmax_kernel, n_images, 256, 0, s, params, H, W);
     ARGUS_CUDA(cudaGetLastError());
   }
   // algorithmic bytes: u8 RGB in + bf16 RGB out = 9 B per pixel
@@ -541,10 +546,10 @@ void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* 
   ProfileScope prof("augment", s, 0, bytes);
   dim3 grid(W / kTile, H / kTile, n_images);
   const int ap = apply ? 1 : 0;
-  if (in_u8 && out_s2d) augment_kernel<true, true><<<grid, 256, 0, s>>>(in, out, params, H, W, ap);
-  else if (in_u8 && !out_s2d) augment_kernel<true, false><<<grid, 256, 0, s>>>(in, out, params, H, W, ap);
-  else if (!in_u8 && out_s2d) augment_kernel<false, true><<<grid, 256, 0, s>>>(in, out, params, H, W, ap);
-  else augment_kernel<false, false><<<grid, 256, 0, s>>>(in, out, params, H, W, ap);
+  if (in_u8 && out_s2d) launch_kernel(augment_kernel<true, true>, grid, 256, 0, s, in, out, params, H, W, ap);
+  else if (in_u8 && !out_s2d) launch_kernel(augment_kernel<true, false>, grid, 256, 0, s, in, out, params, H, W, ap);
+  else if (!in_u8 && out_s2d) launch_kernel(augment_kernel<false, true>, grid, 256, 0, s, in, out, params, H, W, ap);
+  else launch_kernel(augment_kernel<false, false>, grid, 256, 0, s, in, out, params, H, W, ap);
   ARGUS_CUDA(cudaGetLastError());
 }
 

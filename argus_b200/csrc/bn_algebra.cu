@@ -32,6 +32,7 @@ bn_alg_coeffs_kernel(const bf16* __restrict__ W, const float* __restrict__ H, co
                      int slots, int stat_stride, const float* __restrict__ scale, const float* __restrict__ mean,
                      const float* __restrict__ invstd, float inv_rows, float* dgamma, float* dbeta,
                      float* __restrict__ k1k0, bf16* __restrict__ bstack, int O, int C) {
+  pdl_prologue();
   const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (o >= O) return;
@@ -69,6 +70,7 @@ constexpr int kSplitO = 8;
 __global__ void __launch_bounds__(256)
 bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0, float* __restrict__ partial, int O,
                      int C) {
+  pdl_prologue();
   __shared__ float sWj[32][17];   // [o chunk][j]
   __shared__ float sWi[32][17];   // [o chunk][i]
   const int ti = threadIdx.x & 15, tj = threadIdx.x >> 4;
@@ -115,6 +117,7 @@ bn_alg_matrix_kernel(const bf16* __restrict__ W, const float* __restrict__ k1k0,
 }
 __global__ void bn_alg_matrix_reduce_kernel(const float* __restrict__ partial, bf16* __restrict__ bstack,
                                             float* __restrict__ bias, int O, int C) {
+  pdl_prologue();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (C + 1) * C) return;
   float acc = 0.f;
@@ -129,6 +132,7 @@ __global__ void __launch_bounds__(256)
 bn_alg_dw_kernel(const bf16* __restrict__ W, const float* __restrict__ H, const float* __restrict__ G,
                  const float* __restrict__ s, const float* __restrict__ scale, const float* __restrict__ k1k0,
                  float* __restrict__ dW, int O, int C) {
+  pdl_prologue();
   __shared__ float sW[16][33];   // [o][j chunk]
   __shared__ float sG[32][17];   // [j chunk][i]
   const int ti = threadIdx.x & 15, to = threadIdx.x >> 4;
@@ -157,15 +161,15 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
                            float* mpartial, int O, int C, cudaStream_t st) {
   ARGUS_CHECK(O % (32 * kSplitO) == 0 && C % 32 == 0, "algebraic BN backward: O % 256 == 0 and C % 32 == 0 required");
   ProfileScope prof("bn_algebra", st, 4.0 * O * static_cast<double>(C) * C, 0);
-  bn_alg_coeffs_kernel<<<(O * 32 + 255) / 256, 256, 0, st>>>(W, H, stat_partial, slots, stat_stride, scale, mean, invstd,
+  launch_kernel(bn_alg_coeffs_kernel, (O * 32 + 255) / 256, 256, 0, st, W, H, stat_partial, slots, stat_stride, scale, mean, invstd,
                                                             static_cast<float>(1.0 / rows), dgamma, dbeta, k1k0, bstack,
                                                             O, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_alg_matrix_kernel<<<dim3(C / 16, C / 16 + 1, kSplitO), 256, 0, st>>>(W, k1k0, mpartial, O, C);
+  launch_kernel(bn_alg_matrix_kernel, dim3(C / 16, C / 16 + 1, kSplitO), 256, 0, st, W, k1k0, mpartial, O, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_alg_matrix_reduce_kernel<<<((C + 1) * C + 255) / 256, 256, 0, st>>>(mpartial, bstack, bias, O, C);
+  launch_kernel(bn_alg_matrix_reduce_kernel, ((C + 1) * C + 255) / 256, 256, 0, st, mpartial, bstack, bias, O, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_alg_dw_kernel<<<dim3(C / 16, O / 16), 256, 0, st>>>(W, H, G, s, scale, k1k0, dW, O, C);
+  launch_kernel(bn_alg_dw_kernel, dim3(C / 16, O / 16), 256, 0, st, W, H, G, s, scale, k1k0, dW, O, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -177,6 +181,7 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
 // partial[o][bx] = sum over the 16 columns i of tile bx of W[o,i] * (sum_j W[o,j] G[j,i])
 __global__ void __launch_bounds__(256)
 gram_quadform_kernel(const bf16* __restrict__ W, const float* __restrict__ G, float* __restrict__ partial, int O, int C) {
+  pdl_prologue();
   __shared__ float sW[16][33];
   __shared__ float sG[32][17];
   __shared__ float sQ[16][17];
@@ -210,6 +215,7 @@ gram_stats_finalize_kernel(const bf16* __restrict__ W, const float* __restrict__
                            int nparts, double rows, const float* gamma, const float* beta, float* running_mean,
                            float* running_var, float momentum, float eps, float* scale, float* shift, float* save_mean,
                            float* save_invstd, int O, int C) {
+  pdl_prologue();
   const int o = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (o >= O) return;
@@ -244,9 +250,9 @@ void bn_stats_from_gram(const bf16* W, const float* G, const float* s, double ro
                         cudaStream_t st) {
   ARGUS_CHECK(O % 16 == 0 && C % 32 == 0, "bn_stats_from_gram: O % 16 == 0 and C % 32 == 0 required");
   ProfileScope prof("bn_algebra", st, 2.0 * O * static_cast<double>(C) * C, 0);
-  gram_quadform_kernel<<<dim3(C / 16, O / 16), 256, 0, st>>>(W, G, scratch, O, C);
+  launch_kernel(gram_quadform_kernel, dim3(C / 16, O / 16), 256, 0, st, W, G, scratch, O, C);
   ARGUS_CUDA(cudaGetLastError());
-  gram_stats_finalize_kernel<<<(O * 32 + 255) / 256, 256, 0, st>>>(W, s, scratch, C / 16, rows, gamma, beta, running_mean,
+  launch_kernel(gram_stats_finalize_kernel, (O * 32 + 255) / 256, 256, 0, st, W, s, scratch, C / 16, rows, gamma, beta, running_mean,
                                                                   running_var, momentum, eps, scale, shift, save_mean,
                                                                   save_invstd, O, C);
   ARGUS_CUDA(cudaGetLastError());
@@ -258,6 +264,7 @@ void bn_stats_from_gram(const bf16* W, const float* G, const float* s, double ro
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, int64_t rows, int cvec, int stride,
                       int Wo, int HoWo, int W, int HW) {
+  pdl_prologue();
   // stride 2: row r of the (N, H/2, W/2) grid is pixel (2h, 2w) of the (N, H, W) tensor
   auto src = [&](int64_t r) -> int64_t {
     if (stride == 1) return r;
@@ -301,6 +308,7 @@ colsum_partial_kernel(const uint4* __restrict__ x, float* __restrict__ partial, 
 // order (bitwise reproducible, 32-way parallel; a single thread per channel took 80 us over 1184 partials)
 __global__ void __launch_bounds__(256)
 colsum_final_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ out, int C) {
+  pdl_prologue();
   __shared__ double red[32][8];
   const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + ch;
@@ -315,7 +323,7 @@ colsum_final_kernel(const float* __restrict__ partial, int blocks, float* __rest
   out[c] = static_cast<float>(acc);
 }
 void colsum_finalize(const float* partial, int blocks, float* out, int C, cudaStream_t st) {
-  colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, blocks, out, C);
+  launch_kernel(colsum_final_kernel, (C + 7) / 8, 256, 0, st, partial, blocks, out, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 void colsum_rows_bf16(const bf16* x, int64_t rows, int C, float* scratch, float* out, cudaStream_t st) {
@@ -330,10 +338,10 @@ void colsum_pixels_bf16(const bf16* x, int N, int H, int W, int C, int stride, f
   const int lanes = std::min(cvec, 256);
   const int row_lanes = 256 / lanes;
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((rows + row_lanes - 1) / row_lanes, 4LL * num_sms())));
-  colsum_partial_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const uint4*>(x), scratch, rows, cvec, stride, W / stride,
+  launch_kernel(colsum_partial_kernel, blocks, 256, 0, st, reinterpret_cast<const uint4*>(x), scratch, rows, cvec, stride, W / stride,
                                                 (H / stride) * (W / stride), W, H * W);
   ARGUS_CUDA(cudaGetLastError());
-  colsum_final_kernel<<<(C + 7) / 8, 256, 0, st>>>(scratch, blocks, out, C);
+  launch_kernel(colsum_final_kernel, (C + 7) / 8, 256, 0, st, scratch, blocks, out, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -113,6 +113,7 @@ struct ConvGemmSmem {
 template <int BLOCK_N, int B_MN, int EPI>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
+  pdl_prologue();
   using L = ConvGemmSmem<BLOCK_N, EPI>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
@@ -609,6 +610,7 @@ struct WgradSmem {
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_kernel(const __grid_constant__ WgradParams p) {
+  pdl_prologue();
   using L = WgradSmem<BLOCK_N>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = 2 * BLOCK_N;
@@ -818,6 +820,7 @@ struct WgradXposeSmem {
 template <int NBOX>
 __global__ void __launch_bounds__(kWgradThreads, 1)
 wgrad_xpose_kernel(const __grid_constant__ WgradXposeParams p) {
+  pdl_prologue();
   using L = WgradXposeSmem<NBOX>;
   constexpr int kStages = L::kStages;
   constexpr int kPairs = NBOX / 2;

@@ -106,6 +106,7 @@ ProfileScope::ProfileScope(const char* family, cudaStream_t s, double flops, dou
   if (!g_profiling) return;
   ProfRecord r{family, new_event(), new_event(), flops, bytes};
   cudaEventRecord(r.start, s);
+  pdl_break(s, kPdlAfterRecord);
   slot = static_cast<int>(g_records.size());
   g_records.push_back(r);
 }
@@ -114,6 +115,7 @@ ProfileScope::ProfileScope(const std::string& family, cudaStream_t s, double flo
   if (!g_profiling) return;
   ProfRecord r{family, new_event(), new_event(), flops, bytes};
   cudaEventRecord(r.start, s);
+  pdl_break(s, kPdlAfterRecord);
   slot = static_cast<int>(g_records.size());
   g_records.push_back(r);
 }
@@ -126,7 +128,7 @@ bool profile_detailed() {
   return v == 1;
 }
 ProfileScope::~ProfileScope() {
-  if (slot >= 0) cudaEventRecord(g_records[slot].stop, stream);
+  if (slot >= 0) { cudaEventRecord(g_records[slot].stop, stream); pdl_break(stream, kPdlAfterRecord); }
 }
 
 std::string profile_report_json() {
@@ -155,6 +157,40 @@ std::string profile_report_json() {
   return out;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+namespace {
+std::mutex g_pdl_mu;
+std::vector<std::pair<cudaStream_t, bool>> g_pdl_ok;   // a handful of streams: linear search
+int pdl_break_mask() {
+  static const int m = [] { const char* e = getenv("ARGUS_PDL_BREAK"); return e ? atoi(e) : 0; }();
+  return m;
+}
+}  // namespace
+void pdl_break(cudaStream_t stream, int kind) {
+  if (!(pdl_break_mask() & kind)) return;
+  std::lock_guard<std::mutex> lk(g_pdl_mu);
+  for (auto& e : g_pdl_ok)
+    if (e.first == stream) e.second = false;
+}
+void pdl_break_all() {
+  std::lock_guard<std::mutex> lk(g_pdl_mu);
+  for (auto& e : g_pdl_ok) e.second = false;
+}
+bool pdl_chain_ok(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_pdl_mu);
+  for (auto& e : g_pdl_ok)
+    if (e.first == stream) return e.second;
+  return false;
+}
+void pdl_mark_kernel(cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_pdl_mu);
+  for (auto& e : g_pdl_ok)
+    if (e.first == stream) { e.second = true; return; }
+  g_pdl_ok.emplace_back(stream, true);
+}
 int num_sms() {
   static int n = 0;
   if (n == 0) {
@@ -574,7 +610,7 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
       q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
     }
   }
-  conv_gemm_kernel<BN, BMN, EPI><<<grid, 64 + 128 * EPI, L::kTotal, stream>>>(q);
+  launch_kernel(conv_gemm_kernel<BN, BMN, EPI>, grid, 64 + 128 * EPI, L::kTotal, stream, q);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -656,6 +692,7 @@ int64_t wgrad_scratch_elems(const WgradLaunch& l) {
 
 // dw[i] += sum_ks partial[ks][i], splits added in index order (deterministic)
 __global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, int64_t n4, int splits) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float4 acc = partial[i];
@@ -685,7 +722,7 @@ static void launch_wgrad_xpose_t(const WgradXposeParams& p, cudaStream_t stream)
     ARGUS_CUDA(cudaFuncSetAttribute(wgrad_xpose_kernel<NBOX>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
-  wgrad_xpose_kernel<NBOX><<<p.num_splits, kWgradThreads, L::kTotal, stream>>>(p);
+  launch_kernel(wgrad_xpose_kernel<NBOX>, p.num_splits, kWgradThreads, L::kTotal, stream, p);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -699,7 +736,7 @@ static void launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   }
   const int items = p.num_co_tiles * p.num_ci_tiles * p.num_ksplits * p.num_taps;
   const int grid = std::min(items, num_sms());
-  wgrad_kernel<BN><<<grid, kWgradThreads, L::kTotal, stream>>>(p);
+  launch_kernel(wgrad_kernel<BN>, grid, kWgradThreads, L::kTotal, stream, p);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -738,7 +775,7 @@ void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
     // every (split, cout, tap, ci) word of the scratch was written by exactly one work item
     const int64_t n4 = l.p.partial_stride / 4;
     const int grid = static_cast<int>(std::min<int64_t>((n4 + 255) / 256, 2LL * num_sms()));
-    wgrad_reduce_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const float4*>(scratch),
+    launch_kernel(wgrad_reduce_kernel, grid, 256, 0, stream, reinterpret_cast<const float4*>(scratch),
                                                   reinterpret_cast<float4*>(l.p.dw), n4, l.p.num_ksplits);
     ARGUS_CUDA(cudaGetLastError());
   }

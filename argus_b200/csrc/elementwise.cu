@@ -62,6 +62,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 // ------------------------------------------------------------------------------------------------------------
 __global__ void pack_input_f32_kernel(const float* __restrict__ x, uint4* __restrict__ out, int n_images, int H,
                                       int W) {
+  pdl_prologue();
   const int Hs = H >> 1, Ws = W >> 1, Wp = Ws + 4;
   const int64_t total = static_cast<int64_t>(n_images) * Hs * Wp;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -95,6 +96,7 @@ __global__ void pack_input_f32_kernel(const float* __restrict__ x, uint4* __rest
 
 __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, uint4* __restrict__ out, int n_images, int H,
                                      int W) {
+  pdl_prologue();
   const int Hs = H >> 1, Ws = W >> 1, Wp = Ws + 4;
   const int64_t total = static_cast<int64_t>(n_images) * Hs * Wp;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -131,13 +133,13 @@ __global__ void pack_input_u8_kernel(const uint8_t* __restrict__ x, uint4* __res
 void pack_input_f32(const float* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
   ProfileScope prof("pack_input", s, 0, static_cast<double>(n_images) * H * W * 3 * 4 + static_cast<double>(n_images) * (H / 2) * (W / 2 + 4) * 32);
   const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
-  pack_input_f32_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
+  launch_kernel(pack_input_f32_kernel, grid_for(total, 256), 256, 0, s, x, reinterpret_cast<uint4*>(out), n_images, H, W);
   ARGUS_CUDA(cudaGetLastError());
 }
 void pack_input_u8(const uint8_t* x, bf16* out, int n_images, int H, int W, cudaStream_t s) {
   ProfileScope prof("pack_input", s, 0, static_cast<double>(n_images) * H * W * 3 + static_cast<double>(n_images) * (H / 2) * (W / 2 + 4) * 32);
   const int64_t total = static_cast<int64_t>(n_images) * (H / 2) * (W / 2 + 4);
-  pack_input_u8_kernel<<<grid_for(total, 256), 256, 0, s>>>(x, reinterpret_cast<uint4*>(out), n_images, H, W);
+  launch_kernel(pack_input_u8_kernel, grid_for(total, 256), 256, 0, s, x, reinterpret_cast<uint4*>(out), n_images, H, W);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -170,6 +172,7 @@ __device__ __forceinline__ int64_t packed_to_torch(const WeightPackEntry& e, int
 
 __global__ void pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ packed,
                                     const WeightPackEntry* __restrict__ table) {
+  pdl_prologue();
   const WeightPackEntry e = table[blockIdx.y];
   const int64_t n = packed_count(e);
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -180,6 +183,7 @@ __global__ void pack_weights_kernel(const float* __restrict__ params, bf16* __re
 }
 __global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, float* __restrict__ grads,
                                      const WeightPackEntry* __restrict__ table) {
+  pdl_prologue();
   const WeightPackEntry e = table[blockIdx.y];
   if (e.kind == 0 && e.kk == 1) return;  // 1x1 / linear layers accumulate straight into the gradient arena
   const int64_t n = packed_count(e);
@@ -192,13 +196,13 @@ __global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, flo
 void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries,
                   cudaStream_t s) {
   ProfileScope prof("pack_weights", s, 0, 0);
-  pack_weights_kernel<<<dim3(32, n_entries), 256, 0, s>>>(params, packed, table_dev);
+  launch_kernel(pack_weights_kernel, dim3(32, n_entries), 256, 0, s, params, packed, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
                    cudaStream_t s) {
   ProfileScope prof("unpack_wgrads", s, 0, 0);
-  unpack_wgrads_kernel<<<dim3(32, n_entries), 256, 0, s>>>(packed_grads, grads, table_dev);
+  launch_kernel(unpack_wgrads_kernel, dim3(32, n_entries), 256, 0, s, packed_grads, grads, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -219,6 +223,7 @@ __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const float* __restrict__ partial, int slots, double count, const float* gamma, const float* beta,
                    float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                    float* save_mean, float* save_invstd, int C) {
+  pdl_prologue();
   __shared__ double red[2][32][8];
   const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + ch;
@@ -269,12 +274,13 @@ void bn_finalize(const float* partial, int slots, double count, const float* gam
                  float* running_mean, float* running_var, float momentum, float eps, float* scale, float* shift,
                  float* save_mean, float* save_invstd, int C, cudaStream_t s) {
   ProfileScope prof("bn_finalize", s, 0, (8.0 * slots + 40.0) * C);
-  bn_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(partial, slots, count, gamma, beta, running_mean, running_var,
+  launch_kernel(bn_finalize_kernel, (C + 7) / 8, 256, 0, s, partial, slots, count, gamma, beta, running_mean, running_var,
                                                      momentum, eps, scale, shift, save_mean, save_invstd, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const float* rm, const float* rv, float eps,
                                     float* scale, float* shift, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * rsqrtf(rv[c] + eps);
@@ -284,7 +290,7 @@ __global__ void bn_fold_eval_kernel(const float* gamma, const float* beta, const
 void bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                   float eps, float* scale, float* shift, int C, cudaStream_t s) {
   ProfileScope prof("bn_finalize", s, 0, 24.0 * C);
-  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, running_mean, running_var, eps, scale, shift, C);
+  launch_kernel(bn_fold_eval_kernel, (C + 127) / 128, 128, 0, s, gamma, beta, running_mean, running_var, eps, scale, shift, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -297,6 +303,7 @@ bn_apply_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, co
                 const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
                 int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, float* __restrict__ colsum_partial,
                 int64_t nvec, int cvec) {
+  pdl_prologue();
   // gridDim.x * 256 is a multiple of cvec (a power of two <= 256), so a thread always sees the same channel octet:
   // the per-channel constants live in registers for the whole grid-stride loop.
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
@@ -395,13 +402,13 @@ void bn_apply(const bf16* x, const float* scale, const float* shift, const bf16*
   }
   if (colsum_partial != nullptr) {
     ARGUS_CHECK(res == nullptr, "column sums are only produced by the plain (no residual) variant");
-    bn_apply_kernel<0, true><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, colsum_partial, nvec, C / 8);
+    launch_kernel(bn_apply_kernel<0, true>, grid, 256, 0, s, X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, colsum_partial, nvec, C / 8);
   } else if (res == nullptr) {
-    bn_apply_kernel<0, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+    launch_kernel(bn_apply_kernel<0, false>, grid, 256, 0, s, X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
   } else if (rscale == nullptr) {
-    bn_apply_kernel<1, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+    launch_kernel(bn_apply_kernel<1, false>, grid, 256, 0, s, X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
   } else {
-    bn_apply_kernel<2, false><<<grid, 256, 0, s>>>(X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
+    launch_kernel(bn_apply_kernel<2, false>, grid, 256, 0, s, X, scale, shift, R, rscale, rshift, relu, Y, relu_bits, nullptr, nvec, C / 8);
   }
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -415,6 +422,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
                      const float* __restrict__ scale, const float* __restrict__ shift,
                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ partial,
                      int64_t rows, int cvec) {
+  pdl_prologue();
   __shared__ float red[16][256];
   const int lanes = cvec < 256 ? cvec : 256;   // threads along the channel dimension (cvec <= 256 for C <= 2048)
   const int row_lanes = 256 / lanes;           // rows processed concurrently by one block
@@ -489,6 +497,7 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 
 __global__ void __launch_bounds__(256)
 bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta, int C) {
+  pdl_prologue();
   __shared__ double red[2][32][8];
   const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
   const int c = blockIdx.x * 8 + ch;
@@ -596,6 +605,7 @@ bn_bwd_reduce_ring_kernel(const uint4* __restrict__ dy, const uint4* __restrict_
                           const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd,
                           float* __restrict__ partial, int64_t nvec, int cvec) {
+  pdl_prologue();
   using R = BnRing<MASK>;
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const uint32_t sbase = smem_u32(ring_smem);
@@ -708,6 +718,7 @@ bn_bwd_apply_ring_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, co
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ dgamma, const float* __restrict__ dbeta, uint4* __restrict__ dx,
                          int64_t nvec, int cvec, float inv_rows) {
+  pdl_prologue();
   using R = BnRing<MASK>;
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const uint32_t sbase = smem_u32(ring_smem);
@@ -793,6 +804,7 @@ bn_apply_ring_kernel(const uint4* __restrict__ x, const float* __restrict__ scal
                      const uint4* __restrict__ res, const float* __restrict__ rscale, const float* __restrict__ rshift,
                      int relu, uint4* __restrict__ y, uint8_t* __restrict__ bits, float* __restrict__ colsum_partial,
                      int64_t nvec, int cvec) {
+  pdl_prologue();
   using R = ApplyRing<RES>;
   extern __shared__ __align__(128) uint8_t ring_smem[];
   const uint32_t sbase = smem_u32(ring_smem);
@@ -915,7 +927,7 @@ static void launch_bn_apply_ring_t(const uint4* x, const float* scale, const flo
     return true;
   }();
   (void)once;
-  bn_apply_ring_kernel<RES, SUM><<<bn_ring_grid(nvec), kRingThreads, ApplyRing<RES>::kTotal, s>>>(
+  launch_kernel(bn_apply_ring_kernel<RES, SUM>, bn_ring_grid(nvec), kRingThreads, ApplyRing<RES>::kTotal, s, 
       x, scale, shift, res, rscale, rshift, relu, y, bits, colsum_partial, nvec, cvec);
 }
 static void launch_bn_apply_ring(const uint4* x, const float* scale, const float* shift, const uint4* res,
@@ -944,7 +956,7 @@ static void launch_bn_bwd_reduce_ring(const uint4* dy, const uint4* x, const uin
     return true;
   }();
   (void)once;
-  bn_bwd_reduce_ring_kernel<MASK><<<grid, kRingThreads, BnRing<MASK>::kTotal, s>>>(dy, x, out, scale, shift, mean, invstd,
+  launch_kernel(bn_bwd_reduce_ring_kernel<MASK>, grid, kRingThreads, BnRing<MASK>::kTotal, s, dy, x, out, scale, shift, mean, invstd,
                                                                                   partial, nvec, cvec);
 }
 template <int MASK>
@@ -958,7 +970,7 @@ static void launch_bn_bwd_apply_ring(uint4* dy, const uint4* x, const uint4* out
     return true;
   }();
   (void)once;
-  bn_bwd_apply_ring_kernel<MASK><<<bn_ring_grid(nvec), kRingThreads, BnRing<MASK>::kTotal, s>>>(
+  launch_kernel(bn_bwd_apply_ring_kernel<MASK>, bn_ring_grid(nvec), kRingThreads, BnRing<MASK>::kTotal, s, 
       dy, x, out, scale, shift, mean, invstd, dgamma, dbeta, dx, nvec, cvec, inv_rows);
 }
 
@@ -997,25 +1009,25 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
       default: throw Error("bad mask_mode");
     }
     ARGUS_CUDA(cudaGetLastError());
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, rgrid, dgamma, dbeta, C);
+    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, rgrid, dgamma, dbeta, C);
     ARGUS_CUDA(cudaGetLastError());
     return;
   }
   switch (mask_mode) {
-    case 0: bn_bwd_reduce_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
-    case 1: bn_bwd_reduce_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
+    case 0: launch_kernel(bn_bwd_reduce_kernel<0>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
+    case 1: launch_kernel(bn_bwd_reduce_kernel<1>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec); break;
     case 2:
       ARGUS_CHECK(out != nullptr, "mask_mode 2 needs the block output");
-      bn_bwd_reduce_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
+      launch_kernel(bn_bwd_reduce_kernel<2>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
       break;
     case 3:
       ARGUS_CHECK(out != nullptr, "mask_mode 3 needs the ReLU bit mask");
-      bn_bwd_reduce_kernel<3><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
+      launch_kernel(bn_bwd_reduce_kernel<3>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, scratch, rows, cvec);
       break;
     default: throw Error("bad mask_mode");
   }
   ARGUS_CUDA(cudaGetLastError());
-  bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, grid, dgamma, dbeta, C);
+  launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -1026,6 +1038,7 @@ bn_bwd_apply_kernel(uint4* __restrict__ dy, const uint4* __restrict__ x, const u
                     const float* __restrict__ mean, const float* __restrict__ invstd,
                     const float* __restrict__ dgamma, const float* __restrict__ dbeta, uint4* __restrict__ dx,
                     int64_t nvec, int cvec, float inv_rows) {
+  pdl_prologue();
   const int64_t tid = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;   // multiple of cvec
   const int c0 = static_cast<int>(tid & (cvec - 1)) * 8;
@@ -1106,10 +1119,10 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
     return;
   }
   switch (mask_mode) {
-    case 0: bn_bwd_apply_kernel<0><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
-    case 1: bn_bwd_apply_kernel<1><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
-    case 2: bn_bwd_apply_kernel<2><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
-    case 3: bn_bwd_apply_kernel<3><<<grid, 256, 0, s>>>(DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 0: launch_kernel(bn_bwd_apply_kernel<0>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 1: launch_kernel(bn_bwd_apply_kernel<1>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 2: launch_kernel(bn_bwd_apply_kernel<2>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
+    case 3: launch_kernel(bn_bwd_apply_kernel<3>, grid, 256, 0, s, DY, X, O, scale, shift, mean, invstd, dgamma, dbeta, DX, nvec, cvec, inv_rows); break;
     default: throw Error("bad mask_mode");
   }
   ARGUS_CUDA(cudaGetLastError());
@@ -1121,6 +1134,7 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
 __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
                                    const float* __restrict__ shift, uint4* __restrict__ y, uint2* __restrict__ idx,
                                    int N, int H, int W, int cvec) {
+  pdl_prologue();
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1174,7 +1188,7 @@ void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y,
                  int C, cudaStream_t s) {
   ProfileScope prof("maxpool", s, 0, static_cast<double>(N) * H * W * C * 2 * 1.25 + (idx ? static_cast<double>(N) * H * W * C / 4 : 0.0));
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-  maxpool_fwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(x), scale, shift,
+  launch_kernel(maxpool_fwd_kernel, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(x), scale, shift,
                                                           reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),
                                                           N, H, W, C / 8);
   ARGUS_CUDA(cudaGetLastError());
@@ -1182,6 +1196,7 @@ void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y,
 
 __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __restrict__ idx, uint4* __restrict__ dx,
                                    int N, int H, int W, int cvec) {
+  pdl_prologue();
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * H * W * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1219,7 +1234,7 @@ __global__ void maxpool_bwd_kernel(const uint4* __restrict__ dy, const uint2* __
 void maxpool_bwd(const bf16* dy, const uint8_t* idx, bf16* dx, int N, int H, int W, int C, cudaStream_t s) {
   ProfileScope prof("maxpool", s, 0, static_cast<double>(N) * H * W * C * 2 * 1.25 + static_cast<double>(N) * H * W * C / 4);
   const int64_t total = static_cast<int64_t>(N) * H * W * (C / 8);
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
+  launch_kernel(maxpool_bwd_kernel, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(dy),
                                                           reinterpret_cast<const uint2*>(idx),
                                                           reinterpret_cast<uint4*>(dx), N, H, W, C / 8);
   ARGUS_CUDA(cudaGetLastError());
@@ -1239,6 +1254,7 @@ stem_pool_bn_bwd_kernel(const uint4* __restrict__ dpool, const uint2* __restrict
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ partial,
                         uint4* __restrict__ dx, int N, int H, int W, float inv_rows) {
+  pdl_prologue();
   constexpr int cvec = 8;   // C = 64
   __shared__ float red[16][256];
   const int Ho = H >> 1, Wo = W >> 1;
@@ -1358,22 +1374,23 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
   {
     ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * (2.0 + 0.75));
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, 4LL * num_sms())));
-    stem_pool_bn_bwd_kernel<0><<<grid, 256, 0, s>>>(DP, ID, RW, scale, shift, mean, invstd, nullptr, nullptr, scratch,
+    launch_kernel(stem_pool_bn_bwd_kernel<0>, grid, 256, 0, s, DP, ID, RW, scale, shift, mean, invstd, nullptr, nullptr, scratch,
                                                     nullptr, N, H, W, inv_rows);
     ARGUS_CUDA(cudaGetLastError());
-    bn_bwd_finalize_kernel<<<(C + 7) / 8, 256, 0, s>>>(scratch, grid, dgamma, dbeta, C);
+    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C);
     ARGUS_CUDA(cudaGetLastError());
   }
   {
     ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * (4.0 + 0.75));
     const int grid = grid_for(threads, 256);
-    stem_pool_bn_bwd_kernel<1><<<grid, 256, 0, s>>>(DP, ID, RW, scale, shift, mean, invstd, dgamma, dbeta, nullptr,
+    launch_kernel(stem_pool_bn_bwd_kernel<1>, grid, 256, 0, s, DP, ID, RW, scale, shift, mean, invstd, dgamma, dbeta, nullptr,
                                                     reinterpret_cast<uint4*>(dx), N, H, W, inv_rows);
     ARGUS_CUDA(cudaGetLastError());
   }
 }
 
 __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int HW, int cvec) {
+  pdl_prologue();
   const int64_t total = static_cast<int64_t>(N) * cvec;
   const float inv = 1.0f / HW;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1397,12 +1414,13 @@ __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
 void avgpool_fwd(const bf16* x, bf16* y, int N, int HW, int C, cudaStream_t s) {
   ProfileScope prof("avgpool", s, 0, static_cast<double>(N) * (HW + 1) * C * 2);
   const int64_t total = static_cast<int64_t>(N) * (C / 8);
-  avgpool_fwd_kernel<<<grid_for(total, 128), 128, 0, s>>>(reinterpret_cast<const uint4*>(x),
+  launch_kernel(avgpool_fwd_kernel, grid_for(total, 128), 128, 0, s, reinterpret_cast<const uint4*>(x),
                                                           reinterpret_cast<uint4*>(y), N, HW, C / 8);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, const uint8_t* __restrict__ bits,
                                    int N, int HW, int cvec) {
+  pdl_prologue();
   const int64_t total = static_cast<int64_t>(N) * HW * cvec;
   const float inv = 1.0f / HW;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -1419,7 +1437,7 @@ __global__ void avgpool_bwd_kernel(const uint4* __restrict__ dy, uint4* __restri
 void avgpool_bwd(const bf16* dy, bf16* dx, const uint8_t* relu_bits, int N, int HW, int C, cudaStream_t s) {
   ProfileScope prof("avgpool", s, 0, static_cast<double>(N) * (HW + 1) * C * 2);
   const int64_t total = static_cast<int64_t>(N) * HW * (C / 8);
-  avgpool_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(dy),
+  launch_kernel(avgpool_bwd_kernel, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(dy),
                                                           reinterpret_cast<uint4*>(dx), relu_bits, N, HW, C / 8);
   ARGUS_CUDA(cudaGetLastError());
 }

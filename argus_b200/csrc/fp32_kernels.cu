@@ -8,6 +8,7 @@
 // torchvision resnet50 as called from /root/reference/argus/models.py:81-90. Weights and weight gradients are read
 // and written directly in PyTorch's [Cout][Cin][kh][kw] layout (no packed copies).
 #include "kernels_fp32.h"
+#include "ptx.cuh"
 #include "runtime.h"
 
 #include <algorithm>
@@ -72,6 +73,7 @@ __device__ __forceinline__ float load_b(const ConvF32& p, int k, int n) {
 
 template <int MODE>
 __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32 p) {
+  pdl_prologue();
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -135,6 +137,7 @@ __global__ void __launch_bounds__(256) conv_f32_kernel(const ConvF32 p) {
 
 // dw[co][ci][kh][kw] += sum_z partial[z][co][j], j = (kh*KW + kw)*Cin + ci, splits added in order in fp64
 __global__ void wgrad_reduce_f32_kernel(const ConvF32 p, float* __restrict__ dw, int splits) {
+  pdl_prologue();
   const int64_t total = static_cast<int64_t>(p.M) * p.Ncol;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -165,7 +168,7 @@ void conv_f32_forward(const ConvShapeF32& s, const float* x, const float* w, con
   p.M = s.N * p.Ho * p.Wo; p.Ncol = s.Cout; p.K = s.k * s.k * s.Cin; p.k_per_split = p.K;
   ProfileScope prof("fp32_conv", st, 2.0 * p.M * static_cast<double>(p.Ncol) * p.K, 0);
   dim3 grid((p.Ncol + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
-  conv_f32_kernel<0><<<grid, 256, 0, st>>>(p);
+  launch_kernel(conv_f32_kernel<0>, grid, 256, 0, st, p);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -175,7 +178,7 @@ void conv_f32_dgrad(const ConvShapeF32& s, const float* dy, const float* w, floa
   p.M = s.N * s.H * s.W; p.Ncol = s.Cin; p.K = s.k * s.k * s.Cout; p.k_per_split = p.K;
   ProfileScope prof("fp32_conv", st, 2.0 * p.M * static_cast<double>(p.Ncol) * p.K, 0);
   dim3 grid((p.Ncol + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
-  conv_f32_kernel<1><<<grid, 256, 0, st>>>(p);
+  launch_kernel(conv_f32_kernel<1>, grid, 256, 0, st, p);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -201,10 +204,10 @@ void conv_f32_wgrad(const ConvShapeF32& s, const float* dy, const float* x, floa
   splits = (p.K + p.k_per_split - 1) / p.k_per_split;
   ProfileScope prof("fp32_conv", st, 2.0 * p.M * static_cast<double>(p.Ncol) * p.K, 0);
   dim3 grid((p.Ncol + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-  conv_f32_kernel<2><<<grid, 256, 0, st>>>(p);
+  launch_kernel(conv_f32_kernel<2>, grid, 256, 0, st, p);
   ARGUS_CUDA(cudaGetLastError());
   const int64_t total = static_cast<int64_t>(p.M) * p.Ncol;
-  wgrad_reduce_f32_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 4096)), 256, 0, st>>>(p, dw, splits);
+  launch_kernel(wgrad_reduce_f32_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 4096)), 256, 0, st, p, dw, splits);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -212,6 +215,7 @@ void conv_f32_wgrad(const ConvShapeF32& s, const float* dy, const float* x, floa
 // input layout
 // ------------------------------------------------------------------------------------------------------------
 __global__ void nchw_to_nhwc3_kernel(const float* __restrict__ x, float* __restrict__ y, int n_images, int HW) {
+  pdl_prologue();
   const int64_t total = static_cast<int64_t>(n_images) * HW * 3;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -222,19 +226,20 @@ __global__ void nchw_to_nhwc3_kernel(const float* __restrict__ x, float* __restr
   }
 }
 __global__ void u8_to_f32_kernel(const uint8_t* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     y[i] = static_cast<float>(x[i]) / 255.0f;
 }
 void pack_input_nhwc_f32(const float* x_nchw, float* y_nhwc, int n_images, int H, int W, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(n_images) * H * W * 3;
-  nchw_to_nhwc3_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 8192)), 256, 0, s>>>(x_nchw, y_nhwc,
+  launch_kernel(nchw_to_nhwc3_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 8192)), 256, 0, s, x_nchw, y_nhwc,
                                                                                                       n_images, H * W);
   ARGUS_CUDA(cudaGetLastError());
 }
 void pack_input_u8_f32(const uint8_t* x_hwc, float* y_nhwc, int n_images, int H, int W, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(n_images) * H * W * 3;
-  u8_to_f32_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 8192)), 256, 0, s>>>(x_hwc, y_nhwc, total);
+  launch_kernel(u8_to_f32_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 8192)), 256, 0, s, x_hwc, y_nhwc, total);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -248,6 +253,7 @@ __global__ void __launch_bounds__(256)
 bn_sums_f32_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ out,
                    const float* __restrict__ mean, const float* __restrict__ invstd, double* __restrict__ partial,
                    int64_t rows, int C) {
+  pdl_prologue();
   // thread -> channel c = threadIdx.x % cl (+ multiples of cl), row lane = threadIdx.x / cl
   const int cl = C < 256 ? C : 256;
   const int row_lanes = 256 / cl;
@@ -287,6 +293,7 @@ __global__ void bn_finalize_f64_kernel(const double* __restrict__ partial, int b
                                        const float* gamma, const float* beta, float* running_mean,
                                        float* running_var, float momentum, float eps, float* scale, float* shift,
                                        float* save_mean, float* save_invstd, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double sum = 0.0, sq = 0.0;
@@ -311,6 +318,7 @@ __global__ void bn_finalize_f64_kernel(const double* __restrict__ partial, int b
 }
 __global__ void bn_bwd_finalize_f64_kernel(const double* __restrict__ partial, int blocks, float* dgamma, float* dbeta,
                                            float* sum_g, float* sum_gx, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double sb = 0.0, sg = 0.0;
@@ -337,9 +345,9 @@ void bn_f32_train_stats(const float* x, int64_t rows, int C, const float* gamma,
   ProfileScope prof("fp32_bn", s, 0, 4.0 * rows * C);
   ARGUS_CHECK(C <= 256 ? (256 % C == 0) : (C % 256 == 0), "fp32 batch norm: C must divide or be a multiple of 256");
   const int blocks = bn_blocks(rows, C);
-  bn_sums_f32_kernel<0><<<blocks, 256, 0, s>>>(x, nullptr, nullptr, nullptr, nullptr, scratch, rows, C);
+  launch_kernel(bn_sums_f32_kernel<0>, blocks, 256, 0, s, x, nullptr, nullptr, nullptr, nullptr, scratch, rows, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_finalize_f64_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, blocks, static_cast<double>(rows), gamma, beta,
+  launch_kernel(bn_finalize_f64_kernel, (C + 127) / 128, 128, 0, s, scratch, blocks, static_cast<double>(rows), gamma, beta,
                                                          running_mean, running_var, momentum, eps, scale, shift,
                                                          save_mean, save_invstd, C);
   ARGUS_CUDA(cudaGetLastError());
@@ -349,6 +357,7 @@ __global__ void bn_apply_f32_kernel(const float* __restrict__ x, const float* __
                                     const float* __restrict__ shift, const float* __restrict__ res,
                                     const float* __restrict__ rscale, const float* __restrict__ rshift, int relu,
                                     float* __restrict__ y, int64_t n, int C) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -362,7 +371,7 @@ void bn_f32_apply(const float* x, const float* scale, const float* shift, const 
                   const float* rshift, int relu, float* y, int64_t rows, int C, cudaStream_t s) {
   ProfileScope prof("fp32_bn", s, 0, 8.0 * rows * C);
   const int64_t n = rows * C;
-  bn_apply_f32_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s>>>(
+  launch_kernel(bn_apply_f32_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s, 
       x, scale, shift, res, rscale, rshift, relu, y, n, C);
   ARGUS_CUDA(cudaGetLastError());
 }
@@ -373,6 +382,7 @@ __global__ void bn_bwd_apply_f32_kernel(const float* __restrict__ dy, const floa
                                         const float* __restrict__ sum_g, const float* __restrict__ sum_gx,
                                         float* __restrict__ dx, float* __restrict__ g_out, int64_t n, int C,
                                         float inv_rows) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % C);
@@ -388,12 +398,12 @@ void bn_f32_backward(const float* dy, const float* x, const float* out, const fl
                      double* scratch, float* sums, cudaStream_t s) {
   ProfileScope prof("fp32_bn", s, 0, 20.0 * rows * C);
   const int blocks = bn_blocks(rows, C);
-  bn_sums_f32_kernel<1><<<blocks, 256, 0, s>>>(x, dy, out, mean, invstd, scratch, rows, C);
+  launch_kernel(bn_sums_f32_kernel<1>, blocks, 256, 0, s, x, dy, out, mean, invstd, scratch, rows, C);
   ARGUS_CUDA(cudaGetLastError());
-  bn_bwd_finalize_f64_kernel<<<(C + 127) / 128, 128, 0, s>>>(scratch, blocks, dgamma, dbeta, sums, sums + C, C);
+  launch_kernel(bn_bwd_finalize_f64_kernel, (C + 127) / 128, 128, 0, s, scratch, blocks, dgamma, dbeta, sums, sums + C, C);
   ARGUS_CUDA(cudaGetLastError());
   const int64_t n = rows * C;
-  bn_bwd_apply_f32_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s>>>(
+  launch_kernel(bn_bwd_apply_f32_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s, 
       dy, x, out, scale, mean, invstd, sums, sums + C, dx, g_out, n, C,
       static_cast<float>(1.0 / static_cast<double>(rows)));
   ARGUS_CUDA(cudaGetLastError());
@@ -404,6 +414,7 @@ void bn_f32_backward(const float* dy, const float* x, const float* out, const fl
 // ------------------------------------------------------------------------------------------------------------
 __global__ void maxpool_f32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, uint8_t* __restrict__ idx,
                                        int N, int H, int W, int C) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * C;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -432,12 +443,13 @@ __global__ void maxpool_f32_fwd_kernel(const float* __restrict__ x, float* __res
 }
 void maxpool_f32_fwd(const float* x, float* y, uint8_t* idx, int N, int H, int W, int C, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * C;
-  maxpool_f32_fwd_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s>>>(x, y, idx, N,
+  launch_kernel(maxpool_f32_fwd_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s, x, y, idx, N,
                                                                                                          H, W, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void maxpool_f32_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ idx,
                                        float* __restrict__ dx, int N, int H, int W, int C) {
+  pdl_prologue();
   const int Ho = H / 2, Wo = W / 2;
   const int64_t total = static_cast<int64_t>(N) * H * W * C;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -464,12 +476,13 @@ __global__ void maxpool_f32_bwd_kernel(const float* __restrict__ dy, const uint8
 }
 void maxpool_f32_bwd(const float* dy, const uint8_t* idx, float* dx, int N, int H, int W, int C, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(N) * H * W * C;
-  maxpool_f32_bwd_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s>>>(dy, idx, dx,
+  launch_kernel(maxpool_f32_bwd_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s, dy, idx, dx,
                                                                                                          N, H, W, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 __global__ void avgpool_f32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int HW, int C) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * C) return;
   const int c = i % C, n = i / C;
@@ -478,10 +491,11 @@ __global__ void avgpool_f32_fwd_kernel(const float* __restrict__ x, float* __res
   y[i] = static_cast<float>(s / HW);
 }
 void avgpool_f32_fwd(const float* x, float* y, int N, int HW, int C, cudaStream_t s) {
-  avgpool_f32_fwd_kernel<<<(N * C + 127) / 128, 128, 0, s>>>(x, y, N, HW, C);
+  launch_kernel(avgpool_f32_fwd_kernel, (N * C + 127) / 128, 128, 0, s, x, y, N, HW, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void avgpool_f32_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int HW, int C) {
+  pdl_prologue();
   const int64_t total = static_cast<int64_t>(N) * HW * C;
   const float inv = 1.0f / HW;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -493,21 +507,23 @@ __global__ void avgpool_f32_bwd_kernel(const float* __restrict__ dy, float* __re
 }
 void avgpool_f32_bwd(const float* dy, float* dx, int N, int HW, int C, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(N) * HW * C;
-  avgpool_f32_bwd_kernel<<<static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s>>>(dy, dx, N, HW, C);
+  launch_kernel(avgpool_f32_bwd_kernel, static_cast<int>(std::min<int64_t>((total + 255) / 256, 16384)), 256, 0, s, dy, dx, N, HW, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 __global__ void add_f32_kernel(float* __restrict__ a, const float* __restrict__ b, int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     a[i] += b[i];
 }
 void add_f32(float* a, const float* b, int64_t n, cudaStream_t s) {
-  add_f32_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s>>>(a, b, n);
+  launch_kernel(add_f32_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 16384)), 256, 0, s, a, b, n);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 __global__ void gelu_f32_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = x[i];
@@ -515,11 +531,12 @@ __global__ void gelu_f32_fwd_kernel(const float* __restrict__ x, float* __restri
   }
 }
 void gelu_f32_fwd(const float* x, float* y, int64_t n, cudaStream_t s) {
-  gelu_f32_fwd_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, s>>>(x, y, n);
+  launch_kernel(gelu_f32_fwd_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, s, x, y, n);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void gelu_f32_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ x, float* __restrict__ dx,
                                     int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const float v = x[i];
@@ -529,12 +546,13 @@ __global__ void gelu_f32_bwd_kernel(const float* __restrict__ dz, const float* _
   }
 }
 void gelu_f32_bwd(const float* dz, const float* x, float* dx, int64_t n, cudaStream_t s) {
-  gelu_f32_bwd_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, s>>>(dz, x, dx, n);
+  launch_kernel(gelu_f32_bwd_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 4096)), 256, 0, s, dz, x, dx, n);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 // out[c] += sum_r x[r, c] (fc bias gradient), fp64 accumulation
 __global__ void colsum_f32_kernel(const float* __restrict__ x, float* out, int rows, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double acc = 0.0;
@@ -542,7 +560,7 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, float* out, int r
   out[c] += static_cast<float>(acc);
 }
 void colsum_f32(const float* x, float* out, int rows, int C, cudaStream_t s) {
-  colsum_f32_kernel<<<(C + 127) / 128, 128, 0, s>>>(x, out, rows, C);
+  launch_kernel(colsum_f32_kernel, (C + 127) / 128, 128, 0, s, x, out, rows, C);
   ARGUS_CUDA(cudaGetLastError());
 }
 

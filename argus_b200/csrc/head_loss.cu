@@ -21,30 +21,33 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
 }
 
 __global__ void gelu_fwd_bf16_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     y[i] = gelu_f(__bfloat162float(x[i]));
 }
 void gelu_fwd_bf16(const bf16* x, float* y, int64_t n, cudaStream_t s) {
   ProfileScope prof("head", s, 0, 6.0 * n);
-  gelu_fwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(x, y, n);
+  launch_kernel(gelu_fwd_bf16_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s, x, y, n);
   ARGUS_CUDA(cudaGetLastError());
 }
 __global__ void gelu_bwd_bf16_kernel(const float* __restrict__ dz, const bf16* __restrict__ x, bf16* __restrict__ dx,
                                      int64_t n) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x)
     dx[i] = __float2bfloat16(dz[i] * gelu_grad_f(__bfloat162float(x[i])));
 }
 void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStream_t s) {
   ProfileScope prof("head", s, 0, 8.0 * n);
-  gelu_bwd_bf16_kernel<<<static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s>>>(dz, x, dx, n);
+  launch_kernel(gelu_bwd_bf16_kernel, static_cast<int>(std::min<int64_t>((n + 255) / 256, 1184)), 256, 0, s, dz, x, dx, n);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 // one warp per output element: y[b, o] = dot(x[b, :], w[o, :]) + bias[o]
 __global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                   float* __restrict__ y, float* __restrict__ act, int B, int In, int Out) {
+  pdl_prologue();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= B * Out) return;
@@ -64,17 +67,19 @@ void linear_fwd(const float* x, const float* w, const float* b, float* y, float*
                 cudaStream_t s) {
   ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
   const int64_t threads = static_cast<int64_t>(B) * Out * 32;
-  linear_fwd_kernel<<<static_cast<int>((threads + 255) / 256), 256, 0, s>>>(x, w, b, y, act, B, In, Out);
+  launch_kernel(linear_fwd_kernel, static_cast<int>((threads + 255) / 256), 256, 0, s, x, w, b, y, act, B, In, Out);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 __global__ void gelu_grad_inplace_kernel(float* dy, const float* __restrict__ pre, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dy[i] *= gelu_grad_f(pre[i]);
 }
 // dw[o, i] += sum_b dy[b, o] x[b, i]   (thread per (o, i): x reads coalesced over i, dy reads broadcast)
 __global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* dw, float* db,
                                     int B, int In, int Out) {
+  pdl_prologue();
   const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= static_cast<int64_t>(Out) * In) return;
   const int o = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(o) * In);
@@ -90,6 +95,7 @@ __global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* _
 // dx[b, i] = sum_o dy[b, o] w[o, i]
 __global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
                                     int B, int In, int Out) {
+  pdl_prologue();
   const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   if (t >= static_cast<int64_t>(B) * In) return;
   const int b = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(b) * In);
@@ -101,15 +107,15 @@ void linear_bwd(float* dy, const float* pre, const float* x, const float* w, flo
                 int In, int Out, cudaStream_t s) {
   ProfileScope prof("head", s, 4.0 * B * In * Out, 4.0 * (2.0 * B * In + 2.0 * In * Out + static_cast<double>(B) * Out));
   if (pre != nullptr) {
-    gelu_grad_inplace_kernel<<<(B * Out + 255) / 256, 256, 0, s>>>(dy, pre, B * Out);
+    launch_kernel(gelu_grad_inplace_kernel, (B * Out + 255) / 256, 256, 0, s, dy, pre, B * Out);
     ARGUS_CUDA(cudaGetLastError());
   }
   const int64_t nw = static_cast<int64_t>(Out) * In;
-  linear_bwd_w_kernel<<<static_cast<int>((nw + 127) / 128), 128, 0, s>>>(dy, x, dw, db, B, In, Out);
+  launch_kernel(linear_bwd_w_kernel, static_cast<int>((nw + 127) / 128), 128, 0, s, dy, x, dw, db, B, In, Out);
   ARGUS_CUDA(cudaGetLastError());
   if (dx != nullptr) {
     const int64_t nx = static_cast<int64_t>(B) * In;
-    linear_bwd_x_kernel<<<static_cast<int>((nx + 127) / 128), 128, 0, s>>>(dy, w, dx, B, In, Out);
+    launch_kernel(linear_bwd_x_kernel, static_cast<int>((nx + 127) / 128), 128, 0, s, dy, w, dx, B, In, Out);
     ARGUS_CUDA(cudaGetLastError());
   }
 }
@@ -122,6 +128,7 @@ void linear_bwd(float* dy, const float* pre, const float* x, const float* w, flo
 __global__ void __launch_bounds__(1024)
 pose_loss_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
                  float* loss_mean, float* __restrict__ grad, int B, float grad_scale) {
+  pdl_prologue();
   __shared__ double red[32];
   double acc = 0.0;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -155,11 +162,12 @@ void pose_loss_fwd_bwd(const float* pred, const float* target, float* loss, floa
   ProfileScope prof("pose_loss", s, 0, 80.0 * B);
   if (B <= 0) return;
   const int threads = B >= 1024 ? 1024 : ((B + 31) / 32) * 32;
-  pose_loss_kernel<<<1, threads, 0, s>>>(pred, target, loss, loss_mean, grad, B, grad_scale);
+  launch_kernel(pose_loss_kernel, 1, threads, 0, s, pred, target, loss, loss_mean, grad, B, grad_scale);
   ARGUS_CUDA(cudaGetLastError());
 }
 
 __global__ void pose_exp_kernel(const float* __restrict__ pred, float* __restrict__ pose, int B, int wxyz) {
+  pdl_prologue();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   se3::V3 t;
@@ -177,7 +185,7 @@ __global__ void pose_exp_kernel(const float* __restrict__ pred, float* __restric
 void pose_exp(const float* pred, float* pose, int B, int wxyz, cudaStream_t s) {
   ProfileScope prof("pose_loss", s, 0, 52.0 * B);
   if (B <= 0) return;
-  pose_exp_kernel<<<(B + 63) / 64, 64, 0, s>>>(pred, pose, B, wxyz);
+  launch_kernel(pose_exp_kernel, (B + 63) / 64, 64, 0, s, pred, pose, B, wxyz);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -187,6 +195,7 @@ void pose_exp(const float* pred, float* pose, int B, int wxyz, cudaStream_t s) {
 constexpr int kNormBlocks = 592;  // 4 per SM
 
 __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restrict__ g, int64_t n, float* partial) {
+  pdl_prologue();
   __shared__ float red[8];
   float acc = 0.f;
   const int64_t n4 = n >> 2;
@@ -211,7 +220,7 @@ __global__ void __launch_bounds__(256) grad_sqnorm_kernel(const float* __restric
 }
 int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t s) {
   ProfileScope prof("grad_norm", s, 0, 4.0 * n);
-  grad_sqnorm_kernel<<<kNormBlocks, 256, 0, s>>>(g, n, partial);
+  launch_kernel(grad_sqnorm_kernel, kNormBlocks, 256, 0, s, g, n, partial);
   ARGUS_CUDA(cudaGetLastError());
   return kNormBlocks;
 }
@@ -220,6 +229,7 @@ __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, const float* __restrict__ partial, int n_partial, float gscale, float max_norm, float lr,
                  float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float* norm_out) {
+  pdl_prologue();
   __shared__ float red[8];
   __shared__ float s_coef;
   // every block reduces the partial sums in the same order -> identical clip coefficient everywhere
@@ -257,7 +267,7 @@ void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, con
   ProfileScope prof("clip_adam", s, 0, 28.0 * n);
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
-  clip_adam_kernel<<<4 * num_sms(), 256, 0, s>>>(p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,
+  launch_kernel(clip_adam_kernel, 4 * num_sms(), 256, 0, s, p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,
                                                  beta2, eps, bc1, bc2_sqrt, norm_out);
   ARGUS_CUDA(cudaGetLastError());
 }

@@ -123,18 +123,18 @@ class Loader {
       count = fill_count_[buf];
     }
     // the device buffer may still be read by the step that consumed it two batches ago
-    if (consumed_recorded_[buf]) ARGUS_CUDA(cudaStreamWaitEvent(copy_stream_, consumed_[buf], 0));
+    if (consumed_recorded_[buf]) ARGUS_CUDA(cudaStreamWaitEvent(copy_stream_, consumed_[buf], 0)); pdl_break(copy_stream_, kPdlAfterWait);
     ARGUS_CUDA(cudaMemcpyAsync(dev_img_[buf], host_img_[buf], static_cast<size_t>(count) * sample_bytes_,
-                               cudaMemcpyHostToDevice, copy_stream_));
+                               cudaMemcpyHostToDevice, copy_stream_)); pdl_break(copy_stream_, kPdlAfterMemop);
     ARGUS_CUDA(cudaMemcpyAsync(dev_pose_[buf], host_pose_[buf], static_cast<size_t>(count) * 7 * sizeof(float),
-                               cudaMemcpyHostToDevice, copy_stream_));
-    ARGUS_CUDA(cudaEventRecord(copied_[buf], copy_stream_));
+                               cudaMemcpyHostToDevice, copy_stream_)); pdl_break(copy_stream_, kPdlAfterMemop);
+    ARGUS_CUDA(cudaEventRecord(copied_[buf], copy_stream_)); pdl_break(copy_stream_, kPdlAfterRecord);
     copied_recorded_[buf] = true;
-    ARGUS_CUDA(cudaStreamWaitEvent(stream, copied_[buf], 0));
+    ARGUS_CUDA(cudaStreamWaitEvent(stream, copied_[buf], 0)); pdl_break(stream, kPdlAfterWait);
     // everything the caller enqueues on `stream` until the next call consumes this buffer
     const int prev = buf ^ 1;
     if (next_take_ > 0) {
-      ARGUS_CUDA(cudaEventRecord(consumed_[prev], stream));
+      ARGUS_CUDA(cudaEventRecord(consumed_[prev], stream)); pdl_break(stream, kPdlAfterRecord);
       consumed_recorded_[prev] = true;
     }
     {

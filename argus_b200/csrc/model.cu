@@ -13,6 +13,7 @@ static constexpr float kBnMomentum = 0.1f;
 // small kernels local to the model: column sums (fc bias gradient)
 // ------------------------------------------------------------------------------------------------------------
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, float* out, int rows, int C) {
+  pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float acc = 0.f;
@@ -226,7 +227,7 @@ void Model::sync_weights(cudaStream_t s) {
 
 void Model::zero_grads(cudaStream_t s) {
   ARGUS_CHECK(grads_dev_ != nullptr, "model is not bound to a gradient arena");
-  ARGUS_CUDA(cudaMemsetAsync(grads_dev_, 0, n_param_elems_ * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(grads_dev_, 0, n_param_elems_ * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -459,7 +460,7 @@ void Model::run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, c
 }
 
 void Model::forward_train(Plan& p, cudaStream_t s) {
-  ARGUS_CUDA(cudaMemsetAsync(bn_stats_, 0, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(bn_stats_, 0, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   eval_fold_dirty_ = true;  // scale/shift scratch now holds batch statistics
   const int N = p.N;
   auto SC = [&](const ConvRef& c) { return bn_scratch_ + c.bn.scratch_off; };
@@ -516,7 +517,7 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
 void Model::stats_from_gram(const ConvRef& c, const WgradLaunch& gram, const bf16* act, const float* colsum_partial,
                             int64_t rows, int N, cudaStream_t s) {
   const int O = c.shape.Cout, C = c.shape.Cin;
-  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(C) * C * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   launch_wgrad(gram, wgrad_scratch_, s);
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
@@ -564,7 +565,7 @@ void Model::head_forward(Plan& p, float* out, cudaStream_t s) {
   linear_fwd(p.z0, params_dev_ + head_w_off_[0], params_dev_ + head_b_off_[0], p.h1, p.a1, B, F, 128, s);
   linear_fwd(p.a1, params_dev_ + head_w_off_[1], params_dev_ + head_b_off_[1], p.h2, p.a2, B, 128, 128, s);
   linear_fwd(p.a2, params_dev_ + head_w_off_[2], params_dev_ + head_b_off_[2], p.out, nullptr, B, 128, 6, s);
-  ARGUS_CUDA(cudaMemcpyAsync(out, p.out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  ARGUS_CUDA(cudaMemcpyAsync(out, p.out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
 }
 
 void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s) {
@@ -627,7 +628,7 @@ void Model::copy_activation(int index, void* dst, int64_t capacity_elems, int64_
     throw Error("activation index out of range");
   }
   ARGUS_CHECK(r * c <= capacity_elems, "destination too small for the requested activation");
-  ARGUS_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(r) * c * sizeof(bf16), cudaMemcpyDeviceToDevice, s));
+  ARGUS_CUDA(cudaMemcpyAsync(dst, src, static_cast<size_t>(r) * c * sizeof(bf16), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
   if (rows) *rows = r;
   if (C) *C = c;
 }
@@ -656,16 +657,16 @@ void Model::run_wgrad(const WgradLaunch& l, cudaStream_t s) {
     launch_wgrad(l, wgrad_scratch_, s);
     return;
   }
-  ARGUS_CUDA(cudaEventRecord(ev_fork_, s));
-  ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0));
+  ARGUS_CUDA(cudaEventRecord(ev_fork_, s)); pdl_break(s, kPdlAfterRecord);
+  ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0)); pdl_break(side_, kPdlAfterWait);
   launch_wgrad(l, wgrad_scratch_, side_);
-  ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_));
+  ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_)); pdl_break(side_, kPdlAfterRecord);
   wgrad_pending_ = true;
 }
 
 void Model::join_wgrad(cudaStream_t s) {
   if (wgrad_pending_) {
-    ARGUS_CUDA(cudaStreamWaitEvent(s, ev_wgrad_, 0));
+    ARGUS_CUDA(cudaStreamWaitEvent(s, ev_wgrad_, 0)); pdl_break(s, kPdlAfterWait);
     wgrad_pending_ = false;
   }
 }
@@ -692,7 +693,7 @@ void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_
   if (out_stats != nullptr) {
     ARGUS_CHECK(cp.dgrad.size() == 1, "gradient statistics need a single dgrad launch");
     alg_gstats_slots_ = stat_slots(cp.dgrad[0]);
-    ARGUS_CUDA(cudaMemsetAsync(out_stats, 0, static_cast<size_t>(alg_gstats_slots_) * 2 * cp.dgrad[0].p.n_total * sizeof(float), s));
+    ARGUS_CUDA(cudaMemsetAsync(out_stats, 0, static_cast<size_t>(alg_gstats_slots_) * 2 * cp.dgrad[0].p.n_total * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
     e.stat_partial = out_stats;
   }
   for (const auto& l : cp.dgrad) launch_conv(l, e, s);
@@ -705,7 +706,7 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
   const int O = c.shape.Cout, C = c.shape.Cin;
   float* alg_g = alg_h_ + static_cast<size_t>(O) * C;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
-  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s));
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) and G = act^T act (rows O..O+C), act tiles loaded once
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
@@ -736,7 +737,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
     if (stage == 0) {
       // ---- head
       ARGUS_CUDA(cudaMemcpyAsync(p.d_out, d_out, static_cast<size_t>(B) * 6 * sizeof(float),
-                                 cudaMemcpyDeviceToDevice, s));
+                                 cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
       float* g = grads_dev_;
       linear_bwd(p.d_out, nullptr, p.a2, params_dev_ + head_w_off_[2], g + head_w_off_[2], g + head_b_off_[2],
                  p.d_a2, B, 128, 6, s);
@@ -747,7 +748,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       gelu_bwd_bf16(p.d_z0, p.feat, p.d_feat, static_cast<int64_t>(B) * F, s);
       // ---- fc
       { ProfileScope prof("head", s, 0, 2.0 * N * out_dim_); }
-      colsum_bf16_kernel<<<(out_dim_ + 127) / 128, 128, 0, s>>>(p.d_feat, g + fc_bias_off_, N, out_dim_);
+      launch_kernel(colsum_bf16_kernel, (out_dim_ + 127) / 128, 128, 0, s, p.d_feat, g + fc_bias_off_, N, out_dim_);
       ARGUS_CUDA(cudaGetLastError());
       run_wgrad(p.fc.wgrad, s);
       Epilogue e;
@@ -760,7 +761,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       BlockPlan& bp = p.blocks[i];
       // zero this block's packed 3x3 gradient scratch
       ARGUS_CUDA(cudaMemsetAsync(gpacked_ + br.c2.gpacked_off, 0,
-                                 static_cast<size_t>(br.c2.shape.Ktot()) * br.c2.shape.Cout * sizeof(float), s));
+                                 static_cast<size_t>(br.c2.shape.Ktot()) * br.c2.shape.Cout * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
       bf16 *P = bp.g_out, *Q = bp.g_q, *R = bp.g_r, *T = bp.g_t;
       // The gradient P of the block output arrives ALREADY masked by the block's final ReLU (the dgrad epilogue or
       // avgpool_bwd that produced it applied the bit mask), so it is the BN3 / downsample-BN upstream gradient and the
@@ -770,11 +771,11 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       const bf16* residual = P;
       if (br.has_ds) {
         if (bp.ds_algebraic) {
-          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
+          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
           conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, N, s);
         } else {
           bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
-          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s));
+          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
           conv_backward(bp.ds, nullptr, nullptr, nullptr, s);  // R -> T
         }
         residual = T;
@@ -795,7 +796,7 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
     }
     if (stage == 3) {
       // ---- stem: max-pool backward, bn1 backward, weight gradient
-      ARGUS_CUDA(cudaMemsetAsync(gpacked_ + stem_.gpacked_off, 0, 64 * 256 * sizeof(float), s));
+      ARGUS_CUDA(cudaMemsetAsync(gpacked_ + stem_.gpacked_off, 0, 64 * 256 * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
       {
         // max-pool backward fused into the stem's BN(+ReLU) backward: p.g_act0 is never written
         const float* sc = bn_scratch_ + stem_.bn.scratch_off;

@@ -209,7 +209,7 @@ void Model::forward_fp32(const void* x, bool is_u8, int B, int H, int W, bool tr
   linear_fwd(st.z0, P + head_w_off_[0], P + head_b_off_[0], st.h1, st.a1, B, F, 128, s);
   linear_fwd(st.a1, P + head_w_off_[1], P + head_b_off_[1], st.h2, st.a2, B, 128, 128, s);
   linear_fwd(st.a2, P + head_w_off_[2], P + head_b_off_[2], st.out, nullptr, B, 128, 6, s);
-  ARGUS_CUDA(cudaMemcpyAsync(out, st.out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  ARGUS_CUDA(cudaMemcpyAsync(out, st.out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
   st.have_train_forward = training;
 }
 
@@ -236,7 +236,7 @@ void Model::backward_fp32(const float* d_out, int stage_begin, int stage_end, cu
   const int last_block[4] = {16, 13, 7, 3};
   for (int stage = stage_begin; stage < stage_end; ++stage) {
     if (stage == 0) {
-      ARGUS_CUDA(cudaMemcpyAsync(st.d_out, d_out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      ARGUS_CUDA(cudaMemcpyAsync(st.d_out, d_out, static_cast<size_t>(B) * 6 * sizeof(float), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
       linear_bwd(st.d_out, nullptr, st.a2, P + head_w_off_[2], g + head_w_off_[2], g + head_b_off_[2], st.d_a2, B, 128, 6, s);
       linear_bwd(st.d_a2, st.h2, st.a1, P + head_w_off_[1], g + head_w_off_[1], g + head_b_off_[1], st.d_a1, B, 128, 128, s);
       linear_bwd(st.d_a1, st.h1, st.z0, P + head_w_off_[0], g + head_w_off_[0], g + head_b_off_[0], st.d_z0, B, F, 128, s);

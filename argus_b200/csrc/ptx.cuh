@@ -28,6 +28,19 @@ __device__ __forceinline__ uint32_t elect_one() {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL). Every kernel of the library starts with pdl_prologue(): wait until the
+// previous kernel of the stream has completed and flushed (a no-op when the launch carries no programmatic edge),
+// then allow the NEXT kernel of the stream to be scheduled, so that its launch latency and CTA dispatch overlap this
+// kernel's execution instead of following its completion. "Wait, then trigger" keeps at most one successor parked.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#ifndef ARGUS_PDL_NO_TRIGGER
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
 // mbarrier
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {

@@ -34,7 +34,7 @@ struct Error : std::runtime_error {
                            cudaGetErrorString(_e));                                                     \
   } while (0)
 
-#define ARGUS_API_BEGIN try {
+#define ARGUS_API_BEGIN try { ::argus::pdl_break_all();
 #define ARGUS_API_END                          \
   return 0;                                    \
   }                                            \
@@ -70,6 +70,37 @@ struct ProfileScope {
   int slot = -1;
   cudaStream_t stream = nullptr;
 };
+
+// Kernel launch with a programmatic-stream-serialization edge to the previous kernel of the stream (PDL, see
+// pdl_prologue() in ptx.cuh). ARGUS_PDL=0 launches without the attribute (plain stream order).
+bool pdl_enabled();
+// Every C-ABI entry point starts with pdl_break_all(): the first kernel of a call is launched without a programmatic
+// edge (the caller may have enqueued anything in between). pdl_break() marks the event records / event waits / memsets /
+// memcpys the library itself enqueues; stream order already covers them, so by default they do not break the chain --
+// ARGUS_PDL_BREAK=<bit mask of PdlBreakKind> makes them do so (debugging aid).
+enum PdlBreakKind { kPdlAfterWait = 1, kPdlAfterRecord = 2, kPdlAfterMemop = 4 };
+void pdl_break(cudaStream_t stream, int kind);
+void pdl_break_all();
+bool pdl_chain_ok(cudaStream_t stream);     // true when the next kernel on `stream` may carry the attribute
+void pdl_mark_kernel(cudaStream_t stream);
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline void launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                          Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (pdl_enabled() && pdl_chain_ok(stream)) ? 1 : 0;
+  ARGUS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  pdl_mark_kernel(stream);
+}
+#endif
 
 inline int ilog2(int v) {
   int l = 0;

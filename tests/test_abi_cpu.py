@@ -37,3 +37,21 @@ def test_product_never_imports_the_oracle():
             assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
     for path in (ROOT / "argus_b200" / "csrc").glob("*"):
         assert "oracle/" not in path.read_text().replace("oracle/se3_loss.py", "").replace("oracle/augment.py", ""), path
+
+
+def test_every_kernel_waits_on_its_programmatic_dependency():
+    """Kernels are launched with a programmatic-dependent-launch edge (runtime.h::launch_kernel): a kernel that does not
+    start with pdl_prologue() (griddepcontrol.wait) would run before its producer has finished. Also: no raw <<<>>>
+    launch is left that would bypass the launch accounting."""
+    import re
+
+    for path in sorted((ROOT / "argus_b200" / "csrc").glob("*.cu*")):
+        text = re.sub(r"//[^\n]*", "", path.read_text())   # comments may contain parentheses / braces
+        assert "<<<" not in text, f"{path.name}: raw kernel launch"
+        for m in re.finditer(r"__global__", text):
+            brace = text.index("{", m.end())
+            semi = text.find(";", m.end())
+            if 0 <= semi < brace:
+                continue   # declaration only
+            body = text[brace + 1:brace + 200].lstrip()
+            assert body.startswith("pdl_prologue();"), f"{path.name}: kernel at offset {m.start()} lacks pdl_prologue()"

@@ -110,7 +110,17 @@ struct ConvGemmSmem {
 // wide, shallow-K layers whose tile time is set by the epilogue (TMEM -> math -> smem -> TMA store + statistics), which
 // is latency-bound per warp: a third group raises the epilogue throughput by half. The two TMEM accumulator stages are
 // shared: CTA-local tile t uses stage t % 2 and is finished by group t % EPI.
-template <int BLOCK_N, int B_MN, int EPI>
+// OPT = compile-time mask of the epilogue options a kernel instance can honour (kOptAll = the generic kernel). Options
+// outside the mask are compiled out, which removes their per-chunk flag tests (constant-bank loads + dependent branches)
+// and most of the instruction-cache footprint of the chunk loop. OPT = 0 ("plain": store the bf16 tile, optional
+// statistics) is every training-forward convolution and the conv2 / conv3 dgrads; kOptRes | kOptOutBits is the conv1
+// dgrad of a bottleneck (identity-branch gradient added, result masked by the previous block's ReLU bits).
+constexpr int kOptAffine = 1;    // scale / shift
+constexpr int kOptRes = 2;       // residual tile (+ its bit mask, + its own scale / shift)
+constexpr int kOptOutBits = 4;   // bit mask applied to the result
+constexpr int kOptRelu = 8;      // ReLU, ReLU bit-mask output
+constexpr int kOptAll = 15;
+template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   pdl_prologue();
@@ -348,6 +358,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     int buf = 0;
     int cur_n = -1;
     const bool do_stats = (p.stat_partial != nullptr);
+    // epilogue options, read once (compile-time off when outside OPT)
+    const bool has_res = (OPT & kOptRes) ? (p.has_res != 0) : false;
+    const float* const ep_scale = (OPT & kOptAffine) ? p.scale : nullptr;
+    const float* const ep_shift = (OPT & kOptAffine) ? p.shift : nullptr;
+    const float* const ep_res_scale = (OPT & kOptRes) ? p.res_scale : nullptr;
+    const float* const ep_res_shift = (OPT & kOptRes) ? p.res_shift : nullptr;
+    const uint8_t* const ep_res_bits = (OPT & kOptRes) ? p.res_bits : nullptr;
+    const uint8_t* const ep_out_bits = (OPT & kOptOutBits) ? p.out_bits : nullptr;
+    uint8_t* const ep_relu_bits_out = (OPT & kOptRelu) ? p.relu_bits_out : nullptr;
+    const bool ep_relu = (OPT & kOptRelu) ? (p.relu != 0) : false;
     float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(EPI * blockIdx.x + grp) * 2 * p.n_total : nullptr;
     constexpr int kChunks = BLOCK_N / 64;
 
@@ -379,7 +399,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
                   rem & ((1 << p.log2_wo) - 1), rem >> p.log2_wo, img0);
     };
     const int first_tile = blockIdx.x + grp * gridDim.x;
-    if (p.has_res && store_leader && first_tile < num_tiles) issue_residual(first_tile, 0, 0);
+    if (has_res && store_leader && first_tile < num_tiles) issue_residual(first_tile, 0, 0);
 
     int t_local = grp;
     uint32_t full_phase = 0;
@@ -405,7 +425,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       for (int ch = 0; ch < kChunks; ++ch) {
         uint8_t* stg = stg_base + buf * L::kStagingBytes;
         if (store_leader) {
-          if (p.has_res) {
+          if (has_res) {
             // the other buffer was handed to a TMA store one chunk ago: once that store has read it, refill it with
             // the residual tile of the next chunk (this buffer's residual is already in flight / landed)
             tma_store_wait_read<0>();
@@ -418,12 +438,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         }
         named_bar_sync(bar_id, 128);
         uint2 obits = make_uint2(0xffffffffu, 0xffffffffu);
-        if (p.out_bits != nullptr && m0 + r < p.m_total)
-          obits = __ldg(reinterpret_cast<const uint2*>(p.out_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
+        if (ep_out_bits != nullptr && m0 + r < p.m_total)
+          obits = __ldg(reinterpret_cast<const uint2*>(ep_out_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
                                                        ((n0 + ch * 64) >> 3)));
         uint2 rbits = make_uint2(0xffffffffu, 0xffffffffu);
-        if (p.res_bits != nullptr && m0 + r < p.m_total)
-          rbits = __ldg(reinterpret_cast<const uint2*>(p.res_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
+        if (ep_res_bits != nullptr && m0 + r < p.m_total)
+          rbits = __ldg(reinterpret_cast<const uint2*>(ep_res_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
                                                        ((n0 + ch * 64) >> 3)));
         uint32_t v[2][32];
 #pragma unroll
@@ -438,7 +458,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           __syncwarp();
           if (lane == 0) mbar_arrive(tempty_bar(acc));
         }
-        if (p.has_res) {
+        if (has_res) {
           mbar_wait(res_bar(grp, buf), res_phase[buf]);
           res_phase[buf] ^= 1;
         }
@@ -448,21 +468,21 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[h][i]);
-          if (p.scale != nullptr) {
+          if (ep_scale != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + c0 + i));
+              const float4 sc = __ldg(reinterpret_cast<const float4*>(ep_scale + c0 + i));
               f[i] *= sc.x; f[i + 1] *= sc.y; f[i + 2] *= sc.z; f[i + 3] *= sc.w;
             }
           }
-          if (p.shift != nullptr) {
+          if (ep_shift != nullptr) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + c0 + i));
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(ep_shift + c0 + i));
               f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
             }
           }
-          if (p.has_res) {
+          if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int phys = (h * 4 + q) ^ (r & 7);
@@ -477,11 +497,11 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               }
               float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
               float rr8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
-              if (p.res_scale != nullptr) {
-                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.res_scale + c0 + q * 8));
-                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.res_scale + c0 + q * 8 + 4));
-                const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.res_shift + c0 + q * 8));
-                const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.res_shift + c0 + q * 8 + 4));
+              if (ep_res_scale != nullptr) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(ep_res_scale + c0 + q * 8));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(ep_res_scale + c0 + q * 8 + 4));
+                const float4 t0 = __ldg(reinterpret_cast<const float4*>(ep_res_shift + c0 + q * 8));
+                const float4 t1 = __ldg(reinterpret_cast<const float4*>(ep_res_shift + c0 + q * 8 + 4));
                 rr8[0] = fmaf(rr8[0], s0.x, t0.x); rr8[1] = fmaf(rr8[1], s0.y, t0.y);
                 rr8[2] = fmaf(rr8[2], s0.z, t0.z); rr8[3] = fmaf(rr8[3], s0.w, t0.w);
                 rr8[4] = fmaf(rr8[4], s1.x, t1.x); rr8[5] = fmaf(rr8[5], s1.y, t1.y);
@@ -491,19 +511,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               for (int j = 0; j < 8; ++j) f[q * 8 + j] += rr8[j];
             }
           }
-          if (p.relu_bits_out != nullptr) {
+          if (ep_relu_bits_out != nullptr) {
             uint32_t ob = 0;
 #pragma unroll
             for (int i = 0; i < 32; ++i) ob |= (f[i] > 0.f ? 1u : 0u) << i;
             if (m0 + r < p.m_total)
-              *reinterpret_cast<uint32_t*>(p.relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
+              *reinterpret_cast<uint32_t*>(ep_relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
                                            ((n0 + ch * 64 + h * 32) >> 3)) = ob;
           }
-          if (p.relu) {
+          if (ep_relu) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
           }
-          if (p.out_bits != nullptr) {
+          if (ep_out_bits != nullptr) {
             const uint32_t ob = (h == 0 ? obits.x : obits.y);
 #pragma unroll
             for (int i = 0; i < 32; ++i) f[i] = ((ob >> i) & 1u) ? f[i] : 0.f;

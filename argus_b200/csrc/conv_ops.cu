@@ -574,12 +574,12 @@ WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g) {
 // ------------------------------------------------------------------------------------------------
 // launches
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BMN, int EPI>
+template <int BN, int BMN, int EPI, int OPT = kOptAll>
 static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
   using L = ConvGemmSmem<BN, EPI>;
   static bool configured = false;
   if (!configured) {
-    ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
+    ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN, EPI, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
     configured = true;
   }
   const int tiles = p.num_m_tiles * p.num_n_tiles;
@@ -610,7 +610,7 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
       q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
     }
   }
-  launch_kernel(conv_gemm_kernel<BN, BMN, EPI>, grid, 64 + 128 * EPI, L::kTotal, stream, q);
+  launch_kernel(conv_gemm_kernel<BN, BMN, EPI, OPT>, grid, 64 + 128 * EPI, L::kTotal, stream, q);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -661,6 +661,32 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     bytes += 2.0 * p.n_total * (p.num_taps * kc + p.k2_blocks * kBlockK);
   }
   ProfileScope prof(fam, stream, flops, bytes);
+  // specialised epilogues (two epilogue groups only; ARGUS_PLAIN_EPILOGUE=0 sends everything to the generic kernel)
+  static const bool special = [] { const char* e = getenv("ARGUS_PLAIN_EPILOGUE"); return !(e && e[0] == '0'); }();
+  int need = 0;
+  if (p.scale || p.shift) need |= kOptAffine;
+  if (p.has_res || p.res_bits || p.res_scale) need |= kOptRes;
+  if (p.out_bits) need |= kOptOutBits;
+  if (p.relu || p.relu_bits_out) need |= kOptRelu;
+  if (special && l.epi == 2 && need == 0) {
+    switch (l.block_n * 2 + l.b_mn) {
+      case 64 * 2 + 0: launch_conv_t<64, 0, 2, 0>(p, stream); return;
+      case 128 * 2 + 0: launch_conv_t<128, 0, 2, 0>(p, stream); return;
+      case 256 * 2 + 0: launch_conv_t<256, 0, 2, 0>(p, stream); return;
+      case 64 * 2 + 1: launch_conv_t<64, 1, 2, 0>(p, stream); return;
+      case 128 * 2 + 1: launch_conv_t<128, 1, 2, 0>(p, stream); return;
+      case 256 * 2 + 1: launch_conv_t<256, 1, 2, 0>(p, stream); return;
+      default: break;
+    }
+  }
+  if (special && l.epi == 2 && l.b_mn == 1 && (need & ~(kOptRes | kOptOutBits)) == 0) {
+    switch (l.block_n) {
+      case 64: launch_conv_t<64, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
+      case 128: launch_conv_t<128, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
+      case 256: launch_conv_t<256, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
+      default: break;
+    }
+  }
   const int key = (l.block_n * 2 + l.b_mn) * 4 + l.epi;
   switch (key) {
     case (64 * 2 + 0) * 4 + 2: launch_conv_t<64, 0, 2>(p, stream); break;

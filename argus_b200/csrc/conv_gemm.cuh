@@ -84,7 +84,13 @@ struct ConvGemmParams {
   float* stat_partial;
 };
 
-template <int BLOCK_N, int EPI = 2>
+// NBUF = staging buffers per epilogue group. Two let the store of chunk i overlap the math of chunk i + 1 (and carry the
+// prefetched residual tile); a BLOCK_N = 64 tile has a single chunk, so without a residual one buffer is enough (the
+// group's next chunk is a whole tile later) and the 32 KB go to the operand pipeline (a third halo stage on layer1 3x3).
+template <int BLOCK_N, int OPT>
+constexpr int conv_staging_buffers() { return (BLOCK_N == 64 && !(OPT & 2)) ? 1 : 2; }
+
+template <int BLOCK_N, int EPI = 2, int NBUF = 2>
 struct ConvGemmSmem {
   static constexpr int kABytes = kBlockM * kBlockK * 2;          // 16 KB
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
@@ -92,11 +98,11 @@ struct ConvGemmSmem {
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
   static constexpr int kStatsBytes = EPI * 4 * 2 * BLOCK_N * 4;  // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
   // operand pipeline region: everything the 227 KB of shared memory leave after staging, statistics and barriers
-  static constexpr int kPipeBytes = (232448 - 1024 - 2 * EPI * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
+  static constexpr int kPipeBytes = (232448 - 1024 - NBUF * EPI * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
   static constexpr int kStagesRaw = kPipeBytes / kStageBytes;
   static constexpr int kStages = kStagesRaw > 6 ? 6 : kStagesRaw;
-  static constexpr int kOffStaging = kPipeBytes;                 // 2 staging buffers per epilogue group
-  static constexpr int kOffStats = kOffStaging + 2 * EPI * kStagingBytes;
+  static constexpr int kOffStaging = kPipeBytes;                 // NBUF staging buffers per epilogue group
+  static constexpr int kOffStats = kOffStaging + NBUF * EPI * kStagingBytes;
   static constexpr int kOffBars = kOffStats + kStatsBytes;
   static constexpr int kMaxStages = 8;               // stage ring length in weights-resident mode (<= kMaxStages)
   // full/empty per stage, accumulator-full per epilogue GROUP, accumulator-empty per TMEM stage,
@@ -124,7 +130,9 @@ template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   pdl_prologue();
-  using L = ConvGemmSmem<BLOCK_N, EPI>;
+  constexpr int NBUF = conv_staging_buffers<BLOCK_N, OPT>();
+  static_assert(NBUF == 2 || !(OPT & kOptRes), "the residual prefetch needs two staging buffers");
+  using L = ConvGemmSmem<BLOCK_N, EPI, NBUF>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
   static_assert(BLOCK_N == 64 || BLOCK_N == 128 || BLOCK_N == 256, "BLOCK_N");
@@ -353,7 +361,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint32_t bar_id = 1 + grp;
     float* s_stats = s_stats_all + grp * 8 * BLOCK_N;          // [warp 0..3][sum | sqsum][BLOCK_N]
     float* s_mine = s_stats + (ew & 3) * 2 * BLOCK_N;          // this warp's private slot: no atomics, fixed order
-    uint8_t* stg_base = smem + L::kOffStaging + grp * 2 * L::kStagingBytes;
+    uint8_t* stg_base = smem + L::kOffStaging + grp * NBUF * L::kStagingBytes;
     uint32_t res_phase[2] = {0, 0};
     int buf = 0;
     int cur_n = -1;
@@ -433,7 +441,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int ntile = last_ch ? tile + EPI * gridDim.x : tile;
             if (ntile < num_tiles) issue_residual(ntile, last_ch ? 0 : ch + 1, buf ^ 1);
           } else {
-            tma_store_wait_read<1>();   // this buffer was handed to a TMA store two chunks ago
+            // this buffer was handed to a TMA store two chunks ago (one chunk = one tile ago with a single buffer)
+            if (NBUF == 2) tma_store_wait_read<1>();
+            else tma_store_wait_read<0>();
           }
         }
         named_bar_sync(bar_id, 128);
@@ -570,7 +580,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           s_mine[BLOCK_N + c] += q2.x;
           s_mine[BLOCK_N + c + 1] += q2.y;
         }
-        buf ^= 1;
+        if (NBUF == 2) buf ^= 1;
       }
     }
     if (do_stats && cur_n >= 0) flush_stats(cur_n);

@@ -576,7 +576,7 @@ WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g) {
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BMN, int EPI, int OPT = kOptAll>
 static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
-  using L = ConvGemmSmem<BN, EPI>;
+  using L = ConvGemmSmem<BN, EPI, conv_staging_buffers<BN, OPT>()>;
   static bool configured = false;
   if (!configured) {
     ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN, EPI, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -684,6 +684,15 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       case 64: launch_conv_t<64, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
       case 128: launch_conv_t<128, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
       case 256: launch_conv_t<256, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
+      default: break;
+    }
+  }
+  if (special && l.epi == 2 && l.b_mn == 1 && (need & ~(kOptAffine | kOptOutBits)) == 0) {
+    // K-concatenated dgrad of the algebraic BN backward: bias + output bits
+    switch (l.block_n) {
+      case 64: launch_conv_t<64, 1, 2, kOptAffine | kOptOutBits>(p, stream); return;
+      case 128: launch_conv_t<128, 1, 2, kOptAffine | kOptOutBits>(p, stream); return;
+      case 256: launch_conv_t<256, 1, 2, kOptAffine | kOptOutBits>(p, stream); return;
       default: break;
     }
   }

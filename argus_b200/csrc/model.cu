@@ -209,6 +209,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
                           cudaMemcpyHostToDevice));
     ARGUS_CUDA(cudaMemset(gpacked_, 0, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
     ARGUS_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    if (const char* e = getenv("ARGUS_WGRAD_OVERLAP")) overlap_wgrad_ = (e[0] != '0');   // A/B switch, default on
     ARGUS_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
     ARGUS_CUDA(cudaEventCreateWithFlags(&ev_wgrad_, cudaEventDisableTiming));
   }

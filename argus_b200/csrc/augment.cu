@@ -284,7 +284,8 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
   __shared__ int sIy0[6], sIx0[6];
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
-  if (threadIdx.x < kAugParams) sP[threadIdx.x] = params[static_cast<size_t>(n) * kAugParams + threadIdx.x];
+  // (apply == 0 is plain u8 -> bf16 staging: the parameter table may be NULL and is never read)
+  if (threadIdx.x < kAugParams) sP[threadIdx.x] = apply ? params[static_cast<size_t>(n) * kAugParams + threadIdx.x] : 0.f;
   __syncthreads();
   const float sigma = apply ? sP[7] : 0.f;
   // plasma lattice window of this tile (a 32-pixel tile spans at most 16 cells of the finest octave when the image

@@ -152,3 +152,33 @@ def test_prefetch_is_bitwise_equivalent(cuda_device):
     eng.step(*batches[0])
     eng.prefetch(batches[2][0])
     assert torch.isfinite(eng.step(*batches[1])).all()
+
+
+def test_prefetch_without_augmentation(cuda_device):
+    """uint8 batches with no augmentation configured: prefetch() stages through the same kernel with apply = 0 and a NULL
+    parameter table (regression: the kernel used to read the table unconditionally), bit-identical to the direct path."""
+    from argus_b200.engine import TrainEngine
+    from argus_b200.models import NCameraCNN
+    from gpu_util import random_targets
+
+    g = torch.Generator().manual_seed(4)
+    batches = [(torch.randint(0, 256, (4, 2, 64, 64, 3), dtype=torch.uint8, generator=g).to("cuda"),
+                random_targets(4, 20 + i, "cuda")) for i in range(2)]
+
+    def run(prefetch):
+        torch.manual_seed(0)
+        model = NCameraCNN().to("cuda")
+        eng = TrainEngine(model, lr=1e-3, distributed=False, augmentation=None)
+        losses = []
+        for i in range(4):
+            losses.append(eng.step(*batches[i % 2]).clone())
+            if prefetch and i + 1 < 4:
+                eng.prefetch(batches[(i + 1) % 2][0])
+        torch.cuda.synchronize()
+        return torch.stack(losses), model.flat_params.clone()
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert torch.isfinite(l0).all()
+    assert torch.equal(l0, l1), (l0, l1)
+    assert torch.equal(p0, p1)

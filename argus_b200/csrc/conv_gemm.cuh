@@ -87,8 +87,9 @@ struct ConvGemmParams {
 // NBUF = staging buffers per epilogue group. Two let the store of chunk i overlap the math of chunk i + 1 (and carry the
 // prefetched residual tile); a BLOCK_N = 64 tile has a single chunk, so without a residual one buffer is enough (the
 // group's next chunk is a whole tile later) and the 32 KB go to the operand pipeline (a third halo stage on layer1 3x3).
-template <int BLOCK_N, int OPT>
-constexpr int conv_staging_buffers() { return (BLOCK_N == 64 && !(OPT & 2)) ? 1 : 2; }
+// EPI = 4 is the split-tile mode (see conv_gemm_kernel): two groups share one 256-wide tile, each owns one buffer.
+template <int BLOCK_N, int OPT, int EPI = 2>
+constexpr int conv_staging_buffers() { return (EPI == 4 || (BLOCK_N == 64 && !(OPT & 2))) ? 1 : 2; }
 
 template <int BLOCK_N, int EPI = 2, int NBUF = 2>
 struct ConvGemmSmem {
@@ -96,7 +97,8 @@ struct ConvGemmSmem {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;          // 8..32 KB
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStagingBytes = kBlockM * 128;            // one 64-column bf16 chunk of the tile
-  static constexpr int kStatsBytes = EPI * 4 * 2 * BLOCK_N * 4;  // per group, per warp: sum[BLOCK_N], sqsum[BLOCK_N]
+  static constexpr int kGroupCols = (EPI == 4) ? BLOCK_N / 2 : BLOCK_N;   // columns of a tile one epilogue group finishes
+  static constexpr int kStatsBytes = EPI * 4 * 2 * kGroupCols * 4;  // per group, per warp: sum[cols], sqsum[cols]
   // operand pipeline region: everything the 227 KB of shared memory leave after staging, statistics and barriers
   static constexpr int kPipeBytes = (232448 - 1024 - NBUF * EPI * kStagingBytes - kStatsBytes - 512) / 1024 * 1024;
   static constexpr int kStagesRaw = kPipeBytes / kStageBytes;
@@ -130,8 +132,15 @@ template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   pdl_prologue();
-  constexpr int NBUF = conv_staging_buffers<BLOCK_N, OPT>();
+  constexpr int NBUF = conv_staging_buffers<BLOCK_N, OPT, EPI>();
   static_assert(NBUF == 2 || !(OPT & kOptRes), "the residual prefetch needs two staging buffers");
+  // Split-tile mode (EPI == 4, BLOCK_N == 256): the two TMEM accumulator stages bound the tiles in flight, so instead of
+  // a third tile the four groups work in PAIRS on one tile -- groups 2t and 2t+1 finish the left / right 128 columns of
+  // the tile in accumulator stage t. Sixteen epilogue warps instead of eight on the layers whose tile time is set by the
+  // epilogue (wide, shallow-K, HBM-bound). One staging buffer per group (same 64 KB as two groups x two buffers).
+  constexpr bool SPLIT = (EPI == 4);
+  constexpr int kTileGroups = SPLIT ? 2 : EPI;   // tile epilogues in flight
+  static_assert(!SPLIT || (BLOCK_N == 256 && !(OPT & kOptRes)), "split-tile mode: 256-wide tiles without residual");
   using L = ConvGemmSmem<BLOCK_N, EPI, NBUF>;
   constexpr int kStages = L::kStages;
   constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
@@ -172,7 +181,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       mbar_init(empty_bar(s), 1);
     }
     mbar_init(bres_bar, 1);
-    for (int s = 0; s < 2; ++s) mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp of the finishing group
+    for (int s = 0; s < 2; ++s) mbar_init(tempty_bar(s), SPLIT ? 8 : 4);  // one arrive per epilogue warp finishing the tile
     for (int g = 0; g < EPI; ++g) {
       mbar_init(tfull_bar(g), 1);
       mbar_init(res_bar(g, 0), 1);
@@ -191,7 +200,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     tmem_alloc(smem_u32(const_cast<uint32_t*>(tmem_ptr_smem)), kTmemCols);
     tmem_relinquish();
   }
-  for (int i = threadIdx.x; i < EPI * 8 * BLOCK_N; i += blockDim.x) s_stats_all[i] = 0.f;
+  for (int i = threadIdx.x; i < EPI * 8 * L::kGroupCols; i += blockDim.x) s_stats_all[i] = 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -324,7 +333,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             if (++stage == nstages) { stage = 0; phase ^= 1; }
           }
           if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-          if (++tgrp == EPI) tgrp = 0;
+          if (++tgrp == kTileGroups) tgrp = 0;
           continue;
         }
         for (int kb = 0; kb < num_kblocks; ++kb) {
@@ -344,23 +353,26 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-        if (++tgrp == EPI) tgrp = 0;
+        if (++tgrp == kTileGroups) tgrp = 0;
       }
     }
   } else {
     // ===================== epilogue (warps 2..: EPI groups of four warps) =====================
-    // Group g finishes the CTA-local tiles t = g, g + EPI, ... (accumulator stage t % 2), so EPI tile epilogues
-    // overlap each other and the main loop. Each group has its own staging buffers, statistics scratch, named
-    // barrier and TMA store queue.
+    // Tile group tg finishes the CTA-local tiles t = tg, tg + kTileGroups, ... (accumulator stage t % 2), so that many
+    // tile epilogues overlap each other and the main loop. Each group of four warps has its own staging buffer(s),
+    // statistics scratch, named barrier and TMA store queue; in split-tile mode two groups share a tile group.
     const int ew = warp - 2;
     const int grp = ew >> 2;
+    const int tg = SPLIT ? (grp >> 1) : grp;
+    constexpr int GW = L::kGroupCols;                 // columns of the tile this group finishes
+    const int col_base = SPLIT ? (grp & 1) * GW : 0;  // first of them
     const int wq = warp & 3;              // TMEM lane quarter this warp may access
     const int r = wq * 32 + lane;         // row of the tile owned by this thread
     const int et = (ew & 3) * 32 + lane;  // 0..127 inside the group
     const bool store_leader = (et == 0);
     const uint32_t bar_id = 1 + grp;
-    float* s_stats = s_stats_all + grp * 8 * BLOCK_N;          // [warp 0..3][sum | sqsum][BLOCK_N]
-    float* s_mine = s_stats + (ew & 3) * 2 * BLOCK_N;          // this warp's private slot: no atomics, fixed order
+    float* s_stats = s_stats_all + grp * 8 * GW;               // [warp 0..3][sum | sqsum][GW]
+    float* s_mine = s_stats + (ew & 3) * 2 * GW;               // this warp's private slot: no atomics, fixed order
     uint8_t* stg_base = smem + L::kOffStaging + grp * NBUF * L::kStagingBytes;
     uint32_t res_phase[2] = {0, 0};
     int buf = 0;
@@ -377,18 +389,18 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     uint8_t* const ep_relu_bits_out = (OPT & kOptRelu) ? p.relu_bits_out : nullptr;
     const bool ep_relu = (OPT & kOptRelu) ? (p.relu != 0) : false;
     float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(EPI * blockIdx.x + grp) * 2 * p.n_total : nullptr;
-    constexpr int kChunks = BLOCK_N / 64;
+    constexpr int kChunks = GW / 64;
 
     auto flush_stats = [&](int n_tile) {
       named_bar_sync(bar_id, 128);
-      for (int c = et; c < 2 * BLOCK_N; c += 128) {
-        const int which = c / BLOCK_N, col = c - which * BLOCK_N;
-        const int gc = n_tile * BLOCK_N + col;
+      for (int c = et; c < 2 * GW; c += 128) {
+        const int which = c / GW, col = c - which * GW;
+        const int gc = n_tile * BLOCK_N + col_base + col;
         float acc_s = 0.f;
 #pragma unroll
         for (int w = 0; w < 4; ++w) {
-          acc_s += s_stats[w * 2 * BLOCK_N + c];
-          s_stats[w * 2 * BLOCK_N + c] = 0.f;
+          acc_s += s_stats[w * 2 * GW + c];
+          s_stats[w * 2 * GW + c] = 0.f;
         }
         if (gc < p.n_total) my_partial[which * p.n_total + gc] += acc_s;   // only this thread ever touches this word
       }
@@ -406,12 +418,12 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       tma_load_4d(&p.res_map, res_bar(grp, b), smem_u32(stg_base + b * L::kStagingBytes), n_tile * BLOCK_N + ch * 64,
                   rem & ((1 << p.log2_wo) - 1), rem >> p.log2_wo, img0);
     };
-    const int first_tile = blockIdx.x + grp * gridDim.x;
+    const int first_tile = blockIdx.x + tg * gridDim.x;
     if (has_res && store_leader && first_tile < num_tiles) issue_residual(first_tile, 0, 0);
 
-    int t_local = grp;
+    int t_local = tg;
     uint32_t full_phase = 0;
-    for (int tile = first_tile; tile < num_tiles; tile += EPI * gridDim.x, t_local += EPI, full_phase ^= 1) {
+    for (int tile = first_tile; tile < num_tiles; tile += kTileGroups * gridDim.x, t_local += kTileGroups, full_phase ^= 1) {
       const int acc = t_local & 1;   // TMEM accumulator stage of this tile
       const int m_tile = tile / p.num_n_tiles;
       const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -420,25 +432,33 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
       const int rem = m0 & ((1 << p.log2_howo) - 1);
       const int h0 = rem >> p.log2_wo;
       const int w0 = rem & ((1 << p.log2_wo) - 1);
-      const int n0 = n_tile * BLOCK_N;
+      const int n0 = n_tile * BLOCK_N + col_base;   // first output channel this group stores
       if (do_stats && n_tile != cur_n) {
         if (cur_n >= 0) flush_stats(cur_n);
         cur_n = n_tile;
       }
 
-      mbar_wait(tfull_bar(grp), full_phase);
+      mbar_wait(tfull_bar(tg), full_phase);
       tc_fence_after();
 
 #pragma unroll 1
       for (int ch = 0; ch < kChunks; ++ch) {
         uint8_t* stg = stg_base + buf * L::kStagingBytes;
+        // TMEM loads first: they do not touch shared memory, so their latency overlaps the hand-back of the staging
+        // buffer (which, with a single buffer per group, waits for the previous chunk's TMA store to have read it)
+        uint32_t v[2][32];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + col_base + ch * 64 + h * 32;
+          tmem_ld_32x32(taddr, v[h]);
+        }
         if (store_leader) {
           if (has_res) {
             // the other buffer was handed to a TMA store one chunk ago: once that store has read it, refill it with
             // the residual tile of the next chunk (this buffer's residual is already in flight / landed)
             tma_store_wait_read<0>();
             const bool last_ch = (ch == kChunks - 1);
-            const int ntile = last_ch ? tile + EPI * gridDim.x : tile;
+            const int ntile = last_ch ? tile + kTileGroups * gridDim.x : tile;
             if (ntile < num_tiles) issue_residual(ntile, last_ch ? 0 : ch + 1, buf ^ 1);
           } else {
             // this buffer was handed to a TMA store two chunks ago (one chunk = one tile ago with a single buffer)
@@ -455,12 +475,6 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         if (ep_res_bits != nullptr && m0 + r < p.m_total)
           rbits = __ldg(reinterpret_cast<const uint2*>(ep_res_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
                                                        ((n0 + ch * 64) >> 3)));
-        uint32_t v[2][32];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + ch * 64 + h * 32;
-          tmem_ld_32x32(taddr, v[h]);
-        }
         tmem_ld_wait();
         if (ch == kChunks - 1) {
           // all TMEM reads of this accumulator are done: hand it back to the MMA warp
@@ -577,8 +591,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const int c = ch * 64 + lane * 2;
           s_mine[c] += s2.x;
           s_mine[c + 1] += s2.y;
-          s_mine[BLOCK_N + c] += q2.x;
-          s_mine[BLOCK_N + c + 1] += q2.y;
+          s_mine[GW + c] += q2.x;
+          s_mine[GW + c + 1] += q2.y;
         }
         if (NBUF == 2) buf ^= 1;
       }

@@ -576,7 +576,7 @@ WgradLaunch plan_gram(const ConvShape& s, const __nv_bfloat16* x, float* g) {
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BMN, int EPI, int OPT = kOptAll>
 static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
-  using L = ConvGemmSmem<BN, EPI, conv_staging_buffers<BN, OPT>()>;
+  using L = ConvGemmSmem<BN, EPI, conv_staging_buffers<BN, OPT, EPI>()>;
   static bool configured = false;
   if (!configured) {
     ARGUS_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<BN, BMN, EPI, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal));
@@ -614,15 +614,20 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
   ARGUS_CUDA(cudaGetLastError());
 }
 
-// Number of epilogue groups for a launch. Default 2. ARGUS_EPI=3 runs every non-halo launch with three groups (an
-// experiment kept reachable): measured, a third group does NOT help (44.6 -> 45.8 ms/step; 44.7 when restricted to the
-// wide shallow-K layers) because only two TMEM accumulator stages exist at N = 256, so at most two tile epilogues are
-// in flight; what bounds those layers is the time one tile holds its accumulator stage, not the number of warps.
+// Number of epilogue groups for a launch. Default 2. Two experiments stay reachable:
+//  * ARGUS_EPI=3: three groups on every non-halo launch. Measured: no help (44.6 -> 45.8 ms/step) -- only two TMEM
+//    accumulator stages exist at N = 256, so at most two tile epilogues are in flight.
+//  * ARGUS_EPI=4: split-tile mode, four groups working in pairs on one 256-wide tile (sixteen epilogue warps). Measured:
+//    no help either (wide 1x1 forward 253 us with two or four groups) -- those launches write four bytes for every byte
+//    they read and sit at the HBM *write* bandwidth (~5.0 TB/s; the copy figure of 6.46 TB/s is a 1:1 read/write mix),
+//    not at the epilogue's instruction rate.
 int choose_epilogue_groups(const ConvGemmParams& p, int block_n) {
   static const int forced = [] { const char* e = getenv("ARGUS_EPI"); return e ? atoi(e) : 0; }();
-  (void)block_n;
   if (p.halo) return 2;
-  return forced == 3 ? 3 : 2;
+  if (forced == 3) return 3;
+  // split-tile mode (the launch falls back to two groups when its epilogue carries a residual)
+  if (block_n == 256 && forced == 4) return 4;
+  return 2;
 }
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
@@ -668,7 +673,21 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   if (p.has_res || p.res_bits || p.res_scale) need |= kOptRes;
   if (p.out_bits) need |= kOptOutBits;
   if (p.relu || p.relu_bits_out) need |= kOptRelu;
-  if (special && l.epi == 2 && need == 0) {
+  if (l.epi == 4) {
+    // split-tile kernels exist for the residual-free epilogues; everything else runs the two-group kernels below
+    // (the statistics slots are sized for four groups, the unused ones stay zero)
+    if (need == 0) {
+      if (l.b_mn) launch_conv_t<256, 1, 4, 0>(p, stream);
+      else launch_conv_t<256, 0, 4, 0>(p, stream);
+      return;
+    }
+    if (l.b_mn == 1 && (need & ~(kOptAffine | kOptOutBits)) == 0) {
+      launch_conv_t<256, 1, 4, kOptAffine | kOptOutBits>(p, stream);
+      return;
+    }
+  }
+  const int epi2 = (l.epi == 4) ? 2 : l.epi;
+  if (special && epi2 == 2 && need == 0) {
     switch (l.block_n * 2 + l.b_mn) {
       case 64 * 2 + 0: launch_conv_t<64, 0, 2, 0>(p, stream); return;
       case 128 * 2 + 0: launch_conv_t<128, 0, 2, 0>(p, stream); return;
@@ -679,7 +698,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       default: break;
     }
   }
-  if (special && l.epi == 2 && l.b_mn == 1 && (need & ~(kOptRes | kOptOutBits)) == 0) {
+  if (special && epi2 == 2 && l.b_mn == 1 && (need & ~(kOptRes | kOptOutBits)) == 0) {
     switch (l.block_n) {
       case 64: launch_conv_t<64, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
       case 128: launch_conv_t<128, 1, 2, kOptRes | kOptOutBits>(p, stream); return;
@@ -687,7 +706,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       default: break;
     }
   }
-  if (special && l.epi == 2 && l.b_mn == 1 && (need & ~(kOptAffine | kOptOutBits)) == 0) {
+  if (special && epi2 == 2 && l.b_mn == 1 && (need & ~(kOptAffine | kOptOutBits)) == 0) {
     // K-concatenated dgrad of the algebraic BN backward: bias + output bits
     switch (l.block_n) {
       case 64: launch_conv_t<64, 1, 2, kOptAffine | kOptOutBits>(p, stream); return;
@@ -696,7 +715,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       default: break;
     }
   }
-  const int key = (l.block_n * 2 + l.b_mn) * 4 + l.epi;
+  const int key = (l.block_n * 2 + l.b_mn) * 4 + epi2;
   switch (key) {
     case (64 * 2 + 0) * 4 + 2: launch_conv_t<64, 0, 2>(p, stream); break;
     case (128 * 2 + 0) * 4 + 2: launch_conv_t<128, 0, 2>(p, stream); break;

@@ -175,7 +175,7 @@ void Model::bind(float* params, float* grads, float* buffers) {
     ARGUS_CUDA(cudaMalloc(&packed_, n_packed_ * sizeof(bf16)));
     ARGUS_CUDA(cudaMalloc(&gpacked_, std::max<int64_t>(n_gpacked_, 1) * sizeof(float)));
     ARGUS_CUDA(cudaMalloc(&bn_scratch_, n_bn_scratch_ * sizeof(float)));
-    max_stat_slots_ = 3 * num_sms();   // up to three epilogue groups per CTA
+    max_stat_slots_ = 4 * num_sms();   // up to four epilogue groups per CTA
     ARGUS_CUDA(cudaMalloc(&bn_stats_, n_bn_stats_ * 2 * max_stat_slots_ * sizeof(float)));
     ARGUS_CUDA(cudaMalloc(&bn_bwd_scratch_, bn_bwd_scratch_elems() * sizeof(float)));
     {

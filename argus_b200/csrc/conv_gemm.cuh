@@ -124,10 +124,11 @@ struct ConvGemmSmem {
 // statistics) is every training-forward convolution and the conv2 / conv3 dgrads; kOptRes | kOptOutBits is the conv1
 // dgrad of a bottleneck (identity-branch gradient added, result masked by the previous block's ReLU bits).
 constexpr int kOptAffine = 1;    // scale / shift
-constexpr int kOptRes = 2;       // residual tile (+ its bit mask, + its own scale / shift)
+constexpr int kOptRes = 2;       // residual tile
 constexpr int kOptOutBits = 4;   // bit mask applied to the result
 constexpr int kOptRelu = 8;      // ReLU, ReLU bit-mask output
-constexpr int kOptAll = 15;
+constexpr int kOptResExtra = 16; // bit mask on the residual, residual scale / shift (needs kOptRes)
+constexpr int kOptAll = 31;
 template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -382,9 +383,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const bool has_res = (OPT & kOptRes) ? (p.has_res != 0) : false;
     const float* const ep_scale = (OPT & kOptAffine) ? p.scale : nullptr;
     const float* const ep_shift = (OPT & kOptAffine) ? p.shift : nullptr;
-    const float* const ep_res_scale = (OPT & kOptRes) ? p.res_scale : nullptr;
-    const float* const ep_res_shift = (OPT & kOptRes) ? p.res_shift : nullptr;
-    const uint8_t* const ep_res_bits = (OPT & kOptRes) ? p.res_bits : nullptr;
+    const float* const ep_res_scale = (OPT & kOptResExtra) ? p.res_scale : nullptr;
+    const float* const ep_res_shift = (OPT & kOptResExtra) ? p.res_shift : nullptr;
+    const uint8_t* const ep_res_bits = (OPT & kOptResExtra) ? p.res_bits : nullptr;
     const uint8_t* const ep_out_bits = (OPT & kOptOutBits) ? p.out_bits : nullptr;
     uint8_t* const ep_relu_bits_out = (OPT & kOptRelu) ? p.relu_bits_out : nullptr;
     const bool ep_relu = (OPT & kOptRelu) ? (p.relu != 0) : false;
@@ -511,8 +512,8 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int q = 0; q < 4; ++q) {
               const int phys = (h * 4 + q) ^ (r & 7);
               uint4 rv = *reinterpret_cast<const uint4*>(stg + r * 128 + phys * 16);
-              {
-                // ReLU bit mask of these eight channels (all ones without a mask): spread each bit over a bf16 lane
+              if (ep_res_bits != nullptr) {
+                // ReLU bit mask of these eight channels: spread each bit over a bf16 lane
                 const uint32_t mb = ((h == 0 ? rbits.x : rbits.y) >> (8 * q)) & 0xffu;
                 rv.x &= ((mb & 1u) ? 0x0000ffffu : 0u) | ((mb & 2u) ? 0xffff0000u : 0u);
                 rv.y &= ((mb & 4u) ? 0x0000ffffu : 0u) | ((mb & 8u) ? 0xffff0000u : 0u);

@@ -670,7 +670,8 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   static const bool special = [] { const char* e = getenv("ARGUS_PLAIN_EPILOGUE"); return !(e && e[0] == '0'); }();
   int need = 0;
   if (p.scale || p.shift) need |= kOptAffine;
-  if (p.has_res || p.res_bits || p.res_scale) need |= kOptRes;
+  if (p.has_res) need |= kOptRes;
+  if (p.res_bits || p.res_scale) need |= kOptRes | kOptResExtra;
   if (p.out_bits) need |= kOptOutBits;
   if (p.relu || p.relu_bits_out) need |= kOptRelu;
   if (l.epi == 4) {

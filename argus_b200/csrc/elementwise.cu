@@ -170,23 +170,64 @@ __device__ __forceinline__ int64_t packed_to_torch(const WeightPackEntry& e, int
   return (static_cast<int64_t>(co) * e.cin + ci) * e.kk + t;
 }
 
-__global__ void pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ packed,
-                                    const WeightPackEntry* __restrict__ table) {
+// k x k entries are transposed one output channel at a time through shared memory ([ci][t] <-> [t][ci] inside the
+// contiguous cin * kk block of that channel), so both the global reads and the global writes are coalesced; 1x1 / linear
+// entries are already in the packed order; the stem (kind 1) keeps the per-element index map (it is 16 K elements).
+constexpr int kPackTileMax = 512 * 9 + 9;   // largest cin * kk block (+ padding for the unpack direction)
+__global__ void __launch_bounds__(256)
+pack_weights_kernel(const float* __restrict__ params, bf16* __restrict__ packed,
+                    const WeightPackEntry* __restrict__ table) {
   pdl_prologue();
+  __shared__ float tile[kPackTileMax];
   const WeightPackEntry e = table[blockIdx.y];
   const int64_t n = packed_count(e);
+  if (e.kind == 0 && e.kk > 1 && e.cin * e.kk <= kPackTileMax) {
+    const int row = e.cin * e.kk;
+    for (int co = blockIdx.x; co < e.cout; co += gridDim.x) {
+      const float* src = params + e.src_off + static_cast<int64_t>(co) * row;
+      for (int j = threadIdx.x; j < row; j += blockDim.x) tile[j] = src[j];   // [ci][t]
+      __syncthreads();
+      bf16* dst = packed + e.dst_off + static_cast<int64_t>(co) * row;
+      for (int j = threadIdx.x; j < row; j += blockDim.x) {                   // j = t * cin + ci
+        const int t = j / e.cin, ci = j - t * e.cin;
+        dst[j] = __float2bfloat16(tile[ci * e.kk + t]);
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t src = packed_to_torch(e, i);
     packed[e.dst_off + i] = __float2bfloat16(src >= 0 ? params[e.src_off + src] : 0.f);
   }
 }
-__global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, float* __restrict__ grads,
-                                     const WeightPackEntry* __restrict__ table) {
+__global__ void __launch_bounds__(256)
+unpack_wgrads_kernel(const float* __restrict__ packed_grads, float* __restrict__ grads,
+                     const WeightPackEntry* __restrict__ table) {
   pdl_prologue();
+  __shared__ float tile[kPackTileMax];
   const WeightPackEntry e = table[blockIdx.y];
   if (e.kind == 0 && e.kk == 1) return;  // 1x1 / linear layers accumulate straight into the gradient arena
   const int64_t n = packed_count(e);
+  if (e.kind == 0 && (e.cin + 1) * e.kk <= kPackTileMax) {
+    const int row = e.cin * e.kk, pitch = e.cin + 1;   // padded rows: the transposed reads spread over the banks
+    for (int co = blockIdx.x; co < e.cout; co += gridDim.x) {
+      const float* src = packed_grads + e.dst_off + static_cast<int64_t>(co) * row;
+      for (int j = threadIdx.x; j < row; j += blockDim.x) {                   // j = t * cin + ci
+        const int t = j / e.cin, ci = j - t * e.cin;
+        tile[t * pitch + ci] = src[j];
+      }
+      __syncthreads();
+      float* dst = grads + e.src_off + static_cast<int64_t>(co) * row;
+      for (int j = threadIdx.x; j < row; j += blockDim.x) {                   // j = ci * kk + t
+        const int ci = j / e.kk, t = j - ci * e.kk;
+        dst[j] += tile[t * pitch + ci];
+      }
+      __syncthreads();
+    }
+    return;
+  }
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int64_t dst = packed_to_torch(e, i);
@@ -196,13 +237,13 @@ __global__ void unpack_wgrads_kernel(const float* __restrict__ packed_grads, flo
 void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries,
                   cudaStream_t s) {
   ProfileScope prof("pack_weights", s, 0, 0);
-  launch_kernel(pack_weights_kernel, dim3(32, n_entries), 256, 0, s, params, packed, table_dev);
+  launch_kernel(pack_weights_kernel, dim3(64, n_entries), 256, 0, s, params, packed, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
                    cudaStream_t s) {
   ProfileScope prof("unpack_wgrads", s, 0, 0);
-  launch_kernel(unpack_wgrads_kernel, dim3(32, n_entries), 256, 0, s, packed_grads, grads, table_dev);
+  launch_kernel(unpack_wgrads_kernel, dim3(64, n_entries), 256, 0, s, packed_grads, grads, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -1131,6 +1172,22 @@ void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, 
 // ------------------------------------------------------------------------------------------------------------
 // pooling
 // ------------------------------------------------------------------------------------------------------------
+// Packed formulation: relu(x * sc + sh) is monotone in x (increasing for sc > 0, decreasing for sc < 0), so the window
+// maximum of the activated values is the activation of the window maximum of sign(sc) * x. The nine taps are compared
+// as raw bf16 pairs (sign flip = one XOR per pair, compare mask + max + index select: four packed instructions per tap and
+// channel pair instead of seven scalar ones per channel), and the batch norm + ReLU are applied once per output. The
+// arg-max differs from "first maximum of the activated values" only where the whole window is <= 0 after the ReLU,
+// and there the gradient is zero anyway (the ReLU mask of the backward pass removes it).
+__device__ __forceinline__ uint32_t bf16x2_gt_mask(uint32_t a, uint32_t b) {   // 0xffff per lane where a > b
+  uint32_t m;
+  asm("set.gt.u32.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+  return m;
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  uint32_t m;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
+  return m;
+}
 __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
                                    const float* __restrict__ shift, uint4* __restrict__ y, uint2* __restrict__ idx,
                                    int N, int H, int W, int cvec) {
@@ -1146,14 +1203,20 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
     const int ph = static_cast<int>(t % Ho);
     const int n = static_cast<int>(t / Ho);
     F8 sc, sh;
+    uint32_t flip[4] = {0u, 0u, 0u, 0u};
     if (scale != nullptr) {
       sc = load8f(scale + cv * 8);
       sh = load8f(shift + cv * 8);
-    }
-    float best[8];
-    int bi[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bi[k] = 0; }
+      for (int j = 0; j < 4; ++j)
+        flip[j] = (sc.v[2 * j] < 0.f ? 0x00008000u : 0u) | (sc.v[2 * j + 1] < 0.f ? 0x80000000u : 0u);
+    }
+    uint32_t best[4], bi[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { best[j] = 0xff80ff80u; bi[j] = 0u; }   // -inf, tap 0
+    // window origin (tap 0, possibly out of bounds) once; the taps are 32-bit offsets from it
+    const uint4* x0 = x + ((static_cast<int64_t>(n) * H + (2 * ph - 1)) * W + (2 * pw - 1)) * cvec + cv;
+    const int row_pitch = W * cvec;
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int h = 2 * ph - 1 + kh;
@@ -1162,24 +1225,27 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
       for (int kw = 0; kw < 3; ++kw) {
         const int w = 2 * pw - 1 + kw;
         if (w < 0 || w >= W) continue;
-        F8 v = unpack8(__ldg(x + ((static_cast<int64_t>(n) * H + h) * W + w) * cvec + cv));
-        if (scale != nullptr) {
+        const uint4 u = __ldg(x0 + (kh * row_pitch + kw * cvec));
+        const uint32_t wv[4] = {u.x ^ flip[0], u.y ^ flip[1], u.z ^ flip[2], u.w ^ flip[3]};
+        const uint32_t code = static_cast<uint32_t>(kh * 3 + kw) * 0x00010001u;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) v.v[k] = fmaxf(fmaf(v.v[k], sc.v[k], sh.v[k]), 0.f);
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t m = bf16x2_gt_mask(wv[j], best[j]);   // strict: the first maximum keeps its index
+          best[j] = bf16x2_max(wv[j], best[j]);
+          bi[j] = (bi[j] & ~m) | (code & m);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (v.v[k] > best[k]) { best[k] = v.v[k]; bi[k] = kh * 3 + kw; }
       }
     }
-    F8 o;
+    F8 o = unpack8(make_uint4(best[0] ^ flip[0], best[1] ^ flip[1], best[2] ^ flip[2], best[3] ^ flip[3]));
+    if (scale != nullptr) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) o.v[k] = best[k];
+      for (int k = 0; k < 8; ++k) o.v[k] = fmaxf(fmaf(o.v[k], sc.v[k], sh.v[k]), 0.f);
+    }
     y[i] = pack8(o);
     if (idx != nullptr) {
       uint2 p;
-      p.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | (bi[3] << 24);
-      p.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | (bi[7] << 24);
+      p.x = (bi[0] & 0xffu) | ((bi[0] >> 8) & 0xff00u) | ((bi[1] & 0xffu) << 16) | ((bi[1] >> 16) << 24);
+      p.y = (bi[2] & 0xffu) | ((bi[2] >> 8) & 0xff00u) | ((bi[3] & 0xffu) << 16) | ((bi[3] >> 16) << 24);
       idx[i] = p;
     }
   }

@@ -204,10 +204,14 @@ def test_maxpool(cuda_device, N, H, W, C):
     dx = torch.empty(N, H, W, C, device=cuda_device, dtype=torch.bfloat16)
     _lib.call("argus_maxpool_backward", dy, idx, dx, N, H, W, C, _lib.stream_ptr())
     ref.backward(dy.float().permute(0, 3, 1, 2))
-    # ties among equal maxima may route the gradient to a different (equally valid) tap only where values tie
+    # Ties among equal maxima may route the gradient to a different (equally valid) tap. The kernel takes the arg-max on
+    # the raw values (relu(bn(x)) is monotone in x), so a window that is entirely <= 0 after the ReLU -- every tap ties at
+    # 0 -- may pick another tap than torch's "first maximum"; the ReLU backward that always follows zeroes both. Where the
+    # activation is positive the routing must agree (up to exact ties between positive bf16 values).
     want = act.grad.permute(0, 2, 3, 1)
-    mism = ((dx.float() - want).abs() > BF16_EPS * want.abs() * 2 + 1e-6).float().mean().item()
-    assert mism < 0.02, mism
+    live = (act.detach() > 0).permute(0, 2, 3, 1).float()
+    mism = (((dx.float() - want) * live).abs() > BF16_EPS * want.abs() * 2 + 1e-6).float().mean().item()
+    assert mism < 0.004, mism
     assert torch.allclose(dx.float().sum((1, 2)), want.sum((1, 2)), rtol=2e-2, atol=0.5)
     # already-activated input (inference path)
     y2 = torch.empty_like(y)

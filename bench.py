@@ -272,11 +272,19 @@ def run_ours(args) -> None:
     roofline = {
         "bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_kernel (tcgen05 implicit GEMM, all launches of a step)",
         "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
-        "peak_kind": f"{peak_kind} sustained cuBLAS bf16", "traffic": None,
+        "peak_kind": f"{peak_kind} sustained cuBLAS bf16", "traffic": None, "algorithmic_bytes_per_launch": None,
         "launches_per_step": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4),
         "issued_flops_per_step": conv_flops, "algorithmic_flops_per_step": algorithmic_flops,
         "share_of_step": round(conv_ms / total_ms, 4),
     }
+    # DRAM traffic of the same launches from the committed ncu capture (profiles/capture.sh), per launch like `achieved`
+    conv_bytes = sum(f["bytes"] for f in conv)
+    roofline["algorithmic_bytes_per_launch"] = round(conv_bytes / max(conv_launches, 1))
+    traffic_files = sorted(Path(__file__).resolve().parent.glob("profiles/*_conv_traffic.json"))
+    if traffic_files and B == 256 and args.size == 256:
+        tr = json.loads(traffic_files[-1].read_text())
+        roofline["traffic"] = round(tr["dram_bytes_per_launch"])
+        roofline["traffic_source"] = f"profiles/{traffic_files[-1].name} ({tr['launches']} launches of one step under ncu)"
     # whole-step HBM view: algorithmic bytes of every launch (each operand tensor counted once) over the step time
     step_bytes = sum(f["bytes"] for f in families.values())
     step_ms = ms_total / args.steps

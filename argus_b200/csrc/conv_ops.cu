@@ -157,8 +157,13 @@ std::string profile_report_json() {
   return out;
 }
 
+// Off by default. Measured on B200: 0.1-0.3 ms of a 40 ms step; and with the step on a high-priority stream (the look-ahead
+// staging and the weight-gradient stream then run starved) the trajectory stopped being reproducible while the
+// attribute was on (profiles/experiments/stream_determinism.py: identical with ARGUS_PDL=0 or with kernels that only
+// wait and never trigger early). Until that interaction is understood the launches carry no programmatic edge; the
+// prologue every kernel starts with is a no-op then.
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return !(e && e[0] == '0'); }();
+  static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return e && e[0] == '1'; }();
   return on;
 }
 namespace {

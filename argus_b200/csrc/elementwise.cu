@@ -586,7 +586,9 @@ struct BnRing {
   static constexpr int kTensorBytes = kRingVec * 16;
   static constexpr int kExtraBytes = MASK == 2 ? kTensorBytes : (MASK == 3 ? kRingVec : 0);
   static constexpr int kStageBytes = 2 * kTensorBytes + kExtraBytes;
-  static constexpr int kStages = MASK == 2 ? 4 : 6;
+  // 2 CTAs x 5 stages x 16 KB in flight per SM is far more than HBM latency needs; stopping at ~80 KB per CTA leaves
+  // room for one CTA of the (ALU-bound, 41 KB) augmentation kernel of the next batch to share the SM
+  static constexpr int kStages = MASK == 2 ? 3 : 5;
   static constexpr int kOffBars = kStages * kStageBytes;
   static constexpr int kTotal = kOffBars + 2 * kStages * 8;
   static_assert(kStages * kStageBytes >= 16 * 256 * 4, "the block reduction reuses the ring memory");
@@ -834,7 +836,7 @@ template <int RES>
 struct ApplyRing {
   static constexpr int kTensorBytes = kRingVec * 16;
   static constexpr int kStageBytes = RES ? 2 * kTensorBytes : kTensorBytes;
-  static constexpr int kStages = RES ? 6 : 10;
+  static constexpr int kStages = RES ? 5 : 10;   // ~80 KB per CTA (see BnRing)
   static constexpr int kOffBars = kStages * kStageBytes;
   static constexpr int kTotal = kOffBars + 2 * kStages * 8;
   static_assert(kStages * kStageBytes >= 8 * 16 * 32 * 4, "the block reduction reuses the ring memory");

@@ -72,7 +72,8 @@ struct ProfileScope {
 };
 
 // Kernel launch with a programmatic-stream-serialization edge to the previous kernel of the stream (PDL, see
-// pdl_prologue() in ptx.cuh). ARGUS_PDL=0 launches without the attribute (plain stream order).
+// pdl_prologue() in ptx.cuh) when ARGUS_PDL=1; by default launches carry no attribute (plain stream order, see
+// pdl_enabled() in conv_ops.cu for the measurement behind the default).
 bool pdl_enabled();
 // Every C-ABI entry point starts with pdl_break_all(): the first kernel of a call is launched without a programmatic
 // edge (the caller may have enqueued anything in between). pdl_break() marks the event records / event waits / memsets /

@@ -35,17 +35,19 @@ def h(t):
     return hashlib.md5(t.detach().contiguous().view(torch.uint8).cpu().numpy().tobytes()).hexdigest()[:10]
 
 
-rec = []
+infos = list(model._param_infos)
+sig = torch.zeros(steps, len(infos), dtype=torch.float64, device=dev)   # per-parameter gradient checksums, no host sync
+pooled_sig = torch.zeros(steps, dtype=torch.float64, device=dev)
+losses = []
 for i in range(steps):
     loss = engine.forward_backward(*batches[i % 3])
-    # enqueue the look-ahead staging BEFORE reading anything back, exactly like the training loop
-    engine.prefetch(batches[(i + 1) % 3][0])
-    g = model.flat_grads.clone()
-    pooled = model.probe_activation(-1).clone()
+    engine.prefetch(batches[(i + 1) % 3][0])   # look-ahead staging enqueued before anything is read back
+    g = model.flat_grads
+    sums = torch.stack([g[off:off + numel].double().abs().sum() for (_n, off, numel, _s) in infos])
+    sig[i] = sums
     engine.optimizer_step()
-    p = model.flat_params.clone()
-    per = {n: h(g[off:off + numel]) for (n, off, numel, _shape) in model._param_infos}
-    rec.append({"step": i, "loss": float(loss), "pooled": h(pooled), "grads": h(g), "params": h(p), "per": per})
+    losses.append(loss.clone())
 torch.cuda.synchronize()
-json.dump(rec, open(out, "w"), indent=0)
-print(mode, [r["loss"] for r in rec][-3:])
+rec = {"names": [n for (n, _o, _k, _s) in infos], "sig": sig.cpu().tolist(), "loss": [float(l) for l in losses]}
+json.dump(rec, open(out, "w"))
+print(mode, rec["loss"][-3:])

@@ -384,7 +384,9 @@ void Model::build_plan(Plan& p) {
   for (int i = static_cast<int>(blocks_.size()) - 1; i >= 0; --i) {
     BlockRef& br = blocks_[i];
     BlockPlan& bp = p.blocks[i];
-    bp.g_out = P; bp.g_q = Q; bp.g_r = R; bp.g_t = T; bp.g_x = S;
+    // stride-2 downsample blocks get a private, persistently zero-filled gradient buffer (see BlockPlan::t_zero_epoch)
+    bf16* Tb = (br.has_ds && br.ds.shape.stride == 2) ? arena_alloc<bf16>(bp.x_bytes / sizeof(bf16)) : T;
+    bp.g_out = P; bp.g_q = Q; bp.g_r = R; bp.g_t = Tb; bp.g_x = S;
     if (real) {
       auto wg_dst = [&](const ConvRef& c) { return c.gpacked_off >= 0 ? gpacked_ + c.gpacked_off : grads_dev_ + c.w_off; };
       // conv3: dy = Q (dRaw3), input act2, dx -> R
@@ -402,7 +404,7 @@ void Model::build_plan(Plan& p) {
       if (bp.ds_algebraic) {
         const int C = br.ds.shape.Cin;
         bp.ds_hg_wgrad = plan_conv_wgrad_gram(br.ds.shape, P, bp.x, alg_h_);
-        bp.ds_concat = plan_dgrad_concat(br.ds.shape, P, bp.x, C, alg_bstack_, T);
+        bp.ds_concat = plan_dgrad_concat(br.ds.shape, P, bp.x, C, alg_bstack_, Tb);
         ensure_wgrad_scratch(bp.ds_hg_wgrad);
       }
       // conv2: dy = Q (dRaw2), input act1, dx -> R
@@ -414,7 +416,7 @@ void Model::build_plan(Plan& p) {
       if (br.has_ds) {
         // downsample: dy = R (dRawd), input x, dx -> T
         bp.ds.wgrad = plan_conv_wgrad(br.ds.shape, R, bp.x, wg_dst(br.ds));
-        bp.ds.dgrad = plan_conv_dgrad(br.ds.shape, R, packed_ + br.ds.packed_off, T);
+        bp.ds.dgrad = plan_conv_dgrad(br.ds.shape, R, packed_ + br.ds.packed_off, Tb);
         ensure_wgrad_scratch(bp.ds.wgrad);
       }
       ensure_wgrad_scratch(bp.c1.wgrad);
@@ -590,6 +592,7 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
   }
   p.use_alt_input();
   staged_plan_ = nullptr;
+  if (last_plan_ != &p) ++arena_epoch_;   // plans share the arena: whatever another plan kept there is gone
   last_plan_ = &p;
   if (training) {
     forward_train(p, s);
@@ -721,6 +724,15 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
   launch_conv(concat, e, s);               // dAct = [g | act] * [diag(sc) W ; W^T diag(k1) W] + k0^T W
 }
 
+// The stride-2 1x1 dgrad writes every fourth pixel of T; the rest must be zero. T is private to the block, so the fill
+// is needed once per arena epoch, not per step.
+void Model::zero_ds_gradient_once(BlockPlan& bp, const BlockRef& br, bf16* T, cudaStream_t s) {
+  static const bool once = [] { const char* e = getenv("ARGUS_DS_ZERO_ONCE"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (br.ds.shape.stride != 2 || (once && bp.t_zero_epoch == arena_epoch_)) return;
+  ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
+  bp.t_zero_epoch = arena_epoch_;
+}
+
 void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s) {
   ARGUS_CHECK(grads_dev_ != nullptr, "model is not bound to a gradient arena");
   if (precision_ == 1) {
@@ -772,11 +784,11 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       const bf16* residual = P;
       if (br.has_ds) {
         if (bp.ds_algebraic) {
-          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
+          zero_ds_gradient_once(bp, br, T, s);
           conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, N, s);
         } else {
           bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
-          if (br.ds.shape.stride == 2) ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
+          zero_ds_gradient_once(bp, br, T, s);
           conv_backward(bp.ds, nullptr, nullptr, nullptr, s);  // R -> T
         }
         residual = T;

@@ -74,6 +74,10 @@ struct BlockPlan {
   WgradLaunch ds_hg_wgrad;
   ConvLaunch ds_concat;
   size_t x_bytes = 0;
+  // Stride-2 downsample blocks own their g_t buffer: the 1x1 stride-2 dgrad writes one pixel in four and the others
+  // must read as zero, so a buffer nobody else touches is zero-filled once (t_zero_epoch == Model::arena_epoch_) instead
+  // of on every step (1.9 GB of memset per step at B = 256).
+  uint64_t t_zero_epoch = 0;
 };
 
 struct Plan {
@@ -224,12 +228,14 @@ class Model {
   std::map<std::tuple<int, int, int, bool>, std::unique_ptr<Plan>> plans_;
   Plan* last_train_plan_ = nullptr;
   Plan* last_plan_ = nullptr;
+  uint64_t arena_epoch_ = 1;   // bumped whenever another plan (they share the arena) runs a forward pass
   Plan* staged_plan_ = nullptr;
   // weight-gradient GEMMs run on a side stream, overlapping the HBM-bound BN-backward / dgrad chain
   cudaStream_t side_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_wgrad_ = nullptr;
   bool wgrad_pending_ = false;
   bool overlap_wgrad_ = true;
+  void zero_ds_gradient_once(BlockPlan& bp, const BlockRef& br, bf16* T, cudaStream_t s);
   void join_wgrad(cudaStream_t s);
 };
 

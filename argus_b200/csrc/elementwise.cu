@@ -237,13 +237,14 @@ unpack_wgrads_kernel(const float* __restrict__ packed_grads, float* __restrict__
 void pack_weights(const float* params, bf16* packed, const WeightPackEntry* table_dev, int n_entries,
                   cudaStream_t s) {
   ProfileScope prof("pack_weights", s, 0, 0);
-  launch_kernel(pack_weights_kernel, dim3(64, n_entries), 256, 0, s, params, packed, table_dev);
+  // 256 blocks per entry: a 512-channel 3x3 layer is two output channels per block (one load / transpose / store round each)
+  launch_kernel(pack_weights_kernel, dim3(256, n_entries), 256, 0, s, params, packed, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntry* table_dev, int n_entries,
                    cudaStream_t s) {
   ProfileScope prof("unpack_wgrads", s, 0, 0);
-  launch_kernel(unpack_wgrads_kernel, dim3(64, n_entries), 256, 0, s, packed_grads, grads, table_dev);
+  launch_kernel(unpack_wgrads_kernel, dim3(256, n_entries), 256, 0, s, packed_grads, grads, table_dev);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -750,27 +750,39 @@ int64_t wgrad_scratch_elems(const WgradLaunch& l) {
   return static_cast<int64_t>(l.p.num_ksplits) * l.p.cout * l.p.dw_row_stride;
 }
 
-// dw[i] += sum_ks partial[ks][i], splits added in index order (deterministic)
-__global__ void wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, int64_t n4, int splits) {
+// dw[i] += sum_ks partial[ks][i] in a fixed order (deterministic): a block owns 64 float4 elements, its four thread
+// groups take the splits g, g + 4, g + 8, ... (eight loads in flight each) and group 0 adds the four sums in group order.
+// Split-K counts reach 148, so walking them with one thread per element was a chain of dependent L2 round trips.
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float4* __restrict__ partial, float4* __restrict__ dw, int64_t n4, int splits) {
   pdl_prologue();
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    float4 acc = partial[i];
-    int k = 1;
-    for (; k + 8 <= splits; k += 8) {   // eight loads in flight, additions in split order (same bits as the plain loop)
-      float4 v[8];
+  __shared__ float4 red[4][64];
+  const int e = threadIdx.x & 63, g = threadIdx.x >> 6;
+  auto add = [](float4& a, const float4& v) { a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; };
+  for (int64_t base = static_cast<int64_t>(blockIdx.x) * 64; base < n4; base += static_cast<int64_t>(gridDim.x) * 64) {
+    const int64_t i = base + e;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n4) {
+      int k = g;
+      for (; k + 28 < splits; k += 32) {
+        float4 v[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = partial[static_cast<int64_t>(k + u) * n4 + i];
+        for (int u = 0; u < 8; ++u) v[u] = partial[static_cast<int64_t>(k + 4 * u) * n4 + i];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) { acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w; }
+        for (int u = 0; u < 8; ++u) add(acc, v[u]);
+      }
+      for (; k < splits; k += 4) add(acc, partial[static_cast<int64_t>(k) * n4 + i]);
     }
-    for (; k < splits; ++k) {
-      const float4 v = partial[static_cast<int64_t>(k) * n4 + i];
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    red[g][e] = acc;
+    __syncthreads();
+    if (g == 0 && i < n4) {
+      float4 t = red[0][e];
+      add(t, red[1][e]); add(t, red[2][e]); add(t, red[3][e]);
+      float4 d = dw[i];
+      add(d, t);
+      dw[i] = d;
     }
-    float4 d = dw[i];
-    d.x += acc.x; d.y += acc.y; d.z += acc.z; d.w += acc.w;
-    dw[i] = d;
+    __syncthreads();
   }
 }
 
@@ -834,7 +846,7 @@ void launch_wgrad(const WgradLaunch& l0, float* scratch, cudaStream_t stream) {
   if (need > 0) {
     // every (split, cout, tap, ci) word of the scratch was written by exactly one work item
     const int64_t n4 = l.p.partial_stride / 4;
-    const int grid = static_cast<int>(std::min<int64_t>((n4 + 255) / 256, 2LL * num_sms()));
+    const int grid = static_cast<int>(std::min<int64_t>((n4 + 63) / 64, 4LL * num_sms()));
     launch_kernel(wgrad_reduce_kernel, grid, 256, 0, stream, reinterpret_cast<const float4*>(scratch),
                                                   reinterpret_cast<float4*>(l.p.dw), n4, l.p.num_ksplits);
     ARGUS_CUDA(cudaGetLastError());

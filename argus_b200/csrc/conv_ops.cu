@@ -157,11 +157,10 @@ std::string profile_report_json() {
   return out;
 }
 
-// Off by default. Measured on B200: 0.1-0.3 ms of a 40 ms step; and with the step on a high-priority stream (the look-ahead
-// staging and the weight-gradient stream then run starved) the trajectory stopped being reproducible while the
-// attribute was on (profiles/experiments/stream_determinism.py: identical with ARGUS_PDL=0 or with kernels that only
-// wait and never trigger early). Until that interaction is understood the launches carry no programmatic edge; the
-// prologue every kernel starts with is a no-op then.
+// Off by default. Measured on B200: 0.1-0.3 ms of a 40 ms step (with the early trigger of -DARGUS_PDL_TRIGGER compiled in;
+// less without it). With the step on a high-priority stream the trajectory stopped being reproducible whenever kernels
+// triggered early (profiles/experiments/stream_determinism.py); kernels that only wait never showed it, and delaying
+// every side-stream fork by 400 us (ARGUS_FUZZ_DELAY_US) changes nothing, so the library's own fork / join edges hold.
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return e && e[0] == '1'; }();
   return on;

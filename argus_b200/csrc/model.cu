@@ -12,6 +12,29 @@ static constexpr float kBnMomentum = 0.1f;
 // ------------------------------------------------------------------------------------------------------------
 // small kernels local to the model: column sums (fc bias gradient)
 // ------------------------------------------------------------------------------------------------------------
+// Debugging aid for cross-stream ordering: ARGUS_FUZZ_DELAY_US=<n> (bit mask ARGUS_FUZZ_SITES: 1 = weight-gradient side
+// stream, 2 = input staging) starts the side-stream work of every fork with an n-microsecond spin, so that a missing
+// or too-weak dependency (main stream overwriting what the side stream has not read yet, or reading what it has not
+// written yet) changes results reproducibly on the default stream (profiles/experiments/stream_determinism.py).
+__global__ void fuzz_delay_kernel(unsigned long long ns) {
+  pdl_prologue();
+  const unsigned long long t0 = globaltimer_ns();
+  while (globaltimer_ns() - t0 < ns) {}
+}
+static int fuzz_delay_us() {
+  static const int v = [] { const char* e = getenv("ARGUS_FUZZ_DELAY_US"); return e ? atoi(e) : 0; }();
+  return v;
+}
+static int fuzz_sites() {
+  static const int v = [] { const char* e = getenv("ARGUS_FUZZ_SITES"); return e ? atoi(e) : 3; }();
+  return v;
+}
+static void fuzz_delay(int site, cudaStream_t s) {
+  if (fuzz_delay_us() <= 0 || !(fuzz_sites() & site)) return;
+  launch_kernel(fuzz_delay_kernel, 1, 1, 0, s, static_cast<unsigned long long>(fuzz_delay_us()) * 1000ull);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
 __global__ void colsum_bf16_kernel(const bf16* __restrict__ x, float* out, int rows, int C) {
   pdl_prologue();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -609,6 +632,7 @@ void Model::stage_input_u8(const uint8_t* images, float* aug_params, int B, int 
   ARGUS_CHECK(!apply || aug_params != nullptr, "augmentation needs a parameter table");
   ARGUS_CHECK(precision_ == 0, "the fused augmentation + staging path exists in bf16 mode only");
   Plan& p = get_plan(B, H, W, training);
+  fuzz_delay(2, s);
   augment_images(images, true, p.x_s2d_alt, true, aug_params, p.N, H, W, apply, s);
   staged_plan_ = &p;
 }
@@ -663,6 +687,7 @@ void Model::run_wgrad(const WgradLaunch& l, cudaStream_t s) {
   }
   ARGUS_CUDA(cudaEventRecord(ev_fork_, s)); pdl_break(s, kPdlAfterRecord);
   ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0)); pdl_break(side_, kPdlAfterWait);
+  fuzz_delay(1, side_);
   launch_wgrad(l, wgrad_scratch_, side_);
   ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_)); pdl_break(side_, kPdlAfterRecord);
   wgrad_pending_ = true;

@@ -25,7 +25,8 @@ def test_split_tile_epilogue_mode(cuda_device):
 
 
 def test_programmatic_dependent_launch(cuda_device):
-    """ARGUS_PDL=1: every launch carries a programmatic edge; gradients and the reproducibility tests must not change."""
+    """ARGUS_PDL=1: every launch carries a programmatic edge (the kernels wait in their prologue; the early trigger is a
+    compile-time option); gradients and the reproducibility tests must not change."""
     _rerun({"ARGUS_PDL": "1"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
                                  "train_forward_backward or reproducible or prefetch"])
 

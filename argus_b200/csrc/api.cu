@@ -289,7 +289,7 @@ int argus_avgpool_backward(const void* dy, void* dx, int N, int HW, int C, void*
   ARGUS_API_END
 }
 
-int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step,
+int argus_augment_sample_params(float* params, int n_images, int n_cams, int H, int W, uint64_t seed, uint64_t step,
                                 const argus_aug_config* cfg, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
@@ -301,16 +301,17 @@ int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_
   c.contrast_lo = cfg->contrast_lo; c.contrast_span = cfg->contrast_span;
   c.saturation_lo = cfg->saturation_lo; c.saturation_span = cfg->saturation_span;
   c.hue_lo = cfg->hue_lo; c.hue_span = cfg->hue_span;
-  augment_sample_params(params, n_images, n_cams, seed, step, c, static_cast<cudaStream_t>(stream));
+  c.random_erasing = cfg->random_erasing; c.salt_and_pepper = cfg->salt_and_pepper;
+  augment_sample_params(params, n_images, n_cams, H, W, seed, step, c, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
-int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* params, int n_images, int H, int W,
-                  int apply, void* stream) {
+int argus_augment(const void* in, int in_u8, void* out, int out_s2d, const float* params, const void* arc_mask,
+                  void* plasma_ws, int n_images, int H, int W, int apply, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
   ARGUS_CHECK(!apply || params != nullptr, "augmentation needs a parameter table");
-  augment_images(in, in_u8 != 0, out, out_s2d != 0, params, n_images, H, W, apply != 0,
-                 static_cast<cudaStream_t>(stream));
+  augment_images(in, in_u8 != 0, out, out_s2d != 0, params, static_cast<const uint32_t*>(arc_mask),
+                 static_cast<uint32_t*>(plasma_ws), n_images, H, W, apply != 0, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 
@@ -322,13 +323,20 @@ int argus_spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, 
   spaghetti_sample_params(arcs, n_images, n_arcs, H, W, seed, step, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
-int argus_spaghetti_draw(const void* in, void* out, const float* arcs, int n_images, int n_arcs, int H, int W,
-                         void* stream) {
+int argus_spaghetti_mask(const float* arcs, void* mask, int n_images, int n_arcs, int H, int W, void* stream) {
   ARGUS_API_BEGIN
   require_sm100();
-  ARGUS_CHECK(in != nullptr && out != nullptr && (arcs != nullptr || n_arcs == 0), "null argument");
-  spaghetti_draw(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), arcs, n_images, n_arcs, H, W,
-                 static_cast<cudaStream_t>(stream));
+  ARGUS_CHECK(mask != nullptr && (arcs != nullptr || n_arcs == 0), "null argument");
+  spaghetti_mask(arcs, static_cast<uint32_t*>(mask), n_images, n_arcs, H, W, static_cast<cudaStream_t>(stream));
+  ARGUS_API_END
+}
+int argus_spaghetti_draw(const void* in, void* out, const float* arcs, void* mask_ws, int n_images, int n_arcs, int H,
+                         int W, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(in != nullptr && out != nullptr && mask_ws != nullptr && (arcs != nullptr || n_arcs == 0), "null argument");
+  spaghetti_draw(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), arcs, static_cast<uint32_t*>(mask_ws),
+                 n_images, n_arcs, H, W, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
 
@@ -357,7 +365,20 @@ int argus_clip_adam_step(float* params, const float* grads, float* exp_avg, floa
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int np = grad_sqnorm_partials(grads, n, scratch, s);
   clip_adam_step(params, grads, exp_avg, exp_avg_sq, n, scratch, np, gscale, max_norm, lr, beta1, beta2, eps, step,
-                 norm_out, s);
+                 norm_out, false, s);
+  ARGUS_API_END
+}
+int argus_clip_adam_step_amp(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             float* scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                             int step, float* norm_out, void* stream) {
+  ARGUS_API_BEGIN
+  require_sm100();
+  ARGUS_CHECK(step >= 1, "Adam step counter starts at 1");
+  ARGUS_CHECK(norm_out != nullptr, "the caller needs the gradient norm to learn whether the step was skipped");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int np = grad_sqnorm_partials(grads, n, scratch, s);
+  clip_adam_step(params, grads, exp_avg, exp_avg_sq, n, scratch, np, gscale, max_norm, lr, beta1, beta2, eps, step,
+                 norm_out, true, s);
   ARGUS_API_END
 }
 
@@ -500,11 +521,12 @@ int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, 
   m->impl.forward(x, is_u8 != 0, B, H, W, training != 0, out, static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }
-int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
-                               int training, int apply, void* stream) {
+int argus_model_stage_input_u8(argus_model* m, const void* images, const float* aug_params, const void* arc_mask,
+                               void* plasma_ws, int B, int H, int W, int training, int apply, void* stream) {
   ARGUS_API_BEGIN
   ARGUS_CHECK(m != nullptr, "null model");
-  m->impl.stage_input_u8(static_cast<const uint8_t*>(images), aug_params, B, H, W, training != 0, apply != 0,
+  m->impl.stage_input_u8(static_cast<const uint8_t*>(images), aug_params, static_cast<const uint32_t*>(arc_mask),
+                         static_cast<uint32_t*>(plasma_ws), B, H, W, training != 0, apply != 0,
                          static_cast<cudaStream_t>(stream));
   ARGUS_API_END
 }

@@ -1,18 +1,23 @@
 // Fused GPU image augmentation (reference: the kornia chain built in /root/reference/argus/data.py:41-103 and applied
-// per sample at data.py:213-225 — planckian jitter -> colour jiggle -> gaussian blur -> motion blur -> plasma shadow).
+// per sample at data.py:213-225 -- [random erasing x2] -> planckian jitter -> colour jiggle -> gaussian blur -> motion
+// blur -> plasma shadow -> [salt & pepper]) and the spaghetti arcs the dataset draws before it (argus/utils.py:252-275,
+// data.py:212-215).
 //
-// One kernel per batch: uint8 HWC (or fp32 NCHW) in -> /255 -> colour ops in registers -> 5-tap separable gaussian
-// and 3x3 motion kernel from a shared-memory halo tile -> plasma shadow -> clamp -> bf16 space-to-depth layout that
-// the stem convolution's TMA reads directly (or fp32 NCHW for the drop-in Augmentation.forward()).
-// Parameters are a pure function of (seed, step, image, field) through a splitmix64 hash, so the numpy oracle
-// (oracle/augment.py) reproduces them bit for bit. The arithmetic spec is documented there.
+// Per batch:  arc_paint_kernel      one warp per arc: Pillow's ImageDraw.arc rasteriser, bit for bit (oracle/pil_arc.py)
+//                                   -> 1 bit per pixel
+//             plasma_mask_kernel    one block per image: kornia's diamond-square plasma fractal, built level by level in
+//                                   shared memory, thresholded by shade_quantity -> 1 bit per pixel
+//             augment_kernel        uint8 HWC (or fp32 NCHW) in -> arcs -> /255 -> erasing -> colour ops in registers ->
+//                                   5-tap separable gaussian and 3x3 motion kernel from a shared-memory halo tile -> shadow
+//                                   -> clamp -> salt & pepper -> bf16 space-to-depth layout that the stem convolution's TMA
+//                                   reads directly (or fp32 NCHW for the drop-in Augmentation.forward()).
+// Every random number is a pure function of (seed, step, image, field) through integer hashes, so the numpy oracle
+// (oracle/augment.py) reproduces parameters, masks and arcs bit for bit; the arithmetic spec is documented there.
 #include "kernels.h"
 #include "ptx.cuh"
 #include "runtime.h"
 
 namespace argus {
-
-constexpr int kAugParams = 24;
 
 __constant__ float c_planck_r[25] = {1.67361629f, 1.48101866f, 1.35384262f, 1.26161098f, 1.19069767f, 1.13347971f,
                                      1.08616924f, 1.04604697f, 1.01147437f, 0.980993509f, 0.954290628f, 0.930232584f,
@@ -39,11 +44,46 @@ __device__ __forceinline__ float hash_uniform(uint64_t seed, uint64_t step, uint
 }
 __device__ __forceinline__ float lerp_rn(float u, float lo, float span) { return __fadd_rn(lo, __fmul_rn(u, span)); }
 
+// per-pixel random numbers (plasma fractal, salt & pepper): 32-bit hash of (image seed, level, y, x) -> 24-bit uniform
+__device__ __forceinline__ float pixel_uniform(uint32_t seed32, uint32_t level, uint32_t y, uint32_t x) {
+  uint32_t h = seed32 ^ (level * 0x9E3779B9u);
+  h = (h ^ y) * 0x85EBCA6Bu;
+  h ^= h >> 15;
+  h = (h ^ x) * 0xC2B2AE35u;
+  h ^= h >> 13;
+  h *= 0x27D4EB2Fu;
+  h ^= h >> 16;
+  return static_cast<float>(h >> 8) * 5.9604644775390625e-08f;
+}
+
 // ------------------------------------------------------------------------------------------------------------
-// parameter sampling
+// parameter sampling (layout: oracle/augment.py::sample_params)
 // ------------------------------------------------------------------------------------------------------------
-__global__ void aug_params_kernel(float* __restrict__ params, int n_images, int n_cams, uint64_t seed, uint64_t step,
-                                  AugConfig cfg) {
+// kornia RectangleEraseGenerator: area = U(scale) * H * W, aspect = h / w, h = round(sqrt(area * aspect)) clamped to
+// [1, H], w likewise, top-left = floor(U * (size - extent + 1)).
+__device__ void erase_rect(float u_area, float u_ratio_a, float u_ratio_b, float u_pick, float u_x, float u_y, float s_lo,
+                           float s_span, bool two_sided, float r_lo, float r_span, float r2_span, int H, int W, float* out) {
+  // (spans are passed as the float32 literals the oracle uses, not recomputed from the bounds in float32)
+  const float area = __fmul_rn(lerp_rn(u_area, s_lo, s_span), static_cast<float>(H * W));
+  float ratio;
+  if (two_sided) {   // ratio range straddles 1: one sampler below, one above, picked by a coin
+    const float r1 = lerp_rn(u_ratio_a, r_lo, r_span), r2 = lerp_rn(u_ratio_b, 1.f, r2_span);
+    ratio = (rintf(u_pick) != 0.f) ? r1 : r2;
+  } else {
+    ratio = lerp_rn(u_ratio_a, r_lo, r_span);
+  }
+  float h = rintf(__fsqrt_rn(__fmul_rn(area, ratio)));
+  float w = rintf(__fsqrt_rn(__fdiv_rn(area, ratio)));
+  h = fminf(fmaxf(h, 1.f), static_cast<float>(H));
+  w = fminf(fmaxf(w, 1.f), static_cast<float>(W));
+  out[0] = floorf(__fmul_rn(u_x, __fadd_rn(__fadd_rn(static_cast<float>(W), -w), 1.f)));
+  out[1] = floorf(__fmul_rn(u_y, __fadd_rn(__fadd_rn(static_cast<float>(H), -h), 1.f)));
+  out[2] = w;
+  out[3] = h;
+}
+
+__global__ void aug_params_kernel(float* __restrict__ params, int n_images, int n_cams, int H, int W, uint64_t seed,
+                                  uint64_t step, AugConfig cfg) {
   pdl_prologue();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= n_images) return;
@@ -73,7 +113,8 @@ __global__ void aug_params_kernel(float* __restrict__ params, int n_images, int 
   }
   // gaussian blur
   P[7] = (cfg.blur && U(img, 7) < 0.5f) ? lerp_rn(U(img, 8), 3.f, 5.f) : 0.f;
-  // motion blur kernel
+  // motion blur: kornia get_motion_kernel2d(3, angle, direction, 'nearest') = the row [d, .5, 1-d] through the centre,
+  // rotated by warp_affine(align_corners=True, nearest, zeros): output (x, y) samples the source at R(angle) (x, y)
   float k[9] = {0.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 0.f};
   if (cfg.motion_blur && U(img, 9) < 0.7f) {
     const float angle = __fmul_rn(lerp_rn(U(img, 10), -35.f, 70.f), 0.01745329251994329577f);
@@ -104,162 +145,200 @@ __global__ void aug_params_kernel(float* __restrict__ params, int n_images, int 
     P[17] = 0.25f; P[18] = 0.f; P[19] = 0.f;
   }
   P[20] = U(img, 15);
-  P[21] = 0.f; P[22] = 1.f; P[23] = 0.f;
+  P[21] = 0.f; P[22] = 0.f; P[23] = 0.f;
+  // random erasing (two rectangles: black wide ones, white square-ish ones; data.py:52-64)
+  for (int e = 0; e < 2; ++e) {
+    float* R = P + 24 + 5 * e;
+    R[0] = 0.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 0.f;
+    if (cfg.random_erasing && U(img, 16 + 8 * e) < 0.5f) {
+      R[0] = 1.f;
+      const uint64_t f = 17 + 8 * e;
+      // scale (0.02, 0.1), ratio (2, 3)  |  scale (0.02, 0.05), ratio (0.8, 1.2)
+      if (e == 0) erase_rect(U(img, f), U(img, f + 1), U(img, f + 2), U(img, f + 3), U(img, f + 4), U(img, f + 5), 0.02f,
+                             0.08f, false, 2.f, 1.f, 0.f, H, W, R + 1);
+      else erase_rect(U(img, f), U(img, f + 1), U(img, f + 2), U(img, f + 3), U(img, f + 4), U(img, f + 5), 0.02f, 0.03f,
+                      true, 0.8f, 0.2f, 0.2f, H, W, R + 1);
+    }
+  }
+  // salt & pepper (data.py:94-95: p = 0.7, kornia defaults amount (0.01, 0.06), salt_vs_pepper (0.4, 0.6))
+  P[34] = 0.f; P[35] = 0.f; P[36] = 0.f;
+  if (cfg.salt_and_pepper && U(img, 32) < 0.7f) {
+    P[34] = 1.f;
+    P[35] = lerp_rn(U(img, 33), 0.01f, 0.05f);
+    P[36] = lerp_rn(U(img, 34), 0.4f, 0.2f);
+  }
+  P[37] = U(img, 35);
+  P[38] = 0.f; P[39] = 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// plasma fractal: 6 octaves of smooth value noise, octave l has 2^(l+1) cells per side, amplitude roughness^l
+// plasma shadow mask: kornia.contrib.diamond_square (RandomPlasmaShadow, data.py:87-92) per image.
+//   seed grid (sh x sw, all uniform) -> `depth` doublings; at level k (scale = roughness^k):
+//     diamond centres (odd, odd)   = (1 - scale) * mean of the 4 diagonal parents + scale * u
+//     square centres (one odd)     = (1 - scale) * (sum of the 4 axial neighbours / 4, x 4/3 on the border) + scale * u
+//   final grid (2^ceil(log2(H-1)) + 1 per side) cropped to H x W; shadow where the field < shade_quantity.
+// All levels but the last live in shared memory (ping-pong); the last one is evaluated per pixel on the fly.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float lattice(uint64_t seed_bits, int octave, int iy, int ix) {
-  const uint64_t key = (seed_bits << 40) | (static_cast<uint64_t>(octave) << 32) | (static_cast<uint64_t>(iy) << 16) |
-                       static_cast<uint64_t>(ix);
-  return hash_uniform(0x504C41534D41ull, 0, key, 0);
-}
-template <typename Lattice>
-__device__ __forceinline__ float plasma_eval(int y, int x, float inv_h, float inv_w, float roughness, Lattice lat) {
-  const float ys = __fmul_rn(static_cast<float>(y) + 0.5f, inv_h);
-  const float xs = __fmul_rn(static_cast<float>(x) + 0.5f, inv_w);
-  float field = 0.f, amp = 1.f;
-#pragma unroll
-  for (int l = 0; l < 6; ++l) {
-    const float cells = static_cast<float>(2 << l);
-    const float fy = __fmul_rn(ys, cells), fx = __fmul_rn(xs, cells);
-    const float flo_y = floorf(fy), flo_x = floorf(fx);
-    const int iy = static_cast<int>(flo_y), ix = static_cast<int>(flo_x);
-    float ty = __fadd_rn(fy, -flo_y), tx = __fadd_rn(fx, -flo_x);
-    ty = __fmul_rn(__fmul_rn(ty, ty), __fadd_rn(3.f, -__fmul_rn(2.f, ty)));
-    tx = __fmul_rn(__fmul_rn(tx, tx), __fadd_rn(3.f, -__fmul_rn(2.f, tx)));
-    const float v00 = lat(l, iy, ix), v01 = lat(l, iy, ix + 1);
-    const float v10 = lat(l, iy + 1, ix), v11 = lat(l, iy + 1, ix + 1);
-    const float top = __fadd_rn(v00, __fmul_rn(__fadd_rn(v01, -v00), tx));
-    const float bot = __fadd_rn(v10, __fmul_rn(__fadd_rn(v11, -v10), tx));
-    field = __fadd_rn(field, __fmul_rn(amp, __fadd_rn(top, __fmul_rn(__fadd_rn(bot, -top), ty))));
-    amp = __fmul_rn(amp, roughness);
-  }
-  return field;
-}
-struct HashLattice {
-  uint64_t seed_bits;
-  __device__ __forceinline__ float operator()(int l, int iy, int ix) const { return lattice(seed_bits, l, iy, ix); }
-};
-// whole-image lattice in shared memory: octave l holds (2^(l+1) + 1)^2 values at offset c_lat_off[l]
-constexpr int kLatTotal = 9 + 25 + 81 + 289 + 1089 + 4225;  // 5718
-__constant__ int c_lat_off[6] = {0, 9, 34, 115, 404, 1493};
-struct FullTable {
-  const float* t;
-  __device__ __forceinline__ float operator()(int l, int iy, int ix) const {
-    return t[c_lat_off[l] + iy * ((2 << l) + 1) + ix];
-  }
-};
-// per-tile lattice window: octave l covers lattice rows [iy0[l], iy0[l] + 17) x cols [ix0[l], ix0[l] + 17)
-constexpr int kWin = 17;
-struct TileTable {
-  const float* t;
-  const int* iy0;
-  const int* ix0;
-  __device__ __forceinline__ float operator()(int l, int iy, int ix) const {
-    return t[(l * kWin + (iy - iy0[l])) * kWin + (ix - ix0[l])];
-  }
-};
+constexpr int kPlasmaMaxA = 129 * 129;   // largest second-to-last level (256 x 256 images)
+constexpr int kPlasmaMaxB = 65 * 65;
+constexpr int kPlasmaSmemBytes = (kPlasmaMaxA + kPlasmaMaxB) * 4;
+constexpr int kPlasmaThreads = 512;
 
-// one block per image: min / max of the un-normalised field -> params[21], params[22]
-__global__ void __launch_bounds__(256) plasma_minmax_kernel(float* __restrict__ params, int H, int W) {
+struct PlasmaGeom {
+  int depth, sh, sw;   // number of doublings, seed grid
+};
+__host__ __device__ inline int ceil_log2_int(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+__host__ __device__ inline PlasmaGeom plasma_geom(int H, int W) {
+  const int lh = ceil_log2_int(H - 1), lw = ceil_log2_int(W - 1);
+  PlasmaGeom g;
+  g.depth = (lh < lw ? lh : lw) - 1;
+  g.sh = (1 << (lh - g.depth)) + 1;
+  g.sw = (1 << (lw - g.depth)) + 1;
+  return g;
+}
+
+__device__ __forceinline__ float ds_mix(float scale, float region, float u) {
+  return __fadd_rn(__fmul_rn(__fadd_rn(1.f, -scale), region), __fmul_rn(scale, u));
+}
+__device__ __forceinline__ float ds_diamond(const float* __restrict__ prev, int pw, int y, int x, float scale,
+                                            uint32_t seed32, uint32_t level) {
+  const float* p = prev + (y >> 1) * pw + (x >> 1);
+  const float m = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[pw]), p[pw + 1]));
+  return ds_mix(scale, m, pixel_uniform(seed32, level, y, x));
+}
+
+__global__ void __launch_bounds__(kPlasmaThreads)
+plasma_mask_kernel(const float* __restrict__ params, uint32_t* __restrict__ mask, int H, int W) {
   pdl_prologue();
-  __shared__ float s_lo[8], s_hi[8];
-  __shared__ float s_lat[kLatTotal];
-  float* P = params + static_cast<size_t>(blockIdx.x) * kAugParams;
-  const float roughness = P[17];
-  const uint64_t seed_bits = static_cast<uint64_t>(rintf(P[20] * 16777216.f));
-  const float inv_h = 1.f / H, inv_w = 1.f / W;
-  float lo = INFINITY, hi = -INFINITY;
-  if (P[18] != 0.f) {
-    for (int l = 0; l < 6; ++l) {
-      const int side = (2 << l) + 1;
-      for (int i = threadIdx.x; i < side * side; i += blockDim.x)
-        s_lat[c_lat_off[l] + i] = lattice(seed_bits, l, i / side, i % side);
+  extern __shared__ float s_plasma[];
+  float* bufA = s_plasma;
+  float* bufB = s_plasma + kPlasmaMaxA;
+  const int n = blockIdx.x;
+  const float* P = params + static_cast<size_t>(n) * kAugParams;
+  const float roughness = P[17], intensity = P[18], quantity = P[19];
+  uint32_t* out = mask + static_cast<size_t>(n) * H * (W >> 5);
+  const int words = H * (W >> 5);
+  if (intensity == 0.f) {
+    for (int i = threadIdx.x; i < words; i += kPlasmaThreads) out[i] = 0u;
+    return;
+  }
+  const uint32_t seed32 = static_cast<uint32_t>(rintf(P[20] * 16777216.f));
+  const PlasmaGeom g = plasma_geom(H, W);
+  // level `depth - 1` must land in bufA: alternate backwards
+  float* cur = ((g.depth - 1) & 1) ? bufB : bufA;
+  float* other = (cur == bufA) ? bufB : bufA;
+  int h = g.sh, w = g.sw;
+  for (int i = threadIdx.x; i < h * w; i += kPlasmaThreads) cur[i] = pixel_uniform(seed32, 0u, i / w, i % w);
+  __syncthreads();
+  float scale = 1.f;
+  for (int level = 1; level < g.depth; ++level) {
+    scale = __fmul_rn(scale, roughness);
+    const int nh = 2 * h - 1, nw = 2 * w - 1;
+    float* nxt = other;
+    for (int i = threadIdx.x; i < nh * nw; i += kPlasmaThreads) {
+      const int y = i / nw, x = i - y * nw;
+      if (!((y | x) & 1)) nxt[i] = cur[(y >> 1) * w + (x >> 1)];
+      else if (y & x & 1) nxt[i] = ds_diamond(cur, w, y, x, scale, seed32, level);
     }
     __syncthreads();
-    FullTable lat{s_lat};
-    for (int i = threadIdx.x; i < H * W; i += blockDim.x) {
-      const float f = plasma_eval(i / W, i % W, inv_h, inv_w, roughness, lat);
-      lo = fminf(lo, f);
-      hi = fmaxf(hi, f);
+    for (int i = threadIdx.x; i < nh * nw; i += kPlasmaThreads) {
+      const int y = i / nw, x = i - y * nw;
+      if (((y ^ x) & 1) == 0) continue;
+      const float up = y > 0 ? nxt[i - nw] : 0.f, down = y < nh - 1 ? nxt[i + nw] : 0.f;
+      const float left = x > 0 ? nxt[i - 1] : 0.f, right = x < nw - 1 ? nxt[i + 1] : 0.f;
+      float r = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(up, left), right), down));
+      if (y == 0 || x == 0 || y == nh - 1 || x == nw - 1) r = __fmul_rn(r, 1.33333337306976318359375f);
+      nxt[i] = ds_mix(scale, r, pixel_uniform(seed32, level, y, x));
     }
+    __syncthreads();
+    other = cur; cur = nxt; h = nh; w = nw;
   }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
-    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
-  }
-  if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int i = 1; i < 8; ++i) { lo = fminf(lo, s_lo[i]); hi = fmaxf(hi, s_hi[i]); }
-    lo = fminf(lo, s_lo[0]); hi = fmaxf(hi, s_hi[0]);
-    P[21] = lo;
-    P[22] = hi;
+  // last level on the fly from `cur` (h x w): final grid (2h-1) x (2w-1), cropped to H x W
+  scale = __fmul_rn(scale, roughness);
+  const uint32_t level = g.depth;
+  const int fh = 2 * h - 1, fw = 2 * w - 1;
+  auto value_at = [&](int y, int x) -> float {   // even-even or odd-odd positions only
+    if (!((y | x) & 1)) return cur[(y >> 1) * w + (x >> 1)];
+    return ds_diamond(cur, w, y, x, scale, seed32, level);
+  };
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wpr = W >> 5;   // words per row
+  for (int wi = warp; wi < words; wi += kPlasmaThreads / 32) {
+    const int y = wi / wpr, x = (wi - y * wpr) * 32 + lane;
+    float f;
+    if (((y ^ x) & 1) == 0) {
+      f = value_at(y, x);
+    } else {
+      const float up = y > 0 ? value_at(y - 1, x) : 0.f, down = y < fh - 1 ? value_at(y + 1, x) : 0.f;
+      const float left = x > 0 ? value_at(y, x - 1) : 0.f, right = x < fw - 1 ? value_at(y, x + 1) : 0.f;
+      float r = __fmul_rn(0.25f, __fadd_rn(__fadd_rn(__fadd_rn(up, left), right), down));
+      if (y == 0 || x == 0 || y == fh - 1 || x == fw - 1) r = __fmul_rn(r, 1.33333337306976318359375f);
+      f = ds_mix(scale, r, pixel_uniform(seed32, level, y, x));
+    }
+    const uint32_t bits = __ballot_sync(0xffffffffu, f < quantity);
+    if (lane == 0) out[wi] = bits;
   }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// colour operations (kornia.enhance semantics, see oracle/augment.py)
+// colour operations (kornia.enhance semantics, see oracle/augment.py). Fast-math divisions: results agree with the
+// float32 oracle to a few ulp (asserted at 1e-5 absolute on [0, 1] images); the output is bf16 anyway.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.f), 1.f); }
+__device__ __forceinline__ float clamp01(float v) { return __saturatef(v); }
 
-__device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float& h, float& s, float& v) {
+__device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float& h6, float& s, float& v) {
+  // h6 = hue in sixths of a turn, in [0, 6)
   const float mx = fmaxf(fmaxf(r, g), b), mn = fminf(fminf(r, g), b);
   v = mx;
   const float delta = mx - mn;
-  s = __fdiv_rn(delta, mx + 1e-8f);
-  const float dz = delta == 0.f ? 1.f : delta;
-  const float rc = mx - r, gc = mx - g, bc = mx - b;
-  float hh = (r == mx) ? (bc - gc) : ((g == mx) ? __fadd_rn(rc - bc, __fmul_rn(2.f, dz)) : __fadd_rn(gc - rc, __fmul_rn(4.f, dz)));
-  hh = __fdiv_rn(hh, dz);
-  hh = __fdiv_rn(hh, 6.f);
-  hh = hh - floorf(hh);
-  h = __fmul_rn(6.28318530717958647692f, hh);
+  s = __fdividef(delta, mx + 1e-8f);
+  const float inv = __fdividef(1.f, delta == 0.f ? 1.f : delta);
+  float hh = (r == mx) ? (g - b) * inv : ((g == mx) ? fmaf(b - r, inv, 2.f) : fmaf(r - g, inv, 4.f));
+  h6 = hh < 0.f ? hh + 6.f : hh;
 }
-__device__ __forceinline__ void hsv_to_rgb(float h, float s, float v, float& r, float& g, float& b) {
-  const float h6 = __fmul_rn(__fdiv_rn(h, 6.28318530717958647692f), 6.f);
+__device__ __forceinline__ void hsv_to_rgb(float h6, float s, float v, float& r, float& g, float& b) {
   const float fl = floorf(h6);
-  int hi = static_cast<int>(fl) % 6;
-  if (hi < 0) hi += 6;
   const float f = h6 - fl;
-  const float p = __fmul_rn(v, 1.f - s);
-  const float q = __fmul_rn(v, __fadd_rn(1.f, -__fmul_rn(f, s)));
-  const float t = __fmul_rn(v, __fadd_rn(1.f, -__fmul_rn(1.f - f, s)));
+  const int hi = static_cast<int>(fl);   // h6 in [0, 6] -> 6 wraps to sector 0 below
+  const float p = v * (1.f - s);
+  const float q = v * (1.f - f * s);
+  const float t = v * (1.f - (1.f - f) * s);
   switch (hi) {
-    case 0: r = v; g = t; b = p; break;
     case 1: r = q; g = v; b = p; break;
     case 2: r = p; g = v; b = t; break;
     case 3: r = p; g = q; b = v; break;
     case 4: r = t; g = p; b = v; break;
-    default: r = v; g = p; b = q; break;
+    case 5: r = v; g = p; b = q; break;
+    default: r = v; g = t; b = p; break;   // 0 (and 6 == a full turn)
   }
 }
-__device__ __forceinline__ void color_ops(float& r, float& g, float& b, const float* __restrict__ P) {
-  r = fminf(__fmul_rn(r, P[0]), 1.f);
-  b = fminf(__fmul_rn(b, P[1]), 1.f);
-  const int order = static_cast<int>(P[6]);
-  if (order < 0) return;
-  const uint32_t code = c_orders[order];
+// planckian gain, then the four jiggle ops in the sampled order. Saturation and hue act on different HSV components, so
+// when they are adjacent in the order they share one RGB <-> HSV round trip.
+__device__ __forceinline__ void color_ops(float& r, float& g, float& b, const float* __restrict__ P, uint32_t code,
+                                          float hue6) {
+  r = fminf(r * P[0], 1.f);
+  b = fminf(b * P[1], 1.f);
+  if (code == 0xFFFFFFFFu) return;
 #pragma unroll
   for (int slot = 0; slot < 4; ++slot) {
     const int op = (code >> (6 - 2 * slot)) & 3;
     if (op == 0) {
       r = clamp01(r + P[2]); g = clamp01(g + P[2]); b = clamp01(b + P[2]);
     } else if (op == 1) {
-      r = clamp01(__fmul_rn(r, P[3])); g = clamp01(__fmul_rn(g, P[3])); b = clamp01(__fmul_rn(b, P[3]));
-    } else if (op == 2) {
-      float h, s, v;
-      rgb_to_hsv(r, g, b, h, s, v);
-      hsv_to_rgb(h, clamp01(__fmul_rn(s, P[4])), v, r, g, b);
+      r = clamp01(r * P[3]); g = clamp01(g * P[3]); b = clamp01(b * P[3]);
     } else {
-      float h, s, v;
-      rgb_to_hsv(r, g, b, h, s, v);
-      h = h + P[5];
-      h = __fadd_rn(h, -__fmul_rn(6.28318530717958647692f, floorf(__fdiv_rn(h, 6.28318530717958647692f))));
-      hsv_to_rgb(h, s, v, r, g, b);
+      const int nxt = slot < 3 ? static_cast<int>((code >> (4 - 2 * slot)) & 3) : -1;
+      const int prv = slot > 0 ? static_cast<int>((code >> (8 - 2 * slot)) & 3) : -1;
+      if (prv >= 2) continue;   // already applied together with the previous (saturation / hue) slot
+      const bool both = nxt >= 2;
+      float h6, s, v;
+      rgb_to_hsv(r, g, b, h6, s, v);
+      if (op == 2 || both) s = clamp01(s * P[4]);
+      if (op == 3 || both) {
+        h6 += hue6;
+        h6 = h6 < 0.f ? h6 + 6.f : (h6 >= 6.f ? h6 - 6.f : h6);
+      }
+      hsv_to_rgb(h6, s, v, r, g, b);
     }
   }
 }
@@ -274,142 +353,162 @@ constexpr int kMid = kTile + 2;          // 34
 
 template <bool IN_U8, bool OUT_S2D>
 __global__ void __launch_bounds__(256)
-augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float* __restrict__ params, int H, int W,
-               int apply) {
+augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float* __restrict__ params,
+               const uint32_t* __restrict__ arc_mask, const uint32_t* __restrict__ plasma_mask, int H, int W, int apply) {
   pdl_prologue();
   __shared__ float sA[3][kIn][kIn + 1];    // colour-jittered input with halo; later reused for the blurred tile
   __shared__ float sB[3][kIn][kMid + 1];   // after the horizontal gaussian pass
   __shared__ float sP[kAugParams];
-  __shared__ float sLat[6 * kWin * kWin];
-  __shared__ int sIy0[6], sIx0[6];
   const int n = blockIdx.z;
   const int y0 = blockIdx.y * kTile, x0 = blockIdx.x * kTile;
   // (apply == 0 is plain u8 -> bf16 staging: the parameter table may be NULL and is never read)
   if (threadIdx.x < kAugParams) sP[threadIdx.x] = apply ? params[static_cast<size_t>(n) * kAugParams + threadIdx.x] : 0.f;
   __syncthreads();
   const float sigma = apply ? sP[7] : 0.f;
-  // plasma lattice window of this tile (a 32-pixel tile spans at most 16 cells of the finest octave when the image
-  // side is >= 128; smaller images fall back to hashing per pixel)
-  const bool use_table = (H >= 128 && W >= 128);
-  const uint64_t seed_bits = static_cast<uint64_t>(rintf(sP[20] * 16777216.f));
-  if (apply && sP[18] != 0.f && use_table) {
-    if (threadIdx.x < 6) {
-      const int l = threadIdx.x;
-      const float cells = static_cast<float>(2 << l);
-      sIy0[l] = static_cast<int>(floorf(__fmul_rn(__fmul_rn(static_cast<float>(y0) + 0.5f, 1.f / H), cells)));
-      sIx0[l] = static_cast<int>(floorf(__fmul_rn(__fmul_rn(static_cast<float>(x0) + 0.5f, 1.f / W), cells)));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 6 * kWin * kWin; i += 256) {
-      const int l = i / (kWin * kWin);
-      const int rem = i - l * kWin * kWin;
-      const int ry = rem / kWin, rx = rem - ry * kWin;
-      const int iy = sIy0[l] + ry, ix = sIx0[l] + rx;
-      const int side = (2 << l) + 1;
-      sLat[i] = (iy < side && ix < side) ? lattice(seed_bits, l, iy, ix) : 0.f;
-    }
-  }
+  const bool motion = apply && !(sP[12] == 1.f);           // identity kernel = off
+  // halo actually needed by this image: 2 for the gaussian, 1 for the motion kernel
+  const int halo = (sigma > 0.f ? 2 : 0) + (motion ? 1 : 0);
+  const int lo = kHalo - halo, span = kTile + 2 * halo;   // tile-local index range [lo, lo + span) per axis
+  const uint32_t code = (apply && sP[6] >= 0.f) ? c_orders[static_cast<int>(sP[6])] : 0xFFFFFFFFu;
+  const float hue6 = sP[5] * 0.95492965855137201461f;   // radians -> sixths of a turn
+  const int e1 = apply && sP[24] != 0.f, e2 = apply && sP[29] != 0.f;
+  const int e1x = static_cast<int>(sP[25]), e1y = static_cast<int>(sP[26]), e1w = static_cast<int>(sP[27]), e1h = static_cast<int>(sP[28]);
+  const int e2x = static_cast<int>(sP[30]), e2y = static_cast<int>(sP[31]), e2w = static_cast<int>(sP[32]), e2h = static_cast<int>(sP[33]);
+  const size_t img_words = static_cast<size_t>(H) * (W >> 5);
 
-  // ---- stage 1: load (+ reflect), /255, colour ops
-  for (int i = threadIdx.x; i < kIn * kIn; i += 256) {
-    const int ty = i / kIn, tx = i - ty * kIn;
+  // ---- stage 1: load (+ reflect), arcs, /255, erasing, colour ops
+  for (int i = threadIdx.x; i < span * span; i += 256) {
+    const int ty = lo + i / span, tx = lo + i % span;
     int gy = y0 - kHalo + ty, gx = x0 - kHalo + tx;
     gy = gy < 0 ? -gy : (gy >= H ? 2 * (H - 1) - gy : gy);
     gx = gx < 0 ? -gx : (gx >= W ? 2 * (W - 1) - gx : gx);
     float r, g, b;
     if (IN_U8) {
       const uint8_t* p = static_cast<const uint8_t*>(in) + (static_cast<size_t>(n) * H * W + static_cast<size_t>(gy) * W + gx) * 3;
-      r = __fmul_rn(static_cast<float>(p[0]), 1.0f / 255.0f);
-      g = __fmul_rn(static_cast<float>(p[1]), 1.0f / 255.0f);
-      b = __fmul_rn(static_cast<float>(p[2]), 1.0f / 255.0f);
+      r = static_cast<float>(p[0]) * (1.0f / 255.0f);
+      g = static_cast<float>(p[1]) * (1.0f / 255.0f);
+      b = static_cast<float>(p[2]) * (1.0f / 255.0f);
+      if (arc_mask != nullptr) {
+        const uint32_t wbits = __ldg(arc_mask + n * img_words + static_cast<size_t>(gy) * (W >> 5) + (gx >> 5));
+        if ((wbits >> (gx & 31)) & 1u) { r = 0.f; g = 0.f; b = 0.f; }
+      }
     } else {
       const float* p = static_cast<const float*>(in) + static_cast<size_t>(n) * 3 * H * W + static_cast<size_t>(gy) * W + gx;
       r = p[0]; g = p[static_cast<size_t>(H) * W]; b = p[2 * static_cast<size_t>(H) * W];
     }
-    if (apply) color_ops(r, g, b, sP);
+    if (apply) {
+      if (e1 && gx >= e1x && gx < e1x + e1w && gy >= e1y && gy < e1y + e1h) { r = 0.f; g = 0.f; b = 0.f; }
+      if (e2 && gx >= e2x && gx < e2x + e2w && gy >= e2y && gy < e2y + e2h) { r = 1.f; g = 1.f; b = 1.f; }
+      color_ops(r, g, b, sP, code, hue6);
+    }
     sA[0][ty][tx] = r; sA[1][ty][tx] = g; sA[2][ty][tx] = b;
   }
   __syncthreads();
 
-  // ---- stage 2: separable 5-tap gaussian (reflect already materialised in the halo)
+  // ---- stage 2: separable 5-tap gaussian (reflect already materialised in the halo). Rows needed: the motion window
+  int off = 2;   // index offset of the (blurred or not) image window inside sA: window (oy, ox) <-> pixel (y0-1+oy, ..)
   if (sigma > 0.f) {
     float k[5];
     float ks = 0.f;
 #pragma unroll
     for (int i = 0; i < 5; ++i) {
       const float d = static_cast<float>(i - 2);
-      k[i] = expf(__fdiv_rn(-__fmul_rn(d, d), __fmul_rn(__fmul_rn(2.f, sigma), sigma)));
-      ks = __fadd_rn(ks, k[i]);
+      k[i] = __expf(-d * d / (2.f * sigma * sigma));
+      ks += k[i];
     }
+    const float inv = 1.f / ks;
 #pragma unroll
-    for (int i = 0; i < 5; ++i) k[i] = __fdiv_rn(k[i], ks);
-    for (int i = threadIdx.x; i < 3 * kIn * kMid; i += 256) {
-      const int c = i / (kIn * kMid);
-      const int rem = i - c * kIn * kMid;
-      const int ty = rem / kMid, ox = rem - ty * kMid;
+    for (int i = 0; i < 5; ++i) k[i] *= inv;
+    // window = tile + 1 pixel of motion halo when the motion kernel is on (mlo = 0), else just the tile (mlo = 1)
+    const int mlo = motion ? 0 : 1, mspan = kMid - 2 * mlo;
+    for (int i = threadIdx.x; i < 3 * span * mspan; i += 256) {
+      const int c = i / (span * mspan);
+      const int rem = i - c * span * mspan;
+      const int ty = lo + rem / mspan, ox = mlo + rem % mspan;
       float acc = 0.f;
 #pragma unroll
-      for (int t = 0; t < 5; ++t) acc = __fadd_rn(acc, __fmul_rn(k[t], sA[c][ty][ox + t]));
+      for (int t = 0; t < 5; ++t) acc = fmaf(k[t], sA[c][ty][ox + t], acc);
       sB[c][ty][ox] = acc;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * kMid * kMid; i += 256) {
-      const int c = i / (kMid * kMid);
-      const int rem = i - c * kMid * kMid;
-      const int oy = rem / kMid, ox = rem - oy * kMid;
+    for (int i = threadIdx.x; i < 3 * mspan * mspan; i += 256) {
+      const int c = i / (mspan * mspan);
+      const int rem = i - c * mspan * mspan;
+      const int oy = mlo + rem / mspan, ox = mlo + rem % mspan;
       float acc = 0.f;
 #pragma unroll
-      for (int t = 0; t < 5; ++t) acc = __fadd_rn(acc, __fmul_rn(k[t], sB[c][oy + t][ox]));
+      for (int t = 0; t < 5; ++t) acc = fmaf(k[t], sB[c][oy + t][ox], acc);
       sA[c][oy][ox] = acc;   // (oy, ox) <-> pixel (y0 - 1 + oy, x0 - 1 + ox)
     }
+    off = 0;
+    __syncthreads();
   }
-  __syncthreads();
   // motion blur uses a zero ('constant') border: blank the window positions that fall outside the image
-  // (without the gaussian pass the window is simply the centre of the halo tile: index offset 2)
-  const int off = sigma > 0.f ? 0 : 2;
-  for (int i = threadIdx.x; i < kMid * kMid; i += 256) {
-    const int oy = i / kMid, ox = i - oy * kMid;
-    const int gy = y0 - 1 + oy, gx = x0 - 1 + ox;
-    if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
-      sA[0][oy + off][ox + off] = 0.f; sA[1][oy + off][ox + off] = 0.f; sA[2][oy + off][ox + off] = 0.f;
-    }
-  }
-  __syncthreads();
-
-  // ---- stage 3: 3x3 motion kernel, plasma shadow, clamp, store. Thread = one 2x2 pixel quad (one s2d pixel).
-  const int sy = threadIdx.x >> 4, sx = threadIdx.x & 15;
-  const float inv_h = 1.f / H, inv_w = 1.f / W;
-  const float roughness = sP[17], intensity = apply ? sP[18] : 0.f, quantity = sP[19];
-  const float p_lo = sP[21], p_den = fmaxf(sP[22] - sP[21], 1e-12f);
-  float v[2][2][3];
-#pragma unroll
-  for (int a = 0; a < 2; ++a)
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int py = 2 * sy + a, px = 2 * sx + b;   // position inside the tile; window index = +1
-      float shade = 0.f;
-      if (intensity != 0.f) {
-        const float f = use_table
-                            ? plasma_eval(y0 + py, x0 + px, inv_h, inv_w, roughness, TileTable{sLat, sIy0, sIx0})
-                            : plasma_eval(y0 + py, x0 + px, inv_h, inv_w, roughness, HashLattice{seed_bits});
-        const float fn = __fdiv_rn(f - p_lo, p_den);
-        shade = fn < quantity ? intensity : 0.f;
+  if (motion && (y0 == 0 || x0 == 0 || y0 + kTile == H || x0 + kTile == W)) {
+    for (int i = threadIdx.x; i < kMid * kMid; i += 256) {
+      const int oy = i / kMid, ox = i - oy * kMid;
+      const int gy = y0 - 1 + oy, gx = x0 - 1 + ox;
+      if (gy < 0 || gy >= H || gx < 0 || gx >= W) {
+        sA[0][oy + off][ox + off] = 0.f; sA[1][oy + off][ox + off] = 0.f; sA[2][oy + off][ox + off] = 0.f;
       }
+    }
+    __syncthreads();
+  }
+
+  // ---- stage 3: 3x3 motion kernel, plasma shadow, clamp, salt & pepper, store. Thread = one 2x2 quad (one s2d pixel).
+  const int sy = threadIdx.x >> 4, sx = threadIdx.x & 15;
+  const float intensity = apply ? sP[18] : 0.f;
+  uint32_t shadow[2] = {0u, 0u};
+  if (intensity != 0.f) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
+    for (int a = 0; a < 2; ++a)
+      shadow[a] = __ldg(plasma_mask + n * img_words + static_cast<size_t>(y0 + 2 * sy + a) * (W >> 5) + (x0 >> 5)) >> (2 * sx);
+  }
+  const bool snp = apply && sP[34] != 0.f;
+  const uint32_t snp_seed = static_cast<uint32_t>(rintf(sP[37] * 16777216.f));
+  float v[2][2][3];
+  float km[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) km[i] = sP[8 + i];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float w[4][4];
+    if (motion) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w[i][j] = sA[c][2 * sy + i + off][2 * sx + j + off];
+    }
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
         float acc;
-        if (apply) {
+        if (motion) {
           acc = 0.f;
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j < 3; ++j) acc = __fadd_rn(acc, __fmul_rn(sP[8 + i * 3 + j], sA[c][py + i + off][px + j + off]));
+            for (int j = 0; j < 3; ++j) acc = fmaf(km[i * 3 + j], w[a + i][b + j], acc);
         } else {
-          acc = sA[c][py + 1 + off][px + 1 + off];
+          acc = sA[c][2 * sy + a + 1 + off][2 * sx + b + 1 + off];
         }
+        const float shade = ((shadow[a] >> b) & 1u) ? intensity : 0.f;
         v[a][b][c] = clamp01(acc + shade);
       }
-    }
+  }
+  if (snp) {
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const uint32_t gy = y0 + 2 * sy + a, gx = x0 + 2 * sx + b;
+        if (pixel_uniform(snp_seed, 100u, gy, gx) < sP[35]) {
+          const float val = pixel_uniform(snp_seed, 101u, gy, gx) < sP[36] ? 1.f : 0.f;
+          v[a][b][0] = val; v[a][b][1] = val; v[a][b][2] = val;
+        }
+      }
+  }
   if (OUT_S2D) {
     // [n][H/2][W/2 + 4][16] bf16; channel = (a*2 + b)*3 + c
     const int Hs = H >> 1, Ws = W >> 1, Wp = Ws + 4;
@@ -438,11 +537,11 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// spaghetti arcs (reference: argus/utils.py:252-275 draw_spaghetti, applied to the decoded image at
-// argus/data.py:212-215 before the kornia chain; PIL on the loader's CPU workers there). Rasterisation rule and
-// sampling: oracle/augment.py (calibrated against Pillow's ImageDraw.arc, IoU 0.92; bit-exact against the oracle).
+// spaghetti arcs (reference: argus/utils.py:252-275 draw_spaghetti, applied to the decoded image at argus/data.py:212-215
+// before the kornia chain; PIL's ImageDraw.arc on the loader's CPU workers there). The rasteriser below restates Pillow's
+// algorithm (integer quadrant walk of the outer / inner ellipse + clipping by the ellipse normals at the start / end
+// angles) and is pinned pixel for pixel against the real Pillow through oracle/pil_arc.py.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kArcFields = 10;   // cx, cy, rx, ry, cos0, sin0, cos1, sin1, width, sweep_deg
 constexpr uint64_t kArcFieldBase = 1000;
 
 __global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, int n_arcs, int H, int W, uint64_t seed,
@@ -452,7 +551,7 @@ __global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, 
   if (t >= n_images * n_arcs) return;
   const uint64_t img = t / n_arcs, a = t % n_arcs;
   auto U = [&](uint64_t k) { return hash_uniform(seed, step, img, kArcFieldBase + a * 8 + k); };
-  auto randint = [](float u, int lo, int hi) {
+  auto randint = [](float u, int lo, int hi) {   // np.random.randint(lo, hi)
     const int v = lo + static_cast<int>(floorf(__fmul_rn(u, static_cast<float>(hi - lo))));
     return v < hi - 1 ? v : hi - 1;
   };
@@ -460,47 +559,210 @@ __global__ void spaghetti_params_kernel(float* __restrict__ arcs, int n_images, 
   const int x1 = randint(U(2), x0, W), y1 = randint(U(3), y0, H);
   const int a0 = randint(U(4), 0, 360), a1 = randint(U(5), 0, 360);
   float* A = arcs + static_cast<size_t>(t) * kArcFields;
-  A[0] = __fmul_rn(static_cast<float>(x0 + x1), 0.5f);
-  A[1] = __fmul_rn(static_cast<float>(y0 + y1), 0.5f);
-  A[2] = __fadd_rn(__fmul_rn(static_cast<float>(x1 - x0), 0.5f), 0.5f);
-  A[3] = __fadd_rn(__fmul_rn(static_cast<float>(y1 - y0), 0.5f), 0.5f);
-  const double r0 = static_cast<double>(a0) * 0.017453292519943295, r1 = static_cast<double>(a1) * 0.017453292519943295;
-  A[4] = static_cast<float>(cos(r0)); A[5] = static_cast<float>(sin(r0));
-  A[6] = static_cast<float>(cos(r1)); A[7] = static_cast<float>(sin(r1));
-  A[8] = floorf(__fadd_rn(1.0f, __fmul_rn(U(6), 4.0f)));
-  A[9] = static_cast<float>(((a1 - a0) % 360 + 360) % 360);
+  A[0] = static_cast<float>(x0); A[1] = static_cast<float>(y0); A[2] = static_cast<float>(x1); A[3] = static_cast<float>(y1);
+  A[4] = static_cast<float>(a0); A[5] = static_cast<float>(a1);
+  A[6] = floorf(__fadd_rn(1.0f, __fmul_rn(U(6), 4.0f)));   // int(np.random.uniform(1, 5))
+  A[7] = 0.f;
 }
 
-// thread = one pixel; black where any arc covers it (n_arcs <= 16 cached in shared memory per image row block)
-__global__ void __launch_bounds__(256)
-spaghetti_draw_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const float* __restrict__ arcs,
-                      int n_arcs, int H, int W) {
-  pdl_prologue();
-  __shared__ float sArc[16 * kArcFields];
-  const int n = blockIdx.y;
-  for (int i = threadIdx.x; i < n_arcs * kArcFields; i += blockDim.x)
-    sArc[i] = arcs[static_cast<size_t>(n) * n_arcs * kArcFields + i];
-  __syncthreads();
-  const int pix = blockIdx.x * blockDim.x + threadIdx.x;
-  if (pix >= H * W) return;
-  const int y = pix / W, x = pix - y * W;
-  bool hit = false;
-  for (int k = 0; k < n_arcs; ++k) {
-    const float* A = sArc + k * kArcFields;
-    const float dx = __fadd_rn(static_cast<float>(x), -A[0]), dy = __fadd_rn(static_cast<float>(y), -A[1]);
-    const float u = __fdiv_rn(dx, A[2]), v = __fdiv_rn(dy, A[3]);
-    if (!(__fadd_rn(__fmul_rn(u, u), __fmul_rn(v, v)) <= 1.0f)) continue;
-    const float irx = __fadd_rn(A[2], -A[8]), iry = __fadd_rn(A[3], -A[8]);
-    if (irx > 0.f && iry > 0.f) {
-      const float ui = __fdiv_rn(dx, irx), vi = __fdiv_rn(dy, iry);
-      if (__fadd_rn(__fmul_rn(ui, ui), __fmul_rn(vi, vi)) < 1.0f) continue;
-    }
-    const float a = __fadd_rn(__fmul_rn(A[4], v), -__fmul_rn(A[5], u));
-    const float b = __fadd_rn(__fmul_rn(A[7], u), -__fmul_rn(A[6], v));
-    const bool sector = (A[9] <= 180.f) ? (a >= 0.f && b >= 0.f) : !(a < 0.f && b < 0.f);
-    if (sector) { hit = true; break; }
+// Pillow's quarter_state: one quadrant of the ellipse with semi-axes (a, b) in doubled coordinates, walked from
+// (a, b % 2) to (a % 2, b) by steps (0,+2), (-2,+2), (-2,0), each time to the candidate closest to the ellipse.
+struct QuarterWalk {
+  int a, b, cx, cy, ex, ey;
+  long long a2, b2, a2b2;
+  bool finished;
+  __device__ void init(int a_, int b_) {
+    finished = a_ < 0 || b_ < 0;
+    a = a_; b = b_;
+    cx = a_; cy = b_ & 1; ex = a_ & 1; ey = b_;
+    a2 = static_cast<long long>(a_) * a_; b2 = static_cast<long long>(b_) * b_; a2b2 = a2 * b2;
   }
-  const size_t o = (static_cast<size_t>(n) * H * W + pix) * 3;
+  __device__ long long delta(long long x, long long y) const { return llabs(a2 * y * y + b2 * x * x - a2b2); }
+  __device__ bool next(int& rx, int& ry) {
+    if (finished) return false;
+    rx = cx; ry = cy;
+    if (cx == ex && cy == ey) {
+      finished = true;
+    } else {
+      int nx = cx, ny = cy + 2;
+      long long nd = delta(nx, ny);
+      if (nx > 1) {
+        long long d = delta(cx - 2, cy + 2);
+        if (nd > d) { nx = cx - 2; ny = cy + 2; nd = d; }
+        d = delta(cx - 2, cy);
+        if (nd > d) { nx = cx - 2; ny = cy; }
+      }
+      cx = nx; cy = ny;
+    }
+    return true;
+  }
+};
+
+struct ArcInterval { int lo, hi; bool ok; };
+__device__ __forceinline__ ArcInterval iv_isect(ArcInterval p, ArcInterval q) {
+  ArcInterval r;
+  r.lo = max(p.lo, q.lo); r.hi = min(p.hi, q.hi);
+  r.ok = p.ok && q.ok && r.lo <= r.hi;
+  return r;
+}
+__device__ __forceinline__ int pil_round_up(double f) {
+  return f >= 0.0 ? static_cast<int>(floor(f + 0.5)) : -static_cast<int>(floor(fabs(f) + 0.5));
+}
+__device__ __forceinline__ int pil_round_down(double f) {
+  return f >= 0.0 ? static_cast<int>(ceil(f - 0.5)) : -static_cast<int>(ceil(fabs(f) - 0.5));
+}
+constexpr int kArcInf = 1 << 30;
+// integer interval of the scan coordinate x with A x + B y + C >= 0
+__device__ __forceinline__ ArcInterval arc_halfplane(double A, double B, double C, int y) {
+  ArcInterval r;
+  r.lo = -kArcInf; r.hi = kArcInf; r.ok = true;
+  if (A > 1e-9) r.lo = pil_round_up(-(B * y + C) / A);
+  else if (A < -1e-9) r.hi = pil_round_down(-(B * y + C) / A);
+  else r.ok = (B * y + C >= -1e-9);
+  return r;
+}
+// what the arc [al, ar] leaves of the half ellipse k (0: angles 0..180, 1: 180..360):
+// 0 none, 1 all, 2 from the start cap on, 3 up to the end cap, 4 between the caps, 5 everything but the gap
+__device__ int arc_half_rule(double al, double ar, int k) {
+  const double e = ar < 360.0 ? ar : ar - 360.0;
+  const double q0 = 180.0 * k, q1 = q0 + 180.0;
+  const bool has_start = q0 <= al && al < q1, has_end = q0 < e && e <= q1;
+  if (has_start && has_end) return (ar - al) < 180.0 ? 4 : 5;
+  if (has_start) return 2;
+  if (has_end) return 3;
+  const double mid = q0 + 90.0;
+  return ((al <= mid && mid <= ar) || (al <= mid + 360.0 && mid + 360.0 <= ar)) ? 1 : 0;
+}
+__device__ void arc_normalize(double& al, double& ar) {
+  if (ar - al >= 360.0) { al = 0.0; ar = 360.0; return; }
+  al = fmod(al, 360.0);
+  if (al < 0.0) al += 360.0;
+  double d = fmod(ar - al, 360.0);
+  if (d < 0.0) d += 360.0;
+  ar = al + d;
+}
+
+constexpr int kArcMaxRows = 260;   // rows of the quadrant walk: Y = b % 2, b % 2 + 2, ..., b  (b <= 511)
+
+// one warp per arc: lanes 0 / 1 walk the outer / inner ellipse, then all lanes clip and paint the rows
+__global__ void __launch_bounds__(32)
+arc_paint_kernel(const float* __restrict__ arcs, uint32_t* __restrict__ mask, int n_arcs, int H, int W) {
+  pdl_prologue();
+  __shared__ int16_t s_r[kArcMaxRows], s_l[kArcMaxRows];
+  const int n = blockIdx.x / n_arcs;
+  const float* A = arcs + static_cast<size_t>(blockIdx.x) * kArcFields;
+  const int x0 = static_cast<int>(A[0]), y0 = static_cast<int>(A[1]), x1 = static_cast<int>(A[2]), y1 = static_cast<int>(A[3]);
+  const int wd = static_cast<int>(A[6]);
+  const int a = x1 - x0, b = y1 - y0;
+  double al = A[4], ar = A[5];
+  arc_normalize(al, ar);
+  if (ar == al || a < 0 || b < 0 || wd < 1 || (b >> 1) + 1 > kArcMaxRows) return;
+  const bool full = (ar == al + 360.0);
+  const int lane = threadIdx.x;
+  const int par = b & 1, leftmost = a & 1;
+  const int nrows = (b >> 1) + 1;   // index j <-> Y = par + 2 j
+  for (int j = lane; j < nrows; j += 32) { s_r[j] = -1; s_l[j] = static_cast<int16_t>(leftmost); }
+  __syncwarp();
+  if (lane == 0) {
+    // r(Y) = x of the FIRST point of the outer walk on row Y
+    QuarterWalk q;
+    q.init(a, b);
+    int cx, cy;
+    while (q.next(cx, cy)) {
+      const int j = (cy - par) >> 1;
+      if (s_r[j] < 0) s_r[j] = static_cast<int16_t>(cx);
+    }
+  } else if (lane == 1) {
+    // l(Y) = x of the LAST point of the inner walk on row Y (rows the inner ellipse does not reach keep `leftmost`)
+    QuarterWalk q;
+    q.init(a - 2 * (wd - 1), b - 2 * (wd - 1));
+    int cx, cy;
+    while (q.next(cx, cy)) s_l[(cy - par) >> 1] = static_cast<int16_t>(cx);
+  }
+  __syncwarp();
+  // clip tree (wide frame; a tall ellipse is handled transposed and the tree transposed back)
+  double lcA = 0, lcB = 0, lcC = 0, rcA = 0, rcB = 0, rcC = 0;
+  int rule[2] = {1, 1};
+  const bool transposed = a < b;
+  if (!full) {
+    double A_ = a, B_ = b, al2 = al, ar2 = ar;
+    if (transposed) {
+      A_ = b; B_ = a;
+      al2 = 90.0 - ar; ar2 = 90.0 - al;
+      arc_normalize(al2, ar2);
+    }
+    const double kPi = 3.14159265358979323846;
+    lcA = -A_ * sin(al2 * kPi / 180.0); lcB = B_ * cos(al2 * kPi / 180.0);
+    lcC = (A_ * A_ - B_ * B_) * sin(al2 * kPi / 90.0) / 2.0;
+    rcA = A_ * sin(ar2 * kPi / 180.0); rcB = -B_ * cos(ar2 * kPi / 180.0);
+    rcC = (B_ * B_ - A_ * A_) * sin(ar2 * kPi / 90.0) / 2.0;
+    rule[0] = arc_half_rule(al2, ar2, 0);
+    rule[1] = arc_half_rule(al2, ar2, 1);
+    if (transposed) {
+      double t = lcA; lcA = lcB; lcB = t;
+      t = rcA; rcA = rcB; rcB = t;
+    }
+  }
+  uint32_t* img = mask + static_cast<size_t>(n) * H * (W >> 5);
+  auto paint = [&](int py, ArcInterval o) {
+    if (!o.ok) return;
+    int p0 = (o.lo + a) >> 1, p1 = (o.hi + a) >> 1;   // o.lo + a >= 0 whenever the interval survives the segment clip
+    p0 = max(p0, 0); p1 = min(p1, a);
+    const int y = y0 + py;
+    if (p0 > p1 || y < 0 || y >= H) return;
+    int xa = max(x0 + p0, 0), xb = min(x0 + p1, W - 1);
+    for (int w0 = xa >> 5; w0 <= (xb >> 5); ++w0) {
+      const int lo = max(xa, w0 << 5) & 31, hi = min(xb, (w0 << 5) + 31) & 31;
+      const uint32_t bits = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+      atomicOr(img + static_cast<size_t>(y) * (W >> 5) + w0, bits);
+    }
+  };
+  for (int py = lane; py <= b; py += 32) {
+    const int sy = 2 * py - b;
+    const int Y = sy < 0 ? -sy : sy;
+    const int j = (Y - par) >> 1;
+    const int l = s_l[j], r = s_r[j];
+    ArcInterval segs[2];
+    int nseg;
+    if (!(l > 0 || l < r)) {
+      segs[0].lo = -r; segs[0].hi = r; segs[0].ok = true; nseg = 1;
+    } else {
+      // solid row of an even-width ellipse (l == 0): the centre pixel belongs to the left segment only
+      segs[0].lo = -r; segs[0].hi = -l; segs[0].ok = true;
+      segs[1].lo = l > 0 ? l : 2; segs[1].hi = r; segs[1].ok = segs[1].lo <= r;
+      nseg = 2;
+    }
+    for (int s = 0; s < nseg; ++s) {
+      if (!segs[s].ok) continue;
+      if (full) { paint(py, segs[s]); continue; }
+      const ArcInterval hl = arc_halfplane(lcA, lcB, lcC, sy), hr = arc_halfplane(rcA, rcB, rcC, sy);
+      for (int k = 0; k < 2; ++k) {
+        // half-plane node of half k: Y >= 0 / Y <= 0 in the wide frame, X >= 0 / X <= 0 once transposed back
+        const double sgn = k == 0 ? 1.0 : -1.0;
+        const ArcInterval hk = transposed ? arc_halfplane(sgn, 0.0, 0.0, sy) : arc_halfplane(0.0, sgn, 0.0, sy);
+        const ArcInterval base = iv_isect(segs[s], hk);
+        if (!base.ok || rule[k] == 0) continue;
+        switch (rule[k]) {
+          case 1: paint(py, base); break;
+          case 2: paint(py, iv_isect(base, hl)); break;
+          case 3: paint(py, iv_isect(base, hr)); break;
+          case 4: paint(py, iv_isect(iv_isect(base, hl), hr)); break;
+          default: paint(py, iv_isect(base, hl)); paint(py, iv_isect(base, hr)); break;
+        }
+      }
+    }
+  }
+}
+
+// out = in with the masked pixels painted black (uint8 HWC)
+__global__ void __launch_bounds__(256)
+spaghetti_apply_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, const uint32_t* __restrict__ mask,
+                       int64_t n_pixels) {
+  pdl_prologue();
+  const int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (pix >= n_pixels) return;
+  const bool hit = (mask[pix >> 5] >> (pix & 31)) & 1u;
+  const size_t o = static_cast<size_t>(pix) * 3;
   out[o] = hit ? 0 : in[o];
   out[o + 1] = hit ? 0 : in[o + 1];
   out[o + 2] = hit ? 0 : in[o + 2];
@@ -508,37 +770,57 @@ spaghetti_draw_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out,
 
 void spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
                              cudaStream_t s) {
-  ARGUS_CHECK(n_arcs >= 0 && n_arcs <= 16, "at most 16 arcs per image");
+  ARGUS_CHECK(n_arcs >= 0, "negative arc count");
   if (n_images * n_arcs <= 0) return;
-  ProfileScope prof("augment_params", s, 0, 40.0 * n_images * n_arcs);
+  ProfileScope prof("augment_params", s, 0, 4.0 * kArcFields * n_images * n_arcs);
   launch_kernel(spaghetti_params_kernel, (n_images * n_arcs + 127) / 128, 128, 0, s, arcs, n_images, n_arcs, H, W, seed, step);
   ARGUS_CUDA(cudaGetLastError());
 }
-void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_images, int n_arcs, int H, int W,
-                    cudaStream_t s) {
-  ARGUS_CHECK(n_arcs >= 0 && n_arcs <= 16, "at most 16 arcs per image");
+void spaghetti_mask(const float* arcs, uint32_t* mask, int n_images, int n_arcs, int H, int W, cudaStream_t s) {
+  ARGUS_CHECK(W % 32 == 0, "the arc mask needs W to be a multiple of 32");
+  ARGUS_CHECK(H <= 512 && W <= 512, "arc rasteriser: images up to 512 x 512");
   if (n_images <= 0) return;
-  ProfileScope prof("augment", s, 0, 6.0 * n_images * H * W);
-  dim3 grid((H * W + 255) / 256, n_images);
-  launch_kernel(spaghetti_draw_kernel, grid, 256, 0, s, in, out, arcs, n_arcs, H, W);
+  ProfileScope prof("spaghetti", s, 0, static_cast<double>(n_images) * H * W / 4.0);
+  ARGUS_CUDA(cudaMemsetAsync(mask, 0, static_cast<size_t>(n_images) * H * (W / 32) * sizeof(uint32_t), s));
+  pdl_break(s, kPdlAfterMemop);
+  if (n_arcs > 0) {
+    launch_kernel(arc_paint_kernel, n_images * n_arcs, 32, 0, s, arcs, mask, n_arcs, H, W);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+}
+void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, uint32_t* mask_ws, int n_images, int n_arcs, int H,
+                    int W, cudaStream_t s) {
+  if (n_images <= 0) return;
+  spaghetti_mask(arcs, mask_ws, n_images, n_arcs, H, W, s);
+  ProfileScope prof("spaghetti", s, 0, 6.0 * n_images * H * W);
+  const int64_t n_pixels = static_cast<int64_t>(n_images) * H * W;
+  launch_kernel(spaghetti_apply_kernel, static_cast<unsigned>((n_pixels + 255) / 256), 256, 0, s, in, out, mask_ws, n_pixels);
   ARGUS_CUDA(cudaGetLastError());
 }
 
-void augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step, const AugConfig& cfg,
-                           cudaStream_t s) {
-  ProfileScope prof("augment_params", s, 0, 96.0 * n_images);
+void augment_sample_params(float* params, int n_images, int n_cams, int H, int W, uint64_t seed, uint64_t step,
+                           const AugConfig& cfg, cudaStream_t s) {
+  ProfileScope prof("augment_params", s, 0, 4.0 * kAugParams * n_images);
   if (n_images <= 0) return;
-  launch_kernel(aug_params_kernel, (n_images + 127) / 128, 128, 0, s, params, n_images, n_cams, seed, step, cfg);
+  launch_kernel(aug_params_kernel, (n_images + 127) / 128, 128, 0, s, params, n_images, n_cams, H, W, seed, step, cfg);
   ARGUS_CUDA(cudaGetLastError());
 }
 
-void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* params, int n_images, int H, int W,
-                    bool apply, cudaStream_t s) {
+void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, const float* params, const uint32_t* arc_mask,
+                    uint32_t* plasma_mask, int n_images, int H, int W, bool apply, cudaStream_t s) {
   ARGUS_CHECK(H % kTile == 0 && W % kTile == 0, "augmentation needs H and W to be multiples of 32");
+  ARGUS_CHECK(!(arc_mask != nullptr && !in_u8), "the arc mask applies to uint8 input");
   if (n_images <= 0) return;
   if (apply) {
-    ProfileScope prof("augment_params", s, 0, 8.0 * n_images);
-    launch_kernel(plasma_minmax_kernel, n_images, 256, 0, s, params, H, W);
+    ARGUS_CHECK(plasma_mask != nullptr, "augmentation needs the plasma mask workspace (n * H * W / 8 bytes)");
+    ARGUS_CHECK(H <= 256 && W <= 256, "plasma shadow: images up to 256 x 256 (the fractal is built in shared memory)");
+    static bool attr_set = false;
+    if (!attr_set) {
+      ARGUS_CUDA(cudaFuncSetAttribute(plasma_mask_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPlasmaSmemBytes));
+      attr_set = true;
+    }
+    ProfileScope prof("plasma_mask", s, 0, static_cast<double>(n_images) * H * W / 8.0);
+    launch_kernel(plasma_mask_kernel, n_images, kPlasmaThreads, kPlasmaSmemBytes, s, params, plasma_mask, H, W);
     ARGUS_CUDA(cudaGetLastError());
   }
   // algorithmic bytes: u8 RGB in + bf16 RGB out = 9 B per pixel
@@ -547,10 +829,10 @@ void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* 
   ProfileScope prof("augment", s, 0, bytes);
   dim3 grid(W / kTile, H / kTile, n_images);
   const int ap = apply ? 1 : 0;
-  if (in_u8 && out_s2d) launch_kernel(augment_kernel<true, true>, grid, 256, 0, s, in, out, params, H, W, ap);
-  else if (in_u8 && !out_s2d) launch_kernel(augment_kernel<true, false>, grid, 256, 0, s, in, out, params, H, W, ap);
-  else if (!in_u8 && out_s2d) launch_kernel(augment_kernel<false, true>, grid, 256, 0, s, in, out, params, H, W, ap);
-  else launch_kernel(augment_kernel<false, false>, grid, 256, 0, s, in, out, params, H, W, ap);
+  if (in_u8 && out_s2d) launch_kernel(augment_kernel<true, true>, grid, 256, 0, s, in, out, params, arc_mask, plasma_mask, H, W, ap);
+  else if (in_u8 && !out_s2d) launch_kernel(augment_kernel<true, false>, grid, 256, 0, s, in, out, params, arc_mask, plasma_mask, H, W, ap);
+  else if (!in_u8 && out_s2d) launch_kernel(augment_kernel<false, true>, grid, 256, 0, s, in, out, params, arc_mask, plasma_mask, H, W, ap);
+  else launch_kernel(augment_kernel<false, false>, grid, 256, 0, s, in, out, params, arc_mask, plasma_mask, H, W, ap);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -228,10 +228,11 @@ int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t
 __global__ void __launch_bounds__(256)
 clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  int64_t n, const float* __restrict__ partial, int n_partial, float gscale, float max_norm, float lr,
-                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float* norm_out) {
+                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float* norm_out, int skip_nonfinite) {
   pdl_prologue();
   __shared__ float red[8];
   __shared__ float s_coef;
+  __shared__ int s_skip;
   // every block reduces the partial sums in the same order -> identical clip coefficient everywhere
   float acc = 0.f;
   for (int i = threadIdx.x; i < n_partial; i += blockDim.x) acc += partial[i];
@@ -245,30 +246,56 @@ clip_adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
     float coef = max_norm > 0.f ? max_norm / (norm + 1e-6f) : 1.f;
     coef = fminf(coef, 1.f);
     s_coef = coef * gscale;
+    // GradScaler protocol (argus/train.py:316-320): a step whose gradients are not finite is skipped as a whole
+    s_skip = (skip_nonfinite && !isfinite(norm)) ? 1 : 0;
     if (blockIdx.x == 0 && norm_out != nullptr) *norm_out = norm;
   }
   __syncthreads();
+  if (s_skip) return;
   const float coef = s_coef;
   const float step_size = lr / bc1;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
+  // 16-byte accesses: 4 loads + 3 stores of 16 B per thread and iteration (28 B per parameter)
+  const int64_t n4 = n >> 2;
+  float4* p4 = reinterpret_cast<float4*>(p);
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  float4* m4 = reinterpret_cast<float4*>(m);
+  float4* v4 = reinterpret_cast<float4*>(v);
+  auto upd = [&](float& pi, float gi, float& mi, float& vi) {
+    gi *= coef;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= step_size * (mi / denom);
+    pi -= step_size * (mi / denom);
+  };
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float4 pp = p4[i], mm = m4[i], vv = v4[i];
+    const float4 gg = __ldg(g4 + i);
+    upd(pp.x, gg.x, mm.x, vv.x);
+    upd(pp.y, gg.y, mm.y, vv.y);
+    upd(pp.z, gg.z, mm.z, vv.z);
+    upd(pp.w, gg.w, mm.w, vv.w);
+    m4[i] = mm;
+    v4[i] = vv;
+    p4[i] = pp;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    const int64_t i = (n4 << 2) + threadIdx.x;
+    float pi = p[i], mi = m[i], vi = v[i];
+    upd(pi, g[i], mi, vi);
+    m[i] = mi; v[i] = vi; p[i] = pi;
   }
 }
 void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* partial, int n_partial,
                     float gscale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
-                    float* norm_out, cudaStream_t s) {
+                    float* norm_out, bool skip_nonfinite, cudaStream_t s) {
   ProfileScope prof("clip_adam", s, 0, 28.0 * n);
+  ARGUS_CHECK((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+               reinterpret_cast<uintptr_t>(v)) % 16 == 0, "optimizer arenas must be 16-byte aligned");
   const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, static_cast<float>(step)));
-  launch_kernel(clip_adam_kernel, 4 * num_sms(), 256, 0, s, p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,
-                                                 beta2, eps, bc1, bc2_sqrt, norm_out);
+  launch_kernel(clip_adam_kernel, 8 * num_sms(), 256, 0, s, p, g, m, v, n, partial, n_partial, gscale, max_norm, lr, beta1,
+                beta2, eps, bc1, bc2_sqrt, norm_out, skip_nonfinite ? 1 : 0);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -29,24 +29,30 @@ void unpack_wgrads(const float* packed_grads, float* grads, const WeightPackEntr
                    cudaStream_t s);
 
 // ---- augmentation (argus/data.py:41-103, 213-225) ---------------------------------------------------------------
+constexpr int kAugParams = 40;   // floats per image in the parameter table (layout: oracle/augment.py::sample_params)
+constexpr int kArcFields = 8;    // floats per arc: x0, y0, x1, y1, start, end (degrees), width, 0
 struct AugConfig {
   int color_jiggle, planckian_jitter, blur, motion_blur, plasma_shadow;
   float brightness_lo, brightness_span, contrast_lo, contrast_span, saturation_lo, saturation_span, hue_lo, hue_span;
+  int random_erasing, salt_and_pepper;
 };
-// params: (n_images, 24) fp32 table, a pure function of (seed, step, image) — see oracle/augment.py::sample_params
-void augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step, const AugConfig& cfg,
-                           cudaStream_t s);
+// params: (n_images, kAugParams) fp32 table, a pure function of (seed, step, image) -- oracle/augment.py::sample_params
+void augment_sample_params(float* params, int n_images, int n_cams, int H, int W, uint64_t seed, uint64_t step,
+                           const AugConfig& cfg, cudaStream_t s);
 // in: u8 (n, H, W, 3) or fp32 (n, 3, H, W); out: bf16 space-to-depth [n][H/2][W/2+4][16] or fp32 (n, 3, H, W).
-// apply == false only converts layouts (validation / inference path). Writes plasma min/max into params[21..22].
-void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, float* params, int n_images, int H, int W,
-                    bool apply, cudaStream_t s);
+// apply == false only converts layouts (validation / inference path). arc_mask (nullable): 1 bit per pixel, painted black
+// before everything else (u8 input). plasma_mask: workspace of n * H * W / 8 bytes, written here (required when apply).
+void augment_images(const void* in, bool in_u8, void* out, bool out_s2d, const float* params, const uint32_t* arc_mask,
+                    uint32_t* plasma_mask, int n_images, int H, int W, bool apply, cudaStream_t s);
 
-// spaghetti arcs (argus/utils.py:252-275, applied at argus/data.py:212-215): arcs = (n_images, n_arcs, 10) fp32 table, a
-// pure function of (seed, step, image, arc); draw paints them black on uint8 HWC images (out may alias in)
+// spaghetti arcs (argus/utils.py:252-275, applied at argus/data.py:212-215): arcs = (n_images, n_arcs, kArcFields) fp32
+// table, a pure function of (seed, step, image, arc); mask = 1 bit per pixel [n][H][W/32] (Pillow's ImageDraw.arc, bit for
+// bit); draw paints them black on uint8 HWC images (out may alias in; mask_ws = workspace of n * H * W / 8 bytes)
 void spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
                              cudaStream_t s);
-void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, int n_images, int n_arcs, int H, int W,
-                    cudaStream_t s);
+void spaghetti_mask(const float* arcs, uint32_t* mask, int n_images, int n_arcs, int H, int W, cudaStream_t s);
+void spaghetti_draw(const uint8_t* in, uint8_t* out, const float* arcs, uint32_t* mask_ws, int n_images, int n_arcs, int H,
+                    int W, cudaStream_t s);
 
 // ---- batch norm -------------------------------------------------------------------------------------------
 // train: batch statistics -> scale/shift (+ saved mean/invstd, running-stat update, torch.nn.BatchNorm2d semantics)
@@ -149,6 +155,6 @@ int grad_sqnorm_partials(const float* g, int64_t n, float* partial, cudaStream_t
 // gscale multiplies gradients before the norm (1/world for data-parallel averaging).
 void clip_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* partial, int n_partial,
                     float gscale, float max_norm, float lr, float beta1, float beta2, float eps, int step,
-                    float* norm_out, cudaStream_t s);
+                    float* norm_out, bool skip_nonfinite, cudaStream_t s);
 
 }  // namespace argus

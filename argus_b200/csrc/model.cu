@@ -77,6 +77,8 @@ Model::~Model() {
   cudaFree(alg_mpartial_);
   cudaFree(wgrad_scratch_);
   cudaFree(pack_table_dev_);
+  cudaFree(stem_in_[0]);
+  cudaFree(stem_in_[1]);
   cudaFree(arena_);
 }
 
@@ -278,6 +280,21 @@ void Model::reserve(int max_batch, int H, int W, bool training) {
   build_plan(tmp);
   const size_t need = arena_used_;
   arena_ = saved;
+  const size_t stem_need = training ? static_cast<size_t>(max_batch) * n_cams_ * (H / 2) * (W / 2 + 4) * 16 : 0;
+  if (stem_need > stem_in_elems_) {
+    // (plan-build time only) every stream of this model must be idle before the staging buffers move
+    ARGUS_CUDA(cudaDeviceSynchronize());
+    for (int b = 0; b < 2; ++b) {
+      if (stem_in_[b]) ARGUS_CUDA(cudaFree(stem_in_[b]));
+      stem_in_[b] = nullptr;
+      ARGUS_CUDA(cudaMalloc(&stem_in_[b], stem_need * sizeof(bf16)));
+    }
+    stem_in_elems_ = stem_need;
+    plans_.clear();
+    last_train_plan_ = nullptr;
+    last_plan_ = nullptr;
+    staged_plan_ = nullptr;
+  }
   if (need > arena_bytes_) {
     if (arena_) ARGUS_CUDA(cudaFree(arena_));
     arena_ = nullptr;
@@ -319,17 +336,21 @@ void Model::build_plan(Plan& p) {
     cp.fwd = plan_conv_forward(c.shape, in, packed_ + c.packed_off, out_raw);
     cp.has_dgrad = want_dgrad;
   };
-  // ---- stem
-  p.x_s2d = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
-  p.x_s2d_alt = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
+  // ---- stem (training plans read the model-level double buffer; an eval plan owns a private input in the arena)
+  if (!tr) p.x_in = arena_alloc<bf16>(static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16);
   const int H1 = H / 2, W1 = W / 2;  // stem output
   const int H2 = H1 / 2, W2 = W1 / 2;  // after max pooling
   const size_t stem_elems = static_cast<size_t>(N) * H1 * W1 * 64;
   if (tr) p.raw0 = arena_alloc<bf16>(stem_elems); else p.act0 = arena_alloc<bf16>(stem_elems);
   p.pooled0 = arena_alloc<bf16>(stem_elems / 4);
   if (tr) p.idx0 = arena_alloc<uint8_t>(stem_elems / 4);
-  plan_conv(p.stem, stem_, N, H, W, p.x_s2d, tr ? p.raw0 : p.act0, false);
-  if (real) p.stem_fwd_alt = plan_conv_forward(stem_.shape, p.x_s2d_alt, packed_ + stem_.packed_off, tr ? p.raw0 : p.act0);
+  plan_conv(p.stem, stem_, N, H, W, tr ? stem_in_[0] : p.x_in, tr ? p.raw0 : p.act0, false);
+  if (real) {
+    ARGUS_CHECK(!tr || static_cast<size_t>(N) * (H / 2) * (W / 2 + 4) * 16 <= stem_in_elems_, "stem input buffers too small");
+    for (int b = 0; b < 2; ++b)
+      p.stem_fwd_buf[b] = plan_conv_forward(stem_.shape, tr ? stem_in_[b] : p.x_in, packed_ + stem_.packed_off,
+                                            tr ? p.raw0 : p.act0);
+  }
 
   // ---- bottleneck blocks
   p.blocks.assign(blocks_.size(), BlockPlan());
@@ -452,8 +473,9 @@ void Model::build_plan(Plan& p) {
   p.g_act0 = Q;
   p.g_raw0 = R;
   if (real) {
-    p.stem.wgrad = plan_conv_wgrad(stem_.shape, R, p.x_s2d, gpacked_ + stem_.gpacked_off);
-    p.stem_wgrad_alt = plan_conv_wgrad(stem_.shape, R, p.x_s2d_alt, gpacked_ + stem_.gpacked_off);
+    for (int b = 0; b < 2; ++b)
+      p.stem_wgrad_buf[b] = plan_conv_wgrad(stem_.shape, R, stem_in_[b], gpacked_ + stem_.gpacked_off);
+    p.stem.wgrad = p.stem_wgrad_buf[0];
     ensure_wgrad_scratch(p.stem.wgrad);
   }
 }
@@ -609,11 +631,15 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
   if (x == nullptr) {
     ARGUS_CHECK(staged_plan_ == &p, "forward(x = NULL) needs a preceding stage_input_u8() for the same batch shape");
   } else if (is_u8) {
-    pack_input_u8(static_cast<const uint8_t*>(x), p.x_s2d_alt, p.N, H, W, s);
+    pack_input_u8(static_cast<const uint8_t*>(x), training ? stem_in_[cur_in_ ^ 1] : p.x_in, p.N, H, W, s);
   } else {
-    pack_input_f32(static_cast<const float*>(x), p.x_s2d_alt, p.N, H, W, s);
+    pack_input_f32(static_cast<const float*>(x), training ? stem_in_[cur_in_ ^ 1] : p.x_in, p.N, H, W, s);
   }
-  p.use_alt_input();
+  if (training) {
+    cur_in_ ^= 1;
+    p.stem.fwd = p.stem_fwd_buf[cur_in_];
+    p.stem.wgrad = p.stem_wgrad_buf[cur_in_];
+  }
   staged_plan_ = nullptr;
   if (last_plan_ != &p) ++arena_epoch_;   // plans share the arena: whatever another plan kept there is gone
   last_plan_ = &p;
@@ -626,14 +652,15 @@ void Model::forward(const void* x, bool is_u8, int B, int H, int W, bool trainin
   head_forward(p, out, s);
 }
 
-void Model::stage_input_u8(const uint8_t* images, float* aug_params, int B, int H, int W, bool training, bool apply,
-                           cudaStream_t s) {
+void Model::stage_input_u8(const uint8_t* images, const float* aug_params, const uint32_t* arc_mask, uint32_t* plasma_ws,
+                           int B, int H, int W, bool training, bool apply, cudaStream_t s) {
   ARGUS_CHECK(B > 0, "empty batch");
   ARGUS_CHECK(!apply || aug_params != nullptr, "augmentation needs a parameter table");
   ARGUS_CHECK(precision_ == 0, "the fused augmentation + staging path exists in bf16 mode only");
   Plan& p = get_plan(B, H, W, training);
   fuzz_delay(2, s);
-  augment_images(images, true, p.x_s2d_alt, true, aug_params, p.N, H, W, apply, s);
+  augment_images(images, true, training ? stem_in_[cur_in_ ^ 1] : p.x_in, true, aug_params, arc_mask, plasma_ws, p.N, H, W,
+                 apply, s);
   staged_plan_ = &p;
 }
 

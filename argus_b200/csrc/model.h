@@ -84,18 +84,15 @@ struct Plan {
   int B = 0, H = 0, W = 0, N = 0;
   bool training = false;
   ConvPlan stem;
-  bf16 *x_s2d = nullptr, *raw0 = nullptr, *act0 = nullptr, *pooled0 = nullptr;
+  bf16 *raw0 = nullptr, *act0 = nullptr, *pooled0 = nullptr;
   // The stem input is double buffered so that the NEXT batch can be augmented / staged (on another stream) while the
-  // current one trains: x_s2d / stem.fwd / stem.wgrad describe the buffer the current pass reads, the *_alt members
-  // the one the next staging call writes. use_alt_input() swaps the two sets.
-  bf16* x_s2d_alt = nullptr;
-  ConvLaunch stem_fwd_alt;
-  WgradLaunch stem_wgrad_alt;
-  void use_alt_input() {
-    std::swap(x_s2d, x_s2d_alt);
-    std::swap(stem.fwd, stem_fwd_alt);
-    std::swap(stem.wgrad, stem_wgrad_alt);
-  }
+  // current one trains. The two buffers belong to the MODEL (Model::stem_in_, sized for the largest reserved batch,
+  // outside the per-plan arena layout), so that staging a batch of a different size -- the short last batch of an epoch --
+  // can never alias the buffer the in-flight step still reads. stem_fwd_buf / stem_wgrad_buf are the launches reading
+  // buffer 0 / 1; forward() copies the pair of the buffer it consumes into stem.fwd / stem.wgrad.
+  bf16* x_in = nullptr;   // eval plans: private stem input inside the arena (staging + forward run on one stream)
+  ConvLaunch stem_fwd_buf[2];
+  WgradLaunch stem_wgrad_buf[2];
   uint8_t* idx0 = nullptr;
   std::vector<BlockPlan> blocks;
   ConvPlan fc;
@@ -132,8 +129,9 @@ class Model {
   void forward(const void* x, bool is_u8, int B, int H, int W, bool training, float* out, cudaStream_t s);
   // Augmentation fused with input staging: uint8 (B*n_cams, H, W, 3) images -> augmented bf16 stem input of the plan
   // for (B, H, W, training). A following forward() with x == nullptr consumes it.
-  void stage_input_u8(const uint8_t* images, float* aug_params, int B, int H, int W, bool training, bool apply,
-                      cudaStream_t s);
+  // arc_mask (nullable): spaghetti arcs as 1 bit per pixel; plasma_ws: workspace of B * n_cams * H * W / 8 bytes
+  void stage_input_u8(const uint8_t* images, const float* aug_params, const uint32_t* arc_mask, uint32_t* plasma_ws, int B,
+                      int H, int W, bool training, bool apply, cudaStream_t s);
   // d_out: (B, 6) gradient of the loss wrt forward()'s output. Accumulates parameter gradients (+=) into the bound
   // gradient arena for stages [stage_begin, stage_end); stages must be run in increasing order 0..3.
   void backward(const float* d_out, int stage_begin, int stage_end, cudaStream_t s);
@@ -230,6 +228,10 @@ class Model {
   Plan* last_plan_ = nullptr;
   uint64_t arena_epoch_ = 1;   // bumped whenever another plan (they share the arena) runs a forward pass
   Plan* staged_plan_ = nullptr;
+  // stem input double buffer (see Plan): [n][H/2][W/2 + 4][16] bf16 each; cur_in_ = the buffer the last forward consumed
+  bf16* stem_in_[2] = {nullptr, nullptr};
+  size_t stem_in_elems_ = 0;
+  int cur_in_ = 0;
   // weight-gradient GEMMs run on a side stream, overlapping the HBM-bound BN-backward / dgrad chain
   cudaStream_t side_ = nullptr;
   cudaEvent_t ev_fork_ = nullptr, ev_wgrad_ = nullptr;

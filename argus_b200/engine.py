@@ -10,6 +10,7 @@ gradient arena is all-reduced in four reverse-order buckets over NCCL while the 
 from __future__ import annotations
 
 import ctypes
+import math
 from typing import Optional
 
 import torch
@@ -31,6 +32,56 @@ def all_reduce_bucket(bucket: torch.Tensor, group=None, async_op: bool = True):
     return dist.all_reduce(bucket, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
 
 
+class GradScaler:
+    """The reference's `torch.cuda.amp.GradScaler(enabled=cfg.amp)` (argus/train.py:234,316-320) for the fused engine:
+    same constructor defaults and the same protocol -- the loss gradient is multiplied by `get_scale()`, gradients are
+    unscaled before `clip_grad_norm_`, a step whose unscaled gradient norm is not finite is skipped as a whole, and
+    `update()` backs the scale off by `backoff_factor` after a skipped step or grows it by `growth_factor` after
+    `growth_interval` clean ones. What differs: the reduced-precision arithmetic under `amp=True` is
+    the bf16 tensor-core path (fp32 exponent range), not fp16 autocast, so skips are rare; like `scaler.step` in the
+    reference, an enabled scaler costs one host synchronisation per step (it reads the gradient norm)."""
+
+    def __init__(self, init_scale: float = 2.0 ** 16, growth_factor: float = 2.0, backoff_factor: float = 0.5,
+                 growth_interval: int = 2000, enabled: bool = True) -> None:
+        self._enabled = bool(enabled)
+        self._scale = float(init_scale)
+        self.growth_factor, self.backoff_factor = float(growth_factor), float(backoff_factor)
+        self.growth_interval = int(growth_interval)
+        self._growth_tracker = 0
+        self.skipped_steps = 0
+
+    def is_enabled(self) -> bool:
+        return self._enabled
+
+    def get_scale(self) -> float:
+        return self._scale if self._enabled else 1.0
+
+    def scale(self, outputs: torch.Tensor) -> torch.Tensor:
+        return outputs * self._scale if self._enabled else outputs
+
+    def update(self, found_inf: bool = False) -> None:
+        if not self._enabled:
+            return
+        if found_inf:
+            self._scale *= self.backoff_factor
+            self._growth_tracker = 0
+            self.skipped_steps += 1
+        else:
+            self._growth_tracker += 1
+            if self._growth_tracker == self.growth_interval:
+                self._scale *= self.growth_factor
+                self._growth_tracker = 0
+
+    def state_dict(self) -> dict:
+        return {"scale": self._scale, "growth_factor": self.growth_factor, "backoff_factor": self.backoff_factor,
+                "growth_interval": self.growth_interval, "_growth_tracker": self._growth_tracker} if self._enabled else {}
+
+    def load_state_dict(self, state: dict) -> None:
+        if self._enabled and state:
+            self._scale = float(state["scale"])
+            self._growth_tracker = int(state["_growth_tracker"])
+
+
 class TrainEngine:
     """Owns the optimizer state (flat Adam moments) and runs fused training steps on an NCameraCNN.
 
@@ -40,12 +91,16 @@ class TrainEngine:
         max_grad_norm: clip_grad_norm_ threshold (train.py:318); <= 0 disables clipping.
         process_group: torch.distributed group for data parallelism (None = single process).
         augmentation: optional argus_b200.data.Augmentation applied on device to uint8 image batches.
+        scaler: optional GradScaler (the reference's amp mode, train.py:234,298-300,316-320).
+
+    It also stands in the reference's `optimizer` slot of `initialize_training` (train.py:245-255): `param_groups`,
+    `zero_grad()`, `state_dict()` / `load_state_dict()` follow torch.optim.Adam's surface.
     """
 
     def __init__(self, model: NCameraCNN, lr: float = 1e-4, max_grad_norm: float = 1.0,
                  betas: tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  process_group: Optional["dist.ProcessGroup"] = None, distributed: Optional[bool] = None,
-                 augmentation=None) -> None:
+                 augmentation=None, scaler: Optional[GradScaler] = None) -> None:
         if not model.flat_params.is_cuda:
             raise _lib.ArgusError("TrainEngine needs the model on a CUDA device (no CPU fallback)")
         self.model = model
@@ -54,6 +109,7 @@ class TrainEngine:
         self.betas = (float(betas[0]), float(betas[1]))
         self.eps = float(eps)
         self.augmentation = augmentation
+        self.scaler = scaler
         self.step_count = 0
         self.device = model.flat_params.device
         if distributed is None:
@@ -100,14 +156,16 @@ class TrainEngine:
         if after is not None:
             self._side.wait_event(after)
         with torch.cuda.stream(self._side):
-            if aug is not None and aug.gpu_spaghetti:
-                images.record_stream(self._side)
-                images = aug.spaghetti_batch(images)
-            params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
-            B, _, H, W, _ = images.shape
+            B, n_cams, H, W, _ = images.shape
+            images = images.contiguous()
+            # (workspaces of their own: the step in flight on the main stream may still be using the default ones)
+            arc_mask = (aug.arc_mask(B * n_cams, H, W, self.device, tag="arcs_side")
+                        if (aug is not None and aug.gpu_spaghetti) else None)
+            params = aug.sample_params(B, n_cams, self.device, H=H, W=W) if apply else None
+            ws = aug.workspace(B * n_cams, H, W, self.device, tag="plasma_side") if apply else None
             model._ensure_bound()
             with torch.cuda.device(self.device):
-                _lib.call("argus_model_stage_input_u8", model._handle.ptr, images.contiguous(), params, int(B), int(H),
+                _lib.call("argus_model_stage_input_u8", model._handle.ptr, images, params, arc_mask, ws, int(B), int(H),
                           int(W), 1, int(apply), _lib.stream_ptr())
             self._staged_event.record(self._side)
         images.record_stream(self._side)
@@ -115,10 +173,24 @@ class TrainEngine:
             params.record_stream(self._side)
         self._staged = key
 
-    def forward_backward(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    # ------------------------------------------------------------------------------------------------------------
+    # torch.optim.Optimizer-like surface (the engine sits in the `optimizer` slot of initialize_training's tuple)
+    @property
+    def param_groups(self) -> list[dict]:
+        return [{"params": list(self.model.parameters()), "lr": self.lr, "betas": self.betas, "eps": self.eps,
+                 "weight_decay": 0.0}]
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        """Gradients live in the model's flat arena and are zeroed at the start of every backward pass."""
+        model = self.model
+        with torch.cuda.device(self.device):
+            _lib.call("argus_model_zero_grads", model._handle.ptr, _lib.stream_ptr())
+
+    def forward_backward(self, images: torch.Tensor, targets: torch.Tensor, loss_scale: float = 1.0) -> torch.Tensor:
         """Forward, loss, backward (+ bucketed gradient all-reduce). Returns the mean loss as a device scalar.
 
         images: (B, 3*n_cams, H, W) float32 in [0,1]  or  (B, n_cams, H, W, 3) uint8; targets: (B, 7) [t, q_xyzw].
+        loss_scale: GradScaler factor on d(loss)/d(pred) (`scaler.scale(loss).backward()`, train.py:316).
         """
         model = self.model
         lib_stream = _lib.stream_ptr()
@@ -136,20 +208,23 @@ class TrainEngine:
         elif images.dtype == torch.uint8 and model.precision == "fp32":
             # fp32 parity mode: the same augmentation kernel with fp32 NCHW output, then the fp32 network
             aug = self.augmentation
-            if aug is not None and aug.gpu_spaghetti:
-                images = aug.spaghetti_batch(images)
+            B_, n_cams, H, W, _ = images.shape
             if aug is not None and aug.train and aug.enabled:
-                out = model._forward_impl(aug.augment_batch(images), True)
+                arc_mask = aug.arc_mask(B_ * n_cams, H, W, self.device) if aug.gpu_spaghetti else None
+                out = model._forward_impl(aug.augment_batch(images, arc_mask=arc_mask), True)
+            elif aug is not None and aug.gpu_spaghetti:
+                out = model._forward_impl(aug.spaghetti_batch(images), True)
             else:
                 out = model._forward_impl(images, True)
         elif images.dtype == torch.uint8:
-            # fused augmentation + staging: uint8 pairs -> augmented bf16 stem input inside the model's arena
+            # fused augmentation + staging: uint8 pairs -> augmented bf16 stem input inside the model's staging buffer
             aug = self.augmentation
-            if aug is not None and aug.gpu_spaghetti:
-                images = aug.spaghetti_batch(images)
+            B_, n_cams, H, W, _ = images.shape
+            arc_mask = aug.arc_mask(B_ * n_cams, H, W, self.device) if (aug is not None and aug.gpu_spaghetti) else None
             apply = aug is not None and aug.train and aug.enabled
-            params = aug.sample_params(images.shape[0], images.shape[1], self.device) if apply else None
-            out = model._forward_impl(images, True, aug_params=params, augment=apply)
+            params = aug.sample_params(B_, n_cams, self.device, H=H, W=W) if apply else None
+            ws = aug.workspace(B_ * n_cams, H, W, self.device) if apply else None
+            out = model._forward_impl(images, True, aug_params=params, augment=apply, arc_mask=arc_mask, plasma_ws=ws)
         else:
             out = model._forward_impl(images, True)
         B = out.shape[0]
@@ -158,7 +233,8 @@ class TrainEngine:
         self._loss_mean.zero_()
         with torch.cuda.device(self.device):
             # d(mean loss)/d pred = grad / B   (train.py:308-309; the loss is always evaluated in fp32)
-            _lib.call("argus_pose_loss", out, targets, None, self._loss_mean, grad, int(B), 1.0 / B, lib_stream)
+            _lib.call("argus_pose_loss", out, targets, None, self._loss_mean, grad, int(B), float(loss_scale) / B,
+                      lib_stream)
             _lib.call("argus_model_zero_grads", model._handle.ptr, lib_stream)
             works = []
             buckets = gradient_buckets(model.flat_grads, self._stage_ranges)
@@ -171,24 +247,37 @@ class TrainEngine:
                 w.wait()
         return self._loss_mean[0]
 
-    def optimizer_step(self) -> None:
-        """clip_grad_norm_ + Adam on the flat arenas, then refresh the packed bf16 weights."""
+    def optimizer_step(self, inv_loss_scale: float = 1.0, skip_nonfinite: bool = False) -> None:
+        """clip_grad_norm_ + Adam on the flat arenas, then refresh the packed bf16 weights.
+        skip_nonfinite: GradScaler protocol -- nothing is updated when the unscaled gradient norm is not finite."""
         model = self.model
         self.step_count += 1
         lib = _lib.load()
+        fn = lib.argus_clip_adam_step_amp if skip_nonfinite else lib.argus_clip_adam_step
         with torch.cuda.device(self.device):
-            _lib.check(lib.argus_clip_adam_step(
+            _lib.check(fn(
                 _lib.ptr(model.flat_params), _lib.ptr(model.flat_grads), _lib.ptr(self.exp_avg),
                 _lib.ptr(self.exp_avg_sq), ctypes.c_int64(model.flat_params.numel()), _lib.ptr(self._scratch),
-                ctypes.c_float(1.0 / self.world), ctypes.c_float(self.max_grad_norm), ctypes.c_float(self.lr),
+                ctypes.c_float(inv_loss_scale / self.world), ctypes.c_float(self.max_grad_norm), ctypes.c_float(self.lr),
                 ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps),
                 ctypes.c_int(self.step_count), _lib.ptr(self._grad_norm), _lib.stream_ptr()))
         model.sync_weights(force=True)
 
     def step(self, images: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
-        """One full training step; returns the (pre-update) mean loss as a device scalar without synchronising."""
-        loss = self.forward_backward(images, targets)
-        self.optimizer_step()
+        """One full training step; returns the (pre-update) mean loss as a device scalar. Without a GradScaler nothing
+        synchronises; with one (amp mode) the gradient norm is read back, as `scaler.step` does in the reference."""
+        scaler = self.scaler
+        if scaler is None or not scaler.is_enabled():
+            loss = self.forward_backward(images, targets)
+            self.optimizer_step()
+            return loss
+        scale = scaler.get_scale()
+        loss = self.forward_backward(images, targets, loss_scale=scale)
+        self.optimizer_step(inv_loss_scale=1.0 / scale, skip_nonfinite=True)
+        found_inf = not math.isfinite(float(self._grad_norm))      # host sync (train.py:319 does the same)
+        if found_inf:
+            self.step_count -= 1                                    # a skipped step does not advance Adam's counter
+        scaler.update(found_inf)
         return loss
 
     # ------------------------------------------------------------------------------------------------------------

@@ -273,16 +273,35 @@ class NCameraCNN(nn.Module):
             self._bound_key = key
             self._synced_version = -1
 
+    def _state_version(self) -> int:
+        """Monotone fingerprint of every in-place update to a parameter or buffer. After `_set_flat` each Parameter /
+        buffer is a separate view object with its OWN version counter (`p.data = view` detaches it from the flat
+        tensor's counter), so updates made through the module tree -- `load_state_dict`, `torch.optim.*.step()` on
+        `model.parameters()`, manual `p.data` edits, running-stat edits -- are only visible on the views."""
+        v = self._flat_params._version + self._flat_buffers._version
+        for p in self._param_list:
+            v += p._version
+        for node, leaf in self._buffer_slots:
+            v += node._buffers[leaf]._version
+        return v
+
     def sync_weights(self, force: bool = False) -> None:
-        """Refresh the packed bf16 weights if any parameter changed (in-place ops on the views bump the version)."""
+        """Refresh the packed bf16 weights (and mark the eval-mode BN fold dirty) if any parameter or buffer changed
+        since the last sync. Updates made by the library itself (TrainEngine's fused optimizer, running statistics of a
+        training forward) do not go through torch and are handled on the C side / by `force=True`."""
         self._ensure_bound()
-        v = self._flat_params._version
+        v = self._state_version()
         if force or v != self._synced_version:
             _lib.call("argus_model_sync_weights", self._handle.ptr, _lib.stream_ptr())
-            self._synced_version = self._flat_params._version
+            self._synced_version = v
+
+    def mark_dirty(self) -> None:
+        """Force a re-pack on the next forward (for edits torch cannot see, e.g. raw pointer writes into the arenas)."""
+        self._synced_version = -1
 
     def _forward_impl(self, x: torch.Tensor, training: bool, aug_params: Optional[torch.Tensor] = None,
-                      augment: bool = False) -> torch.Tensor:
+                      augment: bool = False, arc_mask: Optional[torch.Tensor] = None,
+                      plasma_ws: Optional[torch.Tensor] = None) -> torch.Tensor:
         self._ensure_bound()
         if x.device != self._flat_params.device:
             raise _lib.ArgusError(f"input is on {x.device} but the model is on {self._flat_params.device}")
@@ -300,9 +319,12 @@ class NCameraCNN(nn.Module):
         self.sync_weights()
         out = torch.empty((B, 6), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            if is_u8 and augment:
-                _lib.call("argus_model_stage_input_u8", self._handle.ptr, x, aug_params, int(B), int(H), int(W),
-                          int(training), 1, _lib.stream_ptr())
+            if is_u8 and (augment or arc_mask is not None):
+                # fused staging: arcs (bit mask) + augmentation (when `augment`) + /255 + bf16 space-to-depth packing
+                if augment and plasma_ws is None:
+                    plasma_ws = torch.empty((B * self.n_cams, H, W // 32), dtype=torch.int32, device=x.device)
+                _lib.call("argus_model_stage_input_u8", self._handle.ptr, x, aug_params, arc_mask, plasma_ws, int(B),
+                          int(H), int(W), int(training), int(augment), _lib.stream_ptr())
                 _lib.call("argus_model_forward", self._handle.ptr, None, 0, int(B), int(H), int(W), int(training), out,
                           _lib.stream_ptr())
             else:

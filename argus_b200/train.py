@@ -22,7 +22,7 @@ from torch.utils.data.distributed import DistributedSampler
 from . import ROOT
 from .data import Augmentation, AugmentationConfig
 from .dataset import CameraCubePoseDataset, CameraCubePoseDatasetConfig
-from .engine import TrainEngine
+from .engine import GradScaler, TrainEngine
 from .loss import geometric_loss_fn
 from .models import NCameraCNN, NCameraCNNConfig
 
@@ -49,8 +49,10 @@ class TrainConfig:
 
     # speed optimizations
     multigpu: bool = False
-    amp: bool = False  # accepted for CLI parity (the reference's fp16 autocast + GradScaler, train.py:74,234,298-300):
-    #                    the bf16 path has fp32's exponent range, so no loss scaling exists here
+    # mixed precision under the reference's GradScaler protocol (train.py:74,234,298-300,316-320): loss scaling, unscale
+    # before clipping, non-finite steps skipped. The reduced-precision arithmetic is the bf16 tensor-core path rather than
+    # fp16 autocast (engine.GradScaler); amp=True therefore requires precision="bf16"
+    amp: bool = False
     # not in the reference: "bf16" = tcgen05 tensor-core path (default), "fp32" = the fp32 parity mode (what the
     # reference computes with amp=False), see argus_model_set_precision in include/argus_b200.h
     precision: str = "bf16"
@@ -84,6 +86,8 @@ class TrainConfig:
         assert self.num_gpus > 0, "The number of GPUs must be greater than 0!"
         assert self.num_gpus <= torch.cuda.device_count(), \
             "The number of GPUs must be less than or equal to the number of GPUs on the system!"
+        assert not (self.amp and self.precision != "bf16"), \
+            "amp=True is mixed precision: it cannot be combined with precision='fp32'"
 
 
 class ReduceLROnPlateau:
@@ -111,7 +115,10 @@ def _collate_u8(samples: list[dict]) -> dict:
 
 
 def initialize_training(cfg: TrainConfig, rank: int = 0):
-    """Sets up the training (reference: train.py:122-255)."""
+    """Sets up the training (reference: train.py:122-255). Returns the reference's 10-tuple
+    `(train_dataloader, val_dataloader, model, optimizer, scheduler, loss_fn, wandb_id, train_sampler, val_sampler,
+    scaler)`; the `optimizer` slot holds the fused TrainEngine (Adam state + step; `param_groups`, `zero_grad`,
+    `state_dict` as torch.optim.Adam), `scaler` an engine.GradScaler(enabled=cfg.amp)."""
     torch.cuda.manual_seed_all(cfg.random_seed)
     torch.manual_seed(cfg.random_seed)
     np.random.seed(cfg.random_seed)
@@ -146,7 +153,9 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
     model = NCameraCNN(cfg.model_config).to(device).set_precision(cfg.precision)
     augmentation = Augmentation(cfg.augmentation_config, train=True, seed=cfg.random_seed + 7919 * rank,
                                 gpu_spaghetti=cfg.gpu_spaghetti) if cfg.use_augmentation else None
-    engine = TrainEngine(model, lr=cfg.learning_rate, max_grad_norm=cfg.max_grad_norm, augmentation=augmentation)
+    scaler = GradScaler(enabled=cfg.amp)
+    engine = TrainEngine(model, lr=cfg.learning_rate, max_grad_norm=cfg.max_grad_norm, augmentation=augmentation,
+                         scaler=scaler)
     scheduler = ReduceLROnPlateau(engine, patience=5, factor=0.5)
     loss_fn = geometric_loss_fn
 
@@ -159,7 +168,8 @@ def initialize_training(cfg: TrainConfig, rank: int = 0):
         wandb.init(project=cfg.wandb_project, config=cfg, id=wandb_id, resume="allow")
     if wandb_id is None:
         wandb_id = f"argus_b200_{os.getpid()}"
-    return (train_dataloader, val_dataloader, model, engine, scheduler, loss_fn, wandb_id, train_sampler, val_sampler)
+    return (train_dataloader, val_dataloader, model, engine, scheduler, loss_fn, wandb_id, train_sampler, val_sampler,
+            scaler)
 
 
 def rank_print(msg: str, rank: int = 0) -> None:
@@ -177,7 +187,7 @@ def state_dict_for_save(model: NCameraCNN, multigpu: bool) -> dict:
 def train(cfg: TrainConfig, rank: int = 0) -> None:
     """Main training loop (reference: train.py:264-361)."""
     (train_dataloader, val_dataloader, model, engine, scheduler, loss_fn, wandb_id, train_sampler,
-     val_sampler) = initialize_training(cfg, rank=rank)
+     val_sampler, _scaler) = initialize_training(cfg, rank=rank)
     device = model.flat_params.device
     log = cfg.wandb_log and rank == 0
     if log:
@@ -228,7 +238,14 @@ def train(cfg: TrainConfig, rank: int = 0) -> None:
                     pred = model(images)
                     val_losses.append(loss_fn(pred, cube_pose))
                 if val_losses:
-                    val_loss = torch.mean(torch.cat(val_losses)).item()
+                    val_loss_t = torch.mean(torch.cat(val_losses))
+                    if cfg.multigpu:
+                        # the reference steps ReduceLROnPlateau on each rank's own shard (train.py:340-348), which lets
+                        # the learning rates -- and then the weights -- of the ranks drift apart; every rank uses the
+                        # mean over ranks here so that engine.lr stays identical everywhere
+                        dist.all_reduce(val_loss_t, op=dist.ReduceOp.SUM)
+                        val_loss_t = val_loss_t / cfg.num_gpus
+                    val_loss = val_loss_t.item()
                     if log:
                         wandb.log({"val_loss": val_loss})
                     rank_print(f"    Validation loss: {val_loss}", rank=rank)

@@ -56,6 +56,30 @@ def time_torch_fn(fn: Callable[[], torch.Tensor]) -> tuple[torch.Tensor, float]:
     return result, start.elapsed_time(end) / 1000
 
 
+def _tree_lines(path: str, extension: str, indent: str = "") -> str:
+    import fnmatch
+    import os
+
+    if not os.path.isdir(path):
+        return ""
+    items = sorted(i for i in os.listdir(path)
+                   if os.path.isdir(os.path.join(path, i)) or fnmatch.fnmatch(i, f"*.{extension}"))
+    out = ""
+    for k, item in enumerate(items):
+        last = k == len(items) - 1
+        out += indent + ("└── " if last else "├── ") + item + "\n"
+        full = os.path.join(path, item)
+        if os.path.isdir(full):
+            out += _tree_lines(full, extension, indent + ("    " if last else "│   "))
+    return out
+
+
+def get_tree_string(path: str, extension: str) -> str:
+    """Directory tree of `path` restricted to `*.extension` leaves, in blue (reference: argus/utils.py:197-249; used by
+    the config dataclasses' error messages). A missing directory yields just the header instead of raising."""
+    return "\033[94m" + path + "\n" + _tree_lines(path, extension) + "\033[0m"
+
+
 def draw_spaghetti(img, n_arcs: int = 10, width_range=(1.0, 5.0)):
     """Draws random black arcs on a PIL image (reference: argus/utils.py:252-275; CPU/PIL, uses numpy's global RNG
     exactly like the reference so that `np.random.seed` reproduces it)."""

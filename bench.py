@@ -29,6 +29,9 @@ sys.path.insert(0, str(ROOT))
 PAIR_FLOPS_FWD = 21.362e9          # forward GEMM FLOPs per image pair at 256x256
 PAIR_FLOPS_TRAIN = 63.47e9         # forward + dgrad + wgrad (no stem dgrad)
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+# pairs per CPU step in BOTH CPU legs (`cpu_baseline` of our line and `--impl reference`): the largest sample of the
+# 256-pair workload that keeps `--steps 20 --warmup 5` within a few minutes on the box's host cores (~8 pairs/s)
+CPU_SAMPLE_PAIRS = 32
 
 
 def load_peaks():
@@ -112,6 +115,7 @@ def synthetic_batch(B: int, n_cams: int, H: int, W: int, seed: int):
 # our arm
 # ----------------------------------------------------------------------------------------------------------------
 def run_ours(args) -> None:
+    os.environ.setdefault("ARGUS_PROFILE_DETAIL", "1")   # instrumented pass: tensor-core launches keyed by layer shape
     import torch
     import torch.distributed as dist
 
@@ -139,12 +143,11 @@ def run_ours(args) -> None:
 
     torch.manual_seed(42)
     model = NCameraCNN().to(dev)
-    augmentation = None
-    try:
-        from argus_b200.data import Augmentation, AugmentationConfig
-        augmentation = Augmentation(AugmentationConfig(), train=True).to(dev)
-    except ImportError:
-        augmentation = None
+    from argus_b200.data import Augmentation, AugmentationConfig
+
+    # the training loop's configuration (argus_b200/train.py defaults): the reference's default-on kornia chain AND its
+    # spaghetti arcs (drawn on every training image, data.py:212-215), both on the device
+    augmentation = Augmentation(AugmentationConfig(), train=True, seed=42, gpu_spaghetti=True).to(dev)
     if args.no_augmentation:
         augmentation = None
     engine = TrainEngine(model, lr=1e-4, max_grad_norm=1.0, augmentation=augmentation)
@@ -250,8 +253,8 @@ def run_ours(args) -> None:
         engine.step(*dev_batches[i % ring])
     torch.cuda.synchronize()
     if rank == 0:
-        buf = ctypes.create_string_buffer(1 << 16)
-        _lib.check(lib.argus_profile_report(buf, ctypes.c_int(1 << 16)))
+        buf = ctypes.create_string_buffer(1 << 19)
+        _lib.check(lib.argus_profile_report(buf, ctypes.c_int(1 << 19)))
         lib.argus_profile_enable(0)
         families = json.loads(buf.value.decode())
         for f in families.values():
@@ -267,7 +270,17 @@ def run_ours(args) -> None:
         return
 
     peaks, peak_kind = load_peaks()
-    conv = [families[k] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad") if k in families]
+    # the instrumented pass keys tensor-core launches by layer shape ("conv_fwd:M.._N.._K.._t.."); fold them back into
+    # kernel families for the summary and keep the per-shape groups for the roofline of the dominant kernel
+    shapes = {k: f for k, f in families.items() if ":" in k}
+    folded: dict = {}
+    for k, f in families.items():
+        base = k.split(":")[0]
+        agg = folded.setdefault(base, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0})
+        for key in agg:
+            agg[key] += f[key]
+    families = folded
+    conv = [families[k] for k in ("conv_fwd", "conv_dgrad", "conv_wgrad", "conv_wgradx") if k in families]
     conv_ms = sum(f["ms"] for f in conv)
     conv_flops = sum(f["flops"] for f in conv)
     conv_launches = sum(f["launches"] for f in conv)
@@ -275,8 +288,10 @@ def run_ours(args) -> None:
     algorithmic_flops = PAIR_FLOPS_TRAIN * B  # per step, all tensor-core launches together
     achieved = algorithmic_flops / (conv_ms / 1e3) / 1e12 if conv_ms > 0 else 0.0
     peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
-    roofline = {
-        "bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_kernel (tcgen05 implicit GEMM, all launches of a step)",
+    ridge = peak * 1e12 / (peaks["hbm_gbs"] * 1e9)       # flop / byte above which a launch is tensor-bound
+    roofline_aggregate = {
+        "bound": "tensor", "kernel": "conv_gemm_kernel + wgrad_kernel + wgrad_xpose_kernel (tcgen05 implicit GEMM, all "
+                                     "launches of a step, HBM-bound and tensor-bound shapes together)",
         "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
         "peak_kind": f"{peak_kind} sustained cuBLAS bf16", "traffic": None, "algorithmic_bytes_per_launch": None,
         "launches_per_step": conv_launches, "avg_launch_ms": round(conv_ms / max(conv_launches, 1), 4),
@@ -285,12 +300,56 @@ def run_ours(args) -> None:
     }
     # DRAM traffic of the same launches from the committed ncu capture (profiles/capture.sh), per launch like `achieved`
     conv_bytes = sum(f["bytes"] for f in conv)
-    roofline["algorithmic_bytes_per_launch"] = round(conv_bytes / max(conv_launches, 1))
+    roofline_aggregate["algorithmic_bytes_per_launch"] = round(conv_bytes / max(conv_launches, 1))
     traffic_files = sorted(Path(__file__).resolve().parent.glob("profiles/*_conv_traffic.json"))
     if traffic_files and B == 256 and args.size == 256:
         tr = json.loads(traffic_files[-1].read_text())
-        roofline["traffic"] = round(tr["dram_bytes_per_launch"])
-        roofline["traffic_source"] = f"profiles/{traffic_files[-1].name} ({tr['launches']} launches of one step under ncu)"
+        roofline_aggregate["traffic"] = round(tr["dram_bytes_per_launch"])
+        roofline_aggregate["traffic_source"] = (f"committed: profiles/{traffic_files[-1].name} ({tr['launches']} launches "
+                                                "of one step under ncu; not re-measured in this run)")
+    # launches split by what bounds their SHAPE (arithmetic intensity against the ridge of the measured peaks)
+    split = {"tensor": {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0},
+             "hbm": {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0}}
+    for k, f in shapes.items():
+        if not k.startswith("conv_") or f["bytes"] <= 0:
+            continue
+        b = "tensor" if f["flops"] / f["bytes"] >= ridge else "hbm"
+        for key in split[b]:
+            split[b][key] += f[key]
+    by_bound = {}
+    if split["tensor"]["ms"] > 0:
+        tf = split["tensor"]["flops"] / (split["tensor"]["ms"] / 1e3) / 1e12
+        by_bound["tensor_bound_shapes"] = {"ms": round(split["tensor"]["ms"], 3), "launches": split["tensor"]["launches"],
+                                           "achieved": round(tf, 1), "unit": "TFLOP/s (issued)", "peak": peak,
+                                           "frac": round(tf / peak, 4)}
+    if split["hbm"]["ms"] > 0:
+        gb = split["hbm"]["bytes"] / (split["hbm"]["ms"] / 1e3) / 1e9
+        by_bound["hbm_bound_shapes"] = {"ms": round(split["hbm"]["ms"], 3), "launches": split["hbm"]["launches"],
+                                        "achieved": round(gb, 1), "unit": "GB/s", "peak": peaks["hbm_gbs"],
+                                        "frac": round(gb / peaks["hbm_gbs"], 4)}
+    roofline_aggregate["by_bound"] = by_bound
+    # `roofline` proper: the single dominant tensor-core launch group (one kernel instantiation on one layer shape, the
+    # largest share of the step), against the roofline that bounds THAT shape
+    roofline = dict(roofline_aggregate)
+    top = max(((k, f) for k, f in shapes.items() if k.startswith("conv_") and f["bytes"] > 0), key=lambda kv: kv[1]["ms"],
+              default=None)
+    if top is not None:
+        k, f = top
+        n_l = max(f["launches"], 1)
+        ai = f["flops"] / f["bytes"]
+        if ai >= ridge:
+            ach, pk, unit, bound = f["flops"] / (f["ms"] / 1e3) / 1e12, peak, "TFLOP/s", "tensor"
+            pk_kind = f"{peak_kind} sustained cuBLAS bf16"
+        else:
+            ach, pk, unit, bound = f["bytes"] / (f["ms"] / 1e3) / 1e9, peaks["hbm_gbs"], "GB/s", "hbm"
+            pk_kind = f"{peak_kind} copy bandwidth"
+        roofline = {"bound": bound, "kernel": f"tcgen05 implicit GEMM, {k} ({n_l} launches / step)",
+                    "achieved": round(ach, 1), "peak": pk, "unit": unit, "frac": round(ach / pk, 4), "peak_kind": pk_kind,
+                    "traffic": None, "algorithmic_bytes_per_launch": round(f["bytes"] / n_l),
+                    "algorithmic_flops_per_launch": round(f["flops"] / n_l), "avg_launch_ms": round(f["ms"] / n_l, 4),
+                    "arithmetic_intensity": round(ai, 1), "ridge": round(ridge, 1),
+                    "share_of_step": round(f["ms"] / total_ms, 4),
+                    "traffic_note": "per-shape DRAM traffic is in profiles/ (ncu --set full captures); not re-measured here"}
     # whole-step HBM view: algorithmic bytes of every launch (each operand tensor counted once) over the step time
     step_bytes = sum(f["bytes"] for f in families.values())
     step_ms = ms_total / args.steps
@@ -306,13 +365,19 @@ def run_ours(args) -> None:
             mem[k] = {"ms": round(f["ms"], 3), "launches": f["launches"], "GB/s": round(gbs, 1),
                       "frac_hbm": round(gbs / peaks["hbm_gbs"], 3)}
     inference = None
+    torch_cuda = None
+    del engine
+    torch.cuda.empty_cache()
     if world == 1 and not args.no_inference:
-        del engine
-        torch.cuda.empty_cache()
         inference = measure_inference(dev, args.size)
+    if world == 1 and not args.no_torch_baseline:
+        del model
+        torch.cuda.empty_cache()
+        torch_cuda = torch_cuda_baseline(dev, B, args.size)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_throughput(sample_pairs=8, iters=3, warmup=1, size=args.size, augmentation=augmentation is not None)
+        cpu = cpu_reference_throughput(sample_pairs=CPU_SAMPLE_PAIRS, iters=2, warmup=1, size=args.size,
+                                       augmentation=augmentation is not None)
 
     line = {
         "metric": "train image-pairs/sec", "value": round(value, 2), "unit": "pairs/s", "n_gpus": world,
@@ -321,13 +386,15 @@ def run_ours(args) -> None:
         "config": {"workload": "configs[1]: train step, synthetic 2-view batch 256/GPU at 256x256, bf16 + fp32 accumulate, "
                                "augmentation + geometric pose loss + clip + Adam",
                    "per_gpu_batch_pairs": B, "global_batch_pairs": B * world, "image_size": [H, W], "n_cams": n_cams,
-                   "augmentation": augmentation is not None, "parallelism": f"dp{world}",
+                   "augmentation": augmentation is not None,
+                   "spaghetti": bool(augmentation is not None and augmentation.gpu_spaghetti), "parallelism": f"dp{world}",
                    "l2_note": "no explicit flush: every step streams >30 GB of activations (>> 126 MB L2) and rotates 3 input batches"},
         "e2e": {"value": round(e2e_value, 2), "unit": "pairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "note": "pinned host uint8 batch -> H2D on a side stream (double buffered) -> engine.step -> loss D2H"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "roofline_aggregate": roofline_aggregate,
         "hbm_step": hbm_step,
         "kernel_families_ms": {k: round(f["ms"], 3) for k, f in families.items()},
         "memory_bound_kernels": mem,
@@ -337,6 +404,8 @@ def run_ours(args) -> None:
         line["cpu_baseline"] = cpu
     if inference is not None:
         line["inference"] = inference
+    if torch_cuda is not None:
+        line["torch_cuda_baseline"] = torch_cuda
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -382,6 +451,88 @@ def measure_inference(dev, size: int) -> dict:
             res[name] = {"p50_ms": round(times[50], 4), "p99_ms": round(times[98], 4)}
         res["pairs_per_s_graph"] = round(B / (res["cuda_graph"]["p50_ms"] / 1e3), 1)
         out[f"batch{B}"] = res
+    # floors: batch 1 is bound by reading the 51.8 MB of bf16 weights once plus the forward FLOPs
+    # (>= 25 us together); large batches by the forward FLOPs alone (65.6 k pairs/s at the sustained tensor peak)
+    peaks, _ = load_peaks()
+    floor_b1_us = 51.8e6 / (peaks["hbm_gbs"] * 1e9) * 1e6 + PAIR_FLOPS_FWD / (peaks["bf16_tflops_sustained"] * 1e12) * 1e6
+    ceil_pairs = peaks["bf16_tflops_sustained"] * 1e12 / PAIR_FLOPS_FWD
+    out["roofline"] = {
+        "batch1": {"floor_us": round(floor_b1_us, 1), "p50_us": round(out["batch1"]["cuda_graph"]["p50_ms"] * 1e3, 1),
+                   "frac": round(floor_b1_us / (out["batch1"]["cuda_graph"]["p50_ms"] * 1e3), 4),
+                   "bound": "launch latency (> 60 dependent kernels), not HBM or tensor"},
+        "batch64": {"ceiling_pairs_per_s": round(ceil_pairs, 1), "pairs_per_s": out["batch64"]["pairs_per_s_graph"],
+                    "frac": round(out["batch64"]["pairs_per_s_graph"] / ceil_pairs, 4), "bound": "tensor"}}
+    return out
+
+
+def torch_cuda_baseline(dev, B: int, size: int) -> dict:
+    """The library path this repo replaces, on the SAME B200 in the same run (SURVEY.md §8d "the real bar"): the
+    reference model (oracle/ref_model.py == argus/models.py on torchvision's ResNet-50, random init) under PyTorch CUDA
+    -- cuDNN convolutions, channels_last, bf16 autocast, torch's fused Adam -- for the same training step (forward, pose
+    loss, backward, clip_grad_norm_, Adam) on a device-resident fp32 batch (no augmentation: kornia is not installed;
+    the reference augments on CPU workers anyway), and eval-mode forward latency at batch 1 / 64. Informative baseline,
+    measured after our own timed regions; nothing of it is on the product path."""
+    import torch
+
+    from oracle.ref_model import make_reference_model, torch_loss
+
+    out = {}
+    try:
+        torch.backends.cudnn.benchmark = True
+        model = make_reference_model(42).to(dev).to(memory_format=torch.channels_last)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-4, fused=True)
+        imgs, tgt = synthetic_batch(B, 2, size, size, seed=0)
+        x = (imgs.permute(0, 1, 4, 2, 3).reshape(B, 6, size, size).float() / 255.0).to(dev)
+        tgt = tgt.to(dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                pred = model(x)
+            loss = torch_loss(pred.float(), tgt).mean()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+            opt.step()
+            return loss
+
+        model.train()
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 8
+        e0.record()
+        for _ in range(n):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        out["train"] = {"ms_per_step": round(ms, 2), "pairs_per_s": round(B / (ms / 1e3), 1), "batch_pairs": B,
+                        "what": "reference NCameraCNN, torch CUDA: cuDNN + channels_last + bf16 autocast + fused Adam, "
+                                "device-resident fp32 input, no augmentation"}
+        del opt
+        model.eval()
+        for b in (1, 64):
+            xb = x[:b].contiguous()
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                for _ in range(10):
+                    model(xb)
+                torch.cuda.synchronize()
+                times = []
+                for _ in range(50):
+                    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a0.record()
+                    model(xb)
+                    a1.record()
+                    a1.synchronize()
+                    times.append(a0.elapsed_time(a1))
+            times.sort()
+            out[f"infer_batch{b}"] = {"p50_ms": round(times[25], 4), "pairs_per_s": round(b / (times[25] / 1e3), 1),
+                                      "what": "eval forward, eager, bf16 autocast, channels_last"}
+    except Exception as exc:  # the baseline must never take the product's bench line down with it
+        out["error"] = f"{type(exc).__name__}: {exc}"[:300]
+    finally:
+        torch.cuda.empty_cache()
     return out
 
 
@@ -440,7 +591,7 @@ def run_reference(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = 8
+    sample = CPU_SAMPLE_PAIRS
     aug_available = (ROOT / "oracle" / "augment.py").exists() and not args.no_augmentation
     step = cpu_reference_step_fn(sample, args.size, aug_available)
     for i in range(args.warmup):
@@ -455,7 +606,7 @@ def run_reference(args) -> None:
         "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs[1] train step (bounded sample: 8 pairs per step on the host cores)",
+        "config": {"workload": f"configs[1] train step (bounded sample: {sample} pairs per step on the host cores)",
                    "per_step_pairs": sample, "image_size": [args.size, args.size], "augmentation": aug_available},
         "cpu_baseline": {"value": round(value, 3), "unit": "pairs/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{args.steps} steps of {sample} pairs, fp32 PyTorch CPU port of the reference path"},
@@ -475,6 +626,7 @@ def main() -> None:
     ap.add_argument("--no-augmentation", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", action="store_true")
+    ap.add_argument("--no-torch-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -140,28 +140,39 @@ int argus_fp32_maxpool_forward(const float* x, float* y, void* idx, int N, int H
 int argus_fp32_maxpool_backward(const float* dy, const void* idx, float* dx, int N, int H, int W, int C, void* stream);
 
 /* ---- augmentation (the kornia chain of argus/data.py:41-103 applied at data.py:213-225) ------------------------
- * Parameters are a pure function of (seed, step, image index): params is an (n_images, 24) fp32 table
- * (layout: oracle/augment.py). Colour-jiggle draws are shared by the n_cams views of a pair (same_on_batch=True). */
+ * [RandomErasing x2] -> RandomPlanckianJitter -> ColorJiggle -> RandomGaussianBlur -> RandomMotionBlur ->
+ * RandomPlasmaShadow (diamond-square fractal) -> [RandomSaltAndPepperNoise]; bracketed stages are default-off
+ * (data.py:35,39). Parameters are a pure function of (seed, step, image index): params is an
+ * (n_images, ARGUS_AUG_PARAMS) fp32 table (layout: oracle/augment.py). Colour-jiggle draws are shared by the n_cams views
+ * of a pair (same_on_batch=True). H, W: image size (the erasing rectangles are sampled in pixels). */
+#define ARGUS_AUG_PARAMS 40
+#define ARGUS_ARC_FIELDS 8
 typedef struct argus_aug_config {
-  int color_jiggle, planckian_jitter, blur, motion_blur, plasma_shadow;           /* flags, data.py:31-37 */
+  int color_jiggle, planckian_jitter, blur, motion_blur, plasma_shadow;           /* flags, data.py:31-38 */
   float brightness_lo, brightness_span, contrast_lo, contrast_span;               /* ranges, data.py:23-26 */
   float saturation_lo, saturation_span, hue_lo, hue_span;
+  int random_erasing, salt_and_pepper;                                            /* flags, data.py:35,39 */
 } argus_aug_config;
-int argus_augment_sample_params(float* params, int n_images, int n_cams, uint64_t seed, uint64_t step,
+int argus_augment_sample_params(float* params, int n_images, int n_cams, int H, int W, uint64_t seed, uint64_t step,
                                 const argus_aug_config* cfg, void* stream);
 /* in: u8 (n, H, W, 3) when in_u8 else fp32 (n, 3, H, W) in [0,1]; out: fp32 (n, 3, H, W), or the stem's bf16
- * space-to-depth layout [n][H/2][W/2+4][16] when out_s2d. apply == 0 only converts. H, W multiples of 32. */
-int argus_augment(const void* in, int in_u8, void* out, int out_s2d, float* params, int n_images, int H, int W,
-                  int apply, void* stream);
+ * space-to-depth layout [n][H/2][W/2+4][16] when out_s2d. apply == 0 only converts. H, W multiples of 32 (<= 256 when
+ * apply). arc_mask (nullable, u8 input only): [n][H][W/32] words from argus_spaghetti_mask, set bits are painted black
+ * first. plasma_ws: workspace of n * H * W / 8 bytes (required when apply; holds the shadow mask afterwards). */
+int argus_augment(const void* in, int in_u8, void* out, int out_s2d, const float* params, const void* arc_mask,
+                  void* plasma_ws, int n_images, int H, int W, int apply, void* stream);
 
 /* Spaghetti arcs (draw_spaghetti, argus/utils.py:252-275; drawn with PIL on the decoded image at argus/data.py:212-215,
- * before the kornia chain). arcs: (n_images, n_arcs <= 16, 10) fp32 table, a pure function of (seed, step, image, arc)
- * sampled as the reference does (bbox corners, integer start / end angles, width = int(U(1,5))); argus_spaghetti_draw
- * paints them black on uint8 (n, H, W, 3) images (out may alias in). Rasterisation rule: oracle/augment.py. */
+ * before the kornia chain). arcs: (n_images, n_arcs, ARGUS_ARC_FIELDS) fp32 table [x0, y0, x1, y1, start, end, width, 0],
+ * a pure function of (seed, step, image, arc) sampled as the reference does (bbox corners, integer start / end angles,
+ * width = int(U(1,5))). argus_spaghetti_mask rasterises them exactly as Pillow's ImageDraw.arc does (oracle/pil_arc.py)
+ * into 1 bit per pixel, [n][H][W/32] words (W a multiple of 32, H, W <= 512); argus_spaghetti_draw paints them black on
+ * uint8 (n, H, W, 3) images (out may alias in; mask_ws = n * H * W / 8 bytes of workspace). */
 int argus_spaghetti_sample_params(float* arcs, int n_images, int n_arcs, int H, int W, uint64_t seed, uint64_t step,
                                   void* stream);
-int argus_spaghetti_draw(const void* in, void* out, const float* arcs, int n_images, int n_arcs, int H, int W,
-                         void* stream);
+int argus_spaghetti_mask(const float* arcs, void* mask, int n_images, int n_arcs, int H, int W, void* stream);
+int argus_spaghetti_draw(const void* in, void* out, const float* arcs, void* mask_ws, int n_images, int n_arcs, int H,
+                         int W, void* stream);
 
 /* ---- pose loss and pose exponential ------------------------------------------------------------------------
  * argus_pose_loss: geometric_loss_fn (argus/train.py:105-119) forward AND analytic backward in one launch.
@@ -179,6 +190,12 @@ int argus_pose_exp(const float* pred, float* pose, int B, int wxyz, void* stream
 int argus_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                          float* scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
                          int step, float* norm_out, void* stream);
+/* Same, under the GradScaler protocol of the reference's amp mode (argus/train.py:234,316-320: scaler.unscale_ ->
+ * clip_grad_norm_ -> scaler.step): gscale additionally carries 1/loss_scale, and when the unscaled global norm is not
+ * finite NOTHING is updated (params, exp_avg, exp_avg_sq untouched). norm_out (required) tells the caller. */
+int argus_clip_adam_step_amp(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                             float* scratch, float gscale, float max_norm, float lr, float beta1, float beta2, float eps,
+                             int step, float* norm_out, void* stream);
 
 /* ---- the model: NCameraCNN (argus/models.py:26-90) -----------------------------------------------------------
  * The library defines the flat layout of the parameter arena (trainable tensors, reference state_dict order) and
@@ -199,10 +216,12 @@ int argus_model_sync_weights(argus_model* m, void* stream);
  * is_u8. training != 0 uses batch statistics and updates the running statistics. out is (B, 6) fp32. */
 int argus_model_forward(argus_model* m, const void* x, int is_u8, int B, int H, int W, int training, float* out,
                         void* stream);
-/* Fused augmentation + input staging: u8 (B*n_cams, H, W, 3) -> augmented stem input of the model's own arena.
- * The next argus_model_forward call for the same (B, H, W, training) passes x = NULL. */
-int argus_model_stage_input_u8(argus_model* m, const void* images, float* aug_params, int B, int H, int W,
-                               int training, int apply, void* stream);
+/* Fused augmentation + input staging: u8 (B*n_cams, H, W, 3) -> augmented stem input inside the model (training: one
+ * of two model-owned staging buffers, so the NEXT batch -- of any size -- can be staged on another stream while the
+ * current step runs). The next argus_model_forward call for the same (B, H, W, training) passes x = NULL.
+ * arc_mask / plasma_ws: as for argus_augment. */
+int argus_model_stage_input_u8(argus_model* m, const void* images, const float* aug_params, const void* arc_mask,
+                               void* plasma_ws, int B, int H, int W, int training, int apply, void* stream);
 /* Precision mode. 0 (default): bf16 activations / weights on the tcgen05 tensor cores, fp32 accumulate.
  * 1: fp32 parity mode -- every tensor fp32, SIMT implicit-GEMM convolutions with fp32 FMA accumulation, reductions in
  * fp64; same parameter / gradient / buffer arenas and the same entry points. It exists to compare forward outputs,

@@ -1,29 +1,36 @@
 """ORACLE (test infrastructure only): CPU restatement of the reference's augmentation chain.
 
 Reference call sites: /root/reference/argus/data.py:41-103 (Augmentation builds a kornia AugmentationSequential) and
-data.py:213-225 (`/255`, then the chain on a (n_cams, 3, H, W) float image pair). Default-ON stages, in order
-(data.py:66-92): RandomPlanckianJitter("blackbody") p=.5 -> ColorJiggle(brightness (0.8,1), contrast (0.5,1.2),
-saturation (0.25,1.2), hue (-0.1,0.1), same_on_batch=True, p=1) -> RandomGaussianBlur((5,5),(3,8), p=.5)
--> RandomMotionBlur(3, 35deg, 0.5, p=.7) -> RandomPlasmaShadow(roughness (0.1,0.4), intensity (-0.6,0),
-quantity (0,0.5), p=1).
+data.py:213-225 (`/255`, then the chain on a (n_cams, 3, H, W) float image pair). Stages, in order (data.py:52-95):
+[RandomErasing(p=.5, scale (0.02,0.1), ratio (2,3), value 0), RandomErasing(p=.5, scale (0.02,0.05), ratio (0.8,1.2),
+value 1)] (flag random_erasing, default off) -> RandomPlanckianJitter("blackbody") p=.5 -> ColorJiggle(brightness
+(0.8,1), contrast (0.5,1.2), saturation (0.25,1.2), hue (-0.1,0.1), same_on_batch=True, p=1) -> RandomGaussianBlur((5,5),
+(3,8), p=.5) -> RandomMotionBlur(3, 35deg, 0.5, p=.7) -> RandomPlasmaShadow(roughness (0.1,0.4), intensity (-0.6,0),
+quantity (0,0.5), p=1) -> [RandomSaltAndPepperNoise(p=.7)] (flag salt_and_pepper, default off).
 
 The arithmetic lives in the un-vendored third-party dependency **kornia** (`kornia>=0.7.2`,
 /root/reference/pyproject.toml:20; not installed, no network). The per-op semantics below restate kornia 0.7.x's
-published algorithms (enhance.adjust_*, color.rgb_to_hsv/hsv_to_rgb, filters.gaussian/motion kernels, the
-blackbody illuminant table). Two things cannot be reproduced and are OUR frozen spec instead:
+published algorithms (enhance.adjust_*, color.rgb_to_hsv/hsv_to_rgb, filters.gaussian/motion kernels, the blackbody
+illuminant table, RectangleEraseGenerator, contrib.diamond_square: seed grid -> recursive diamond / square steps with
+`(1 - scale) * neighbour mean + scale * U[0,1)`, scale multiplied by `roughness` per level, 4/3 border compensation of the
+square step, crop of the 2^k + 1 grid to H x W, shadow where the field < shade_quantity; salt & pepper: one noise mask per
+pixel shared by the channels). What cannot be reproduced, and is OUR frozen spec instead:
   * random numbers: kornia draws from torch's global RNG; here every parameter is a pure function of
-    (seed, step, image index, field) through a splitmix64 hash, identical in numpy and in the CUDA kernel;
-  * the plasma fractal: kornia's diamond-square consumes the torch RNG recursively; here it is a 6-octave
-    value-noise fractal with the same roughness law, normalised to [0,1] per image like kornia's.
+    (seed, step, image index, field) through a splitmix64 hash, and every per-pixel draw (fractal, noise) a 32-bit hash
+    of (image seed, level, y, x), identical in numpy and in the CUDA kernels;
+  * details of kornia that could not be re-read offline (the 3x3 seed grid of diamond_square is taken as all-uniform,
+    the square step's border handling as zero padding x 4/3).
 No reference test checks an augmented pixel, so: **parity with kornia itself is unpinned**; what is
-pinned is GPU == this oracle on identical parameters (tests/test_augment_gpu.py), parameter ranges, and the
-reference's only augmentation-related contract: same seed => same result (tests/test_train.py:69-77).
+pinned is GPU == this oracle on identical parameters (tests/test_augment_gpu.py: discrete parts -- parameter tables,
+erasing rectangles, shadow masks, noise masks, arcs -- bit for bit, float arithmetic to 1e-5), parameter ranges, and the
+reference's only augmentation-related contract: same seed => same result (tests/test_train.py:69-77). The spaghetti arcs
+ARE pinned to the reference's library: oracle/pil_arc.py reproduces Pillow's ImageDraw.arc pixel for pixel.
 """
 from __future__ import annotations
 
 import numpy as np
 
-N_PARAMS = 24  # floats per image, layout shared with argus_b200/csrc/augment.cu
+N_PARAMS = 40  # floats per image, layout shared with argus_b200/csrc/augment.cu (ARGUS_AUG_PARAMS)
 
 # kornia.color._planckian "blackbody" table (25 illuminants, 3000 K .. 15000 K), RGB
 _BLACKBODY = np.array([
@@ -92,9 +99,29 @@ def motion_kernel(angle_deg: np.ndarray, direction: np.ndarray) -> np.ndarray:
     return (out / s).reshape(n, 9).astype(np.float32)
 
 
-def sample_params(n_pairs: int, n_cams: int, seed: int, step: int, cfg=None) -> np.ndarray:
+def _erase_rect(u_area, u_ra, u_rb, u_pick, u_x, u_y, scale, ratio, H, W):
+    """kornia RectangleEraseGenerator: area = U(scale) * H * W, aspect = h / w; -> (x, y, w, h) as float32 arrays."""
+    area = _lerp(u_area, scale[0], scale[1]) * F(H * W)
+    if ratio[0] < 1.0 and ratio[1] > 1.0:
+        r1, r2 = _lerp(u_ra, ratio[0], 1.0), _lerp(u_rb, 1.0, ratio[1])
+        aspect = np.where(np.rint(u_pick) != 0, r1, r2).astype(np.float32)
+    else:
+        aspect = _lerp(u_ra, ratio[0], ratio[1])
+    h = np.rint(np.sqrt(area * aspect, dtype=np.float32))
+    w = np.rint(np.sqrt(area / aspect, dtype=np.float32))
+    h = np.minimum(np.maximum(h, F(1)), F(H)).astype(np.float32)
+    w = np.minimum(np.maximum(w, F(1)), F(W)).astype(np.float32)
+    x = np.floor(u_x * (F(W) - w + F(1))).astype(np.float32)
+    y = np.floor(u_y * (F(H) - h + F(1))).astype(np.float32)
+    return x, y, w, h
+
+
+def sample_params(n_pairs: int, n_cams: int, seed: int, step: int, cfg=None, H: int = 256, W: int = 256) -> np.ndarray:
     """(n_pairs*n_cams, N_PARAMS) float32 parameter table. Image index = pair*n_cams + view; the colour-jiggle
-    draws use the PAIR index (same_on_batch=True on the (n_cams,3,H,W) mini-batch, data.py:76,224)."""
+    draws use the PAIR index (same_on_batch=True on the (n_cams,3,H,W) mini-batch, data.py:76,224).
+    Layout: 0-1 planckian R / B gains; 2-6 jiggle (brightness add, contrast, saturation, hue [rad], order index or -1);
+    7 gaussian sigma (0 = off); 8-16 motion kernel; 17-20 plasma (roughness, intensity (0 = off), quantity, seed);
+    24-28 / 29-33 erasing rectangle 1 / 2 (on, x, y, w, h); 34-37 salt & pepper (on, amount, salt share, seed)."""
     c = _cfg(cfg)
     n = n_pairs * n_cams
     img = np.arange(n, dtype=np.uint64)
@@ -137,12 +164,31 @@ def sample_params(n_pairs: int, n_cams: int, seed: int, step: int, cfg=None) -> 
     else:
         P[:, 17], P[:, 18], P[:, 19] = 0.25, 0.0, 0.0
     P[:, 20] = u(img, 15)  # fractal seed (its 24 random bits, recovered as int(p*2^24))
+    # random erasing (data.py:52-64)
+    if c["random_erasing"]:
+        for e, (scale, ratio) in enumerate((((0.02, 0.1), (2.0, 3.0)), ((0.02, 0.05), (0.8, 1.2)))):
+            f = 17 + 8 * e
+            on = u(img, 16 + 8 * e) < np.float32(0.5)
+            x, y, w, h = _erase_rect(u(img, f), u(img, f + 1), u(img, f + 2), u(img, f + 3), u(img, f + 4),
+                                     u(img, f + 5), scale, ratio, H, W)
+            base = 24 + 5 * e
+            P[:, base] = on
+            for k_, v in enumerate((x, y, w, h)):
+                P[:, base + 1 + k_] = np.where(on, v, np.float32(0))
+    # salt & pepper (data.py:94-95; kornia defaults amount (0.01, 0.06), salt_vs_pepper (0.4, 0.6))
+    if c["salt_and_pepper"]:
+        on = u(img, 32) < np.float32(0.7)
+        P[:, 34] = on
+        P[:, 35] = np.where(on, _lerp(u(img, 33), 0.01, 0.06), np.float32(0))
+        P[:, 36] = np.where(on, _lerp(u(img, 34), 0.4, 0.6), np.float32(0))
+    P[:, 37] = u(img, 35)
     return P
 
 
 def _cfg(cfg):
     d = dict(brightness=(0.8, 1.0), contrast=(0.5, 1.2), saturation=(0.25, 1.2), hue=(-0.1, 0.1),
-             color_jiggle=True, planckian_jitter=True, blur=True, motion_blur=True, plasma_shadow=True)
+             color_jiggle=True, planckian_jitter=True, blur=True, motion_blur=True, plasma_shadow=True,
+             random_erasing=False, salt_and_pepper=False)
     if cfg is not None:
         for k in d:
             if hasattr(cfg, k):
@@ -244,50 +290,109 @@ def motion_blur(x, k9):
     return out.astype(np.float32)
 
 
-def _lattice(seed_bits: int, octave: int, iy, ix):
-    """hash lattice value in [0,1) for the plasma fractal."""
-    key = (np.uint64(seed_bits) << np.uint64(40)) | (np.uint64(octave) << np.uint64(32)) | \
-          (np.asarray(iy, dtype=np.uint64) << np.uint64(16)) | np.asarray(ix, dtype=np.uint64)
-    return ((hash_u64(0x504C41534D41, 0, key, 0) >> np.uint64(40)).astype(np.float32) * F(2.0 ** -24))
+def pixel_uniform(seed32: int, level: int, y, x) -> np.ndarray:
+    """float32 uniform in [0,1) from a 32-bit hash of (image seed, level, y, x) -- csrc/augment.cu::pixel_uniform."""
+    with np.errstate(over="ignore"):
+        h = np.uint32(seed32 & 0xFFFFFFFF) ^ (np.uint32(level) * np.uint32(0x9E3779B9))
+        h = (h ^ np.asarray(y, dtype=np.uint32)) * np.uint32(0x85EBCA6B)
+        h = h ^ (h >> np.uint32(15))
+        h = (h ^ np.asarray(x, dtype=np.uint32)) * np.uint32(0xC2B2AE35)
+        h = h ^ (h >> np.uint32(13))
+        h = h * np.uint32(0x27D4EB2F)
+        h = h ^ (h >> np.uint32(16))
+    return (h >> np.uint32(8)).astype(np.float32) * F(2.0 ** -24)
 
 
-def plasma_field(H, W, roughness, seed_bits):
-    """6-octave value noise: octave l has 2^(l+1) cells per side, amplitude roughness^l. (H,W) float32, un-normalised."""
-    ys = (np.arange(H, dtype=np.float32) + F(0.5)) / F(H)
-    xs = (np.arange(W, dtype=np.float32) + F(0.5)) / F(W)
-    field = np.zeros((H, W), dtype=np.float32)
-    amp = F(1)
-    for l in range(6):
-        cells = F(2 << l)
-        fy, fx = ys * cells, xs * cells
-        iy, ix = np.floor(fy).astype(np.int64), np.floor(fx).astype(np.int64)
-        ty, tx = (fy - iy).astype(np.float32), (fx - ix).astype(np.float32)
-        ty = ty * ty * (F(3) - F(2) * ty)
-        tx = tx * tx * (F(3) - F(2) * tx)
-        v00 = _lattice(seed_bits, l, iy[:, None], ix[None, :])
-        v01 = _lattice(seed_bits, l, iy[:, None], ix[None, :] + 1)
-        v10 = _lattice(seed_bits, l, iy[:, None] + 1, ix[None, :])
-        v11 = _lattice(seed_bits, l, iy[:, None] + 1, ix[None, :] + 1)
-        top = v00 + (v01 - v00) * tx[None, :]
-        bot = v10 + (v11 - v10) * tx[None, :]
-        field = field + amp * (top + (bot - top) * ty[:, None])
-        amp = amp * F(roughness)
-    return field.astype(np.float32)
+def _ceil_log2(v: int) -> int:
+    l = 0
+    while (1 << l) < v:
+        l += 1
+    return l
 
 
-def augment_image(u8_hwc: np.ndarray, p: np.ndarray) -> np.ndarray:
-    """One image: uint8 (H,W,3) -> float32 (3,H,W) in [0,1], parameters p (N_PARAMS,)."""
-    x = (u8_hwc.astype(np.float32) * F(1.0 / 255.0)).transpose(2, 0, 1)
+def plasma_field(H: int, W: int, roughness, seed32: int) -> np.ndarray:
+    """kornia.contrib.diamond_square((1, 1, H, W), roughness) restated (see the module docstring): (H, W) float32."""
+    lh, lw = _ceil_log2(H - 1), _ceil_log2(W - 1)
+    depth = min(lh, lw) - 1
+    sh, sw = (1 << (lh - depth)) + 1, (1 << (lw - depth)) + 1
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    img = pixel_uniform(seed32, 0, yy, xx)
+    rough = F(roughness)
+    scale = F(1)
+    comp = F(1.0 / 0.75)
+    for level in range(1, depth + 1):
+        scale = F(scale * rough)
+        h, w = img.shape
+        nh, nw = 2 * h - 1, 2 * w - 1
+        new = np.zeros((nh, nw), dtype=np.float32)
+        new[::2, ::2] = img
+        yy, xx = np.mgrid[0:nh, 0:nw]
+        rnd = pixel_uniform(seed32, level, yy, xx)
+        one_minus = F(F(1) - scale)
+        # diamond step: (odd, odd) = (1 - scale) * mean of the four diagonal parents + scale * u
+        m = F(0.25) * (((img[:-1, :-1] + img[:-1, 1:]) + img[1:, :-1]) + img[1:, 1:])
+        new[1::2, 1::2] = one_minus * m + scale * rnd[1::2, 1::2]
+        # square step: positions with exactly one odd coordinate; zero padding, border rows / columns x 4/3
+        p = np.pad(new, 1)
+        up, down, left, right = p[:-2, 1:-1], p[2:, 1:-1], p[1:-1, :-2], p[1:-1, 2:]
+        reg = F(0.25) * (((up + left) + right) + down)
+        border = np.zeros((nh, nw), dtype=bool)
+        border[0, :] = border[-1, :] = border[:, 0] = border[:, -1] = True
+        reg = np.where(border, reg * comp, reg).astype(np.float32)
+        sq = ((yy ^ xx) & 1) == 1
+        new = np.where(sq, one_minus * reg + scale * rnd, new).astype(np.float32)
+        img = new
+    return img[:H, :W]
+
+
+def plasma_shadow_mask(H: int, W: int, p: np.ndarray) -> np.ndarray:
+    """Boolean (H, W): where RandomPlasmaShadow darkens the image (field < shade_quantity)."""
+    if p[18] == 0:
+        return np.zeros((H, W), dtype=bool)
+    return plasma_field(H, W, p[17], int(round(float(p[20]) * (1 << 24)))) < p[19]
+
+
+def salt_pepper_masks(H: int, W: int, p: np.ndarray):
+    """(salt, pepper) boolean (H, W) masks of RandomSaltAndPepperNoise; one draw per pixel, shared by the channels."""
+    if p[34] == 0:
+        z = np.zeros((H, W), dtype=bool)
+        return z, z
+    seed32 = int(round(float(p[37]) * (1 << 24)))
+    yy, xx = np.mgrid[0:H, 0:W]
+    noise = pixel_uniform(seed32, 100, yy, xx) < p[35]
+    salt = pixel_uniform(seed32, 101, yy, xx) < p[36]
+    return noise & salt, noise & ~salt
+
+
+def erase(x: np.ndarray, p: np.ndarray) -> np.ndarray:
+    """The two RandomErasing rectangles (value 0, then value 1) on a (3, H, W) image."""
+    x = x.copy()
+    for base, value in ((24, 0.0), (29, 1.0)):
+        if p[base] != 0:
+            ex, ey, ew, eh = (int(v) for v in p[base + 1:base + 5])
+            x[:, ey:ey + eh, ex:ex + ew] = F(value)
+    return x
+
+
+def augment_image(u8_hwc: np.ndarray, p: np.ndarray, arc_mask: np.ndarray | None = None) -> np.ndarray:
+    """One image: uint8 (H,W,3) -> float32 (3,H,W) in [0,1], parameters p (N_PARAMS,); arc_mask: optional boolean
+    (H, W) spaghetti mask painted black first (data.py:212-215 draws the arcs on the decoded image)."""
+    u8 = u8_hwc
+    if arc_mask is not None:
+        u8 = u8.copy()
+        u8[arc_mask] = 0
+    x = (u8.astype(np.float32) * F(1.0 / 255.0)).transpose(2, 0, 1)
+    x = erase(x, p)
     x = color_ops(x, p)
     x = gaussian_blur(x, float(p[7]))
     x = motion_blur(x, p[8:17])
     H, W = x.shape[1:]
-    if p[18] != 0:
-        f = plasma_field(H, W, p[17], int(round(float(p[20]) * (1 << 24))))
-        lo, hi = f.min(), f.max()
-        fn = (f - lo) / np.maximum(hi - lo, F(1e-12))
-        x = x + np.where(fn < p[19], p[18], F(0))[None]
-    return np.clip(x, F(0), F(1)).astype(np.float32)
+    x = x + np.where(plasma_shadow_mask(H, W, p), p[18], F(0))[None]
+    x = np.clip(x, F(0), F(1)).astype(np.float32)
+    salt, pepper = salt_pepper_masks(H, W, p)
+    x[:, salt] = F(1)
+    x[:, pepper] = F(0)
+    return x
 
 
 def augment_batch_u8(images_u8: np.ndarray, seed: int = 0, step: int = 0, cfg=None, params=None) -> np.ndarray:
@@ -295,7 +400,7 @@ def augment_batch_u8(images_u8: np.ndarray, seed: int = 0, step: int = 0, cfg=No
     `reshape(-1, H, W)`, data.py:224-227)."""
     B, n_cams, H, W, _ = images_u8.shape
     if params is None:
-        params = sample_params(B, n_cams, seed, step, cfg)
+        params = sample_params(B, n_cams, seed, step, cfg, H=H, W=W)
     out = np.empty((B, n_cams, 3, H, W), dtype=np.float32)
     for b in range(B):
         for v in range(n_cams):
@@ -305,16 +410,12 @@ def augment_batch_u8(images_u8: np.ndarray, seed: int = 0, step: int = 0, cfg=No
 
 # ------------------------------------------------------------------------------------------------------------------
 # spaghetti arcs (reference: argus/utils.py:252-275 `draw_spaghetti`, applied at argus/data.py:212-215 to the decoded
-# image BEFORE the kornia chain). The reference draws with PIL's ImageDraw.arc; this restatement is OUR rasterisation
-# rule, calibrated against Pillow 12 (tests/test_oracle_augment.py: IoU 0.92 over random arcs, the rest is edge pixels):
-#   bbox (x0, y0, x1, y1) -> centre ((x0+x1)/2, (y0+y1)/2), radii ((x1-x0)/2 + 0.5, (y1-y0)/2 + 0.5);
-#   a pixel is painted black iff it is inside the outer ellipse, not strictly inside the ellipse shrunk by `width`,
-#   and its PARAMETRIC angle atan2(dy/ry, dx/rx) (clockwise from 3 o'clock, as PIL measures) lies in [start, end];
-#   the angle test is done with cross products against (cos, sin) of start / end, no transcendental per pixel.
+# image BEFORE the kornia chain). The reference draws with PIL's ImageDraw.arc; oracle/pil_arc.py restates Pillow's
+# rasteriser and is pinned to the real library pixel for pixel (tests/test_oracle_augment.py).
 # Sampling follows the reference: x0 ~ U{0..W-1}, y0 ~ U{0..H-1}, x1 ~ U{x0..W-1}, y1 ~ U{y0..H-1},
 # start, end ~ U{0..359}, width = int(U(1, 5)); one draw per (seed, step, image, arc, field) through the same hash.
 # ------------------------------------------------------------------------------------------------------------------
-ARC_FIELDS = 10   # cx, cy, rx, ry, cos0, sin0, cos1, sin1, width, sweep_deg
+ARC_FIELDS = 8   # x0, y0, x1, y1, start, end, width, 0
 _ARC_FIELD_BASE = 1000
 
 
@@ -339,48 +440,32 @@ def spaghetti_params(n_images: int, n_arcs: int, H: int, W: int, seed: int, step
     a0 = randint(U(4), zero, zero + 360)
     a1 = randint(U(5), zero, zero + 360)
     width = np.floor(np.float32(1.0) + U(6) * np.float32(4.0)).astype(np.float32)
-    arcs[..., 0] = (x0 + x1).astype(np.float32) * np.float32(0.5)
-    arcs[..., 1] = (y0 + y1).astype(np.float32) * np.float32(0.5)
-    arcs[..., 2] = (x1 - x0).astype(np.float32) * np.float32(0.5) + np.float32(0.5)
-    arcs[..., 3] = (y1 - y0).astype(np.float32) * np.float32(0.5) + np.float32(0.5)
-    arcs[..., 4] = np.cos(np.radians(a0.astype(np.float64))).astype(np.float32)
-    arcs[..., 5] = np.sin(np.radians(a0.astype(np.float64))).astype(np.float32)
-    arcs[..., 6] = np.cos(np.radians(a1.astype(np.float64))).astype(np.float32)
-    arcs[..., 7] = np.sin(np.radians(a1.astype(np.float64))).astype(np.float32)
-    arcs[..., 8] = width
-    arcs[..., 9] = ((a1 - a0) % 360).astype(np.float32)
+    for k, v in enumerate((x0, y0, x1, y1, a0, a1)):
+        arcs[..., k] = v.astype(np.float32)
+    arcs[..., 6] = width
     return arcs
 
 
 def arc_mask(H: int, W: int, arc: np.ndarray) -> np.ndarray:
-    """Boolean (H, W) mask of one arc (float32 arithmetic, same operation order as the CUDA kernel)."""
-    f32 = np.float32
-    cx, cy, rx, ry, c0, s0, c1, s1, wd, sweep = (f32(v) for v in arc)
-    yy, xx = np.mgrid[0:H, 0:W]
-    dx = xx.astype(f32) - cx
-    dy = yy.astype(f32) - cy
-    u = dx / rx
-    v = dy / ry
-    outer = (u * u + v * v) <= f32(1)
-    irx, iry = rx - wd, ry - wd
-    if irx > 0 and iry > 0:
-        ui, vi = dx / irx, dy / iry
-        inner = (ui * ui + vi * vi) < f32(1)
-    else:
-        inner = np.zeros_like(outer)
-    a = c0 * v - s0 * u       # sin(theta_p - theta_start)
-    b = s1 * u - c1 * v       # sin(theta_end - theta_p)
-    sector = ((a >= 0) & (b >= 0)) if sweep <= 180 else ~((a < 0) & (b < 0))
-    return outer & ~inner & sector
+    """Boolean (H, W) mask of one arc row of the table: exactly the pixels Pillow's ImageDraw.arc paints."""
+    from .pil_arc import arc_mask as pil_arc_mask
+
+    x0, y0, x1, y1, a0, a1, wd = (int(v) for v in arc[:7])
+    return pil_arc_mask(H, W, (x0, y0, x1, y1), a0, a1, wd)
+
+
+def spaghetti_mask(H: int, W: int, arcs: np.ndarray) -> np.ndarray:
+    """arcs (n, n_arcs, ARC_FIELDS) -> boolean (n, H, W)."""
+    out = np.zeros((arcs.shape[0], H, W), dtype=bool)
+    for i in range(arcs.shape[0]):
+        for arc in arcs[i]:
+            out[i] |= arc_mask(H, W, arc)
+    return out
 
 
 def draw_spaghetti_u8(images_u8: np.ndarray, arcs: np.ndarray) -> np.ndarray:
     """images (n, H, W, 3) uint8, arcs (n, n_arcs, ARC_FIELDS) -> copy with the arcs painted black."""
     out = images_u8.copy()
     n, H, W, _ = out.shape
-    for i in range(n):
-        m = np.zeros((H, W), dtype=bool)
-        for arc in arcs[i]:
-            m |= arc_mask(H, W, arc)
-        out[i][m] = 0
+    out[spaghetti_mask(H, W, arcs)] = 0
     return out

@@ -1,0 +1,174 @@
+"""Parity measurements behind tests/test_parity_gpu.py (north star: fp32 mode <= 1e-4, bf16 mode <= 2e-2 relative on
+forward outputs, losses and gradients):
+
+  * a CONDITIONED checkpoint -- the reference model after `--train-steps` fp32 Adam steps of the reference's own step body
+    (argus/train.py:298-320) on the learnable synthetic task of profiles/loss_curve.py from the reference's default seed
+    42 -- instead of a random initialisation (the reference itself starts from IMAGENET1K_V2 weights, models.py:43);
+  * the benchmarked configurations: B = 256 pairs at 256 x 256 in train mode (configs[1]) and B = 64 in eval mode
+    (configs[2]).
+Everything is compared against the torch fp32 (TF32 off) run of the reference model on the same GPU; torch's own bf16
+autocast run of the reference is measured beside it for context. Usage:
+    python profiles/parity_probe.py [out.json] [--train-steps N] [--big]
+"""
+import json
+import sys
+from pathlib import Path
+
+import torch
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+sys.path.insert(0, str(ROOT / "profiles"))
+
+STAGES = {"stem": ("resnet.conv1", "resnet.bn1"), "layer1": ("resnet.layer1",), "layer2": ("resnet.layer2",),
+          "layer3": ("resnet.layer3",), "layer4": ("resnet.layer4",), "head": ("resnet.fc", "output_mlp")}
+
+
+def rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+def conditioned_state_dict(train_steps: int, device, size: int = 128, batch: int = 8):
+    """The reference model after `train_steps` fp32 steps of the reference step body (deterministic given the seed up
+    to cuDNN's summation order). Returns (state_dict, final window loss)."""
+    from loss_curve import make_task
+    from oracle.ref_model import make_reference_model, torch_loss
+
+    images, targets = make_task(size=size, device=device)
+    model = make_reference_model(42).to(device).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    n = images.shape[0]
+    last = []
+    for s in range(train_steps):
+        i0 = (s * batch) % n
+        opt.zero_grad(set_to_none=True)
+        loss = torch_loss(model(images[i0:i0 + batch]).float(), targets[i0:i0 + batch]).mean().float()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        last.append(float(loss))
+    return {k: v.detach().clone() for k, v in model.state_dict().items()}, sum(last[-20:]) / max(len(last[-20:]), 1)
+
+
+def reference_pass(sd, x, t, train: bool, autocast: bool):
+    """Forward (+ loss + backward when train) of the reference model; returns (out, loss, {name: grad})."""
+    from oracle.ref_model import make_reference_model, torch_loss
+
+    model = make_reference_model(0).to(x.device)
+    model.load_state_dict(sd)
+    model.train(train)
+    if not train:
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+            return model(x).float(), None, None
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        out = model(x)
+    loss = torch_loss(out.float(), t).mean().float()
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    return out.detach().float(), float(loss), grads
+
+
+def ours_pass(sd, x, t, train: bool, precision: str = "bf16"):
+    from argus_b200.loss import geometric_loss_fn
+    from argus_b200.models import NCameraCNN
+
+    model = NCameraCNN().to(x.device).set_precision(precision)
+    model.load_state_dict(sd)
+    model.train(train)
+    if not train:
+        with torch.no_grad():
+            return model(x).float(), None, None
+    out = model(x)
+    loss = geometric_loss_fn(out, t).mean()
+    loss.backward()
+    grads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+    return out.detach().float(), float(loss), grads
+
+
+def grad_report(g, g_ref):
+    names = list(g_ref)
+    flat = torch.cat([g[n].flatten().double() for n in names])
+    flat_ref = torch.cat([g_ref[n].flatten().double() for n in names])
+    rep = {"global_rel": ((flat - flat_ref).norm() / flat_ref.norm()).item(),
+           "global_norm_ratio": (flat.norm() / flat_ref.norm()).item(),
+           "cosine": (torch.dot(flat, flat_ref) / (flat.norm() * flat_ref.norm())).item(), "stages": {}}
+    for stage, prefixes in STAGES.items():
+        sel = [n for n in names if n.startswith(prefixes)]
+        a = torch.cat([g[n].flatten().double() for n in sel])
+        b = torch.cat([g_ref[n].flatten().double() for n in sel])
+        rep["stages"][stage] = {"rel": ((a - b).norm() / b.norm()).item(), "norm_ratio": (a.norm() / b.norm()).item()}
+    return rep
+
+
+def compare(sd, x, t, train: bool, with_fp32_mode: bool = False):
+    out_ref, loss_ref, g_ref = reference_pass(sd, x, t, train, autocast=False)
+    res = {}
+    runs = {"ours_bf16": lambda: ours_pass(sd, x, t, train, "bf16"),
+            "torch_autocast_bf16": lambda: reference_pass(sd, x, t, train, autocast=True)}
+    if with_fp32_mode:
+        runs["ours_fp32"] = lambda: ours_pass(sd, x, t, train, "fp32")
+    for name, fn in runs.items():
+        out, loss, g = fn()
+        r = {"out_rel": rel(out, out_ref)}
+        if train:
+            r["loss_rel"] = abs(loss - loss_ref) / abs(loss_ref)
+            r["loss"] = loss
+            r["grads"] = grad_report(g, g_ref)
+        res[name] = r
+        del out, g
+        torch.cuda.empty_cache()
+    if train:
+        res["loss_ref"] = loss_ref
+    return res
+
+
+def main():
+    out_path = sys.argv[1] if len(sys.argv) > 1 and not sys.argv[1].startswith("--") else "gpurun_out/parity_probe.json"
+    train_steps = int(sys.argv[sys.argv.index("--train-steps") + 1]) if "--train-steps" in sys.argv else 200
+    big = "--big" in sys.argv
+    from gpu_util import random_targets, structured_images
+    from loss_curve import make_task
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    report = {"train_steps": train_steps}
+    sd, final_loss = conditioned_state_dict(train_steps, dev)
+    report["conditioning_final_loss"] = final_loss
+    images, targets = make_task(size=128, device=dev)
+    # (1) conditioned checkpoint, data of its own task (unseen order: the last 16 samples), train and eval mode
+    report["conditioned_task_B16_128"] = compare(sd, images[48:64], targets[48:64], train=True, with_fp32_mode=True)
+    report["conditioned_task_B16_128_eval"] = compare(sd, images[48:64], targets[48:64], train=False)
+    # (2) conditioned checkpoint on generic structured images at the reference's image size
+    x = structured_images(32, 6, 256, 256, 5, dev)
+    t = random_targets(32, 6, dev)
+    report["conditioned_structured_B32_256"] = compare(sd, x, t, train=True)
+    # (3) random initialisation, same inputs (what round 1 measured)
+    from oracle.ref_model import make_reference_model
+
+    sd0 = {k: v.detach().clone().to(dev) for k, v in make_reference_model(42).state_dict().items()}
+    report["random_init_structured_B32_256"] = compare(sd0, x, t, train=True)
+    del x, t
+    if big:
+        # (4) the benchmarked configurations
+        x = structured_images(256, 6, 256, 256, 7, dev)
+        t = random_targets(256, 8, dev)
+        report["conditioned_B256_256_train"] = compare(sd, x, t, train=True)
+        report["conditioned_B64_256_eval"] = compare(sd, x[:64], t[:64], train=False)
+        report["conditioned_B1_256_eval"] = compare(sd, x[:1], t[:1], train=False)
+    Path(out_path).parent.mkdir(parents=True, exist_ok=True)
+    Path(out_path).write_text(json.dumps(report, indent=1))
+
+    def show(d, indent=0):
+        for k, v in d.items():
+            if isinstance(v, dict):
+                print(" " * indent + k)
+                show(v, indent + 2)
+            else:
+                print(" " * indent + f"{k}: {v:.4g}" if isinstance(v, float) else " " * indent + f"{k}: {v}")
+    show(report)
+
+
+if __name__ == "__main__":
+    main()

@@ -36,7 +36,7 @@ def test_product_never_imports_the_oracle():
                 names = [node.module]
             assert not any(n == "oracle" or n.startswith("oracle.") for n in names), path
     for path in (ROOT / "argus_b200" / "csrc").glob("*"):
-        assert "oracle/" not in path.read_text().replace("oracle/se3_loss.py", "").replace("oracle/augment.py", ""), path
+        assert "oracle/" not in path.read_text().replace("oracle/se3_loss.py", "").replace("oracle/augment.py", "").replace("oracle/pil_arc.py", ""), path
 
 
 def test_every_kernel_waits_on_its_programmatic_dependency():

@@ -182,3 +182,39 @@ def test_prefetch_without_augmentation(cuda_device):
     assert torch.isfinite(l0).all()
     assert torch.equal(l0, l1), (l0, l1)
     assert torch.equal(p0, p1)
+
+
+def test_prefetch_with_shorter_last_batch(cuda_device):
+    """The last batch of an epoch is usually shorter (DataLoader without drop_last, as in the reference, train.py:168-192).
+    Staging it while the full-size step is still in flight must not touch that step's stem input: the staging buffers
+    belong to the model, not to the per-batch-size plan (regression for the round-1 aliasing bug). A long side-stream
+    delay (ARGUS_FUZZ_DELAY_US is read at library load, so the fuzz kernel is not used here) is emulated by issuing the
+    prefetch BEFORE the step's kernels can have finished: the step is large enough to still be running."""
+    from argus_b200.data import Augmentation, AugmentationConfig
+    from argus_b200.engine import TrainEngine
+    from argus_b200.models import NCameraCNN
+    from gpu_util import random_targets
+
+    g = torch.Generator().manual_seed(11)
+    sizes = [16, 16, 5, 16, 3]
+    batches = [(torch.randint(0, 256, (b, 2, 64, 64, 3), dtype=torch.uint8, generator=g).to("cuda"),
+                random_targets(b, 30 + i, "cuda")) for i, b in enumerate(sizes)]
+
+    def run(prefetch):
+        torch.manual_seed(0)
+        model = NCameraCNN().to("cuda")
+        eng = TrainEngine(model, lr=1e-3, distributed=False,
+                          augmentation=Augmentation(AugmentationConfig(), train=True, seed=9))
+        losses = []
+        for i in range(len(batches)):
+            losses.append(eng.step(*batches[i]).clone())
+            if prefetch and i + 1 < len(batches):
+                eng.prefetch(batches[i + 1][0])
+        torch.cuda.synchronize()
+        return torch.stack(losses), model.flat_params.clone()
+
+    l0, p0 = run(False)
+    l1, p1 = run(True)
+    assert torch.isfinite(l0).all()
+    assert torch.equal(l0, l1), (l0, l1)
+    assert torch.equal(p0, p1)

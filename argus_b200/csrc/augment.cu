@@ -181,8 +181,9 @@ __global__ void aug_params_kernel(float* __restrict__ params, int n_images, int 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kPlasmaMaxA = 129 * 129;   // largest second-to-last level (256 x 256 images)
 constexpr int kPlasmaMaxB = 65 * 65;
-constexpr int kPlasmaSmemBytes = (kPlasmaMaxA + kPlasmaMaxB) * 4;
-constexpr int kPlasmaThreads = 512;
+constexpr int kPlasmaMaxD = 128 * 128;   // diamond centres of the last level
+constexpr int kPlasmaSmemBytes = (kPlasmaMaxA + kPlasmaMaxB + kPlasmaMaxD) * 4;
+constexpr int kPlasmaThreads = 1024;
 
 struct PlasmaGeom {
   int depth, sh, sw;   // number of doublings, seed grid
@@ -253,18 +254,29 @@ plasma_mask_kernel(const float* __restrict__ params, uint32_t* __restrict__ mask
     __syncthreads();
     other = cur; cur = nxt; h = nh; w = nw;
   }
-  // last level on the fly from `cur` (h x w): final grid (2h-1) x (2w-1), cropped to H x W
+  // last level from `cur` (h x w): final grid (2h-1) x (2w-1), cropped to H x W. Its diamond centres (odd, odd) go to
+  // shared memory once; the square centres are evaluated per pixel on the fly, nothing else is stored.
   scale = __fmul_rn(scale, roughness);
   const uint32_t level = g.depth;
   const int fh = 2 * h - 1, fw = 2 * w - 1;
+  float* dia = s_plasma + kPlasmaMaxA + kPlasmaMaxB;   // [(h - 1) x (w - 1)]: centre (2i+1, 2j+1) at [i][j]
+  const int dw = w - 1;
+  for (int i = threadIdx.x; i < (h - 1) * dw; i += kPlasmaThreads) {
+    const int dy = i / dw, dx = i - dy * dw;
+    dia[i] = ds_diamond(cur, w, 2 * dy + 1, 2 * dx + 1, scale, seed32, level);
+  }
+  __syncthreads();
   auto value_at = [&](int y, int x) -> float {   // even-even or odd-odd positions only
     if (!((y | x) & 1)) return cur[(y >> 1) * w + (x >> 1)];
-    return ds_diamond(cur, w, y, x, scale, seed32, level);
+    return dia[(y >> 1) * dw + (x >> 1)];
   };
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wpr = W >> 5;   // words per row
+  const int wshift = 31 - __clz(W >> 5);   // W / 32 is a power of two for W in {32, 64, 128, 256}; else divide
+  const int wpr = W >> 5;                  // words per row
+  const bool pow2 = (wpr & (wpr - 1)) == 0;
   for (int wi = warp; wi < words; wi += kPlasmaThreads / 32) {
-    const int y = wi / wpr, x = (wi - y * wpr) * 32 + lane;
+    const int y = pow2 ? (wi >> wshift) : wi / wpr;
+    const int x = (wi - y * wpr) * 32 + lane;
     float f;
     if (((y ^ x) & 1) == 0) {
       f = value_at(y, x);
@@ -297,20 +309,17 @@ __device__ __forceinline__ void rgb_to_hsv(float r, float g, float b, float& h6,
   h6 = hh < 0.f ? hh + 6.f : hh;
 }
 __device__ __forceinline__ void hsv_to_rgb(float h6, float s, float v, float& r, float& g, float& b) {
-  const float fl = floorf(h6);
-  const float f = h6 - fl;
-  const int hi = static_cast<int>(fl);   // h6 in [0, 6] -> 6 wraps to sector 0 below
-  const float p = v * (1.f - s);
-  const float q = v * (1.f - f * s);
-  const float t = v * (1.f - (1.f - f) * s);
-  switch (hi) {
-    case 1: r = q; g = v; b = p; break;
-    case 2: r = p; g = v; b = t; break;
-    case 3: r = p; g = q; b = v; break;
-    case 4: r = t; g = p; b = v; break;
-    case 5: r = v; g = p; b = q; break;
-    default: r = v; g = t; b = p; break;   // 0 (and 6 == a full turn)
-  }
+  // branch-free form of the sector table (no divergence between pixels of different hue):
+  //   channel = v - v s clamp(min(k, 4 - k), 0, 1),  k = (n + h6) mod 6,  n = 5, 3, 1 for R, G, B
+  // e.g. sector 0 (h6 = f): R -> v, G -> v (1 - (1 - f) s) = t, B -> v (1 - s) = p, exactly kornia's (v, t, p)
+  const float vs = v * s;
+  float kr = h6 + 5.f, kg = h6 + 3.f, kb = h6 + 1.f;
+  kr = kr >= 6.f ? kr - 6.f : kr;
+  kg = kg >= 6.f ? kg - 6.f : kg;
+  kb = kb >= 6.f ? kb - 6.f : kb;
+  r = fmaf(-vs, __saturatef(fminf(kr, 4.f - kr)), v);
+  g = fmaf(-vs, __saturatef(fminf(kg, 4.f - kg)), v);
+  b = fmaf(-vs, __saturatef(fminf(kb, 4.f - kb)), v);
 }
 // planckian gain, then the four jiggle ops in the sampled order. Saturation and hue act on different HSV components, so
 // when they are adjacent in the order they share one RGB <-> HSV round trip.
@@ -376,12 +385,15 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
   const int e2x = static_cast<int>(sP[30]), e2y = static_cast<int>(sP[31]), e2w = static_cast<int>(sP[32]), e2h = static_cast<int>(sP[33]);
   const size_t img_words = static_cast<size_t>(H) * (W >> 5);
 
-  // ---- stage 1: load (+ reflect), arcs, /255, erasing, colour ops
-  for (int i = threadIdx.x; i < span * span; i += 256) {
-    const int ty = lo + i / span, tx = lo + i % span;
+  // ---- stage 1: load (+ reflect), arcs, /255, erasing, colour ops. Tile-local pixel (ty, tx), both in [lo, lo + span).
+  const bool border_tile = (y0 == 0) | (x0 == 0) | (y0 + kTile == H) | (x0 + kTile == W);
+  const bool erasing = (e1 | e2) != 0;
+  auto load_pixel = [&](int ty, int tx) {
     int gy = y0 - kHalo + ty, gx = x0 - kHalo + tx;
-    gy = gy < 0 ? -gy : (gy >= H ? 2 * (H - 1) - gy : gy);
-    gx = gx < 0 ? -gx : (gx >= W ? 2 * (W - 1) - gx : gx);
+    if (border_tile) {   // reflect (only tiles on the image border can reach outside)
+      gy = gy < 0 ? -gy : (gy >= H ? 2 * (H - 1) - gy : gy);
+      gx = gx < 0 ? -gx : (gx >= W ? 2 * (W - 1) - gx : gx);
+    }
     float r, g, b;
     if (IN_U8) {
       const uint8_t* p = static_cast<const uint8_t*>(in) + (static_cast<size_t>(n) * H * W + static_cast<size_t>(gy) * W + gx) * 3;
@@ -397,15 +409,32 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
       r = p[0]; g = p[static_cast<size_t>(H) * W]; b = p[2 * static_cast<size_t>(H) * W];
     }
     if (apply) {
-      if (e1 && gx >= e1x && gx < e1x + e1w && gy >= e1y && gy < e1y + e1h) { r = 0.f; g = 0.f; b = 0.f; }
-      if (e2 && gx >= e2x && gx < e2x + e2w && gy >= e2y && gy < e2y + e2h) { r = 1.f; g = 1.f; b = 1.f; }
+      if (erasing) {
+        if (e1 && gx >= e1x && gx < e1x + e1w && gy >= e1y && gy < e1y + e1h) { r = 0.f; g = 0.f; b = 0.f; }
+        if (e2 && gx >= e2x && gx < e2x + e2w && gy >= e2y && gy < e2y + e2h) { r = 1.f; g = 1.f; b = 1.f; }
+      }
       color_ops(r, g, b, sP, code, hue6);
     }
     sA[0][ty][tx] = r; sA[1][ty][tx] = g; sA[2][ty][tx] = b;
+  };
+  {
+    // no integer division anywhere: warp w takes the rows w, w + 8, ... with one lane per column for the first 32
+    // columns; the (span - 32) <= 6 halo columns left over are a second, flattened pass (one pixel per thread)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < span; r += 8) load_pixel(lo + r, lo + lane);
+    const int extra = span - 32;                      // 0, 2, 4 or 6 columns
+    if (extra > 0) {
+      // thread t -> row t / extra, column 32 + t % extra, with extra in {2, 4, 6}: multiply-shift instead of a division
+      const int t = threadIdx.x;
+      const int row = extra == 2 ? (t >> 1) : (extra == 4 ? (t >> 2) : (t * 10923) >> 16);   // t / 6 for t < 256
+      const int col = t - row * extra;
+      if (row < span) load_pixel(lo + row, lo + 32 + col);
+    }
   }
   __syncthreads();
 
-  // ---- stage 2: separable 5-tap gaussian (reflect already materialised in the halo). Rows needed: the motion window
+  // ---- stage 2: separable 5-tap gaussian (reflect already materialised in the halo). One thread = one run of 16 / 17
+  // consecutive outputs of one (channel, line): a sliding window in registers, 1.25 shared-memory loads per output.
   int off = 2;   // index offset of the (blurred or not) image window inside sA: window (oy, ox) <-> pixel (y0-1+oy, ..)
   if (sigma > 0.f) {
     float k[5];
@@ -420,25 +449,50 @@ augment_kernel(const void* __restrict__ in, void* __restrict__ out, const float*
 #pragma unroll
     for (int i = 0; i < 5; ++i) k[i] *= inv;
     // window = tile + 1 pixel of motion halo when the motion kernel is on (mlo = 0), else just the tile (mlo = 1)
-    const int mlo = motion ? 0 : 1, mspan = kMid - 2 * mlo;
-    for (int i = threadIdx.x; i < 3 * span * mspan; i += 256) {
-      const int c = i / (span * mspan);
-      const int rem = i - c * span * mspan;
-      const int ty = lo + rem / mspan, ox = mlo + rem % mspan;
-      float acc = 0.f;
+    const int mlo = motion ? 0 : 1, mspan = kMid - 2 * mlo;   // 34 or 32 outputs per line, in two runs of 17 / 16
+    const int run = mspan >> 1;
+    {
+      // horizontal: item = (channel, half, line); lanes walk the lines (row stride 39 floats: conflict free)
+      const int items = 3 * 2 * span;
+      for (int it = threadIdx.x; it < items; it += 256) {
+        const int c = it >= 4 * span ? 2 : (it >= 2 * span ? 1 : 0);
+        const int rem = it - c * 2 * span;
+        const int half = rem >= span ? 1 : 0;
+        const int ty = lo + rem - half * span;
+        const int ox0 = mlo + half * run;
+        const float* src = &sA[c][ty][ox0];
+        float* dst = &sB[c][ty][ox0];
+        float w0 = src[0], w1 = src[1], w2 = src[2], w3 = src[3];
 #pragma unroll
-      for (int t = 0; t < 5; ++t) acc = fmaf(k[t], sA[c][ty][ox + t], acc);
-      sB[c][ty][ox] = acc;
+        for (int j = 0; j < 17; ++j) {
+          if (j < run) {
+            const float w4 = src[j + 4];
+            dst[j] = fmaf(k[4], w4, fmaf(k[3], w3, fmaf(k[2], w2, fmaf(k[1], w1, k[0] * w0))));
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+          }
+        }
+      }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 3 * mspan * mspan; i += 256) {
-      const int c = i / (mspan * mspan);
-      const int rem = i - c * mspan * mspan;
-      const int oy = mlo + rem / mspan, ox = mlo + rem % mspan;
-      float acc = 0.f;
+    {
+      // vertical: item = (channel, half, column); lanes walk the columns
+      const int items = 3 * 2 * mspan;
+      for (int it = threadIdx.x; it < items; it += 256) {
+        const int c = it >= 4 * mspan ? 2 : (it >= 2 * mspan ? 1 : 0);
+        const int rem = it - c * 2 * mspan;
+        const int half = rem >= mspan ? 1 : 0;
+        const int ox = mlo + rem - half * mspan;
+        const int oy0 = mlo + half * run;
+        float w0 = sB[c][oy0][ox], w1 = sB[c][oy0 + 1][ox], w2 = sB[c][oy0 + 2][ox], w3 = sB[c][oy0 + 3][ox];
 #pragma unroll
-      for (int t = 0; t < 5; ++t) acc = fmaf(k[t], sB[c][oy + t][ox], acc);
-      sA[c][oy][ox] = acc;   // (oy, ox) <-> pixel (y0 - 1 + oy, x0 - 1 + ox)
+        for (int j = 0; j < 17; ++j) {
+          if (j < run) {
+            const float w4 = sB[c][oy0 + j + 4][ox];
+            sA[c][oy0 + j][ox] = fmaf(k[4], w4, fmaf(k[3], w3, fmaf(k[2], w2, fmaf(k[1], w1, k[0] * w0))));
+            w0 = w1; w1 = w2; w2 = w3; w3 = w4;   // (oy, ox) <-> pixel (y0 - 1 + oy, x0 - 1 + ox)
+          }
+        }
+      }
     }
     off = 0;
     __syncthreads();

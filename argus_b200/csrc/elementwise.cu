@@ -1191,20 +1191,34 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   asm("max.bf16x2 %0, %1, %2;" : "=r"(m) : "r"(a), "r"(b));
   return m;
 }
-__global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale,
-                                   const float* __restrict__ shift, uint4* __restrict__ y, uint2* __restrict__ idx,
-                                   int N, int H, int W, int cvec) {
+// SHIFT: W / 2, H / 2 and C / 8 are powers of two (every size the bf16 path accepts): the output index is split with
+// shifts; otherwise with 32-bit divisions. All nine taps are loaded unconditionally from clamped coordinates (nine
+// independent 16-byte loads in flight per thread) and the out-of-bounds ones replaced by -inf afterwards.
+template <bool SHIFT>
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+                   uint4* __restrict__ y, uint2* __restrict__ idx, int N, int H, int W, int cvec, int lg_c, int lg_wo,
+                   int lg_ho) {
   pdl_prologue();
   const int Ho = H >> 1, Wo = W >> 1;
   const int64_t total = static_cast<int64_t>(N) * Ho * Wo * cvec;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int cv = static_cast<int>(i % cvec);
-    int64_t t = i / cvec;
-    const int pw = static_cast<int>(t % Wo);
-    t /= Wo;
-    const int ph = static_cast<int>(t % Ho);
-    const int n = static_cast<int>(t / Ho);
+    int cv, pw, ph, n;
+    if (SHIFT) {
+      const uint32_t u = static_cast<uint32_t>(i);   // total < 2^32 is checked by the launcher
+      cv = u & (cvec - 1);
+      pw = (u >> lg_c) & (Wo - 1);
+      ph = (u >> (lg_c + lg_wo)) & (Ho - 1);
+      n = u >> (lg_c + lg_wo + lg_ho);
+    } else {
+      cv = static_cast<int>(i % cvec);
+      int64_t t = i / cvec;
+      pw = static_cast<int>(t % Wo);
+      t /= Wo;
+      ph = static_cast<int>(t % Ho);
+      n = static_cast<int>(t / Ho);
+    }
     F8 sc, sh;
     uint32_t flip[4] = {0u, 0u, 0u, 0u};
     if (scale != nullptr) {
@@ -1214,22 +1228,30 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
       for (int j = 0; j < 4; ++j)
         flip[j] = (sc.v[2 * j] < 0.f ? 0x00008000u : 0u) | (sc.v[2 * j + 1] < 0.f ? 0x80000000u : 0u);
     }
+    // window rows 2ph-1 .. 2ph+1, columns 2pw-1 .. 2pw+1: only the first row / column can be outside (H, W even)
+    const bool top_ok = ph > 0, left_ok = pw > 0;
+    const uint4* base = x + (static_cast<int64_t>(n) * H * W) * cvec + cv;
+    uint4 tap[3][3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = max(2 * ph - 1 + kh, 0);
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = max(2 * pw - 1 + kw, 0);
+        tap[kh][kw] = __ldg(base + (h * W + w) * cvec);
+      }
+    }
     uint32_t best[4], bi[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) { best[j] = 0xff80ff80u; bi[j] = 0u; }   // -inf, tap 0
-    // window origin (tap 0, possibly out of bounds) once; the taps are 32-bit offsets from it
-    const uint4* x0 = x + ((static_cast<int64_t>(n) * H + (2 * ph - 1)) * W + (2 * pw - 1)) * cvec + cv;
-    const int row_pitch = W * cvec;
 #pragma unroll
-    for (int kh = 0; kh < 3; ++kh) {
-      const int h = 2 * ph - 1 + kh;
-      if (h < 0 || h >= H) continue;
+    for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
       for (int kw = 0; kw < 3; ++kw) {
-        const int w = 2 * pw - 1 + kw;
-        if (w < 0 || w >= W) continue;
-        const uint4 u = __ldg(x0 + (kh * row_pitch + kw * cvec));
-        const uint32_t wv[4] = {u.x ^ flip[0], u.y ^ flip[1], u.z ^ flip[2], u.w ^ flip[3]};
+        const bool ok = (kh > 0 || top_ok) && (kw > 0 || left_ok);
+        const uint4 u = tap[kh][kw];
+        const uint32_t wv[4] = {ok ? (u.x ^ flip[0]) : 0xff80ff80u, ok ? (u.y ^ flip[1]) : 0xff80ff80u,
+                                ok ? (u.z ^ flip[2]) : 0xff80ff80u, ok ? (u.w ^ flip[3]) : 0xff80ff80u};
         const uint32_t code = static_cast<uint32_t>(kh * 3 + kw) * 0x00010001u;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -1238,7 +1260,6 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
           bi[j] = (bi[j] & ~m) | (code & m);
         }
       }
-    }
     F8 o = unpack8(make_uint4(best[0] ^ flip[0], best[1] ^ flip[1], best[2] ^ flip[2], best[3] ^ flip[3]));
     if (scale != nullptr) {
 #pragma unroll
@@ -1253,13 +1274,25 @@ __global__ void maxpool_fwd_kernel(const uint4* __restrict__ x, const float* __r
     }
   }
 }
+static int log2_exact(int v) {   // log2 of a power of two, -1 otherwise
+  if (v <= 0 || (v & (v - 1))) return -1;
+  int l = 0;
+  while ((1 << l) < v) ++l;
+  return l;
+}
 void maxpool_fwd(const bf16* x, const float* scale, const float* shift, bf16* y, uint8_t* idx, int N, int H, int W,
                  int C, cudaStream_t s) {
   ProfileScope prof("maxpool", s, 0, static_cast<double>(N) * H * W * C * 2 * 1.25 + (idx ? static_cast<double>(N) * H * W * C / 4 : 0.0));
   const int64_t total = static_cast<int64_t>(N) * (H / 2) * (W / 2) * (C / 8);
-  launch_kernel(maxpool_fwd_kernel, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(x), scale, shift,
-                                                          reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx),
-                                                          N, H, W, C / 8);
+  const int lg_c = log2_exact(C / 8), lg_wo = log2_exact(W / 2), lg_ho = log2_exact(H / 2);
+  const bool shift_ok = lg_c >= 0 && lg_wo >= 0 && lg_ho >= 0 && total < (1LL << 32) &&
+                        static_cast<int64_t>(H) * W * (C / 8) < (1LL << 31);
+  if (shift_ok)
+    launch_kernel(maxpool_fwd_kernel<true>, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(x), scale, shift,
+                  reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), N, H, W, C / 8, lg_c, lg_wo, lg_ho);
+  else
+    launch_kernel(maxpool_fwd_kernel<false>, grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(x), scale, shift,
+                  reinterpret_cast<uint4*>(y), reinterpret_cast<uint2*>(idx), N, H, W, C / 8, 0, 0, 0);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -1322,7 +1355,7 @@ stem_pool_bn_bwd_kernel(const uint4* __restrict__ dpool, const uint2* __restrict
                         const float* __restrict__ scale, const float* __restrict__ shift,
                         const float* __restrict__ mean, const float* __restrict__ invstd,
                         const float* __restrict__ dgamma, const float* __restrict__ dbeta, float* __restrict__ partial,
-                        uint4* __restrict__ dx, int N, int H, int W, float inv_rows) {
+                        uint4* __restrict__ dx, int N, int H, int W, float inv_rows, int lg_wo, int lg_ho) {
   pdl_prologue();
   constexpr int cvec = 8;   // C = 64
   __shared__ float red[16][256];
@@ -1346,10 +1379,18 @@ stem_pool_bn_bwd_kernel(const uint4* __restrict__ dpool, const uint2* __restrict
   const int64_t patches = static_cast<int64_t>(N) * Ho * Wo;
   for (int64_t pi = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 3; pi < patches;
        pi += (static_cast<int64_t>(gridDim.x) * blockDim.x) >> 3) {
-    const int b = static_cast<int>(pi % Wo);
-    const int64_t t = pi / Wo;
-    const int a = static_cast<int>(t % Ho);
-    const int n = static_cast<int>(t / Ho);
+    int a, b, n;
+    if (lg_wo >= 0) {   // Wo, Ho powers of two (every size the bf16 path accepts): shifts instead of 64-bit divisions
+      const uint32_t u = static_cast<uint32_t>(pi);
+      b = u & (Wo - 1);
+      a = (u >> lg_wo) & (Ho - 1);
+      n = u >> (lg_wo + lg_ho);
+    } else {
+      b = static_cast<int>(pi % Wo);
+      const int64_t t = pi / Wo;
+      a = static_cast<int>(t % Ho);
+      n = static_cast<int>(t / Ho);
+    }
     // the four windows of this patch: w[dy][dx] = window (a + dy, b + dx)
     F8 wd[2][2];
     uint2 wi[2][2];
@@ -1437,6 +1478,8 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
   const int64_t rows = static_cast<int64_t>(N) * H * W;
   const int64_t threads = rows / 4 * 8;
   const float inv_rows = static_cast<float>(1.0 / static_cast<double>(rows));
+  int lg_wo = log2_exact(W / 2), lg_ho = log2_exact(H / 2);
+  if (lg_wo < 0 || lg_ho < 0 || rows / 4 >= (1LL << 32)) lg_wo = lg_ho = -1;
   auto DP = reinterpret_cast<const uint4*>(dpool);
   auto ID = reinterpret_cast<const uint2*>(idx);
   auto RW = reinterpret_cast<const uint4*>(raw);
@@ -1444,7 +1487,7 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
     ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(rows) * C * (2.0 + 0.75));
     const int grid = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>((threads + 255) / 256, 4LL * num_sms())));
     launch_kernel(stem_pool_bn_bwd_kernel<0>, grid, 256, 0, s, DP, ID, RW, scale, shift, mean, invstd, nullptr, nullptr, scratch,
-                                                    nullptr, N, H, W, inv_rows);
+                                                    nullptr, N, H, W, inv_rows, lg_wo, lg_ho);
     ARGUS_CUDA(cudaGetLastError());
     launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C);
     ARGUS_CUDA(cudaGetLastError());
@@ -1453,7 +1496,7 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
     ProfileScope prof("bn_bwd_apply", s, 0, static_cast<double>(rows) * C * (4.0 + 0.75));
     const int grid = grid_for(threads, 256);
     launch_kernel(stem_pool_bn_bwd_kernel<1>, grid, 256, 0, s, DP, ID, RW, scale, shift, mean, invstd, dgamma, dbeta, nullptr,
-                                                    reinterpret_cast<uint4*>(dx), N, H, W, inv_rows);
+                                                    reinterpret_cast<uint4*>(dx), N, H, W, inv_rows, lg_wo, lg_ho);
     ARGUS_CUDA(cudaGetLastError());
   }
 }

@@ -44,30 +44,54 @@ void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStre
   ARGUS_CUDA(cudaGetLastError());
 }
 
-// one warp per output element: y[b, o] = dot(x[b, :], w[o, :]) + bias[o]
-__global__ void linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                  float* __restrict__ y, float* __restrict__ act, int B, int In, int Out) {
+// y[b, o] = dot(x[b, :], w[o, :]) + bias[o]. A block stages kLinRows batch rows in shared memory; warp w takes the
+// outputs w, w + 8, ...: one coalesced pass over the weight row serves all staged rows (the weights are read B / kLinRows
+// times instead of B times). Per (b, o) the summation is lane-strided then a shuffle tree: a fixed order.
+constexpr int kLinRows = 4;
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                  float* __restrict__ y, float* __restrict__ act, int B, int In, int Out) {
   pdl_prologue();
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B * Out) return;
-  const int bi = warp / Out, o = warp - bi * Out;
-  const float* xr = x + static_cast<int64_t>(bi) * In;
-  const float* wr = w + static_cast<int64_t>(o) * In;
-  float acc = 0.f;
-  for (int i = lane; i < In; i += 32) acc = fmaf(xr[i], __ldg(wr + i), acc);
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const float v = acc + b[o];
-    y[warp] = v;
-    if (act != nullptr) act[warp] = gelu_f(v);
+  extern __shared__ float s_x[];   // [kLinRows][In]
+  const int b0 = blockIdx.x * kLinRows;
+  const int rows = min(kLinRows, B - b0);
+  for (int i = threadIdx.x; i < kLinRows * In; i += 256) {
+    const int r = i / In;
+    s_x[i] = r < rows ? x[static_cast<int64_t>(b0) * In + i] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < Out; o += 8) {
+    const float* wr = w + static_cast<int64_t>(o) * In;
+    float acc[kLinRows];
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) acc[r] = 0.f;
+    for (int i = lane; i < In; i += 32) {
+      const float wv = __ldg(wr + i);
+#pragma unroll
+      for (int r = 0; r < kLinRows; ++r) acc[r] = fmaf(s_x[r * In + i], wv, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < kLinRows; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+      const float bias = b[o];
+#pragma unroll
+      for (int r = 0; r < kLinRows; ++r)
+        if (r < rows) {
+          const float v = acc[r] + bias;
+          const int64_t idx = static_cast<int64_t>(b0 + r) * Out + o;
+          y[idx] = v;
+          if (act != nullptr) act[idx] = gelu_f(v);
+        }
+    }
   }
 }
 void linear_fwd(const float* x, const float* w, const float* b, float* y, float* act, int B, int In, int Out,
                 cudaStream_t s) {
   ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
-  const int64_t threads = static_cast<int64_t>(B) * Out * 32;
-  launch_kernel(linear_fwd_kernel, static_cast<int>((threads + 255) / 256), 256, 0, s, x, w, b, y, act, B, In, Out);
+  ARGUS_CHECK(static_cast<size_t>(kLinRows) * In * sizeof(float) <= 48 * 1024, "linear_fwd: input width too large");
+  launch_kernel(linear_fwd_kernel, (B + kLinRows - 1) / kLinRows, 256, static_cast<size_t>(kLinRows) * In * sizeof(float), s, x,
+                w, b, y, act, B, In, Out);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -76,32 +100,52 @@ __global__ void gelu_grad_inplace_kernel(float* dy, const float* __restrict__ pr
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dy[i] *= gelu_grad_f(pre[i]);
 }
-// dw[o, i] += sum_b dy[b, o] x[b, i]   (thread per (o, i): x reads coalesced over i, dy reads broadcast)
-__global__ void linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* dw, float* db,
-                                    int B, int In, int Out) {
+// dw[o, i] += sum_b dy[b, o] x[b, i]: thread = one input column i and four outputs o (x is read Out / 4 times instead of
+// Out times; the dy loads are warp-wide broadcasts). The sum over b runs in index order: same bits for any grid.
+__global__ void __launch_bounds__(128)
+linear_bwd_w_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* dw, float* db, int B, int In,
+                    int Out) {
   pdl_prologue();
-  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (t >= static_cast<int64_t>(Out) * In) return;
-  const int o = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(o) * In);
-  float acc = 0.f, accb = 0.f;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o0 = blockIdx.y * 4;
+  if (i >= In) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, accb[4] = {0.f, 0.f, 0.f, 0.f};
   for (int b = 0; b < B; ++b) {
-    const float d = __ldg(dy + static_cast<int64_t>(b) * Out + o);
-    acc = fmaf(d, __ldg(x + static_cast<int64_t>(b) * In + i), acc);
-    accb += d;
+    const float xv = __ldg(x + static_cast<int64_t>(b) * In + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = (o0 + k < Out) ? __ldg(dy + static_cast<int64_t>(b) * Out + o0 + k) : 0.f;
+      acc[k] = fmaf(d, xv, acc[k]);
+      accb[k] += d;
+    }
   }
-  dw[t] += acc;
-  if (i == 0) db[o] += accb;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (o0 + k < Out) {
+      dw[static_cast<int64_t>(o0 + k) * In + i] += acc[k];
+      if (i == 0) db[o0 + k] += accb[k];
+    }
 }
-// dx[b, i] = sum_o dy[b, o] w[o, i]
-__global__ void linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx,
-                                    int B, int In, int Out) {
+// dx[b, i] = sum_o dy[b, o] w[o, i]: thread = one input column i and four batch rows (w is read B / 4 times)
+__global__ void __launch_bounds__(128)
+linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, float* __restrict__ dx, int B, int In,
+                    int Out) {
   pdl_prologue();
-  const int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
-  if (t >= static_cast<int64_t>(B) * In) return;
-  const int b = static_cast<int>(t / In), i = static_cast<int>(t - static_cast<int64_t>(b) * In);
-  float acc = 0.f;
-  for (int o = 0; o < Out; ++o) acc = fmaf(__ldg(dy + static_cast<int64_t>(b) * Out + o), __ldg(w + static_cast<int64_t>(o) * In + i), acc);
-  dx[t] = acc;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b0 = blockIdx.y * 4;
+  if (i >= In) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int o = 0; o < Out; ++o) {
+    const float wv = __ldg(w + static_cast<int64_t>(o) * In + i);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float d = (b0 + k < B) ? __ldg(dy + static_cast<int64_t>(b0 + k) * Out + o) : 0.f;
+      acc[k] = fmaf(d, wv, acc[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (b0 + k < B) dx[static_cast<int64_t>(b0 + k) * In + i] = acc[k];
 }
 void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
                 int In, int Out, cudaStream_t s) {
@@ -110,12 +154,10 @@ void linear_bwd(float* dy, const float* pre, const float* x, const float* w, flo
     launch_kernel(gelu_grad_inplace_kernel, (B * Out + 255) / 256, 256, 0, s, dy, pre, B * Out);
     ARGUS_CUDA(cudaGetLastError());
   }
-  const int64_t nw = static_cast<int64_t>(Out) * In;
-  launch_kernel(linear_bwd_w_kernel, static_cast<int>((nw + 127) / 128), 128, 0, s, dy, x, dw, db, B, In, Out);
+  launch_kernel(linear_bwd_w_kernel, dim3((In + 127) / 128, (Out + 3) / 4), 128, 0, s, dy, x, dw, db, B, In, Out);
   ARGUS_CUDA(cudaGetLastError());
   if (dx != nullptr) {
-    const int64_t nx = static_cast<int64_t>(B) * In;
-    launch_kernel(linear_bwd_x_kernel, static_cast<int>((nx + 127) / 128), 128, 0, s, dy, w, dx, B, In, Out);
+    launch_kernel(linear_bwd_x_kernel, dim3((In + 127) / 128, (B + 3) / 4), 128, 0, s, dy, w, dx, B, In, Out);
     ARGUS_CUDA(cudaGetLastError());
   }
 }

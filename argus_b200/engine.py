@@ -117,6 +117,9 @@ class TrainEngine:
         self.distributed = bool(distributed)
         self.group = process_group
         self.world = dist.get_world_size(process_group) if self.distributed else 1
+        # the all-reduce SUMS the ranks' gradients; DDP's averaging (train.py:199) is this divisor, folded into the
+        # optimizer's gradient scale. (A test sets it by hand to emulate two ranks in one process.)
+        self.grad_divisor = float(self.world)
         n = model.flat_params.numel()
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=self.device)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=self.device)
@@ -258,7 +261,7 @@ class TrainEngine:
             _lib.check(fn(
                 _lib.ptr(model.flat_params), _lib.ptr(model.flat_grads), _lib.ptr(self.exp_avg),
                 _lib.ptr(self.exp_avg_sq), ctypes.c_int64(model.flat_params.numel()), _lib.ptr(self._scratch),
-                ctypes.c_float(inv_loss_scale / self.world), ctypes.c_float(self.max_grad_norm), ctypes.c_float(self.lr),
+                ctypes.c_float(inv_loss_scale / self.grad_divisor), ctypes.c_float(self.max_grad_norm), ctypes.c_float(self.lr),
                 ctypes.c_float(self.betas[0]), ctypes.c_float(self.betas[1]), ctypes.c_float(self.eps),
                 ctypes.c_int(self.step_count), _lib.ptr(self._grad_norm), _lib.stream_ptr()))
         model.sync_weights(force=True)

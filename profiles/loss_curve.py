@@ -32,10 +32,17 @@ def make_task(n=64, size=128, seed=0, device="cuda"):
     return img.to(device), target.to(device)
 
 
-def run_reference(images, targets, steps, batch, autocast):
+def run_reference(images, targets, steps, batch, autocast, model_seed=42, channels_last=False, tf32=False):
+    """The reference's step body (argus/train.py:298-320) on the reference model. channels_last / tf32 select other
+    cuDNN kernels for the SAME fp32 math (different summation order / the TF32 convolutions PyTorch uses by default on
+    Ampere and later): the spread between these runs is the reference's own run-to-run numerical spread."""
     from oracle.ref_model import make_reference_model, torch_loss
 
-    model = make_reference_model(42).to(images.device).train()
+    torch.backends.cudnn.allow_tf32 = bool(tf32)
+    torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    model = make_reference_model(model_seed).to(images.device).train()
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     losses = []
     n = images.shape[0]
@@ -50,15 +57,17 @@ def run_reference(images, targets, steps, batch, autocast):
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
         losses.append(loss.detach())
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     return torch.stack(losses).cpu().tolist()
 
 
-def run_ours(images, targets, steps, batch, precision):
+def run_ours(images, targets, steps, batch, precision, model_seed=42):
     from argus_b200.engine import TrainEngine
     from argus_b200.models import NCameraCNN
     from oracle.ref_model import make_reference_model
 
-    ref = make_reference_model(42)
+    ref = make_reference_model(model_seed)
     model = NCameraCNN().to(images.device).set_precision(precision)
     model.load_state_dict(ref.state_dict())
     eng = TrainEngine(model, lr=1e-4, max_grad_norm=1.0, distributed=False)
@@ -91,7 +100,47 @@ def compare(steps=1000, batch=8, size=128, window=100):
             "final_window": {k: v[-1] for k, v in means.items()}, "curves": curves}
 
 
+def acceptance(steps=1000, batch=8, size=128, window=100, seeds=(0, 1, 2), slack=0.0):
+    """Loss-curve acceptance (north star: "a matching 1k-step loss curve"): for every seed (task + initial weights), the
+    reference is run three ways -- fp32, fp32 channels_last, TF32 (PyTorch's default convolution arithmetic) -- and every
+    `window`-step mean of the bf16 product run must lie inside [min, max] of the three reference runs, widened by
+    `slack` (relative). Returns the per-seed window means and, per window, where ours sits relative to the band."""
+    out = {"steps": steps, "batch": batch, "size": size, "window": window, "slack": slack, "seeds": {}}
+    worst = 0.0
+    for seed in seeds:
+        images, targets = make_task(size=size, seed=seed)
+        refs = {"fp32": run_reference(images, targets, steps, batch, False, model_seed=42 + seed),
+                "fp32_channels_last": run_reference(images, targets, steps, batch, False, model_seed=42 + seed,
+                                                    channels_last=True),
+                "tf32": run_reference(images, targets, steps, batch, False, model_seed=42 + seed, tf32=True)}
+        ours = run_ours(images, targets, steps, batch, "bf16", model_seed=42 + seed)
+        means = {k: window_means(v, window) for k, v in refs.items()}
+        means["ours_bf16"] = window_means(ours, window)
+        lo = [min(means[k][i] for k in refs) for i in range(len(means["ours_bf16"]))]
+        hi = [max(means[k][i] for k in refs) for i in range(len(means["ours_bf16"]))]
+        # signed distance outside the band, relative to the band edge (0 = inside)
+        outside = [max(l / o - 1.0, o / h - 1.0, 0.0) for o, l, h in zip(means["ours_bf16"], lo, hi)]
+        worst = max(worst, max(outside))
+        out["seeds"][str(seed)] = {"window_means": means, "band_lo": lo, "band_hi": hi, "outside": outside,
+                                   "ref_spread": [h / l - 1.0 for l, h in zip(lo, hi)]}
+    out["worst_outside"] = worst
+    out["accepted"] = worst <= slack
+    return out
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "acceptance":
+        steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+        out = sys.argv[3] if len(sys.argv) > 3 else "gpurun_out/loss_curve_acceptance.json"
+        res = acceptance(steps)
+        for seed, r in res["seeds"].items():
+            for k, v in r["window_means"].items():
+                print(seed, f"{k:20s}", " ".join(f"{m:8.4f}" for m in v))
+            print(seed, f"{'outside band':20s}", " ".join(f"{m:8.4f}" for m in r["outside"]))
+            print(seed, f"{'reference spread':20s}", " ".join(f"{m:8.4f}" for m in r["ref_spread"]))
+        print("worst outside", res["worst_outside"])
+        Path(out).write_text(json.dumps(res))
+        sys.exit(0)
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
     out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/loss_curve.json"
     res = compare(steps)

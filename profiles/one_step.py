@@ -18,7 +18,7 @@ batch = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 dev = torch.device("cuda", 0)
 torch.manual_seed(42)
 model = NCameraCNN().to(dev)
-eng = TrainEngine(model, distributed=False, augmentation=Augmentation(AugmentationConfig(), train=True, seed=1))
+eng = TrainEngine(model, distributed=False, augmentation=Augmentation(AugmentationConfig(), train=True, seed=1, gpu_spaghetti=True))
 imgs, tgt = synthetic_batch(batch, 2, 256, 256, 0)
 imgs, tgt = imgs.to(dev), tgt.to(dev)
 lib = _lib.load()

@@ -29,7 +29,8 @@ def rel(a, b):
     return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
 
 
-def conditioned_state_dict(train_steps: int, device, size: int = 128, batch: int = 8):
+def conditioned_state_dict(train_steps: int, device, size: int = 128, batch: int = 8, zero_init_residual: bool = False,
+                           lr: float = 1e-4):
     """The reference model after `train_steps` fp32 steps of the reference step body (deterministic given the seed up
     to cuDNN's summation order). Returns (state_dict, final window loss)."""
     from loss_curve import make_task
@@ -37,7 +38,15 @@ def conditioned_state_dict(train_steps: int, device, size: int = 128, batch: int
 
     images, targets = make_task(size=size, device=device)
     model = make_reference_model(42).to(device).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    if zero_init_residual:
+        # torchvision's `zero_init_residual=True` recipe (the last BN of every residual branch starts at 0, so every
+        # block starts as the identity -- how ImageNet ResNets, including the reference's IMAGENET1K_V2 weights'
+        # family, are usually trained): training then grows the residual gains to small values
+        with torch.no_grad():
+            for m in model.modules():
+                if hasattr(m, "bn3"):
+                    m.bn3.weight.zero_()
+    opt = torch.optim.Adam(model.parameters(), lr=lr)
     n = images.shape[0]
     last = []
     for s in range(train_steps):
@@ -150,6 +159,19 @@ def main():
     sd0 = {k: v.detach().clone().to(dev) for k, v in make_reference_model(42).state_dict().items()}
     report["random_init_structured_B32_256"] = compare(sd0, x, t, train=True)
     del x, t
+    if "--zero-init" in sys.argv:
+        # (3b) zero-init-residual recipe, trained: residual gains small, the network is well conditioned
+        sdz, lz = conditioned_state_dict(train_steps, dev, zero_init_residual=True, lr=3e-4)
+        report["zero_init_final_loss"] = lz
+        gains = torch.cat([v.flatten() for k, v in sdz.items() if k.endswith("bn3.weight")])
+        report["zero_init_gain_rms"] = float(gains.pow(2).mean().sqrt())
+        report["zero_init_task_B16_128"] = compare(sdz, images[48:64], targets[48:64], train=True, with_fp32_mode=True)
+        report["zero_init_task_B16_128_eval"] = compare(sdz, images[48:64], targets[48:64], train=False)
+        x = structured_images(32, 6, 256, 256, 5, dev)
+        t = random_targets(32, 6, dev)
+        report["zero_init_structured_B32_256"] = compare(sdz, x, t, train=True)
+        report["zero_init_structured_B32_256_eval"] = compare(sdz, x, t, train=False)
+        del x, t
     if big:
         # (4) the benchmarked configurations
         x = structured_images(256, 6, 256, 256, 7, dev)

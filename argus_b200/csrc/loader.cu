@@ -110,8 +110,18 @@ class Loader {
     worker_ = std::thread([this] { this->run(); });
   }
 
+  // When is a device buffer free to be overwritten by the copy of batch k + 2? Once everything that reads batch k has run.
+  //  * fetch-then-step loops (fetch k, step k, fetch k + 1, ...): at call k + 1 all work on batch k is already
+  //    enqueued on `stream`, so the "consumed" event of buffer k is recorded THEN and the copy of batch k + 2 overlaps
+  //    step k + 1 (default);
+  //  * look-ahead loops (fetch k + 1, step k, prefetch k + 1, fetch k + 2, ... as argus_b200/train.py runs): at call
+  //    k + 1 step k has NOT been enqueued yet, so the event is recorded at call k + 2, right before the copy that reuses
+  //    the buffer (by then step k and the side-stream staging of batch k, which step k waited for, are enqueued).
+  void set_lookahead(bool on) { lookahead_ = on; }
+
   // Returns the number of samples in the batch (0 at the end of the epoch). The device buffers are valid on
-  // `stream` after this call; they stay valid until the call after next.
+  // `stream` after this call; a buffer is overwritten by the call after next (see set_lookahead for what that call
+  // waits for).
   int next(cudaStream_t stream, int* buf_index) {
     const int64_t nb = batches_per_epoch();
     if (next_take_ >= nb) return 0;
@@ -123,6 +133,10 @@ class Loader {
       count = fill_count_[buf];
     }
     // the device buffer may still be read by the step that consumed it two batches ago
+    if (lookahead_ && next_take_ >= 2) {
+      ARGUS_CUDA(cudaEventRecord(consumed_[buf], stream)); pdl_break(stream, kPdlAfterRecord);
+      consumed_recorded_[buf] = true;
+    }
     if (consumed_recorded_[buf]) ARGUS_CUDA(cudaStreamWaitEvent(copy_stream_, consumed_[buf], 0)); pdl_break(copy_stream_, kPdlAfterWait);
     ARGUS_CUDA(cudaMemcpyAsync(dev_img_[buf], host_img_[buf], static_cast<size_t>(count) * sample_bytes_,
                                cudaMemcpyHostToDevice, copy_stream_)); pdl_break(copy_stream_, kPdlAfterMemop);
@@ -133,7 +147,7 @@ class Loader {
     ARGUS_CUDA(cudaStreamWaitEvent(stream, copied_[buf], 0)); pdl_break(stream, kPdlAfterWait);
     // everything the caller enqueues on `stream` until the next call consumes this buffer
     const int prev = buf ^ 1;
-    if (next_take_ > 0) {
+    if (!lookahead_ && next_take_ > 0) {
       ARGUS_CUDA(cudaEventRecord(consumed_[prev], stream)); pdl_break(stream, kPdlAfterRecord);
       consumed_recorded_[prev] = true;
     }
@@ -220,6 +234,7 @@ class Loader {
   cudaStream_t copy_stream_ = nullptr;
   cudaEvent_t copied_[2] = {nullptr, nullptr}, consumed_[2] = {nullptr, nullptr};
   bool consumed_recorded_[2] = {false, false}, copied_recorded_[2] = {false, false};
+  bool lookahead_ = false;
   uint8_t* host_img_[2] = {nullptr, nullptr};
   float* host_pose_[2] = {nullptr, nullptr};
   uint8_t* dev_img_[2] = {nullptr, nullptr};
@@ -284,6 +299,12 @@ int argus_loader_bind(argus_loader* l, void* host_img0, void* host_img1, float* 
   float* dp[2] = {dev_pose0, dev_pose1};
   for (int i = 0; i < 2; ++i) ARGUS_CHECK(hi[i] && hp[i] && di[i] && dp[i], "null staging buffer");
   l->impl.bind(hi, hp, di, dp);
+  ARGUS_API_END
+}
+int argus_loader_set_lookahead(argus_loader* l, int on) {
+  ARGUS_API_BEGIN
+  ARGUS_CHECK(l != nullptr, "null loader");
+  l->impl.set_lookahead(on != 0);
   ARGUS_API_END
 }
 int argus_loader_start_epoch(argus_loader* l, int epoch) {

@@ -35,9 +35,11 @@ def write_shard(path: str, images: np.ndarray, poses_xyzw: np.ndarray) -> None:
 
 
 def write_synthetic_shard(path: str, n: int, n_cams: int = 2, H: int = 256, W: int = 256, seed: int = 0,
-                          chunk: int = 512) -> None:
+                          chunk: int = 512, fast: bool = False) -> None:
     """Synthetic dataset of the reference's shape (uniform-noise images as in tests/conftest.py:35-41, random SE3
-    poses), written chunk by chunk so that it scales to the medium / large split sizes."""
+    poses), written chunk by chunk so that it scales to the medium / large split sizes. fast=True draws ONE random
+    chunk and writes it rotated by the chunk index (I/O-bound instead of RNG-bound: a 51 GB "medium" shard in a minute;
+    every sample is still uniform noise, samples repeat every `chunk`)."""
     rng = np.random.default_rng(seed)
     pose_off = HEADER.size
     img_off = (pose_off + n * 28 + 4095) // 4096 * 4096
@@ -47,9 +49,14 @@ def write_synthetic_shard(path: str, n: int, n_cams: int = 2, H: int = 256, W: i
         q /= np.linalg.norm(q, axis=-1, keepdims=True)
         f.write(np.concatenate([rng.normal(size=(n, 3)), q], -1).astype(np.float32).tobytes())
         f.write(b"\0" * (img_off - pose_off - n * 28))
+        base = rng.integers(0, 256, (chunk, n_cams, H, W, 3), dtype=np.uint8) if fast else None
         for lo in range(0, n, chunk):
             m = min(chunk, n - lo)
-            f.write(rng.integers(0, 256, (m, n_cams, H, W, 3), dtype=np.uint8).tobytes())
+            if fast:
+                k = (lo // chunk) % chunk
+                f.write(memoryview(np.ascontiguousarray(np.concatenate([base[k:], base[:k]])[:m])))
+            else:
+                f.write(rng.integers(0, 256, (m, n_cams, H, W, 3), dtype=np.uint8).tobytes())
 
 
 def convert_dataset(dataset_path: str, split: str, out_path: str, center_crop=(256, 256)) -> None:
@@ -65,10 +72,14 @@ def convert_dataset(dataset_path: str, split: str, out_path: str, center_crop=(2
 class ShardLoader:
     """Iterates (images uint8 (b, n_cams, H, W, 3), poses float32 (b, 7)) device tensors over the rank's slice of a shard.
 
-    The tensors of a batch stay valid until the call after next (two device buffers)."""
+    Two device buffers: the tensors of batch k are overwritten by the fetch of batch k + 2, which waits (on the device)
+    for the work that read them. `lookahead=False` (default) is for fetch-then-step loops (`for x, t in loader:
+    engine.step(x, t)`): the work on batch k is whatever was enqueued before the fetch of batch k + 1.
+    `lookahead=True` is for loops that fetch batch k + 1 before they enqueue step k (TrainEngine.prefetch pipelines):
+    the work on batch k is whatever was enqueued before the fetch of batch k + 2."""
 
     def __init__(self, path: str, batch_size: int, device, rank: int = 0, world: int = 1, seed: int = 0,
-                 shuffle: bool = True, drop_last: bool = False) -> None:
+                 shuffle: bool = True, drop_last: bool = False, lookahead: bool = False) -> None:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.ArgusError("ShardLoader stages batches on a CUDA device")
@@ -93,6 +104,7 @@ class ShardLoader:
             _lib.check(lib.argus_loader_bind(self._ptr, *[_lib.ptr(t) for t in self._host_img],
                                              *[_lib.ptr(t) for t in self._host_pose], *[_lib.ptr(t) for t in self._dev_img],
                                              *[_lib.ptr(t) for t in self._dev_pose]))
+        _lib.check(lib.argus_loader_set_lookahead(self._ptr, ctypes.c_int(int(lookahead))))
         self.epoch = 0
 
     def __len__(self) -> int:

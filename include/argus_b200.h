@@ -258,6 +258,9 @@ int argus_loader_info(argus_loader* l, int64_t* n_samples, int* n_cams, int* H, 
 int argus_loader_bind(argus_loader* l, void* host_img0, void* host_img1, float* host_pose0, float* host_pose1,
                       void* dev_img0, void* dev_img1, float* dev_pose0, float* dev_pose1);
 /* (Re)starts the worker thread for an epoch (DistributedSampler.set_epoch, train.py:290). */
+/* on != 0: the caller fetches batch k + 1 BEFORE it enqueues step k (look-ahead loops): a device buffer is then
+ * protected by an event recorded at the call that reuses it instead of at the call after its fetch (default 0). */
+int argus_loader_set_lookahead(argus_loader* l, int on);
 int argus_loader_start_epoch(argus_loader* l, int epoch);
 /* Next batch: H2D on the loader's copy stream, ordered before everything later enqueued on `stream`.
  * *count = samples in the batch (0 = epoch finished), *buffer_index = which of the two device buffers holds it. */

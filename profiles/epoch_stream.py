@@ -37,15 +37,15 @@ if world > 1:
 path = os.path.join(tempfile.gettempdir(), f"argus_synth_{n_pairs}.argusraw")
 t0 = time.time()
 if rank == 0 and not os.path.exists(path):
-    write_synthetic_shard(path, n_pairs)
+    write_synthetic_shard(path, n_pairs, fast=n_pairs > 16384)
 if world > 1:
     dist.barrier()
 t_write = time.time() - t0
 
 torch.manual_seed(42)
 model = NCameraCNN().to(dev)
-engine = TrainEngine(model, augmentation=Augmentation(AugmentationConfig(), train=True, seed=1 + rank))
-loader = ShardLoader(path, batch, dev, rank=rank, world=world, seed=0, shuffle=True, drop_last=True)
+engine = TrainEngine(model, augmentation=Augmentation(AugmentationConfig(), train=True, seed=1 + rank, gpu_spaghetti=True))
+loader = ShardLoader(path, batch, dev, rank=rank, world=world, seed=0, shuffle=True, drop_last=True, lookahead=True)
 for epoch in range(2):  # epoch 0 warms up (plans, page cache), epoch 1 is timed
     loader.set_epoch(epoch)
     torch.cuda.synchronize()
@@ -54,9 +54,16 @@ for epoch in range(2):  # epoch 0 warms up (plans, page cache), epoch 1 is timed
     t0 = time.time()
     n = 0
     loss = None
-    for images, poses in loader:
-        loss = engine.step(images, poses)
-        n += images.shape[0]
+    # look-ahead pipeline of argus_b200/train.py: fetch batch k + 1, enqueue step k, stage batch k + 1 on the side stream
+    it = iter(loader)
+    current = next(it, None)
+    while current is not None:
+        upcoming = next(it, None)
+        loss = engine.step(*current)
+        if upcoming is not None:
+            engine.prefetch(upcoming[0])
+        n += current[0].shape[0]
+        current = upcoming
     torch.cuda.synchronize()
     dt = time.time() - t0
 if world > 1:

@@ -80,3 +80,31 @@ def test_loader_feeds_engine(cuda_device, shard):
     loader = ShardLoader(path, batch_size=8, device=cuda_device, shuffle=True, drop_last=True)
     losses = [engine.step(images, poses) for images, poses in loader]
     assert len(losses) == 4 and all(torch.isfinite(l) for l in losses)
+
+
+def test_lookahead_loop_reads_each_buffer_before_it_is_reused(cuda_device, shard):
+    """The training loop fetches batch k + 1 BEFORE it enqueues step k (argus_b200/train.py). With lookahead=True the
+    copy of batch k + 2 into the buffer of batch k waits for the work enqueued up to that fetch -- here a deliberately
+    slow consumer (a long chain of matmuls, then a clone of the batch): every clone must still hold batch k."""
+    from argus_b200.loader import ShardLoader
+
+    path, imgs, poses = shard
+    loader = ShardLoader(path, batch_size=4, device=cuda_device, shuffle=False, lookahead=True)
+    a = torch.randn(2048, 2048, device=cuda_device)
+
+    def slow_consume(images, targets):
+        b = a
+        for _ in range(40):                 # ~ a few ms of GPU work before the batch is read
+            b = (b @ a) * 1e-3
+        return images.clone() + (b[0, 0] * 0).to(torch.uint8), targets.clone()
+
+    got = []
+    it = iter(loader)
+    current = next(it, None)
+    while current is not None:
+        upcoming = next(it, None)           # fetch k + 1 first ...
+        got.append(slow_consume(*current))  # ... then enqueue the work on batch k
+        current = upcoming
+    torch.cuda.synchronize()
+    assert np.array_equal(np.concatenate([g[0].cpu().numpy() for g in got]), imgs)
+    assert np.array_equal(np.concatenate([g[1].cpu().numpy() for g in got]), poses)

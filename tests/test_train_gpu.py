@@ -92,28 +92,27 @@ def test_loss_decreases_when_overfitting(cuda_device):
     assert all(np.isfinite(losses))
 
 
-def test_loss_curve_tracks_reference(cuda_device):
-    """North star: "a matching ... loss curve". 300 steps of the bf16 product path against the same 300 steps of the
-    reference (PyTorch fp32, TF32 off) from identical weights on an identical batch sequence (profiles/loss_curve.py;
-    the committed 1000-step run is profiles/r1_loss_curve_1k.json). The trajectories separate chaotically after ~100
-    steps -- torch's own bf16 autocast run of the reference deviates from its fp32 run by up to 50 % per window -- so
-    the assertion is on the trend: every 100-step window mean within 2.5x of the reference's, and the same descent."""
+def test_loss_curve_matches_reference_within_its_own_spread(cuda_device):
+    """North star: "a matching ... loss curve". Acceptance criterion (profiles/loss_curve.py::acceptance): for every seed
+    (task + initial weights) the reference's step body runs three ways -- fp32, fp32 channels_last, TF32 (PyTorch's default
+    convolution arithmetic): the same math with other cuDNN kernels / summation orders, i.e. the reference's OWN
+    run-to-run spread -- and every 100-step window mean of the bf16 product run must lie inside [min, max] of those three
+    runs, widened by 15 %. The committed 3-seed x 1000-step run (profiles/r2_loss_curve_acceptance.json) is at most 7.7 %
+    outside the band in 30 windows, while the band itself is 5-55 % wide (the trajectories are chaotic: the reference
+    does not reproduce itself any better); here 2 seeds x 500 steps to bound the test time."""
     import sys
     from pathlib import Path
 
     sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "profiles"))
-    from loss_curve import make_task, run_ours, run_reference, window_means
+    from loss_curve import acceptance
 
-    torch.backends.cudnn.allow_tf32 = False
-    torch.backends.cuda.matmul.allow_tf32 = False
-    images, targets = make_task(size=128)
-    ref = window_means(run_reference(images, targets, 300, 8, autocast=False), 100)
-    ours = window_means(run_ours(images, targets, 300, 8, "bf16"), 100)
-    print("loss windows: reference fp32", ref, " ours bf16", ours)
-    assert abs(ours[0] - ref[0]) / ref[0] < 0.1          # the first 100 steps still coincide closely
-    for a, b in zip(ours, ref):
-        assert 0.4 < a / b < 2.5, (ours, ref)
-    assert ours[-1] < 0.35 * ours[0] and ref[-1] < 0.35 * ref[0]
+    res = acceptance(steps=500, seeds=(0, 1), slack=0.15)
+    for seed, r in res["seeds"].items():
+        print("seed", seed, "ours", [round(v, 4) for v in r["window_means"]["ours_bf16"]], "band",
+              [(round(a, 4), round(b, 4)) for a, b in zip(r["band_lo"], r["band_hi"])], "outside", r["outside"])
+        ours = r["window_means"]["ours_bf16"]
+        assert ours[-1] < 0.25 * ours[0]                     # and it trains: the loss falls by 4x in 500 steps
+    assert res["accepted"], res["worst_outside"]
 
 
 def test_prefetch_is_bitwise_equivalent(cuda_device):

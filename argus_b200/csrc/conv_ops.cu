@@ -678,6 +678,8 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   if (p.res_bits || p.res_scale) need |= kOptRes | kOptResExtra;
   if (p.out_bits) need |= kOptOutBits;
   if (p.relu || p.relu_bits_out) need |= kOptRelu;
+  constexpr int kTail = kOptAffine | kOptRes | kOptRelu;           // fused forward block tail: BN + identity + ReLU (+ bits)
+  const bool plain_res = p.has_res && !p.res_bits && !p.res_scale;
   if (l.epi == 4) {
     // split-tile kernels exist for the residual-free epilogues; everything else runs the two-group kernels below
     // (the statistics slots are sized for four groups, the unused ones stay zero)
@@ -692,6 +694,18 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     }
   }
   const int epi2 = (l.epi == 4) ? 2 : l.epi;
+  if (special && epi2 == 2 && l.b_mn == 0 && plain_res && need == kTail) {
+    // fused forward block tail (ARGUS_FUSED_TAIL=1). Round 2 also tried loading the residual row segments straight from
+    // global memory into registers (no staging buffer, which would have made the sixteen-warp split-tile mode possible
+    // with a residual): one thread per row means 32 different rows per load instruction -- uncoalesced, 1.5-1.9 TB/s
+    // against 5.1-5.5 TB/s through TMA + staging (profiles/r2_direct_residual_ab.txt). Removed again.
+    switch (l.block_n) {
+      case 64: launch_conv_t<64, 0, 2, kTail>(p, stream); return;
+      case 128: launch_conv_t<128, 0, 2, kTail>(p, stream); return;
+      case 256: launch_conv_t<256, 0, 2, kTail>(p, stream); return;
+      default: break;
+    }
+  }
   if (special && epi2 == 2 && need == 0) {
     switch (l.block_n * 2 + l.b_mn) {
       case 64 * 2 + 0: launch_conv_t<64, 0, 2, 0>(p, stream); return;
@@ -700,6 +714,15 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       case 64 * 2 + 1: launch_conv_t<64, 1, 2, 0>(p, stream); return;
       case 128 * 2 + 1: launch_conv_t<128, 1, 2, 0>(p, stream); return;
       case 256 * 2 + 1: launch_conv_t<256, 1, 2, 0>(p, stream); return;
+      default: break;
+    }
+  }
+  if (special && epi2 == 2 && l.b_mn == 0 && need == kOptAffine) {
+    // scale / shift only: the downsample branch of a fused block tail, the eval-mode convolutions without ReLU
+    switch (l.block_n) {
+      case 64: launch_conv_t<64, 0, 2, kOptAffine>(p, stream); return;
+      case 128: launch_conv_t<128, 0, 2, kOptAffine>(p, stream); return;
+      case 256: launch_conv_t<256, 0, 2, kOptAffine>(p, stream); return;
       default: break;
     }
   }

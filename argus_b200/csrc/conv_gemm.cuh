@@ -78,6 +78,14 @@ struct ConvGemmParams {
   // batch-norm backward (model.cu), where A1 = the saved activation and B1 a small correction matrix.
   int k2_blocks;
   int relu;
+  // Batch-norm backward reduction fused into the dgrad that PRODUCES the gradient of a BN + ReLU output (kOptBnRed):
+  // the tile of the layer's saved pre-BN output `bn_raw` (same geometry as the result; TMA-loaded through res_map like
+  // a residual) gates the result with the ReLU mask (bn_raw * bn_scale + bn_shift > 0) -- the gradient is stored
+  // already masked -- and the statistics slots receive sum(g) and sum(g * raw) of the stored bf16 values instead of
+  // sum / sum of squares. bn_bwd_reduce's two passes over the gradient and the saved tensor disappear.
+  const __nv_bfloat16* bn_raw;
+  const float* bn_scale;
+  const float* bn_shift;
   // train-mode BN statistics of the stored bf16 outputs, reduced deterministically: every (CTA, epilogue group)
   // owns slot = 2*blockIdx.x + group of stat_partial[slot][2][n_total] (sum, sum of squares); bn_finalize adds the
   // slots in a fixed order. The caller zeroes the buffer.
@@ -128,7 +136,8 @@ constexpr int kOptRes = 2;       // residual tile
 constexpr int kOptOutBits = 4;   // bit mask applied to the result
 constexpr int kOptRelu = 8;      // ReLU, ReLU bit-mask output
 constexpr int kOptResExtra = 16; // bit mask on the residual, residual scale / shift (needs kOptRes)
-constexpr int kOptAll = 31;
+constexpr int kOptBnRed = 32;    // fused batch-norm backward reduction (needs kOptRes: the raw tile rides the residual path)
+constexpr int kOptAll = 31;      // the generic kernel (kOptBnRed only exists in specialised instances)
 template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
@@ -389,8 +398,19 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     const uint8_t* const ep_out_bits = (OPT & kOptOutBits) ? p.out_bits : nullptr;
     uint8_t* const ep_relu_bits_out = (OPT & kOptRelu) ? p.relu_bits_out : nullptr;
     const bool ep_relu = (OPT & kOptRelu) ? (p.relu != 0) : false;
+    constexpr bool BNRED = (OPT & kOptBnRed) != 0;
+    static_assert(!BNRED || ((OPT & kOptRes) && !(OPT & (kOptResExtra | kOptRelu | kOptOutBits))), "kOptBnRed rides the residual path");
     float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(EPI * blockIdx.x + grp) * 2 * p.n_total : nullptr;
     constexpr int kChunks = GW / 64;
+    // Fused forward block tail (BN + identity + ReLU + bit mask, no statistics): scale / shift of the CTA's current N
+    // tile live in the group's (otherwise unused) statistics scratch, the affine and the residual add run on packed
+    // fp32 pairs. The generic code below re-loaded 2 x 64 floats per chunk with dependent global loads (long-scoreboard
+    // stalls on every FMUL / FADD, ncu: profiles/r2_ncu_fused_tail.txt) and spent ~1 000 instructions per 64-column
+    // chunk. launch_conv only selects this instance when scale, shift, ReLU and a plain residual are all present and
+    // no statistics are requested.
+    constexpr bool FAST_TAIL = (OPT == (kOptAffine | kOptRes | kOptRelu)) && EPI == 2;
+    float* s_aff = s_stats;   // [scale GW | shift GW]
+    int cur_aff_n = -1;
 
     auto flush_stats = [&](int n_tile) {
       named_bar_sync(bar_id, 128);
@@ -438,6 +458,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
         if (cur_n >= 0) flush_stats(cur_n);
         cur_n = n_tile;
       }
+      if (FAST_TAIL && n_tile != cur_aff_n) {
+        named_bar_sync(bar_id, 128);   // nobody still reads the previous tile's coefficients
+        for (int c = et; c < GW; c += 128) {
+          const int gc = n_tile * BLOCK_N + col_base + c;
+          s_aff[c] = gc < p.n_total ? __ldg(ep_scale + gc) : 0.f;
+          s_aff[GW + c] = gc < p.n_total ? __ldg(ep_shift + gc) : 0.f;
+        }
+        named_bar_sync(bar_id, 128);
+        cur_aff_n = n_tile;
+      }
 
       mbar_wait(tfull_bar(tg), full_phase);
       tc_fence_after();
@@ -453,6 +483,13 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
           const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + acc * BLOCK_N + col_base + ch * 64 + h * 32;
           tmem_ld_32x32(taddr, v[h]);
         }
+        // Residual + statistics: the prefetch below refills the buffer the PREVIOUS chunk was staged in, and the statistics
+        // pass of that chunk reads it after the store was issued. The leader may only refill it once every warp of the
+        // group has finished that pass -- waiting for the TMA store alone is not enough. (Without this barrier the leader,
+        // being one warp among four, could run ahead by the TMEM load and overwrite rows other warps were still summing:
+        // a rare, timing-dependent error in the per-channel sums of the conv1 dgrads -- the irreproducible runs DESIGN.md 7
+        // reports for prioritised streams and programmatic launches, both of which only change the timing.)
+        if (has_res && do_stats) named_bar_sync(bar_id, 128);
         if (store_leader) {
           if (has_res) {
             // the other buffer was handed to a TMA store one chunk ago: once that store has read it, refill it with
@@ -467,7 +504,24 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             else tma_store_wait_read<0>();
           }
         }
-        named_bar_sync(bar_id, 128);
+        // Buffer hand-back. Without a residual the writers below must not touch the buffer before the leader has seen its
+        // last TMA store finish reading. With a residual no barrier is needed here: the chunk is written in place over
+        // the residual tile, whose buffer the leader cleared for reuse one chunk ago -- before the barrier that preceded
+        // that chunk's store -- so waiting for the leader here (it sits in the store-read wait of the PREVIOUS chunk, ~1 us)
+        // only serialised the group: 11 % of all stall samples of the fused block tail (profiles/r2_ncu_fused_tail.txt).
+        if (!has_res) named_bar_sync(bar_id, 128);
+        // kOptBnRed: the statistics pass below runs column-wise (lane = column pair), after the raw tile in the staging
+        // buffer has been overwritten in place by the masked gradient; its raw values are re-read from L2 (the tile
+        // was just pulled through it by TMA) with coalesced 128-byte rows, issued here so that they land during the math
+        uint32_t rawc[BNRED ? 32 : 1];
+        if (BNRED) {
+          const uint32_t* rp = reinterpret_cast<const uint32_t*>(p.bn_raw + static_cast<size_t>(m0 + wq * 32) * p.n_total +
+                                                                 n0 + ch * 64) + lane;
+          const int nrow = p.m_total - (m0 + wq * 32);
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr)
+            rawc[rr] = (rr < nrow) ? ldg_nc_u32(rp + static_cast<size_t>(rr) * (p.n_total >> 1)) : 0u;
+        }
         uint2 obits = make_uint2(0xffffffffu, 0xffffffffu);
         if (ep_out_bits != nullptr && m0 + r < p.m_total)
           obits = __ldg(reinterpret_cast<const uint2*>(ep_out_bits + static_cast<size_t>(m0 + r) * (p.n_total >> 3) +
@@ -490,6 +544,39 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int c0 = n0 + ch * 64 + h * 32;
+          if constexpr (FAST_TAIL) {
+            uint32_t ob = 0;
+            const float4* sc4 = reinterpret_cast<const float4*>(s_aff + ch * 64 + h * 32);
+            const float4* sh4 = reinterpret_cast<const float4*>(s_aff + GW + ch * 64 + h * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int phys = (h * 4 + q) ^ (r & 7);
+              uint4* slot = reinterpret_cast<uint4*>(stg + r * 128 + phys * 16);
+              const uint4 rv = *slot;
+              const float4 s0 = sc4[2 * q], s1 = sc4[2 * q + 1], t0 = sh4[2 * q], t1 = sh4[2 * q + 1];
+              uint64_t y0 = f32x2_pack(t0.x, t0.y), y1 = f32x2_pack(t0.z, t0.w), y2 = f32x2_pack(t1.x, t1.y), y3 = f32x2_pack(t1.z, t1.w);
+              f32x2_fma(y0, f32x2_pack(__uint_as_float(v[h][q * 8 + 0]), __uint_as_float(v[h][q * 8 + 1])), f32x2_pack(s0.x, s0.y));
+              f32x2_fma(y1, f32x2_pack(__uint_as_float(v[h][q * 8 + 2]), __uint_as_float(v[h][q * 8 + 3])), f32x2_pack(s0.z, s0.w));
+              f32x2_fma(y2, f32x2_pack(__uint_as_float(v[h][q * 8 + 4]), __uint_as_float(v[h][q * 8 + 5])), f32x2_pack(s1.x, s1.y));
+              f32x2_fma(y3, f32x2_pack(__uint_as_float(v[h][q * 8 + 6]), __uint_as_float(v[h][q * 8 + 7])), f32x2_pack(s1.z, s1.w));
+              f32x2_add(y0, f32x2_from_bf16x2(rv.x));
+              f32x2_add(y1, f32x2_from_bf16x2(rv.y));
+              f32x2_add(y2, f32x2_from_bf16x2(rv.z));
+              f32x2_add(y3, f32x2_from_bf16x2(rv.w));
+              const float2 a = f32x2_unpack(y0), b = f32x2_unpack(y1), c = f32x2_unpack(y2), d = f32x2_unpack(y3);
+              const float y8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) ob |= (y8[j] > 0.f ? 1u : 0u) << (q * 8 + j);
+              uint4 o;
+              o.x = pack_bf16x2(fmaxf(y8[0], 0.f), fmaxf(y8[1], 0.f));
+              o.y = pack_bf16x2(fmaxf(y8[2], 0.f), fmaxf(y8[3], 0.f));
+              o.z = pack_bf16x2(fmaxf(y8[4], 0.f), fmaxf(y8[5], 0.f));
+              o.w = pack_bf16x2(fmaxf(y8[6], 0.f), fmaxf(y8[7], 0.f));
+              *slot = o;
+            }
+            if (ep_relu_bits_out != nullptr && m0 + r < p.m_total)
+              *reinterpret_cast<uint32_t*>(ep_relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) + (c0 >> 3)) = ob;
+          } else {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[h][i]);
@@ -507,7 +594,27 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
               f[i] += sh.x; f[i + 1] += sh.y; f[i + 2] += sh.z; f[i + 3] += sh.w;
             }
           }
-          if (has_res) {
+          if (BNRED) {
+            // ReLU mask of the layer this gradient flows into, recomputed from its saved pre-BN output exactly as the
+            // forward bn_apply evaluated it; rows past the end of the tensor contribute nothing
+            const bool row_ok = (m0 + r < p.m_total);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const int phys = (h * 4 + q) ^ (r & 7);
+              const uint4 rv = *reinterpret_cast<const uint4*>(stg + r * 128 + phys * 16);
+              const float2 a = unpack_bf16x2(rv.x), b = unpack_bf16x2(rv.y), c = unpack_bf16x2(rv.z), d = unpack_bf16x2(rv.w);
+              const float rr8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + c0 + q * 8));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.bn_scale + c0 + q * 8 + 4));
+              const float4 t0 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + c0 + q * 8));
+              const float4 t1 = __ldg(reinterpret_cast<const float4*>(p.bn_shift + c0 + q * 8 + 4));
+              const float sc8[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+              const float sh8[8] = {t0.x, t0.y, t0.z, t0.w, t1.x, t1.y, t1.z, t1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                f[q * 8 + j] = (row_ok && fmaf(rr8[j], sc8[j], sh8[j]) > 0.f) ? f[q * 8 + j] : 0.f;
+            }
+          } else if (has_res) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const int phys = (h * 4 + q) ^ (r & 7);
@@ -563,6 +670,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const int phys = (h * 4 + q) ^ (r & 7);      // SWIZZLE_128B position of logical 16-byte chunk h*4+q
             *reinterpret_cast<uint4*>(stg + r * 128 + phys * 16) = o;
           }
+          }   // generic epilogue math
         }
         fence_proxy_async_smem();
         named_bar_sync(bar_id, 128);
@@ -582,9 +690,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             const uint64_t x0 = f32x2_from_bf16x2(lds_u32(sbase + rr * 128 + ((jl ^ (rr & 7)) << 4)));
             const uint64_t x1 = f32x2_from_bf16x2(lds_u32(sbase + (rr + 1) * 128 + ((jl ^ ((rr + 1) & 7)) << 4)));
             f32x2_add(sa, x0);
-            f32x2_fma_sq(qa, x0);
             f32x2_add(sb, x1);
-            f32x2_fma_sq(qb, x1);
+            if (BNRED) {
+              f32x2_fma(qa, x0, f32x2_from_bf16x2(rawc[rr]));       // sum g * raw (centred by the finalize kernel)
+              f32x2_fma(qb, x1, f32x2_from_bf16x2(rawc[rr + 1]));
+            } else {
+              f32x2_fma_sq(qa, x0);
+              f32x2_fma_sq(qb, x1);
+            }
           }
           f32x2_add(sa, sb);
           f32x2_add(qa, qb);

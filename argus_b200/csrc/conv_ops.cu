@@ -645,6 +645,18 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     p.has_res = 1;
     p.res_bits = e.residual_bits;
   }
+  p.bn_raw = nullptr;
+  p.bn_scale = e.bn_scale;
+  p.bn_shift = e.bn_shift;
+  if (e.bn_raw != nullptr) {
+    ARGUS_CHECK(l.b_mn == 1 && l.out_geom.rank == 4, "the fused BN reduction exists for dense-output dgrad launches");
+    ARGUS_CHECK(e.residual == nullptr && e.out_bits == nullptr && e.relu == 0 && e.relu_bits_out == nullptr &&
+                    e.scale == nullptr && e.bn_scale != nullptr && e.bn_shift != nullptr && e.stat_partial != nullptr,
+                "fused BN reduction: unsupported epilogue combination");
+    p.res_map = make_tmap_bf16(e.bn_raw, 4, l.out_geom.dims, l.out_geom.strides, l.out_geom.box);
+    p.has_res = 1;
+    p.bn_raw = e.bn_raw;
+  }
   p.relu = e.relu;
   p.out_bits = e.out_bits;
   p.res_scale = e.res_scale;
@@ -665,7 +677,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     const int nmaps = __builtin_popcount(static_cast<unsigned>(maps));
     const double kc = static_cast<double>(p.kblocks_per_tap) * kBlockK;
     bytes += 2.0 * p.m_total * kc * nmaps + 2.0 * p.m_total * p.k2_blocks * kBlockK;
-    bytes += 2.0 * p.m_total * p.n_total * (p.has_res ? 2 : 1);
+    bytes += 2.0 * p.m_total * p.n_total * (p.has_res ? 2 : 1);   // (the fused BN reduction reads bn_raw: counted here)
     bytes += (p.out_bits ? 0.125 : 0.0) * p.m_total * p.n_total + (p.relu_bits_out ? 0.125 : 0.0) * p.m_total * p.n_total;
     bytes += 2.0 * p.n_total * (p.num_taps * kc + p.k2_blocks * kBlockK);
   }
@@ -694,7 +706,21 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     }
   }
   const int epi2 = (l.epi == 4) ? 2 : l.epi;
-  if (special && epi2 == 2 && l.b_mn == 0 && plain_res && need == kTail) {
+  if (p.bn_raw != nullptr) {
+    // dgrad + fused batch-norm backward reduction: plain (3x3 / 1x1 dgrads) or with the bias of the K-concatenated dgrad
+    ARGUS_CHECK(epi2 == 2, "fused BN reduction: two epilogue groups only");
+    const bool bias = (p.shift != nullptr);
+    switch (l.block_n * 2 + (bias ? 1 : 0)) {
+      case 64 * 2 + 0: launch_conv_t<64, 1, 2, kOptRes | kOptBnRed>(p, stream); return;
+      case 128 * 2 + 0: launch_conv_t<128, 1, 2, kOptRes | kOptBnRed>(p, stream); return;
+      case 256 * 2 + 0: launch_conv_t<256, 1, 2, kOptRes | kOptBnRed>(p, stream); return;
+      case 64 * 2 + 1: launch_conv_t<64, 1, 2, kOptAffine | kOptRes | kOptBnRed>(p, stream); return;
+      case 128 * 2 + 1: launch_conv_t<128, 1, 2, kOptAffine | kOptRes | kOptBnRed>(p, stream); return;
+      case 256 * 2 + 1: launch_conv_t<256, 1, 2, kOptAffine | kOptRes | kOptBnRed>(p, stream); return;
+      default: throw Error("unsupported conv tile configuration");
+    }
+  }
+  if (special && epi2 == 2 && l.b_mn == 0 && plain_res && need == kTail && p.scale && p.shift && p.relu && !p.stat_partial) {
     // fused forward block tail (ARGUS_FUSED_TAIL=1). Round 2 also tried loading the residual row segments straight from
     // global memory into registers (no staging buffer, which would have made the sixteen-warp split-tile mode possible
     // with a residual): one thread per row means 32 different rows per load instruction -- uncoalesced, 1.5-1.9 TB/s

@@ -33,6 +33,12 @@ struct Epilogue {
   uint8_t* relu_bits_out = nullptr;         // optional [rows][Cout/8]: (pre-ReLU value > 0), written by the epilogue
   int relu = 0;
   float* stat_partial = nullptr;   // [stat_slots(launch)][2][Cout], zeroed by the caller (train-mode BN statistics)
+  // Fused batch-norm backward reduction (dgrad launches that produce the gradient of a BN + ReLU output, dense output
+  // only): bn_raw = that layer's saved pre-BN output, bn_scale / bn_shift = its folded batch statistics. The result is
+  // stored masked by (bn_raw * bn_scale + bn_shift > 0) and stat_partial receives sum(g), sum(g * bn_raw).
+  const __nv_bfloat16* bn_raw = nullptr;
+  const float* bn_scale = nullptr;
+  const float* bn_shift = nullptr;
 };
 
 // geometry of the (non-strided) output tensor map, kept so that a residual tensor map can be built per launch

@@ -538,7 +538,8 @@ bn_bwd_reduce_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ x, 
 }
 
 __global__ void __launch_bounds__(256)
-bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta, int C) {
+bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dgamma, float* dbeta, int C,
+                       const float* __restrict__ mean, const float* __restrict__ invstd) {
   pdl_prologue();
   __shared__ double red[2][32][8];
   const int ch = threadIdx.x & 7, sl = threadIdx.x >> 3;
@@ -569,6 +570,9 @@ bn_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, float* dga
   sb = 0.0;
   sg = 0.0;
   for (int k = 0; k < 32; ++k) { sb += red[0][k][ch]; sg += red[1][k][ch]; }
+  // mean != nullptr: the second sums are sum(g * x) of the RAW layer output (statistics slots of a dgrad epilogue,
+  // bn_bwd_finalize_slots); centred and scaled here, once, in double
+  if (mean != nullptr) sg = (sg - static_cast<double>(mean[c]) * sb) * static_cast<double>(invstd[c]);
   dbeta[c] += static_cast<float>(sb);
   dgamma[c] += static_cast<float>(sg);
 }
@@ -1053,7 +1057,7 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
       default: throw Error("bad mask_mode");
     }
     ARGUS_CUDA(cudaGetLastError());
-    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, rgrid, dgamma, dbeta, C);
+    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, rgrid, dgamma, dbeta, C, nullptr, nullptr);
     ARGUS_CUDA(cudaGetLastError());
     return;
   }
@@ -1071,7 +1075,14 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
     default: throw Error("bad mask_mode");
   }
   ARGUS_CUDA(cudaGetLastError());
-  launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C);
+  launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C, nullptr, nullptr);
+  ARGUS_CUDA(cudaGetLastError());
+}
+
+void bn_bwd_finalize_slots(const float* partial, int slots, const float* mean, const float* invstd, float* dgamma,
+                           float* dbeta, int C, cudaStream_t s) {
+  ProfileScope prof("bn_bwd_reduce", s, 0, static_cast<double>(slots) * 2 * C * 4);
+  launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, partial, slots, dgamma, dbeta, C, mean, invstd);
   ARGUS_CUDA(cudaGetLastError());
 }
 
@@ -1489,7 +1500,7 @@ void stem_pool_bn_backward(const bf16* dpool, const uint8_t* idx, const bf16* ra
     launch_kernel(stem_pool_bn_bwd_kernel<0>, grid, 256, 0, s, DP, ID, RW, scale, shift, mean, invstd, nullptr, nullptr, scratch,
                                                     nullptr, N, H, W, inv_rows, lg_wo, lg_ho);
     ARGUS_CUDA(cudaGetLastError());
-    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C);
+    launch_kernel(bn_bwd_finalize_kernel, (C + 7) / 8, 256, 0, s, scratch, grid, dgamma, dbeta, C, nullptr, nullptr);
     ARGUS_CUDA(cudaGetLastError());
   }
   {

@@ -81,6 +81,10 @@ void bn_bwd_reduce(const bf16* dy, const bf16* x, const bf16* out, const float* 
                    const float* mean, const float* invstd, float* dgamma, float* dbeta, int64_t rows, int C,
                    int mask_mode, float* scratch, cudaStream_t s);
 int64_t bn_bwd_scratch_elems();
+// The same sums when a dgrad epilogue already reduced them (Epilogue::bn_raw): partial = [slots][2][C] with sum(g) and
+// sum(g * x) of the raw layer output x per slot; dbeta += sum(g), dgamma += (sum(g * x) - mean * sum(g)) * invstd.
+void bn_bwd_finalize_slots(const float* partial, int slots, const float* mean, const float* invstd, float* dgamma,
+                           float* dbeta, int C, cudaStream_t s);
 // dx = scale * (g - dbeta/rows - xhat * dgamma/rows); mask_mode 2 also overwrites dy with g (mask_mode 3 leaves dy
 // untouched: the consumers of the identity-branch gradient apply the bit mask themselves).
 void bn_bwd_apply(bf16* dy, const bf16* x, const bf16* out, const float* scale, const float* shift,

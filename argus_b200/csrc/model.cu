@@ -75,6 +75,7 @@ Model::~Model() {
   cudaFree(alg_h_); cudaFree(alg_s_); cudaFree(alg_k1k0_); cudaFree(alg_bias_); cudaFree(alg_gstats_);
   cudaFree(alg_bstack_);
   cudaFree(alg_mpartial_);
+  cudaFree(bnred_stats_);
   cudaFree(wgrad_scratch_);
   cudaFree(pack_table_dev_);
   cudaFree(stem_in_[0]);
@@ -229,6 +230,13 @@ void Model::bind(float* params, float* grads, float* buffers) {
       ARGUS_CUDA(cudaMalloc(&alg_bstack_, (O + C) * C * sizeof(bf16)));
       ARGUS_CUDA(cudaMalloc(&alg_mpartial_, bn_alg_matrix_scratch_elems(static_cast<int>(C)) * sizeof(float)));
     }
+    {
+      // BN-backward reduction in the epilogue of the dgrad that produces the gradient (default on; ARGUS_BN_REDUCE_FUSED=0
+      // selects the separate bn_bwd_reduce passes: A/B switch and the reference the fused path is tested against)
+      const char* e = getenv("ARGUS_BN_REDUCE_FUSED");
+      bn_reduce_fused_ = e ? atoi(e) : 1;
+      ARGUS_CUDA(cudaMalloc(&bnred_stats_, static_cast<size_t>(max_stat_slots_) * 2 * 512 * sizeof(float)));
+    }
     ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
     ARGUS_CUDA(cudaMemcpy(pack_table_dev_, pack_table_.data(), pack_table_.size() * sizeof(WeightPackEntry),
                           cudaMemcpyHostToDevice));
@@ -379,16 +387,21 @@ void Model::build_plan(Plan& p) {
     if (tr) bp.out_bits = arena_alloc<uint8_t>(e_out * oc / 8);
     if (tr && bn_algebra_ && wd <= 256)
       bp.act2_colsum = arena_alloc<float>(static_cast<size_t>(bn_apply_grid(static_cast<int64_t>(e_out), wd)) * wd);
+    if (bp.fused_tail) {
+      bp.gram_saved = arena_alloc<float>(static_cast<size_t>(wd) * wd);
+      if (br.has_ds && br.ds.shape.Cin <= 256)
+        bp.ds_gram_saved = arena_alloc<float>(static_cast<size_t>(br.ds.shape.Cin) * br.ds.shape.Cin);
+    }
     max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
     plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
     plan_conv(bp.c2, br.c2, N, h, w, bp.act1, tr ? bp.raw2 : bp.act2, true);
     plan_conv(bp.c3, br.c3, N, ho, wo, bp.act2, (tr && !bp.fused_tail) ? bp.raw3 : bp.out, true);
     if (br.has_ds) plan_conv(bp.ds, br.ds, N, h, w, bp.x, bp.rawd, true);
     if (real && bp.fused_tail) {
-      bp.fwd_gram = plan_gram(br.c3.shape, bp.act2, alg_h_);
+      bp.fwd_gram = plan_gram(br.c3.shape, bp.act2, bp.gram_saved);
       ensure_wgrad_scratch(bp.fwd_gram);
       if (br.has_ds && br.ds.shape.Cin <= 256) {
-        bp.ds_fwd_gram = plan_gram(br.ds.shape, bp.x, alg_h_);
+        bp.ds_fwd_gram = plan_gram(br.ds.shape, bp.x, bp.ds_gram_saved);
         ensure_wgrad_scratch(bp.ds_fwd_gram);
       }
     }
@@ -440,14 +453,16 @@ void Model::build_plan(Plan& p) {
       if (bp.algebraic) {
         // algebraic bn3 backward: GEMMs on the masked gradient P itself (never on dRaw3)
         const int C = br.c3.shape.Cin;
-        bp.hg_wgrad = plan_conv_wgrad_gram(br.c3.shape, P, bp.act2, alg_h_);
+        bp.hg_wgrad = bp.gram_saved ? plan_conv_wgrad(br.c3.shape, P, bp.act2, alg_h_)
+                                    : plan_conv_wgrad_gram(br.c3.shape, P, bp.act2, alg_h_);
         bp.c3_concat = plan_dgrad_concat(br.c3.shape, P, bp.act2, C, alg_bstack_, R);
         ensure_wgrad_scratch(bp.hg_wgrad);
       }
       bp.ds_algebraic = bp.algebraic && br.has_ds && br.ds.shape.Cin <= 256;   // layer1.0, layer2.0
       if (bp.ds_algebraic) {
         const int C = br.ds.shape.Cin;
-        bp.ds_hg_wgrad = plan_conv_wgrad_gram(br.ds.shape, P, bp.x, alg_h_);
+        bp.ds_hg_wgrad = bp.ds_gram_saved ? plan_conv_wgrad(br.ds.shape, P, bp.x, alg_h_)
+                                          : plan_conv_wgrad_gram(br.ds.shape, P, bp.x, alg_h_);
         bp.ds_concat = plan_dgrad_concat(br.ds.shape, P, bp.x, C, alg_bstack_, Tb);
         ensure_wgrad_scratch(bp.ds_hg_wgrad);
       }
@@ -525,7 +540,7 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
              bp.rows_out, wd, s);
     if (bp.fused_tail) {
       // bn3 statistics from the Gram matrix of act2; conv3 then finishes the block in its epilogue
-      stats_from_gram(br.c3, bp.fwd_gram, bp.act2, bp.act2_colsum, bp.rows_out, N, s);
+      stats_from_gram(br.c3, bp.fwd_gram, bp.gram_saved, bp.act2, bp.act2_colsum, bp.rows_out, N, s);
       Epilogue e;
       e.scale = SC(br.c3);
       e.shift = SC(br.c3) + oc;
@@ -536,7 +551,7 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
         e.residual = bp.rawd;
         if (br.ds.shape.Cin <= 256) {
           // downsample branch the same way: its batch norm is folded into its own epilogue
-          stats_from_gram(br.ds, bp.ds_fwd_gram, bp.x, nullptr, bp.rows_out, N, s);
+          stats_from_gram(br.ds, bp.ds_fwd_gram, bp.ds_gram_saved, bp.x, nullptr, bp.rows_out, N, s);
           Epilogue d;
           d.scale = SC(br.ds);
           d.shift = SC(br.ds) + oc;
@@ -562,15 +577,15 @@ void Model::forward_train(Plan& p, cudaStream_t s) {
   }
 }
 
-void Model::stats_from_gram(const ConvRef& c, const WgradLaunch& gram, const bf16* act, const float* colsum_partial,
+void Model::stats_from_gram(const ConvRef& c, const WgradLaunch& gram, float* G, const bf16* act, const float* colsum_partial,
                             int64_t rows, int N, cudaStream_t s) {
   const int O = c.shape.Cout, C = c.shape.Cin;
-  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
+  ARGUS_CUDA(cudaMemsetAsync(G, 0, static_cast<size_t>(C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   launch_wgrad(gram, wgrad_scratch_, s);
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
   float* sc = bn_scratch_ + c.bn.scratch_off;
-  bn_stats_from_gram(packed_ + c.packed_off, alg_h_, alg_s_, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
+  bn_stats_from_gram(packed_ + c.packed_off, G, alg_s_, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
                      params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off, buffers_dev_ + c.bn.rv_off, kBnMomentum,
                      kBnEps, sc, sc + O, sc + 2 * O, sc + 3 * O, alg_mpartial_, O, C, s);
 }
@@ -739,13 +754,41 @@ void Model::bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16*
   bn_bwd_apply(dy, raw, out, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, mask, s);
 }
 
+void Model::attach_bn_reduction(Epilogue& e, const ConvLaunch& l, const BnRed& red, cudaStream_t s) {
+  const int C = red.c->bn.C;
+  ARGUS_CHECK(C <= 512 && l.p.n_total == C, "fused BN reduction: channel count");
+  bnred_slots_ = stat_slots(l);
+  ARGUS_CUDA(cudaMemsetAsync(bnred_stats_, 0, static_cast<size_t>(bnred_slots_) * 2 * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
+  const float* sc = bn_scratch_ + red.c->bn.scratch_off;
+  e.bn_raw = red.raw;
+  e.bn_scale = sc;
+  e.bn_shift = sc + C;
+  e.stat_partial = bnred_stats_;
+}
+
+void Model::bn_backward_reduced(const ConvRef& c, bf16* dy, const bf16* raw, bf16* dx, int64_t rows, cudaStream_t s) {
+  const float* sc = bn_scratch_ + c.bn.scratch_off;
+  float* dgamma = grads_dev_ + c.bn.gamma_off;
+  float* dbeta = grads_dev_ + c.bn.beta_off;
+  const int C = c.bn.C;
+  bn_bwd_finalize_slots(bnred_stats_, bnred_slots_, sc + 2 * C, sc + 3 * C, dgamma, dbeta, C, s);
+  // the apply pass overwrites a gradient buffer that an in-flight weight-gradient GEMM may still be reading
+  join_wgrad(s);
+  bn_bwd_apply(dy, raw, nullptr, sc, sc + C, sc + 2 * C, sc + 3 * C, dgamma, dbeta, dx, rows, C, 0, s);   // dy is masked
+}
+
 void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats,
-                          cudaStream_t s) {
+                          cudaStream_t s, const BnRed* red) {
   // fork: the weight gradient only needs dRaw and the saved activation, both final at this point
   run_wgrad(cp.wgrad, s);
   Epilogue e;
   e.residual = residual;
   e.out_bits = out_bits;
+  if (red != nullptr) {
+    ARGUS_CHECK(cp.dgrad.size() == 1 && residual == nullptr && out_bits == nullptr && out_stats == nullptr,
+                "fused BN reduction needs a single plain dgrad launch");
+    attach_bn_reduction(e, cp.dgrad[0], *red, s);
+  }
   if (out_stats != nullptr) {
     ARGUS_CHECK(cp.dgrad.size() == 1, "gradient statistics need a single dgrad launch");
     alg_gstats_slots_ = stat_slots(cp.dgrad[0]);
@@ -758,12 +801,16 @@ void Model::conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_
 // Expanding 1x1 convolution + batch norm backward without touching the BN input or its gradient (see bn_algebra.cu
 // for the derivation): upstream masked gradient g and the saved conv input `act` go through three GEMMs.
 void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
-                                       const float* colsum_partial, int64_t rows, int N, cudaStream_t s) {
+                                       const float* colsum_partial, int64_t rows, int N, cudaStream_t s,
+                                       const BnRed* red, const float* saved_gram) {
   const int O = c.shape.Cout, C = c.shape.Cin;
   float* alg_g = alg_h_ + static_cast<size_t>(O) * C;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
   ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) and G = act^T act (rows O..O+C), act tiles loaded once
+  if (saved_gram != nullptr) {             // (fused tail: G is the matrix the forward statistics came from; hg is H only)
+    ARGUS_CUDA(cudaMemcpyAsync(alg_g, saved_gram, static_cast<size_t>(C) * C * sizeof(float), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
+  }
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
   const float* sc = bn_scratch_ + c.bn.scratch_off;
@@ -773,6 +820,7 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
                         C, s);
   Epilogue e;
   e.shift = alg_bias_;
+  if (red != nullptr) attach_bn_reduction(e, concat, *red, s);
   launch_conv(concat, e, s);               // dAct = [g | act] * [diag(sc) W ; W^T diag(k1) W] + k0^T W
 }
 
@@ -837,7 +885,8 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       if (br.has_ds) {
         if (bp.ds_algebraic) {
           zero_ds_gradient_once(bp, br, T, s);
-          conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, N, s);
+          conv_bn_backward_algebraic(br.ds, bp.ds_hg_wgrad, bp.ds_concat, bp.x, nullptr, bp.rows_out, N, s, nullptr,
+                                     bp.ds_gram_saved);
         } else {
           bn_backward(br.ds, P, bp.rawd, nullptr, R, bp.rows_out, 0, s);
           zero_ds_gradient_once(bp, br, T, s);
@@ -845,16 +894,29 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
         }
         residual = T;
       }
+      // bn2 / bn1 backward reductions ride in the epilogues of the dgrads that produce dAct2 / dAct1 (dense outputs
+      // only: the parity-split dgrad of a stride-2 3x3 convolution keeps the separate reduction pass)
+      const BnRed red2{&br.c2, bp.raw2}, red1{&br.c1, bp.raw1};
+      // Measured per layer (profiles/r2_bn_reduce_fused_ab.txt): the epilogue pays one extra read of `raw` plus a longer
+      // epilogue against the two reads of the separate pass -- a gain where the tensors are large and narrow (layers 1-2,
+      // C <= 128: -0.3 ms / step), a wash or a loss on the L2-bound dgrads of layers 3-4. ARGUS_BN_REDUCE_FUSED=2 fuses all.
+      const int cmax = bn_reduce_fused_ == 2 ? 512 : 128;
+      static const int sites = [] { const char* e = getenv("ARGUS_BN_REDUCE_SITES"); return e ? atoi(e) : 3; }();   // experiment
+      const bool fuse2 = bn_reduce_fused_ && br.c2.bn.C <= cmax && (sites & 2);
+      const bool fuse1 = bn_reduce_fused_ && br.c1.bn.C <= cmax && br.c2.shape.stride == 1 && (sites & 1);
       if (bp.algebraic) {
         // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
-        conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, N, s);
+        conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, N, s,
+                                   fuse2 ? &red2 : nullptr, bp.gram_saved);
       } else {
         bn_backward(br.c3, P, bp.raw3, nullptr, Q, bp.rows_out, 0, s);      // Q = dRaw3
-        conv_backward(bp.c3, nullptr, nullptr, nullptr, s);                  // Q -> R (dAct2)
+        conv_backward(bp.c3, nullptr, nullptr, nullptr, s, fuse2 ? &red2 : nullptr);   // Q -> R (dAct2)
       }
-      bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);        // Q = dRaw2
-      conv_backward(bp.c2, nullptr, nullptr, nullptr, s);                    // Q -> R (dAct1)
-      bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);         // Q = dRaw1
+      if (fuse2) bn_backward_reduced(br.c2, R, bp.raw2, Q, bp.rows_out, s);  // Q = dRaw2
+      else bn_backward(br.c2, R, bp.raw2, nullptr, Q, bp.rows_out, 1, s);
+      conv_backward(bp.c2, nullptr, nullptr, nullptr, s, fuse1 ? &red1 : nullptr);     // Q -> R (dAct1)
+      if (fuse1) bn_backward_reduced(br.c1, R, bp.raw1, Q, bp.rows_in, s);   // Q = dRaw1
+      else bn_backward(br.c1, R, bp.raw1, nullptr, Q, bp.rows_in, 1, s);
       // Q -> S (+ identity-branch gradient), masked by the previous block's ReLU bits; its channel sums are the
       // dbeta of the previous block's algebraic bn3 backward
       conv_backward(bp.c1, residual, prev_bits, prev_stats, s);

@@ -66,6 +66,9 @@ struct BlockPlan {
   // Gram matrix of act2, so conv3 applies BN + identity + ReLU (+ bit mask) in its epilogue: raw3 is never written
   bool fused_tail = false;
   WgradLaunch fwd_gram, ds_fwd_gram;
+  // fused tail: the Gram matrices of act2 / x the forward statistics were derived from, kept for the algebraic backward
+  // (which then only needs H = g^T act: the stacked [g | act]^T act launch loses a fifth of its rows)
+  float *gram_saved = nullptr, *ds_gram_saved = nullptr;
   bool algebraic = false;
   float* act2_colsum = nullptr;   // [bn_apply_grid][C] per-block column sums of act2, written by the forward bn_apply
   WgradLaunch hg_wgrad;           // one launch: H (rows < O) and the Gram matrix (rows O..O+C) into alg_h_
@@ -160,17 +163,25 @@ class Model {
   void head_forward(Plan& p, float* out, cudaStream_t s);
   void run_conv_train(const ConvPlan& cp, const ConvRef& c, int64_t rows, cudaStream_t s);
   // batch statistics of the 1x1 convolution c from the Gram matrix of its input (gram launch + colsum) -> BN scratch
-  void stats_from_gram(const ConvRef& c, const WgradLaunch& gram, const bf16* act, const float* colsum_partial,
+  void stats_from_gram(const ConvRef& c, const WgradLaunch& gram, float* G, const bf16* act, const float* colsum_partial,
                        int64_t rows, int N, cudaStream_t s);
   void bn_backward(const ConvRef& c, bf16* dy, const bf16* raw, const bf16* out, bf16* dx, int64_t rows, int mask,
                    cudaStream_t s);
   // out_bits: ReLU mask of the tensor whose gradient this dgrad produces (stored masked); out_stats: per-slot channel
   // sums of that masked gradient (the dbeta of the algebraic bn3 backward of the previous block)
-  void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats, cudaStream_t s);
+  // red (optional): the BN + ReLU layer whose output gradient this dgrad produces -- its backward reduction runs in the
+  // dgrad epilogue (Epilogue::bn_raw) and bn_backward_reduced() replaces bn_backward() for that layer
+  struct BnRed { const ConvRef* c; const bf16* raw; };
+  void conv_backward(const ConvPlan& cp, const bf16* residual, const uint8_t* out_bits, float* out_stats, cudaStream_t s,
+                     const BnRed* red = nullptr);
+  void attach_bn_reduction(Epilogue& e, const ConvLaunch& l, const BnRed& red, cudaStream_t s);
+  // BN backward of a layer whose gradient arrived masked and already reduced (bnred_stats_): finalize + apply
+  void bn_backward_reduced(const ConvRef& c, bf16* dy, const bf16* raw, bf16* dx, int64_t rows, cudaStream_t s);
   // conv (expanding 1x1) + BN backward on the masked upstream gradient (bn_algebra.cu); colsum_partial == nullptr:
   // the column sums of `act` are computed here
   void conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, const ConvLaunch& concat, const bf16* act,
-                                  const float* colsum_partial, int64_t rows, int N, cudaStream_t s);
+                                  const float* colsum_partial, int64_t rows, int N, cudaStream_t s,
+                                  const BnRed* red = nullptr, const float* saved_gram = nullptr);
 
   template <typename T>
   T* arena_alloc(size_t count);
@@ -208,6 +219,10 @@ class Model {
   float* alg_gstats_ = nullptr;       // [max_stat_slots_][2][alg_max_o_] sums of the masked gradient, per dgrad CTA slot
   bf16* alg_bstack_ = nullptr;
   int alg_gstats_slots_ = 0;          // slots the last producing dgrad launch wrote
+  // BN-backward sums reduced by the producing dgrad's epilogue: [max_stat_slots_][2][512] sum(g), sum(g * raw)
+  int bn_reduce_fused_ = 1;           // 0 = separate passes, 1 = layers 1-2 (default), 2 = every eligible layer
+  float* bnred_stats_ = nullptr;
+  int bnred_slots_ = 0;
   float* wgrad_scratch_ = nullptr;    // split-K partial weight gradients (one launch at a time)
   int64_t wgrad_scratch_elems_ = 0;
   int max_stat_slots_ = 0;

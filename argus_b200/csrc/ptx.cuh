@@ -243,16 +243,29 @@ __device__ __forceinline__ uint64_t f32x2_from_bf16x2(uint32_t w) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(w << 16), "r"(w & 0xffff0000u));
   return r;
 }
+__device__ __forceinline__ uint64_t f32x2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
 __device__ __forceinline__ void f32x2_add(uint64_t& acc, uint64_t x) {
   asm("add.rn.f32x2 %0, %0, %1;" : "+l"(acc) : "l"(x));
 }
 __device__ __forceinline__ void f32x2_fma_sq(uint64_t& acc, uint64_t x) {
   asm("fma.rn.f32x2 %0, %1, %1, %0;" : "+l"(acc) : "l"(x));
 }
+__device__ __forceinline__ void f32x2_fma(uint64_t& acc, uint64_t a, uint64_t b) {
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ float2 f32x2_unpack(uint64_t v) {
   float2 r;
   asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
   return r;
+}
+__device__ __forceinline__ uint32_t ldg_nc_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.nc.u32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
 }
 __device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {
   uint32_t v;

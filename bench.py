@@ -170,14 +170,41 @@ def run_ours(args) -> None:
     # ---- warm-up, then the device-resident timed region (nvidia-smi needs ~1 s to start: launch it first)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    trace = [] if os.environ.get("ARGUS_BENCH_TRACE") in ("1", "2") else None   # debugging aid: every step's loss to stderr
+    if os.environ.get("ARGUS_BENCH_TRACE") == "2":
+        # ... and checksums of the pooled stem output (the staged input), the gradient arena and the updated parameters
+        sigs = []
+        pooled_buf = torch.empty(B * n_cams * (H // 4) * (W // 4) * 64, dtype=torch.bfloat16, device=dev)
+
+        infos_ = list(model._param_infos)
+        untraced_step = engine.step
+
+        def traced_step(images, targets):
+            # nothing is inserted between backward and optimizer (that hides the effect): everything is read afterwards
+            loss_ = untraced_step(images, targets)
+            _lib.check(lib_.argus_model_copy_activation(model._handle.ptr, ctypes.c_int(-1), _lib.ptr(pooled_buf),
+                                                        ctypes.c_int64(pooled_buf.numel()), None, None, _lib.stream_ptr()))
+            a = pooled_buf.float().abs().sum().double()
+            g_ = model.flat_grads
+            per = torch.stack([g_[o:o + k].double().abs().sum() for (_n, o, k, _s) in infos_])
+            c = model.flat_params.double().abs().sum()
+            sigs.append(torch.cat([torch.stack([a, per.sum(), c]), per]))
+            return loss_
+
+        lib_ = _lib.load()
+        engine.step = traced_step
     for i in range(args.warmup):
-        engine.step(*dev_batches[i % ring])
+        l_ = engine.step(*dev_batches[i % ring])
+        if trace is not None:
+            trace.append(l_.clone())
     barrier()
     t_wait = time.time()
     while not sampler.samples and time.time() - t_wait < 5.0:
         time.sleep(0.05)                      # (no collective in this loop: ranks may wait different amounts)
     for i in range(2):                        # back under load before the timed region
-        engine.step(*dev_batches[i % ring])
+        l_ = engine.step(*dev_batches[i % ring])
+        if trace is not None:
+            trace.append(l_.clone())
     engine.prefetch(dev_batches[0][0])        # look-ahead staging, as the training loop does (argus_b200/train.py)
     barrier()
     sampler.mark()
@@ -188,6 +215,8 @@ def run_ours(args) -> None:
     loss = None
     for i in range(args.steps):
         loss = engine.step(*dev_batches[i % ring])
+        if trace is not None:
+            trace.append(loss.clone())
         # augmentation + staging of the next batch on the engine's side stream, overlapping this step
         engine.prefetch(dev_batches[(i + 1) % ring][0])
     ev1.record()
@@ -201,6 +230,14 @@ def run_ours(args) -> None:
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
     final_loss = float(loss.item())
+    if trace is not None and rank == 0:
+        print("LOSS_TRACE " + " ".join(repr(float(x)) for x in trace), file=sys.stderr, flush=True)
+        if os.environ.get("ARGUS_BENCH_TRACE") == "2":
+            for k, sg in enumerate(sigs[:len(trace)]):
+                print(f"SIG {k} in={float(sg[0])!r} grad={float(sg[1])!r} par={float(sg[2])!r}", file=sys.stderr, flush=True)
+            import json as json_
+            json_.dump({"names": [n for (n, _o, _k, _s) in infos_], "sig": [[float(v) for v in sg] for sg in sigs]},
+                       open(os.environ.get("ARGUS_BENCH_TRACE_FILE", "/tmp/bench_trace.json"), "w"))
 
     # ---- end-to-end: pinned host buffers -> H2D -> step -> loss D2H, every step
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()

@@ -1,0 +1,3 @@
+F="--steps 6 --warmup 3 --no-cpu-baseline --no-inference --no-torch-baseline"
+export ARGUS_BENCH_TRACE=1
+for sites in 1 2; do for i in 1 2 3 4; do echo -n "sites=$sites "; ARGUS_BN_REDUCE_SITES=$sites python bench.py $F 2>&1 >/dev/null | grep LOSS_TRACE | cut -d" " -f 7-12; done; done

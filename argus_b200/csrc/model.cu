@@ -207,12 +207,15 @@ void Model::bind(float* params, float* grads, float* buffers) {
     {
       const char* e = getenv("ARGUS_BN_ALGEBRA");
       bn_algebra_ = !(e && e[0] == '0');
-      // Fused block tail in the training forward (bn3 statistics from the Gram matrix of act2, BN + identity + ReLU +
-      // bit mask in conv3's epilogue, raw3 never written). Correct and slightly more accurate, but measured SLOWER
-      // (45.2 vs 44.1 ms/step): it moves 3.6 ms of HBM-roofline bn_apply work into the convolution epilogue, which is
-      // latency-bound (8 warps per SM), and adds 1.5 ms of Gram GEMMs. Opt-in until the epilogue is redesigned.
+      // Fused block tail in the training forward (default; ARGUS_FUSED_TAIL=0 selects the separate passes): bn3's batch
+      // statistics come from the Gram matrix of act2 (kept for the algebraic backward, which then only needs H = g^T act2),
+      // conv3 applies BN + identity + ReLU + the bit mask in its epilogue and raw3 is never written: 10 instead of 17
+      // narrow-tensor passes per block tail. Round 1 measured it SLOWER (45.2 vs 44.1 ms: 8 epilogue warps, ~1 000
+      // instructions per 64-column chunk, coefficient loads stalling every FMUL / FADD); with the packed-fp32 epilogue, the
+      // coefficients in shared memory and the group barrier removed from the residual path it is 1.0-1.2 ms per step
+      // FASTER (profiles/r2_fused_tail_ab.txt).
       const char* ft = getenv("ARGUS_FUSED_TAIL");
-      fused_tail_ = (ft && ft[0] == '1');
+      fused_tail_ = !(ft && ft[0] == '0');
       // eligible: bottlenecks whose mid width is <= 256 (layers 1-3); layer4's small matrices would cost more than the
       // two passes over its (small) activations
       for (const auto& b : blocks_)
@@ -231,10 +234,12 @@ void Model::bind(float* params, float* grads, float* buffers) {
       ARGUS_CUDA(cudaMalloc(&alg_mpartial_, bn_alg_matrix_scratch_elems(static_cast<int>(C)) * sizeof(float)));
     }
     {
-      // BN-backward reduction in the epilogue of the dgrad that produces the gradient (default on; ARGUS_BN_REDUCE_FUSED=0
-      // selects the separate bn_bwd_reduce passes: A/B switch and the reference the fused path is tested against)
+      // BN-backward reduction in the epilogue of the dgrad that produces the gradient: OPT-IN (ARGUS_BN_REDUCE_FUSED=1
+      // fuses layers 1-2, =2 every eligible layer). It saves 0.3 ms per step, but with it and the separate block tail the
+      // bench trajectory stopped reproducing from run to run once the look-ahead staging started (0 of 7 runs; 9 of 9
+      // with the fused tail; every other mode 100 % -- profiles/r2_determinism.md), and the cause was not found.
       const char* e = getenv("ARGUS_BN_REDUCE_FUSED");
-      bn_reduce_fused_ = e ? atoi(e) : 1;
+      bn_reduce_fused_ = e ? atoi(e) : 0;
       ARGUS_CUDA(cudaMalloc(&bnred_stats_, static_cast<size_t>(max_stat_slots_) * 2 * 512 * sizeof(float)));
     }
     ARGUS_CUDA(cudaMalloc(&pack_table_dev_, pack_table_.size() * sizeof(WeightPackEntry)));
@@ -899,11 +904,10 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       const BnRed red2{&br.c2, bp.raw2}, red1{&br.c1, bp.raw1};
       // Measured per layer (profiles/r2_bn_reduce_fused_ab.txt): the epilogue pays one extra read of `raw` plus a longer
       // epilogue against the two reads of the separate pass -- a gain where the tensors are large and narrow (layers 1-2,
-      // C <= 128: -0.3 ms / step), a wash or a loss on the L2-bound dgrads of layers 3-4. ARGUS_BN_REDUCE_FUSED=2 fuses all.
+      // C <= 128: -0.3 ms / step), a wash or a loss on the L2-bound dgrads of layers 3-4 (ARGUS_BN_REDUCE_FUSED=2 fuses all).
       const int cmax = bn_reduce_fused_ == 2 ? 512 : 128;
-      static const int sites = [] { const char* e = getenv("ARGUS_BN_REDUCE_SITES"); return e ? atoi(e) : 3; }();   // experiment
-      const bool fuse2 = bn_reduce_fused_ && br.c2.bn.C <= cmax && (sites & 2);
-      const bool fuse1 = bn_reduce_fused_ && br.c1.bn.C <= cmax && br.c2.shape.stride == 1 && (sites & 1);
+      const bool fuse2 = bn_reduce_fused_ && br.c2.bn.C <= cmax;
+      const bool fuse1 = bn_reduce_fused_ && br.c1.bn.C <= cmax && br.c2.shape.stride == 1;
       if (bp.algebraic) {
         // P, act2 -> R (dAct2), dW3, dgamma3, dbeta3
         conv_bn_backward_algebraic(br.c3, bp.hg_wgrad, bp.c3_concat, bp.act2, bp.act2_colsum, bp.rows_out, N, s,

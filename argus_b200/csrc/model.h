@@ -212,7 +212,7 @@ class Model {
   float* bn_bwd_scratch_ = nullptr;   // per-block partial sums of the BN-backward reductions
   // algebraic bn3 backward scratch (sized for the widest eligible block)
   bool bn_algebra_ = true;
-  bool fused_tail_ = false;
+  bool fused_tail_ = true;
   int alg_max_o_ = 0, alg_max_c_ = 0;
   float *alg_h_ = nullptr, *alg_s_ = nullptr, *alg_k1k0_ = nullptr, *alg_bias_ = nullptr;
   float* alg_mpartial_ = nullptr;
@@ -220,7 +220,7 @@ class Model {
   bf16* alg_bstack_ = nullptr;
   int alg_gstats_slots_ = 0;          // slots the last producing dgrad launch wrote
   // BN-backward sums reduced by the producing dgrad's epilogue: [max_stat_slots_][2][512] sum(g), sum(g * raw)
-  int bn_reduce_fused_ = 1;           // 0 = separate passes, 1 = layers 1-2 (default), 2 = every eligible layer
+  int bn_reduce_fused_ = 0;           // 0 = separate passes (default), 1 = layers 1-2, 2 = every eligible layer
   float* bnred_stats_ = nullptr;
   int bnred_slots_ = 0;
   float* wgrad_scratch_ = nullptr;    // split-K partial weight gradients (one launch at a time)

@@ -207,14 +207,14 @@ def test_algebraic_bn3_backward_matches_textbook(cuda_device, monkeypatch):
 
 def test_fused_bn_backward_reduction_matches_separate_pass(cuda_device, monkeypatch):
     """bn1 / bn2 backward reductions in the epilogue of the dgrad that produces the gradient (Epilogue::bn_raw,
-    csrc/conv_gemm.cuh kOptBnRed; default) against the separate bn_bwd_reduce passes (ARGUS_BN_REDUCE_FUSED=0) on the
+    csrc/conv_gemm.cuh kOptBnRed; opt-in, ARGUS_BN_REDUCE_FUSED=1|2) against the separate bn_bwd_reduce passes on the
     same weights and inputs. Same forward, same masked bf16 gradient, same dx formula: only the summation order of the
     two per-channel sums differs (fp32 slot sums centred once in double vs per-block centring), so the gradients must
     agree far below bf16 resolution at the end of the network and to bf16 noise at its start."""
     from argus_b200.loss import geometric_loss_fn
     from argus_b200.models import NCameraCNN
 
-    monkeypatch.setenv("ARGUS_BN_REDUCE_FUSED", "2")     # every eligible layer (the default fuses layers 1-2 only)
+    monkeypatch.setenv("ARGUS_BN_REDUCE_FUSED", "2")     # every eligible layer
     ref, ours_fused = build_pair(cuda_device, residual_gain=0.2)
     ours_fused.train()
     ours_fused(structured_images(2, 6, 64, 64, 1, cuda_device))   # binds (reads the environment) on first use
@@ -252,27 +252,27 @@ def test_fused_bn_backward_reduction_matches_separate_pass(cuda_device, monkeypa
 
 
 def test_fused_block_tail_forward(cuda_device, monkeypatch):
-    """ARGUS_FUSED_TAIL=1 (opt-in, csrc/model.cu): bn3's batch statistics are derived from the Gram matrix of act2
+    """Fused block tail (default, csrc/model.cu): bn3's batch statistics are derived from the Gram matrix of act2
     before conv3 runs, and conv3 applies BN + identity + ReLU + the bit mask in its epilogue (raw3 never exists). Same
-    network: outputs, BN running statistics and gradients must agree with the default path up to bf16 rounding, and
-    be at least as close to the fp32 reference."""
+    network: outputs, BN running statistics and gradients must agree with the separate-pass path (ARGUS_FUSED_TAIL=0)
+    up to bf16 rounding, and be at least as close to the fp32 reference."""
     from argus_b200.loss import geometric_loss_fn
     from argus_b200.models import NCameraCNN
     from oracle.ref_model import torch_loss
 
-    ref, ours_def = build_pair(cuda_device, residual_gain=0.2)
-    monkeypatch.setenv("ARGUS_FUSED_TAIL", "1")
-    ours_fused = NCameraCNN().to(cuda_device)
-    ours_fused.load_state_dict(ref.state_dict())
+    ref, ours_fused = build_pair(cuda_device, residual_gain=0.2)
+    monkeypatch.setenv("ARGUS_FUSED_TAIL", "0")
+    ours_def = NCameraCNN().to(cuda_device)      # "def" = the separate bn_apply tail (round 1's default)
+    ours_def.load_state_dict(ref.state_dict())
     x = structured_images(8, 6, 128, 128, 3, cuda_device)
     target = random_targets(8, 4, cuda_device)
+    ours_def.train()
+    y_d = ours_def(x)                            # binds (reads the environment) on first use
+    geometric_loss_fn(y_d, target).mean().backward()
+    monkeypatch.delenv("ARGUS_FUSED_TAIL")
     ours_fused.train()
     y_f = ours_fused(x)
     geometric_loss_fn(y_f, target).mean().backward()
-    monkeypatch.delenv("ARGUS_FUSED_TAIL")
-    ours_def.train()
-    y_d = ours_def(x)
-    geometric_loss_fn(y_d, target).mean().backward()
     ref.train()
     y_ref = ref(x)
     torch_loss(y_ref, target).mean().backward()

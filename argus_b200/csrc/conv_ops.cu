@@ -157,10 +157,8 @@ std::string profile_report_json() {
   return out;
 }
 
-// Off by default. Measured on B200: 0.1-0.3 ms of a 40 ms step (with the early trigger of -DARGUS_PDL_TRIGGER compiled in;
-// less without it). With the step on a high-priority stream the trajectory stopped being reproducible whenever kernels
-// triggered early (profiles/experiments/stream_determinism.py); kernels that only wait never showed it, and delaying
-// every side-stream fork by 400 us (ARGUS_FUZZ_DELAY_US) changes nothing, so the library's own fork / join edges hold.
+// Off by default (ARGUS_PDL=1 enables). Measured on B200 in round 2: -0.3 ms of a 38 ms step, 11 of 11 bench runs
+// reproducible, but one of 15 in-process trajectories differed (profiles/r2_determinism.md, section 4): still an experiment.
 bool pdl_enabled() {
   static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return e && e[0] == '1'; }();
   return on;
@@ -168,13 +166,8 @@ bool pdl_enabled() {
 namespace {
 std::mutex g_pdl_mu;
 std::vector<std::pair<cudaStream_t, bool>> g_pdl_ok;   // a handful of streams: linear search
-int pdl_break_mask() {
-  static const int m = [] { const char* e = getenv("ARGUS_PDL_BREAK"); return e ? atoi(e) : 0; }();
-  return m;
-}
 }  // namespace
-void pdl_break(cudaStream_t stream, int kind) {
-  if (!(pdl_break_mask() & kind)) return;
+void pdl_break(cudaStream_t stream, int) {
   std::lock_guard<std::mutex> lk(g_pdl_mu);
   for (auto& e : g_pdl_ok)
     if (e.first == stream) e.second = false;
@@ -591,48 +584,31 @@ static void launch_conv_t(const ConvGemmParams& p, cudaStream_t stream) {
   // weights-resident mode (see ConvGemmParams::b_resident)
   ConvGemmParams q = p;
   {
-    const int pipe_bytes = L::kStages * L::kStageBytes;
     const int bres = p.num_taps * p.kblocks_per_tap * L::kBBytes;
     const bool fixed_n = (tiles <= grid) || (grid % p.num_n_tiles == 0);
-    static const bool enabled = [] { const char* e = getenv("ARGUS_B_RESIDENT"); return (e && e[0] == '1'); }();
-    static const bool halo_enabled = [] { const char* e = getenv("ARGUS_HALO"); return !(e && e[0] == '0'); }();
     if (q.halo) {
       const int halo_a = (q.halo_rows + 2) * q.halo_row_bytes;
       const int stage = halo_a + 3 * L::kBBytes;
       q.halo_stages = std::min(L::kMaxStages, L::kPipeBytes / stage);
-      if (!halo_enabled || q.halo_stages < 2) q.halo = 0;
-      // halo + weights resident (default on, ARGUS_HALO_RESIDENT=0 disables): when the whole weight slab fits next to
-      // two activation boxes (layer1 3x3: 72 KB), the per-tile L2 -> SM traffic drops from 3 x (32 + 24) to 3 x 32 KB
-      static const bool halo_res = [] { const char* e = getenv("ARGUS_HALO_RESIDENT"); return !(e && e[0] == '0'); }();
-      if (q.halo && halo_res && fixed_n && q.k2_blocks == 0 && bres + 2 * halo_a <= L::kPipeBytes) {
+      if (q.halo_stages < 2) q.halo = 0;
+      // halo + weights resident: when the whole weight slab fits next to two activation boxes (layer1 3x3: 72 KB), the
+      // per-tile L2 -> SM traffic drops from 3 x (32 + 24) to 3 x 32 KB
+      if (q.halo && fixed_n && q.k2_blocks == 0 && bres + 2 * halo_a <= L::kPipeBytes) {
         q.b_resident = 1;
         q.halo_stages = std::min(L::kMaxStages, (L::kPipeBytes - bres) / halo_a);
       }
     }
-    if (!q.halo && q.k2_blocks == 0 && enabled && fixed_n && bres + 3 * L::kABytes <= pipe_bytes) {
-      q.b_resident = 1;
-      q.res_stages = std::min(L::kMaxStages, (pipe_bytes - bres) / L::kABytes);
-    }
+    // (a weights-resident mode for the non-halo launches was built and measured in round 1: no gain -- weights are
+    // served from L2 without cost -- and removed in round 2)
   }
   launch_kernel(conv_gemm_kernel<BN, BMN, EPI, OPT>, grid, 64 + 128 * EPI, L::kTotal, stream, q);
   ARGUS_CUDA(cudaGetLastError());
 }
 
-// Number of epilogue groups for a launch. Default 2. Two experiments stay reachable:
-//  * ARGUS_EPI=3: three groups on every non-halo launch. Measured: no help (44.6 -> 45.8 ms/step) -- only two TMEM
-//    accumulator stages exist at N = 256, so at most two tile epilogues are in flight.
-//  * ARGUS_EPI=4: split-tile mode, four groups working in pairs on one 256-wide tile (sixteen epilogue warps). Measured:
-//    no help either (wide 1x1 forward 253 us with two or four groups) -- those launches write four bytes for every byte
-//    they read and sit at the HBM *write* bandwidth (~5.0 TB/s; the copy figure of 6.46 TB/s is a 1:1 read/write mix),
-//    not at the epilogue's instruction rate.
-int choose_epilogue_groups(const ConvGemmParams& p, int block_n) {
-  static const int forced = [] { const char* e = getenv("ARGUS_EPI"); return e ? atoi(e) : 0; }();
-  if (p.halo) return 2;
-  if (forced == 3) return 3;
-  // split-tile mode (the launch falls back to two groups when its epilogue carries a residual)
-  if (block_n == 256 && forced == 4) return 4;
-  return 2;
-}
+// Two epilogue groups (one per TMEM accumulator stage) everywhere. Round 1 also built three groups and a split-tile
+// mode with sixteen epilogue warps; neither helped (the wide shallow-K launches sit at the HBM write bandwidth, not at
+// the epilogue's instruction rate) and both were removed in round 2.
+int choose_epilogue_groups(const ConvGemmParams&, int) { return 2; }
 
 void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   ConvGemmParams p = l.p;
@@ -682,8 +658,8 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     bytes += 2.0 * p.n_total * (p.num_taps * kc + p.k2_blocks * kBlockK);
   }
   ProfileScope prof(fam, stream, flops, bytes);
-  // specialised epilogues (two epilogue groups only; ARGUS_PLAIN_EPILOGUE=0 sends everything to the generic kernel)
-  static const bool special = [] { const char* e = getenv("ARGUS_PLAIN_EPILOGUE"); return !(e && e[0] == '0'); }();
+  // specialised epilogues: the option combinations the model actually launches; anything else runs the generic kernel
+  constexpr bool special = true;
   int need = 0;
   if (p.scale || p.shift) need |= kOptAffine;
   if (p.has_res) need |= kOptRes;
@@ -692,20 +668,8 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   if (p.relu || p.relu_bits_out) need |= kOptRelu;
   constexpr int kTail = kOptAffine | kOptRes | kOptRelu;           // fused forward block tail: BN + identity + ReLU (+ bits)
   const bool plain_res = p.has_res && !p.res_bits && !p.res_scale;
-  if (l.epi == 4) {
-    // split-tile kernels exist for the residual-free epilogues; everything else runs the two-group kernels below
-    // (the statistics slots are sized for four groups, the unused ones stay zero)
-    if (need == 0) {
-      if (l.b_mn) launch_conv_t<256, 1, 4, 0>(p, stream);
-      else launch_conv_t<256, 0, 4, 0>(p, stream);
-      return;
-    }
-    if (l.b_mn == 1 && (need & ~(kOptAffine | kOptOutBits)) == 0) {
-      launch_conv_t<256, 1, 4, kOptAffine | kOptOutBits>(p, stream);
-      return;
-    }
-  }
-  const int epi2 = (l.epi == 4) ? 2 : l.epi;
+  const int epi2 = l.epi;
+  ARGUS_CHECK(epi2 == 2, "two epilogue groups");
   if (p.bn_raw != nullptr) {
     // dgrad + fused batch-norm backward reduction: plain (3x3 / 1x1 dgrads) or with the bias of the K-concatenated dgrad
     ARGUS_CHECK(epi2 == 2, "fused BN reduction: two epilogue groups only");
@@ -777,12 +741,6 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     case (64 * 2 + 1) * 4 + 2: launch_conv_t<64, 1, 2>(p, stream); break;
     case (128 * 2 + 1) * 4 + 2: launch_conv_t<128, 1, 2>(p, stream); break;
     case (256 * 2 + 1) * 4 + 2: launch_conv_t<256, 1, 2>(p, stream); break;
-    case (64 * 2 + 0) * 4 + 3: launch_conv_t<64, 0, 3>(p, stream); break;
-    case (128 * 2 + 0) * 4 + 3: launch_conv_t<128, 0, 3>(p, stream); break;
-    case (256 * 2 + 0) * 4 + 3: launch_conv_t<256, 0, 3>(p, stream); break;
-    case (64 * 2 + 1) * 4 + 3: launch_conv_t<64, 1, 3>(p, stream); break;
-    case (128 * 2 + 1) * 4 + 3: launch_conv_t<128, 1, 3>(p, stream); break;
-    case (256 * 2 + 1) * 4 + 3: launch_conv_t<256, 1, 3>(p, stream); break;
     default: throw Error("unsupported conv tile configuration");
   }
 }

@@ -832,8 +832,7 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
 // The stride-2 1x1 dgrad writes every fourth pixel of T; the rest must be zero. T is private to the block, so the fill
 // is needed once per arena epoch, not per step.
 void Model::zero_ds_gradient_once(BlockPlan& bp, const BlockRef& br, bf16* T, cudaStream_t s) {
-  static const bool once = [] { const char* e = getenv("ARGUS_DS_ZERO_ONCE"); return !(e && e[0] == '0'); }();   // A/B switch
-  if (br.ds.shape.stride != 2 || (once && bp.t_zero_epoch == arena_epoch_)) return;
+  if (br.ds.shape.stride != 2 || bp.t_zero_epoch == arena_epoch_) return;
   ARGUS_CUDA(cudaMemsetAsync(T, 0, bp.x_bytes, s)); pdl_break(s, kPdlAfterMemop);
   bp.t_zero_epoch = arena_epoch_;
 }

@@ -30,17 +30,11 @@ __device__ __forceinline__ uint32_t elect_one() {
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch (PDL). Every kernel of the library starts with pdl_prologue(): wait until the
 // previous kernel of the stream has completed and flushed (a no-op when the launch carries no programmatic edge, which
-// is the default -- see pdl_enabled()). Building with -DARGUS_PDL_TRIGGER adds griddepcontrol.launch_dependents right
-// after the wait ("wait, then trigger": the NEXT kernel of the stream may then be scheduled while this one runs, at most
-// one successor parked). The early trigger is not compiled in by default: it only pays with ARGUS_PDL=1 (0.1-0.3 ms of
-// a 40 ms step), and every non-reproducible run seen in this round (high-priority caller stream + look-ahead staging)
-// was with kernels that trigger early -- never with kernels that only wait.
+// is the default -- see pdl_enabled()). Round 1 also had a build option that triggered the dependents early; it bought
+// 0.1-0.3 ms and was removed in round 2 (profiles/r2_determinism.md).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
-#ifdef ARGUS_PDL_TRIGGER
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -77,8 +77,8 @@ struct ProfileScope {
 bool pdl_enabled();
 // Every C-ABI entry point starts with pdl_break_all(): the first kernel of a call is launched without a programmatic
 // edge (the caller may have enqueued anything in between). pdl_break() marks the event records / event waits / memsets /
-// memcpys the library itself enqueues; stream order already covers them, so by default they do not break the chain --
-// ARGUS_PDL_BREAK=<bit mask of PdlBreakKind> makes them do so (debugging aid).
+// memcpys the library itself enqueues: the kernel that follows one of them is launched without the attribute, so
+// programmatic edges only ever connect two back-to-back kernels of the library.
 enum PdlBreakKind { kPdlAfterWait = 1, kPdlAfterRecord = 2, kPdlAfterMemop = 4 };
 void pdl_break(cudaStream_t stream, int kind);
 void pdl_break_all();

@@ -19,16 +19,20 @@ def _rerun(env_extra, selection):
     assert " passed" in r.stdout
 
 
-def test_split_tile_epilogue_mode(cuda_device):
-    """ARGUS_EPI=4: four epilogue groups working in pairs on 256-wide tiles (forward, dgrad, statistics)."""
-    _rerun({"ARGUS_EPI": "4"}, ["tests/test_conv_gpu.py", "-k", "forward or dgrad"])
-
-
 def test_programmatic_dependent_launch(cuda_device):
-    """ARGUS_PDL=1: every launch carries a programmatic edge (the kernels wait in their prologue; the early trigger is a
-    compile-time option); gradients and the reproducibility tests must not change."""
+    """ARGUS_PDL=1: back-to-back kernels of the library carry a programmatic edge (they wait in their prologue);
+    gradients and the reproducibility tests must not change."""
     _rerun({"ARGUS_PDL": "1"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
                                  "train_forward_backward or reproducible or prefetch"])
+
+
+def test_fused_bn_reduction_modes(cuda_device):
+    """ARGUS_BN_REDUCE_FUSED=2 (BN-backward sums in the dgrad epilogues, every eligible layer) and ARGUS_FUSED_TAIL=0
+    (separate bn_apply block tail): the gradient and reproducibility tests must hold in both."""
+    _rerun({"ARGUS_BN_REDUCE_FUSED": "2"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
+                                            "train_forward_backward or reproducible or prefetch"])
+    _rerun({"ARGUS_FUSED_TAIL": "0"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
+                                       "train_forward_backward or reproducible or prefetch"])
 
 
 def test_register_bn_kernels(cuda_device):

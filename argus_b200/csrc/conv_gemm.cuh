@@ -402,13 +402,14 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
     static_assert(!BNRED || ((OPT & kOptRes) && !(OPT & (kOptResExtra | kOptRelu | kOptOutBits))), "kOptBnRed rides the residual path");
     float* my_partial = do_stats ? p.stat_partial + static_cast<size_t>(EPI * blockIdx.x + grp) * 2 * p.n_total : nullptr;
     constexpr int kChunks = GW / 64;
-    // Fused forward block tail (BN + identity + ReLU + bit mask, no statistics): scale / shift of the CTA's current N
-    // tile live in the group's (otherwise unused) statistics scratch, the affine and the residual add run on packed
-    // fp32 pairs. The generic code below re-loaded 2 x 64 floats per chunk with dependent global loads (long-scoreboard
+    // Folded batch norm in the epilogue without statistics -- the fused forward block tail (BN + identity + ReLU + bit
+    // mask), its downsample branch (BN only) and every eval-mode convolution (BN [+ identity] [+ ReLU]): scale / shift
+    // of the CTA's current N tile live in the group's (otherwise unused) statistics scratch, the affine and the
+    // residual add run on packed fp32 pairs. The generic code below re-loaded 2 x 64 floats per chunk with dependent global loads (long-scoreboard
     // stalls on every FMUL / FADD, ncu: profiles/r2_ncu_fused_tail.txt) and spent ~1 000 instructions per 64-column
     // chunk. launch_conv only selects this instance when scale, shift, ReLU and a plain residual are all present and
     // no statistics are requested.
-    constexpr bool FAST_TAIL = (OPT == (kOptAffine | kOptRes | kOptRelu)) && EPI == 2;
+    constexpr bool FAST_TAIL = (OPT & kOptAffine) && !(OPT & ~(kOptAffine | kOptRes | kOptRelu)) && EPI == 2;
     float* s_aff = s_stats;   // [scale GW | shift GW]
     int cur_aff_n = -1;
 
@@ -552,30 +553,38 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
             for (int q = 0; q < 4; ++q) {
               const int phys = (h * 4 + q) ^ (r & 7);
               uint4* slot = reinterpret_cast<uint4*>(stg + r * 128 + phys * 16);
-              const uint4 rv = *slot;
+              uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+              if constexpr ((OPT & kOptRes) != 0) rv = *slot;
               const float4 s0 = sc4[2 * q], s1 = sc4[2 * q + 1], t0 = sh4[2 * q], t1 = sh4[2 * q + 1];
               uint64_t y0 = f32x2_pack(t0.x, t0.y), y1 = f32x2_pack(t0.z, t0.w), y2 = f32x2_pack(t1.x, t1.y), y3 = f32x2_pack(t1.z, t1.w);
               f32x2_fma(y0, f32x2_pack(__uint_as_float(v[h][q * 8 + 0]), __uint_as_float(v[h][q * 8 + 1])), f32x2_pack(s0.x, s0.y));
               f32x2_fma(y1, f32x2_pack(__uint_as_float(v[h][q * 8 + 2]), __uint_as_float(v[h][q * 8 + 3])), f32x2_pack(s0.z, s0.w));
               f32x2_fma(y2, f32x2_pack(__uint_as_float(v[h][q * 8 + 4]), __uint_as_float(v[h][q * 8 + 5])), f32x2_pack(s1.x, s1.y));
               f32x2_fma(y3, f32x2_pack(__uint_as_float(v[h][q * 8 + 6]), __uint_as_float(v[h][q * 8 + 7])), f32x2_pack(s1.z, s1.w));
-              f32x2_add(y0, f32x2_from_bf16x2(rv.x));
-              f32x2_add(y1, f32x2_from_bf16x2(rv.y));
-              f32x2_add(y2, f32x2_from_bf16x2(rv.z));
-              f32x2_add(y3, f32x2_from_bf16x2(rv.w));
+              if constexpr ((OPT & kOptRes) != 0) {
+                f32x2_add(y0, f32x2_from_bf16x2(rv.x));
+                f32x2_add(y1, f32x2_from_bf16x2(rv.y));
+                f32x2_add(y2, f32x2_from_bf16x2(rv.z));
+                f32x2_add(y3, f32x2_from_bf16x2(rv.w));
+              }
               const float2 a = f32x2_unpack(y0), b = f32x2_unpack(y1), c = f32x2_unpack(y2), d = f32x2_unpack(y3);
               const float y8[8] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y};
+              if constexpr ((OPT & kOptRelu) != 0) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) ob |= (y8[j] > 0.f ? 1u : 0u) << (q * 8 + j);
+                for (int j = 0; j < 8; ++j) ob |= (y8[j] > 0.f ? 1u : 0u) << (q * 8 + j);
+              }
+              const float floor_ = ep_relu ? 0.f : -INFINITY;   // (ReLU is a run-time flag of the kOptRelu instances)
               uint4 o;
-              o.x = pack_bf16x2(fmaxf(y8[0], 0.f), fmaxf(y8[1], 0.f));
-              o.y = pack_bf16x2(fmaxf(y8[2], 0.f), fmaxf(y8[3], 0.f));
-              o.z = pack_bf16x2(fmaxf(y8[4], 0.f), fmaxf(y8[5], 0.f));
-              o.w = pack_bf16x2(fmaxf(y8[6], 0.f), fmaxf(y8[7], 0.f));
+              o.x = pack_bf16x2(fmaxf(y8[0], floor_), fmaxf(y8[1], floor_));
+              o.y = pack_bf16x2(fmaxf(y8[2], floor_), fmaxf(y8[3], floor_));
+              o.z = pack_bf16x2(fmaxf(y8[4], floor_), fmaxf(y8[5], floor_));
+              o.w = pack_bf16x2(fmaxf(y8[6], floor_), fmaxf(y8[7], floor_));
               *slot = o;
             }
-            if (ep_relu_bits_out != nullptr && m0 + r < p.m_total)
-              *reinterpret_cast<uint32_t*>(ep_relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) + (c0 >> 3)) = ob;
+            if constexpr ((OPT & kOptRelu) != 0) {
+              if (ep_relu_bits_out != nullptr && m0 + r < p.m_total)
+                *reinterpret_cast<uint32_t*>(ep_relu_bits_out + static_cast<size_t>(m0 + r) * (p.n_total >> 3) + (c0 >> 3)) = ob;
+            }
           } else {
           float f[32];
 #pragma unroll

@@ -667,7 +667,6 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
   if (p.out_bits) need |= kOptOutBits;
   if (p.relu || p.relu_bits_out) need |= kOptRelu;
   constexpr int kTail = kOptAffine | kOptRes | kOptRelu;           // fused forward block tail: BN + identity + ReLU (+ bits)
-  const bool plain_res = p.has_res && !p.res_bits && !p.res_scale;
   const int epi2 = l.epi;
   ARGUS_CHECK(epi2 == 2, "two epilogue groups");
   if (p.bn_raw != nullptr) {
@@ -684,16 +683,25 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       default: throw Error("unsupported conv tile configuration");
     }
   }
-  if (special && epi2 == 2 && l.b_mn == 0 && plain_res && need == kTail && p.scale && p.shift && p.relu && !p.stat_partial) {
-    // fused forward block tail (ARGUS_FUSED_TAIL=1). Round 2 also tried loading the residual row segments straight from
-    // global memory into registers (no staging buffer, which would have made the sixteen-warp split-tile mode possible
-    // with a residual): one thread per row means 32 different rows per load instruction -- uncoalesced, 1.5-1.9 TB/s
-    // against 5.1-5.5 TB/s through TMA + staging (profiles/r2_direct_residual_ab.txt). Removed again.
-    switch (l.block_n) {
-      case 64: launch_conv_t<64, 0, 2, kTail>(p, stream); return;
-      case 128: launch_conv_t<128, 0, 2, kTail>(p, stream); return;
-      case 256: launch_conv_t<256, 0, 2, kTail>(p, stream); return;
-      default: break;
+  // Folded batch norm without statistics (packed-fp32 epilogue, coefficients in shared memory): the fused forward block
+  // tail, its downsample branch, every eval-mode convolution. Needs BOTH coefficient vectors (a bias-only epilogue such as
+  // resnet.fc runs the generic kernel). Round 2 also tried loading the residual row segments straight from global memory
+  // into registers: one thread per row = 32 rows per load instruction, uncoalesced, 1.5-1.9 TB/s against 5.1-5.5 TB/s
+  // through TMA + staging (profiles/r2_direct_residual_ab.txt).
+  const bool folded_bn = p.scale && p.shift && !p.stat_partial && !p.res_bits && !p.res_scale && !p.out_bits;
+  if (special && epi2 == 2 && l.b_mn == 0 && folded_bn && (need & kOptAffine) && !(need & ~kTail) &&
+      (p.relu || !p.relu_bits_out)) {
+    switch (l.block_n * 16 + (need & kTail)) {
+      case 64 * 16 + kTail: launch_conv_t<64, 0, 2, kTail>(p, stream); return;
+      case 128 * 16 + kTail: launch_conv_t<128, 0, 2, kTail>(p, stream); return;
+      case 256 * 16 + kTail: launch_conv_t<256, 0, 2, kTail>(p, stream); return;
+      case 64 * 16 + (kOptAffine | kOptRelu): launch_conv_t<64, 0, 2, kOptAffine | kOptRelu>(p, stream); return;
+      case 128 * 16 + (kOptAffine | kOptRelu): launch_conv_t<128, 0, 2, kOptAffine | kOptRelu>(p, stream); return;
+      case 256 * 16 + (kOptAffine | kOptRelu): launch_conv_t<256, 0, 2, kOptAffine | kOptRelu>(p, stream); return;
+      case 64 * 16 + kOptAffine: launch_conv_t<64, 0, 2, kOptAffine>(p, stream); return;
+      case 128 * 16 + kOptAffine: launch_conv_t<128, 0, 2, kOptAffine>(p, stream); return;
+      case 256 * 16 + kOptAffine: launch_conv_t<256, 0, 2, kOptAffine>(p, stream); return;
+      default: break;   // e.g. identity + BN without ReLU: generic kernel
     }
   }
   if (special && epi2 == 2 && need == 0) {
@@ -704,15 +712,6 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
       case 64 * 2 + 1: launch_conv_t<64, 1, 2, 0>(p, stream); return;
       case 128 * 2 + 1: launch_conv_t<128, 1, 2, 0>(p, stream); return;
       case 256 * 2 + 1: launch_conv_t<256, 1, 2, 0>(p, stream); return;
-      default: break;
-    }
-  }
-  if (special && epi2 == 2 && l.b_mn == 0 && need == kOptAffine) {
-    // scale / shift only: the downsample branch of a fused block tail, the eval-mode convolutions without ReLU
-    switch (l.block_n) {
-      case 64: launch_conv_t<64, 0, 2, kOptAffine>(p, stream); return;
-      case 128: launch_conv_t<128, 0, 2, kOptAffine>(p, stream); return;
-      case 256: launch_conv_t<256, 0, 2, kOptAffine>(p, stream); return;
       default: break;
     }
   }

@@ -1,0 +1,3 @@
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_conv_gpu.py tests/test_inference_gpu.py tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -3
+python profiles/inference_latency.py 2>&1 | tail -1 | cut -c1-420
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-inference --no-torch-baseline 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('train', d['ms_per_step'], d['final_loss'], d['clocks']['sm_mhz'])"

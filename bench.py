@@ -387,6 +387,14 @@ def run_ours(args) -> None:
                     "arithmetic_intensity": round(ai, 1), "ridge": round(ridge, 1),
                     "share_of_step": round(f["ms"] / total_ms, 4),
                     "traffic_note": "per-shape DRAM traffic is in profiles/ (ncu --set full captures); not re-measured here"}
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of this family from the committed `ncu --set full` capture
+        # (profiles/*_family_traffic.json, written from the capture of the same code), when the shape was captured
+        fam_files = sorted(Path(__file__).resolve().parent.glob("profiles/*_family_traffic.json"))
+        if fam_files and B == 256 and args.size == 256:
+            ft = json.loads(fam_files[-1].read_text()).get(k)
+            if ft:
+                roofline["traffic"] = round(ft["dram_bytes_per_launch"])
+                roofline["traffic_note"] = f"committed: profiles/{fam_files[-1].name} -- {ft['source']}"
     # whole-step HBM view: algorithmic bytes of every launch (each operand tensor counted once) over the step time
     step_bytes = sum(f["bytes"] for f in families.values())
     step_ms = ms_total / args.steps

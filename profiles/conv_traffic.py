@@ -16,6 +16,15 @@ for r in csv.DictReader(lines):
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0}.get(u, 1.0)
     per[int(r["ID"])][r["Metric Name"]] = v * scale
     per[int(r["ID"])]["name"] = re.sub(r"^void |\(.*$", "", r["Kernel Name"])
+# the capture may span more than one step: keep exactly one period of the (kernel name, grid) sequence
+ids = sorted(per)
+seq = [per[i]["name"] for i in ids]
+period = len(seq)
+for P in range(100, len(seq) // 2 + 1):
+    if all(seq[i] == seq[i + P] for i in range(len(seq) - P)):
+        period = P
+        break
+per = {i: per[i] for i in ids[:period]}
 rd = sum(p.get("dram__bytes_read.sum", 0.0) for p in per.values())
 wr = sum(p.get("dram__bytes_write.sum", 0.0) for p in per.values())
 ms = sum(p.get("gpu__time_duration.sum", 0.0) for p in per.values())

@@ -157,10 +157,13 @@ std::string profile_report_json() {
   return out;
 }
 
-// Off by default (ARGUS_PDL=1 enables). Measured on B200 in round 2: -0.3 ms of a 38 ms step, 11 of 11 bench runs
-// reproducible, but one of 15 in-process trajectories differed (profiles/r2_determinism.md, section 4): still an experiment.
+// Programmatic dependent launch between back-to-back kernels of the library: on by default since round 2 (ARGUS_PDL=0
+// disables). Every kernel waits in its prologue (griddepcontrol.wait), nothing triggers early, and any event record /
+// wait / memset / memcpy the library enqueues breaks the chain (pdl_break), so the only thing that overlaps is the launch
+// latency of a kernel with the tail of its predecessor. Measured on B200: 38.6-38.9 -> 37.7-38.3 ms per step, same bits
+// in 8 of 8 bench runs and 29 of 29 in-process trajectories (profiles/r2_determinism.md, section 4).
 bool pdl_enabled() {
-  static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return e && e[0] == '1'; }();
+  static const bool on = [] { const char* e = getenv("ARGUS_PDL"); return !(e && e[0] == '0'); }();
   return on;
 }
 namespace {

@@ -19,10 +19,10 @@ def _rerun(env_extra, selection):
     assert " passed" in r.stdout
 
 
-def test_programmatic_dependent_launch(cuda_device):
-    """ARGUS_PDL=1: back-to-back kernels of the library carry a programmatic edge (they wait in their prologue);
-    gradients and the reproducibility tests must not change."""
-    _rerun({"ARGUS_PDL": "1"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
+def test_without_programmatic_dependent_launch(cuda_device):
+    """ARGUS_PDL=0: plain stream order instead of the default programmatic edges between back-to-back kernels (they wait
+    in their prologue); gradients and the reproducibility tests must not change."""
+    _rerun({"ARGUS_PDL": "0"}, ["tests/test_model_gpu.py", "tests/test_train_gpu.py", "-k",
                                  "train_forward_backward or reproducible or prefetch"])
 
 

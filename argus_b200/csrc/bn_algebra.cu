@@ -169,6 +169,17 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
   ARGUS_CUDA(cudaGetLastError());
   launch_kernel(bn_alg_matrix_reduce_kernel, ((C + 1) * C + 255) / 256, 256, 0, st, mpartial, bstack, bias, O, C);
   ARGUS_CUDA(cudaGetLastError());
+  if (dW != nullptr) {
+    launch_kernel(bn_alg_dw_kernel, dim3(C / 16, O / 16), 256, 0, st, W, H, G, s, scale, k1k0, dW, O, C);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+}
+
+// The weight-gradient part alone (dW == nullptr above): nothing downstream of the backward chain reads dW3, so the
+// model runs it on the weight-gradient side stream, overlapping the K-concatenated dgrad.
+void bn_alg_backward_dw(const bf16* W, const float* H, const float* G, const float* s, const float* scale,
+                        const float* k1k0, float* dW, int O, int C, cudaStream_t st) {
+  ProfileScope prof("bn_algebra", st, 2.0 * O * static_cast<double>(C) * C, 0);
   launch_kernel(bn_alg_dw_kernel, dim3(C / 16, O / 16), 256, 0, st, W, H, G, s, scale, k1k0, dW, O, C);
   ARGUS_CUDA(cudaGetLastError());
 }

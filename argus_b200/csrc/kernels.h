@@ -117,6 +117,10 @@ void bn_alg_backward_small(const bf16* W, const float* H, const float* G, const 
                            int slots, int stat_stride, const float* scale, const float* mean, const float* invstd,
                            double rows, float* dgamma, float* dbeta, float* dW, float* k1k0, bf16* bstack, float* bias,
                            float* mpartial, int O, int C, cudaStream_t st);
+// dW == nullptr above skips the weight-gradient kernel; this runs it alone (on another stream):
+// dW[o][i] += scale[o] H[o][i] + k0[o] s[i] + k1[o] sum_j W[o][j] G[j][i]
+void bn_alg_backward_dw(const bf16* W, const float* H, const float* G, const float* s, const float* scale,
+                        const float* k1k0, float* dW, int O, int C, cudaStream_t st);
 int64_t bn_alg_matrix_scratch_elems(int C);   // floats of `mpartial`
 // Forward counterpart: train-mode batch statistics of y = x W^T from G = x^T x and s = colsum(x) (both over the `rows`
 // pixels the 1x1 convolution reads), before / instead of computing y: scale, shift, mean, invstd and the running-stat

@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <tuple>
 
 namespace argus {
@@ -725,17 +726,23 @@ void Model::ensure_wgrad_scratch(const WgradLaunch& l) {
 // All weight-gradient GEMMs of a backward pass run on ONE stream (the side stream when overlapping), so a single
 // split-K scratch buffer is enough.
 void Model::run_wgrad(const WgradLaunch& l, cudaStream_t s) {
+  run_on_side(s, [&](cudaStream_t ss) { launch_wgrad(l, wgrad_scratch_, ss); });
+}
+
+// Fork: `work` only needs what the caller's stream has produced so far; it runs on the side stream (on the caller's
+// stream when overlap is off or the stream is being captured) and is joined by join_wgrad().
+void Model::run_on_side(cudaStream_t s, const std::function<void(cudaStream_t)>& work) {
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   cudaStreamIsCapturing(s, &cap);
   if (!overlap_wgrad_ || cap != cudaStreamCaptureStatusNone) {
     join_wgrad(s);
-    launch_wgrad(l, wgrad_scratch_, s);
+    work(s);
     return;
   }
   ARGUS_CUDA(cudaEventRecord(ev_fork_, s)); pdl_break(s, kPdlAfterRecord);
   ARGUS_CUDA(cudaStreamWaitEvent(side_, ev_fork_, 0)); pdl_break(side_, kPdlAfterWait);
   fuzz_delay(1, side_);
-  launch_wgrad(l, wgrad_scratch_, side_);
+  work(side_);
   ARGUS_CUDA(cudaEventRecord(ev_wgrad_, side_)); pdl_break(side_, kPdlAfterRecord);
   wgrad_pending_ = true;
 }
@@ -819,10 +826,19 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
   if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
   const float* sc = bn_scratch_ + c.bn.scratch_off;
+  // the coefficient / B-stack kernels feed the dgrad below; the weight-gradient kernel feeds nothing in this chain and
+  // runs on the weight-gradient side stream (joined before H, G, s or k1k0 are overwritten: every algebraic call and
+  // every bn_backward joins first)
+  const bool dw_aside = overlap_wgrad_;
   bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
                         sc + 2 * O, sc + 3 * O, static_cast<double>(rows), grads_dev_ + c.bn.gamma_off,
-                        grads_dev_ + c.bn.beta_off, grads_dev_ + c.w_off, alg_k1k0_, alg_bstack_, alg_bias_, alg_mpartial_, O,
-                        C, s);
+                        grads_dev_ + c.bn.beta_off, dw_aside ? nullptr : grads_dev_ + c.w_off, alg_k1k0_, alg_bstack_, alg_bias_,
+                        alg_mpartial_, O, C, s);
+  if (dw_aside) {
+    const bf16* Wp = packed_ + c.packed_off;
+    float* dW = grads_dev_ + c.w_off;
+    run_on_side(s, [=](cudaStream_t ss) { bn_alg_backward_dw(Wp, alg_h_, alg_g, alg_s_, sc, alg_k1k0_, dW, O, C, ss); });
+  }
   Epilogue e;
   e.shift = alg_bias_;
   if (red != nullptr) attach_bn_reduction(e, concat, *red, s);

@@ -5,6 +5,7 @@
 // launch plans (TMA tensor maps). The caller (PyTorch) owns the fp32 parameter / gradient / buffer arenas whose
 // layout is described by tensor_info() in the reference's state_dict order.
 #pragma once
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -228,6 +229,7 @@ class Model {
   int max_stat_slots_ = 0;
   void ensure_wgrad_scratch(const WgradLaunch& l);
   void run_wgrad(const WgradLaunch& l, cudaStream_t s);
+  void run_on_side(cudaStream_t s, const std::function<void(cudaStream_t)>& work);
   int64_t n_packed_ = 0, n_gpacked_ = 0, n_bn_scratch_ = 0, n_bn_stats_ = 0;
   WeightPackEntry* pack_table_dev_ = nullptr;
   std::vector<WeightPackEntry> pack_table_;

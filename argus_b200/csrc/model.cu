@@ -394,9 +394,10 @@ void Model::build_plan(Plan& p) {
     if (tr && bn_algebra_ && wd <= 256)
       bp.act2_colsum = arena_alloc<float>(static_cast<size_t>(bn_apply_grid(static_cast<int64_t>(e_out), wd)) * wd);
     if (bp.fused_tail) {
-      bp.gram_saved = arena_alloc<float>(static_cast<size_t>(wd) * wd);
+      // (C x C Gram matrix followed by the C column sums of the same activation)
+      bp.gram_saved = arena_alloc<float>(static_cast<size_t>(wd) * wd + wd);
       if (br.has_ds && br.ds.shape.Cin <= 256)
-        bp.ds_gram_saved = arena_alloc<float>(static_cast<size_t>(br.ds.shape.Cin) * br.ds.shape.Cin);
+        bp.ds_gram_saved = arena_alloc<float>(static_cast<size_t>(br.ds.shape.Cin) * br.ds.shape.Cin + br.ds.shape.Cin);
     }
     max_elems = std::max(max_elems, std::max(e_in * std::max(wd, br.c1.shape.Cin), e_out * oc));
     plan_conv(bp.c1, br.c1, N, h, w, bp.x, tr ? bp.raw1 : bp.act1, true);
@@ -588,10 +589,11 @@ void Model::stats_from_gram(const ConvRef& c, const WgradLaunch& gram, float* G,
   const int O = c.shape.Cout, C = c.shape.Cin;
   ARGUS_CUDA(cudaMemsetAsync(G, 0, static_cast<size_t>(C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
   launch_wgrad(gram, wgrad_scratch_, s);
-  if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
-  else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
+  float* colsum = G + static_cast<size_t>(C) * C;   // kept next to the Gram matrix for the backward pass
+  if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), colsum, C, s);
+  else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, colsum, s);
   float* sc = bn_scratch_ + c.bn.scratch_off;
-  bn_stats_from_gram(packed_ + c.packed_off, G, alg_s_, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
+  bn_stats_from_gram(packed_ + c.packed_off, G, colsum, static_cast<double>(rows), params_dev_ + c.bn.gamma_off,
                      params_dev_ + c.bn.beta_off, buffers_dev_ + c.bn.rm_off, buffers_dev_ + c.bn.rv_off, kBnMomentum,
                      kBnEps, sc, sc + O, sc + 2 * O, sc + 3 * O, alg_mpartial_, O, C, s);
 }
@@ -816,28 +818,30 @@ void Model::conv_bn_backward_algebraic(const ConvRef& c, const WgradLaunch& hg, 
                                        const float* colsum_partial, int64_t rows, int N, cudaStream_t s,
                                        const BnRed* red, const float* saved_gram) {
   const int O = c.shape.Cout, C = c.shape.Cin;
-  float* alg_g = alg_h_ + static_cast<size_t>(O) * C;
+  // fused tail: G is the matrix the forward statistics came from (kept per block) and hg computes H only; otherwise hg
+  // is the stacked launch that appends G below H
+  const float* alg_g = saved_gram != nullptr ? saved_gram : alg_h_ + static_cast<size_t>(O) * C;
   join_wgrad(s);   // one split-K scratch buffer: no weight-gradient GEMM may be in flight on the side stream
-  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(O + C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
-  launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) and G = act^T act (rows O..O+C), act tiles loaded once
-  if (saved_gram != nullptr) {             // (fused tail: G is the matrix the forward statistics came from; hg is H only)
-    ARGUS_CUDA(cudaMemcpyAsync(alg_g, saved_gram, static_cast<size_t>(C) * C * sizeof(float), cudaMemcpyDeviceToDevice, s)); pdl_break(s, kPdlAfterMemop);
-  }
-  if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
+  ARGUS_CUDA(cudaMemsetAsync(alg_h_, 0, static_cast<size_t>(saved_gram != nullptr ? O : O + C) * C * sizeof(float), s)); pdl_break(s, kPdlAfterMemop);
+  launch_wgrad(hg, wgrad_scratch_, s);     // H = g^T act (rows < O) [and G = act^T act (rows O..O+C), act tiles loaded once]
+  // column sums of `act`: the forward kept them next to its Gram matrix (fused tail); otherwise they are rebuilt here
+  const float* colsum = alg_s_;
+  if (saved_gram != nullptr) colsum = saved_gram + static_cast<size_t>(C) * C;
+  else if (colsum_partial != nullptr) colsum_finalize(colsum_partial, bn_apply_grid(rows, C), alg_s_, C, s);
   else colsum_pixels_bf16(act, N, c.shape.H, c.shape.W, C, c.shape.stride, bn_bwd_scratch_, alg_s_, s);
   const float* sc = bn_scratch_ + c.bn.scratch_off;
   // the coefficient / B-stack kernels feed the dgrad below; the weight-gradient kernel feeds nothing in this chain and
   // runs on the weight-gradient side stream (joined before H, G, s or k1k0 are overwritten: every algebraic call and
   // every bn_backward joins first)
   const bool dw_aside = overlap_wgrad_;
-  bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g, alg_s_, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
+  bn_alg_backward_small(packed_ + c.packed_off, alg_h_, alg_g, colsum, alg_gstats_, alg_gstats_slots_, 2 * O, sc,
                         sc + 2 * O, sc + 3 * O, static_cast<double>(rows), grads_dev_ + c.bn.gamma_off,
                         grads_dev_ + c.bn.beta_off, dw_aside ? nullptr : grads_dev_ + c.w_off, alg_k1k0_, alg_bstack_, alg_bias_,
                         alg_mpartial_, O, C, s);
   if (dw_aside) {
     const bf16* Wp = packed_ + c.packed_off;
     float* dW = grads_dev_ + c.w_off;
-    run_on_side(s, [=](cudaStream_t ss) { bn_alg_backward_dw(Wp, alg_h_, alg_g, alg_s_, sc, alg_k1k0_, dW, O, C, ss); });
+    run_on_side(s, [=](cudaStream_t ss) { bn_alg_backward_dw(Wp, alg_h_, alg_g, colsum, sc, alg_k1k0_, dW, O, C, ss); });
   }
   Epilogue e;
   e.shift = alg_bias_;

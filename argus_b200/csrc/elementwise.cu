@@ -1523,8 +1523,23 @@ __global__ void avgpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restric
     float acc[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc[k] = 0.f;
-    for (int p = 0; p < HW; ++p) {
-      const F8 v = unpack8(ldg_stream(x + (static_cast<int64_t>(n) * HW + p) * cvec + cv));
+    // eight independent 16-byte loads in flight, added in pixel order (same bits as a plain loop, an eighth of the
+    // latency chain: the batch-1 inference forward spent 23 us here)
+    const uint4* src = x + static_cast<int64_t>(n) * HW * cvec + cv;
+    int p = 0;
+    for (; p + 8 <= HW; p += 8) {
+      uint4 u[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) u[j] = ldg_stream(src + static_cast<int64_t>(p + j) * cvec);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const F8 v = unpack8(u[j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
+      }
+    }
+    for (; p < HW; ++p) {
+      const F8 v = unpack8(ldg_stream(src + static_cast<int64_t>(p) * cvec));
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] += v.v[k];
     }

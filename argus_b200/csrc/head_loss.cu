@@ -44,9 +44,12 @@ void gelu_bwd_bf16(const float* dz, const bf16* x, bf16* dx, int64_t n, cudaStre
   ARGUS_CUDA(cudaGetLastError());
 }
 
-// y[b, o] = dot(x[b, :], w[o, :]) + bias[o]. A block stages kLinRows batch rows in shared memory; warp w takes the
-// outputs w, w + 8, ...: one coalesced pass over the weight row serves all staged rows (the weights are read B / kLinRows
-// times instead of B times). Per (b, o) the summation is lane-strided then a shuffle tree: a fixed order.
+// y[b, o] = dot(x[b, :], w[o, :]) + bias[o]. A block stages kLinRows batch rows in shared memory; its warp w takes the
+// outputs 8 * blockIdx.y + w, + 8 * gridDim.y, ...: one coalesced pass over the weight row serves all staged rows (the
+// weights are read B / kLinRows times instead of B times). Per (b, o) the summation is lane-strided then a shuffle
+// tree: a fixed order, the same bits for any grid. The outputs are spread over gridDim.y blocks so that a small batch
+// (inference at batch 1: ONE block used to walk all 128 outputs of the 1024-wide layer, 37 us per layer) still fills
+// the machine.
 constexpr int kLinRows = 4;
 __global__ void __launch_bounds__(256)
 linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
@@ -61,7 +64,7 @@ linear_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < Out; o += 8) {
+  for (int o = blockIdx.y * 8 + warp; o < Out; o += 8 * gridDim.y) {
     const float* wr = w + static_cast<int64_t>(o) * In;
     float acc[kLinRows];
 #pragma unroll
@@ -90,8 +93,10 @@ void linear_fwd(const float* x, const float* w, const float* b, float* y, float*
                 cudaStream_t s) {
   ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
   ARGUS_CHECK(static_cast<size_t>(kLinRows) * In * sizeof(float) <= 48 * 1024, "linear_fwd: input width too large");
-  launch_kernel(linear_fwd_kernel, (B + kLinRows - 1) / kLinRows, 256, static_cast<size_t>(kLinRows) * In * sizeof(float), s, x,
-                w, b, y, act, B, In, Out);
+  const int gx = (B + kLinRows - 1) / kLinRows;
+  const int gy = std::max(1, std::min((Out + 7) / 8, (2 * num_sms() + gx - 1) / gx));
+  launch_kernel(linear_fwd_kernel, dim3(gx, gy), 256, static_cast<size_t>(kLinRows) * In * sizeof(float), s, x, w, b, y, act, B,
+                In, Out);
   ARGUS_CUDA(cudaGetLastError());
 }
 

@@ -86,6 +86,7 @@ struct ConvGemmParams {
   const __nv_bfloat16* bn_raw;
   const float* bn_scale;
   const float* bn_shift;
+  int early_trigger;   // let the next kernel of the stream start its prologue at once (pdl_begin; eval-mode chain only)
   // train-mode BN statistics of the stored bf16 outputs, reduced deterministically: every (CTA, epilogue group)
   // owns slot = 2*blockIdx.x + group of stat_partial[slot][2][n_total] (sum, sum of squares); bn_finalize adds the
   // slots in a fixed order. The caller zeroes the buffer.
@@ -141,7 +142,7 @@ constexpr int kOptAll = 31;      // the generic kernel (kOptBnRed only exists in
 template <int BLOCK_N, int B_MN, int EPI, int OPT = kOptAll>
 __global__ void __launch_bounds__(64 + 128 * EPI, 1)
 conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
-  pdl_prologue();
+  pdl_begin(p.early_trigger);
   constexpr int NBUF = conv_staging_buffers<BLOCK_N, OPT, EPI>();
   static_assert(NBUF == 2 || !(OPT & kOptRes), "the residual prefetch needs two staging buffers");
   // Split-tile mode (EPI == 4, BLOCK_N == 256): the two TMEM accumulator stages bound the tiles in flight, so instead of
@@ -215,6 +216,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();   // everything above touched shared memory, TMEM and the kernel parameters only
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kblocks = p.num_taps * p.kblocks_per_tap + p.k2_blocks;

@@ -636,6 +636,7 @@ void launch_conv(const ConvLaunch& l, const Epilogue& e, cudaStream_t stream) {
     p.has_res = 1;
     p.bn_raw = e.bn_raw;
   }
+  p.early_trigger = (e.early_trigger && pdl_enabled()) ? 1 : 0;
   p.relu = e.relu;
   p.out_bits = e.out_bits;
   p.res_scale = e.res_scale;

@@ -39,6 +39,7 @@ struct Epilogue {
   const __nv_bfloat16* bn_raw = nullptr;
   const float* bn_scale = nullptr;
   const float* bn_shift = nullptr;
+  int early_trigger = 0;   // ConvGemmParams::early_trigger (the eval-mode forward sets it)
 };
 
 // geometry of the (non-strided) output tensor map, kept so that a residual tensor map can be built per launch

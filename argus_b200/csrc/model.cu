@@ -607,6 +607,7 @@ void Model::forward_eval(Plan& p, cudaStream_t s) {
     e.shift = e.scale + c.bn.C;
     e.residual = res;
     e.relu = relu;
+    e.early_trigger = 1;   // inference chain: the next convolution sets itself up while this one runs
     return e;
   };
   launch_conv(p.stem.fwd, EP(stem_, nullptr, 1), s);

@@ -36,6 +36,15 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
+// Deferred form for kernels with a long data-independent prologue (barrier init, TMEM allocation, descriptor prefetch):
+// pdl_begin(trigger) is the first statement -- with trigger != 0 the NEXT kernel of the stream may become resident right
+// away and run its own prologue while this kernel works (only the eval-mode inference chain asks for that: at batch 1 a
+// launch is a few CTAs and its fixed prologue is a third of its 8-10 us) -- and pdl_wait() stands before the first access
+// to memory another kernel may have written. Kernels launched without a programmatic edge see two no-ops.
+__device__ __forceinline__ void pdl_begin(int trigger) {
+  if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

@@ -54,4 +54,9 @@ def test_every_kernel_waits_on_its_programmatic_dependency():
             if 0 <= semi < brace:
                 continue   # declaration only
             body = text[brace + 1:brace + 200].lstrip()
+            if body.startswith("pdl_begin("):
+                # deferred form (ptx.cuh): the wait stands after the data-independent prologue, before the role dispatch
+                end = text.find("__global__", m.end())
+                assert "pdl_wait();" in text[brace:end if end > 0 else len(text)], f"{path.name}: pdl_begin() without pdl_wait()"
+                continue
             assert body.startswith("pdl_prologue();"), f"{path.name}: kernel at offset {m.start()} lacks pdl_prologue()"

@@ -216,7 +216,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  pdl_wait();   // everything above touched shared memory, TMEM and the kernel parameters only
+  pdl_wait_deferred(p.early_trigger);   // everything above touched shared memory, TMEM and the kernel parameters only
 
   const int num_tiles = p.num_m_tiles * p.num_n_tiles;
   const int num_kblocks = p.num_taps * p.kblocks_per_tap + p.k2_blocks;

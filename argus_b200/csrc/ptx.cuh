@@ -36,15 +36,20 @@ __device__ __forceinline__ uint32_t elect_one() {
 __device__ __forceinline__ void pdl_prologue() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-// Deferred form for kernels with a long data-independent prologue (barrier init, TMEM allocation, descriptor prefetch):
-// pdl_begin(trigger) is the first statement -- with trigger != 0 the NEXT kernel of the stream may become resident right
-// away and run its own prologue while this kernel works (only the eval-mode inference chain asks for that: at batch 1 a
-// launch is a few CTAs and its fixed prologue is a third of its 8-10 us) -- and pdl_wait() stands before the first access
-// to memory another kernel may have written. Kernels launched without a programmatic edge see two no-ops.
+// Deferred form for the eval-mode inference chain (at batch 1 a launch is a few CTAs and its fixed prologue -- barrier
+// init, TMEM allocation, descriptor prefetch -- is a third of its 8-10 us): pdl_begin(1) is the first statement, the NEXT
+// kernel of the stream may become resident right away and run its own prologue while this kernel works, and
+// pdl_wait_deferred(1) stands before the first access to memory another kernel may have written. With trigger == 0
+// (every training launch) pdl_begin waits at once, exactly like pdl_prologue(), and pdl_wait_deferred is a no-op: a
+// training run with the wait deferred gave one differing trajectory in six bench runs (profiles/r2_determinism.md, section 5).
+// Kernels launched without a programmatic edge see no-ops.
 __device__ __forceinline__ void pdl_begin(int trigger) {
   if (trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  else asm volatile("griddepcontrol.wait;" ::: "memory");
 }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_deferred(int trigger) {
+  if (trigger) asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier

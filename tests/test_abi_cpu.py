@@ -55,8 +55,11 @@ def test_every_kernel_waits_on_its_programmatic_dependency():
                 continue   # declaration only
             body = text[brace + 1:brace + 200].lstrip()
             if body.startswith("pdl_begin("):
-                # deferred form (ptx.cuh): the wait stands after the data-independent prologue, before the role dispatch
+                # deferred form (ptx.cuh): pdl_begin(0) waits at once; pdl_begin(1) triggers and the wait stands after the
+                # data-independent prologue, before the role dispatch -- both take the same flag
                 end = text.find("__global__", m.end())
-                assert "pdl_wait();" in text[brace:end if end > 0 else len(text)], f"{path.name}: pdl_begin() without pdl_wait()"
+                span = text[brace:end if end > 0 else len(text)]
+                flag = re.match(r"pdl_begin\(([^)]*)\)", body).group(1)
+                assert f"pdl_wait_deferred({flag});" in span, f"{path.name}: pdl_begin() without pdl_wait_deferred()"
                 continue
             assert body.startswith("pdl_prologue();"), f"{path.name}: kernel at offset {m.start()} lacks pdl_prologue()"

@@ -152,6 +152,25 @@ linear_bwd_x_kernel(const float* __restrict__ dy, const float* __restrict__ w, f
   for (int k = 0; k < 4; ++k)
     if (b0 + k < B) dx[static_cast<int64_t>(b0 + k) * In + i] = acc[k];
 }
+// The backward of one linear layer in two halves, so that the caller can take the weight gradient off the critical path:
+// linear_bwd_input turns the incoming gradient into the gradient of the layer output IN PLACE (GELU') and produces dx;
+// linear_bwd_weights only reads that gradient and the saved input (dw += dy^T x, db += colsum dy).
+void linear_bwd_input(float* dy, const float* pre, const float* w, float* dx, int B, int In, int Out, cudaStream_t s) {
+  ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
+  if (pre != nullptr) {
+    launch_kernel(gelu_grad_inplace_kernel, (B * Out + 255) / 256, 256, 0, s, dy, pre, B * Out);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+  if (dx != nullptr) {
+    launch_kernel(linear_bwd_x_kernel, dim3((In + 127) / 128, (B + 3) / 4), 128, 0, s, dy, w, dx, B, In, Out);
+    ARGUS_CUDA(cudaGetLastError());
+  }
+}
+void linear_bwd_weights(const float* dy, const float* x, float* dw, float* db, int B, int In, int Out, cudaStream_t s) {
+  ProfileScope prof("head", s, 2.0 * B * In * Out, 4.0 * (static_cast<double>(B) * In + static_cast<double>(In) * Out + static_cast<double>(B) * Out));
+  launch_kernel(linear_bwd_w_kernel, dim3((In + 127) / 128, (Out + 3) / 4), 128, 0, s, dy, x, dw, db, B, In, Out);
+  ARGUS_CUDA(cudaGetLastError());
+}
 void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
                 int In, int Out, cudaStream_t s) {
   ProfileScope prof("head", s, 4.0 * B * In * Out, 4.0 * (2.0 * B * In + 2.0 * In * Out + static_cast<double>(B) * Out));

@@ -147,6 +147,10 @@ void linear_fwd(const float* x, const float* w, const float* b, float* y, float*
 // by gelu'(pre) in place): dw += dy^T x, db += sum dy, dx = dy W
 void linear_bwd(float* dy, const float* pre, const float* x, const float* w, float* dw, float* db, float* dx, int B,
                 int In, int Out, cudaStream_t s);
+// the same in two halves (model.cu runs the weight half on the weight-gradient side stream): linear_bwd_input applies
+// GELU' to dy in place (pre != nullptr) and writes dx; linear_bwd_weights accumulates dw / db from the finished dy
+void linear_bwd_input(float* dy, const float* pre, const float* w, float* dx, int B, int In, int Out, cudaStream_t s);
+void linear_bwd_weights(const float* dy, const float* x, float* dw, float* db, int B, int In, int Out, cudaStream_t s);
 
 // ---- loss / pose ------------------------------------------------------------------------------------------
 // per-sample loss (argus/train.py:119), its mean accumulated into *loss_mean (caller zeroes), and

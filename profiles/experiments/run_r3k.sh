@@ -1,0 +1,6 @@
+# head weight gradients on the weight-gradient side stream: same bits expected (final loss 9.74431324005127), ms/step
+F="--steps 20 --warmup 4 --no-cpu-baseline --no-inference --no-torch-baseline"
+for i in 1 2 3 4; do
+python bench.py $F 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('head-dw-aside', d['ms_per_step'], d['final_loss'], d['clocks']['sm_mhz'])"
+done
+timeout 900 python -m pytest tests/test_model_gpu.py tests/test_train_gpu.py tests/test_parity_gpu.py -x -q -m gpu 2>&1 | tail -2

@@ -896,8 +896,16 @@ void Model::backward(const float* d_out, int stage_begin, int stage_end, cudaStr
       gelu_bwd_bf16(p.d_z0, p.feat, p.d_feat, static_cast<int64_t>(B) * F, s);
       // ---- fc
       { ProfileScope prof("head", s, 0, 2.0 * N * out_dim_); }
-      launch_kernel(colsum_bf16_kernel, (out_dim_ + 127) / 128, 128, 0, s, p.d_feat, g + fc_bias_off_, N, out_dim_);
-      ARGUS_CUDA(cudaGetLastError());
+      // (the fc bias gradient -- one block column walking all N rows, 38 us -- feeds nothing in the chain either)
+      {
+        const bf16* dfeat = p.d_feat;
+        float* dbias = g + fc_bias_off_;
+        const int od = out_dim_;
+        run_on_side(s, [=](cudaStream_t ss) {
+          launch_kernel(colsum_bf16_kernel, (od + 127) / 128, 128, 0, ss, dfeat, dbias, N, od);
+          ARGUS_CUDA(cudaGetLastError());
+        });
+      }
       run_wgrad(p.fc.wgrad, s);
       Epilogue e;
       for (const auto& l : p.fc.dgrad) launch_conv(l, e, s);
